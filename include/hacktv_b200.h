@@ -1,0 +1,246 @@
+/* hacktv_b200 - the C-ABI of the B200-native composite-video -> IQ hot path.
+ *
+ * This header is the drop-in boundary. Everything here is `extern "C"`, plain
+ * pointers and sizes; no CUDA, torch or C++ types appear in any signature
+ * (a CUDA stream is passed as an opaque `void *`).
+ *
+ * Each entry point replaces one piece of fsphil/hacktv's encoder interface.
+ * "ref" = the reference's src/ directory; the adapter a hacktv maintainer adds
+ * (video_b200.c, which implements video.h's vid_* symbols on top of these) is
+ * shown in INTEGRATION.md and lives in integration/video_b200.c.
+ *
+ *   htv_config_t            <- vid_config_t               ref video.h:125-292 (hot-path subset, same names)
+ *   htv_modes[], htv_find_mode <- vid_configs[]           ref video.c:1956-2008, hacktv.c:1078-1087
+ *   htv_init                <- vid_init                   ref video.c:3812-4704
+ *   htv_free                <- vid_free                   ref video.c:4706-4843
+ *   htv_info                <- vid_info                   ref video.c:4846-4860
+ *   htv_get_framebuffer_length <- vid_get_framebuffer_length  ref video.c:4862-4865
+ *   htv_next_line           <- vid_next_line              ref video.c:4936-4952
+ *   htv_line_t              <- vid_line_t                 ref video.h:306-329
+ *   htv_av_t + callbacks    <- av_t, av_read_video_t ...  ref av.h:64-116, video.c:4873-4904, 3280
+ *   htv_av_test_open        <- av_test_open               ref av_test.c:71-205
+ *   htv_rf_t, htv_rf_write, htv_rf_close <- rf_t, rf_write, rf_close   ref rf.h:39-54, rf.c:23-51
+ *   htv_rf_file_open        <- rf_file_open (int16 only)  ref rf_file.c:290-373
+ *   htv_render / htv_render_host: NOT in the reference - the batched extension a
+ *       per-line C call cannot replace: N scan lines per call.
+ *
+ * Error convention follows the reference (video.h:45-47): 0 OK, -1 error,
+ * -2 out of memory; htv_next_line returns NULL at end of stream.
+ * Without a usable CUDA device htv_init fails with HTV_ERROR and a message on
+ * stderr - there is no CPU fallback.
+ */
+#ifndef HACKTV_B200_H
+#define HACKTV_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTV_OK             0
+#define HTV_ERROR         -1
+#define HTV_OUT_OF_MEMORY -2
+
+/* output_type (ref rf.h:26-28) */
+#define HTV_INT16_COMPLEX 0
+#define HTV_INT16_REAL    1
+/* modulation (ref video.h:71-74) */
+#define HTV_NONE 0
+#define HTV_AM   1
+#define HTV_VSB  2
+#define HTV_FM   3
+/* type (ref video.h:49-59); only these two rasters are on the hot path */
+#define HTV_RASTER_625 0
+#define HTV_RASTER_525 1
+/* colour_mode (ref video.h:76-82) */
+#define HTV_MONOCHROME 0
+#define HTV_PAL        1
+#define HTV_NTSC       2
+#define HTV_SECAM      3
+/* audio pre-emphasis (ref video.h:84-88) */
+#define HTV_50US 1
+#define HTV_75US 2
+#define HTV_J17  3
+
+/* The hot-path subset of vid_config_t, same field names and meaning. */
+typedef struct {
+	int32_t output_type;
+	int32_t modulation;
+	double video_bw;
+	double vsb_upper_bw;
+	double vsb_lower_bw;
+	double level;
+	int32_t swap_iq;
+	int32_t invert_video;
+	int64_t offset;
+	double video_level;
+	double fm_mono_level;
+	double am_audio_level;
+	double nicam_level;
+	int32_t type;
+	int32_t lines;
+	int64_t frame_rate_num;
+	int64_t frame_rate_den;
+	int32_t hline;
+	int32_t interlaced;
+	int32_t active_lines;
+	int32_t vfilter;
+	double hsync_width;
+	double vsync_short_width;
+	double vsync_long_width;
+	double sync_rise;
+	double white_level;
+	double black_level;
+	double blanking_level;
+	double sync_level;
+	double active_width;
+	double active_left;
+	double gamma;
+	double rw_co;
+	double gw_co;
+	double bw_co;
+	int32_t colour_mode;
+	int32_t volume;
+	int64_t colour_carrier_num;
+	int64_t colour_carrier_den;
+	double colour_bw;
+	double burst_width;
+	double burst_left;
+	double burst_level;
+	double burst_rise;
+	double ev_co;
+	double eu_co;
+	double fm_mono_carrier;
+	double fm_mono_deviation;
+	int32_t fm_mono_preemph;
+	int32_t reserved0;
+	double nicam_carrier;
+	double nicam_beta;
+	double am_mono_carrier;
+} htv_config_t;
+
+typedef struct {
+	const char *id;
+	const htv_config_t *conf;
+	const char *desc;
+} htv_mode_t;
+
+extern const htv_mode_t htv_modes[];
+extern const htv_config_t *htv_find_mode(const char *id);
+extern size_t htv_config_size(void);
+
+/* ---- AV source (pull model, as the reference's av_t) ------------------- */
+
+typedef struct {
+	int width;                    /* pixels per row */
+	int height;                   /* rows */
+	const uint32_t *framebuffer;  /* RGBx, row-major, tightly packed */
+	uint64_t serial;              /* changes whenever the pixel data changes; a source
+	                                 that returns the same image every frame (the test
+	                                 pattern) keeps it constant so the upload is skipped */
+} htv_frame_t;
+
+typedef int (*htv_read_video_t)(void *ctx, htv_frame_t *frame);
+typedef int (*htv_read_audio_t)(void *ctx, const int16_t **samples, size_t *npairs);
+typedef int (*htv_av_close_t)(void *ctx);
+
+typedef struct {
+	int width;                    /* set by htv_init: active_width */
+	int height;                   /* set by htv_init: active_lines */
+	void *ctx;
+	htv_read_video_t read_video;  /* once per frame, at line 1 (ref video.c:4873-4881) */
+	htv_read_audio_t read_audio;  /* 32 kHz stereo int16, any block size (ref video.c:3280) */
+	htv_av_close_t close;
+} htv_av_t;
+
+/* ---- encoder ----------------------------------------------------------- */
+
+typedef struct htv_t htv_t;
+
+typedef struct {
+	int16_t *output;   /* int16 I,Q interleaved, 2 * width values (Q = 0 for real modes) */
+	int width;
+	int frame;         /* 1-based */
+	int line;          /* 1-based */
+} htv_line_t;
+
+extern int htv_init(htv_t **s, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf);
+extern void htv_free(htv_t *s);
+extern void htv_info(htv_t *s);
+extern size_t htv_get_framebuffer_length(htv_t *s);
+extern htv_av_t *htv_av(htv_t *s);
+extern int htv_av_test_open(htv_av_t *av);
+extern void htv_av_close(htv_av_t *av);
+
+extern htv_line_t *htv_next_line(htv_t *s);
+
+/* Batched extension. Renders the next `nlines` scan lines of the stream.
+ * htv_render: `d_out` is DEVICE memory (at least htv_samples_per_line(s) *
+ *   nlines * htv_bytes_per_sample(s) bytes); work is enqueued on `cuda_stream`
+ *   (a cudaStream_t, or NULL for the default stream) and the call returns
+ *   without synchronising.
+ * htv_render_host: `h_out` is HOST memory; the call uploads what the batch
+ *   needs, renders, copies the result back and returns when it is there.
+ * Both return HTV_OK or an error; *nsamples (may be NULL) receives the number
+ * of samples produced. Output layout is what the reference's file sink writes
+ * (rf_file.c:97-116, 226-233): int16 I,Q interleaved for complex modes, int16
+ * I only for real modes. */
+extern int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream);
+extern int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples);
+
+/* Geometry / state accessors (fields hacktv.c reads from vid_t, ref video.h:358-420) */
+extern int htv_samples_per_line(const htv_t *s);   /* vid_t.width */
+extern int htv_active_width(const htv_t *s);
+extern int htv_active_lines(const htv_t *s);
+extern int htv_lines_per_frame(const htv_t *s);
+extern int htv_sample_rate(const htv_t *s);
+extern int htv_is_complex(const htv_t *s);
+extern int htv_bytes_per_sample(const htv_t *s);   /* 4 complex, 2 real */
+extern int64_t htv_lines_rendered(const htv_t *s);
+/* Kernel launches issued by this encoder since htv_init (for bench accounting) */
+extern uint64_t htv_kernel_launches(const htv_t *s);
+/* Duration of the dominant kernel's most recent launch, measured with CUDA
+ * events on the stream it ran on; 0 if timing is off. */
+extern void htv_set_kernel_timing(htv_t *s, int on);
+extern float htv_last_line_kernel_ms(htv_t *s);
+
+/* ---- host-only table generation (no GPU needed; used by htv_init) ------ */
+
+typedef struct htv_tables_t htv_tables_t;
+
+extern htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_rate);
+extern void htv_tables_free(htv_tables_t *t);
+/* Named int32 views for tests: "sync0".."sync4", "sync_off", "burst_win",
+ * "chroma_taps", "vsb_itaps", "vsb_qtaps", "levels", "nicam_taps", "geometry",
+ * "secam_lpf", "secam_notch". Returns NULL for an unknown / absent table. */
+extern const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count);
+
+/* ---- RF sink (int16 file sink only) ------------------------------------ */
+
+typedef int (*htv_rf_write_t)(void *ctx, const int16_t *iq_data, size_t samples);
+typedef int (*htv_rf_close_t)(void *ctx);
+
+typedef struct {
+	void *ctx;
+	htv_rf_write_t write;
+	htv_rf_close_t close;
+} htv_rf_t;
+
+extern int htv_rf_write(htv_rf_t *s, const int16_t *iq_data, size_t samples);
+extern int htv_rf_close(htv_rf_t *s);
+extern int htv_rf_file_open(htv_rf_t *s, const char *filename, int complex);
+
+/* The built-in test source's data, exposed for tests (ref av_test.c:94-196) */
+extern void htv_test_pattern(int width, int height, uint32_t *rgb);
+extern size_t htv_test_tone_pairs(void);
+extern void htv_test_tone(int16_t *pcm);
+
+extern const char *htv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
