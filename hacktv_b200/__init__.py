@@ -1,0 +1,329 @@
+"""hacktv_b200 - Python view of the C-ABI in include/hacktv_b200.h.
+
+The product is the shared library ``libhacktv_b200.so`` (C host layer + sm_100a
+CUDA kernels). This module only loads it with ctypes and mirrors the
+reference-facing call sequence (reference hacktv.c:1440-1601):
+
+    enc = Encoder("i", 16_000_000, vfilter=True)   # vid_configs lookup + vid_init
+    enc.open_test_source()                          # av_test_open
+    iq = enc.render_host(625)                       # 625 x vid_next_line + rf_write
+    enc.close()                                     # vid_free
+
+There is no CPU fallback: without the built library, or without a CUDA device,
+construction raises. Nothing here imports or links anything under ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhacktv_b200.so")
+
+HTV_OK, HTV_ERROR, HTV_OUT_OF_MEMORY = 0, -1, -2
+
+
+class Config(C.Structure):
+    """htv_config_t (include/hacktv_b200.h) = the hot-path subset of vid_config_t."""
+
+    _fields_ = [
+        ("output_type", C.c_int32), ("modulation", C.c_int32),
+        ("video_bw", C.c_double), ("vsb_upper_bw", C.c_double), ("vsb_lower_bw", C.c_double),
+        ("level", C.c_double),
+        ("swap_iq", C.c_int32), ("invert_video", C.c_int32), ("offset", C.c_int64),
+        ("video_level", C.c_double), ("fm_mono_level", C.c_double),
+        ("am_audio_level", C.c_double), ("nicam_level", C.c_double),
+        ("type", C.c_int32), ("lines", C.c_int32),
+        ("frame_rate_num", C.c_int64), ("frame_rate_den", C.c_int64),
+        ("hline", C.c_int32), ("interlaced", C.c_int32), ("active_lines", C.c_int32), ("vfilter", C.c_int32),
+        ("hsync_width", C.c_double), ("vsync_short_width", C.c_double),
+        ("vsync_long_width", C.c_double), ("sync_rise", C.c_double),
+        ("white_level", C.c_double), ("black_level", C.c_double),
+        ("blanking_level", C.c_double), ("sync_level", C.c_double),
+        ("active_width", C.c_double), ("active_left", C.c_double), ("gamma", C.c_double),
+        ("rw_co", C.c_double), ("gw_co", C.c_double), ("bw_co", C.c_double),
+        ("colour_mode", C.c_int32), ("volume", C.c_int32),
+        ("colour_carrier_num", C.c_int64), ("colour_carrier_den", C.c_int64),
+        ("colour_bw", C.c_double), ("burst_width", C.c_double), ("burst_left", C.c_double),
+        ("burst_level", C.c_double), ("burst_rise", C.c_double),
+        ("ev_co", C.c_double), ("eu_co", C.c_double),
+        ("fm_mono_carrier", C.c_double), ("fm_mono_deviation", C.c_double),
+        ("fm_mono_preemph", C.c_int32), ("reserved0", C.c_int32),
+        ("nicam_carrier", C.c_double), ("nicam_beta", C.c_double), ("am_mono_carrier", C.c_double),
+    ]
+
+    def copy(self) -> "Config":
+        c = Config()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(Config))
+        return c
+
+
+class _Mode(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("conf", C.POINTER(Config)), ("desc", C.c_char_p)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("framebuffer", C.c_void_p), ("serial", C.c_uint64)]
+
+
+_READ_VIDEO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Frame))
+_READ_AUDIO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+_CLOSE = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class AV(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("ctx", C.c_void_p),
+                ("read_video", _READ_VIDEO), ("read_audio", _READ_AUDIO), ("close", _CLOSE)]
+
+
+class Line(C.Structure):
+    _fields_ = [("output", C.POINTER(C.c_int16)), ("width", C.c_int), ("frame", C.c_int), ("line", C.c_int)]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the C host layer and the sm_100a kernels in-tree (csrc/Makefile)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("hacktv_b200: build failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load libhacktv_b200.so (raises if it has not been built - no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"hacktv_b200: {LIB_PATH} is missing - run `make -C hacktv_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
+    L.htv_find_mode.restype = C.POINTER(Config); L.htv_find_mode.argtypes = [C.c_char_p]
+    L.htv_config_size.restype = sz
+    L.htv_init.restype = C.c_int; L.htv_init.argtypes = [C.POINTER(vp), C.c_uint, C.c_uint, C.POINTER(Config)]
+    L.htv_free.restype = None; L.htv_free.argtypes = [vp]
+    L.htv_info.restype = None; L.htv_info.argtypes = [vp]
+    L.htv_get_framebuffer_length.restype = sz; L.htv_get_framebuffer_length.argtypes = [vp]
+    L.htv_av.restype = C.POINTER(AV); L.htv_av.argtypes = [vp]
+    L.htv_av_test_open.restype = C.c_int; L.htv_av_test_open.argtypes = [C.POINTER(AV)]
+    L.htv_av_close.restype = None; L.htv_av_close.argtypes = [C.POINTER(AV)]
+    L.htv_next_line.restype = C.POINTER(Line); L.htv_next_line.argtypes = [vp]
+    L.htv_render.restype = C.c_int; L.htv_render.argtypes = [vp, C.c_int, vp, C.POINTER(sz), vp]
+    L.htv_render_host.restype = C.c_int; L.htv_render_host.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
+    for f in ("htv_samples_per_line", "htv_active_width", "htv_active_lines", "htv_lines_per_frame",
+              "htv_sample_rate", "htv_is_complex", "htv_bytes_per_sample"):
+        getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
+    L.htv_lines_rendered.restype = i64; L.htv_lines_rendered.argtypes = [vp]
+    L.htv_kernel_launches.restype = C.c_uint64; L.htv_kernel_launches.argtypes = [vp]
+    L.htv_set_kernel_timing.restype = None; L.htv_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.htv_last_line_kernel_ms.restype = C.c_float; L.htv_last_line_kernel_ms.argtypes = [vp]
+    L.htv_tables_create.restype = vp; L.htv_tables_create.argtypes = [C.POINTER(Config), C.c_uint]
+    L.htv_tables_free.restype = None; L.htv_tables_free.argtypes = [vp]
+    L.htv_tables_get.restype = C.POINTER(C.c_int32); L.htv_tables_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
+    L.htv_test_pattern.restype = None; L.htv_test_pattern.argtypes = [C.c_int, C.c_int, vp]
+    L.htv_test_tone_pairs.restype = sz
+    L.htv_test_tone.restype = None; L.htv_test_tone.argtypes = [vp]
+    L.htv_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def modes() -> dict:
+    """id -> (Config copy, description), the in-scope rows of the reference's vid_configs[]."""
+    L = lib()
+    arr = (_Mode * 64).in_dll(L, "htv_modes")
+    out = {}
+    for m in arr:
+        if not m.id:
+            break
+        out[m.id.decode()] = (m.conf.contents.copy(), m.desc.decode())
+    return out
+
+
+def mode_config(mode: str, *, vfilter=False, nocolour=False, noaudio=False, nonicam=False,
+                offset=0, swap_iq=False, level=1.0, volume=1.0, invert_video=False) -> Config:
+    """Mode lookup + the command-line overrides of reference hacktv.c:1107-1437 (in-scope options)."""
+    p = lib().htv_find_mode(mode.encode())
+    if not p:
+        raise ValueError(f"Unrecognised TV mode {mode!r}")
+    c = p.contents.copy()
+    if nocolour and c.colour_mode in (1, 2, 3):
+        c.colour_mode = 0
+    if noaudio:
+        c.fm_mono_level = c.am_audio_level = c.nicam_level = 0.0
+        c.fm_mono_carrier = c.nicam_carrier = c.am_mono_carrier = 0.0
+    if nonicam:
+        c.nicam_level = 0.0
+        c.nicam_carrier = 0.0
+    c.level *= float(np.float32(level))
+    if vfilter:
+        c.vfilter = 1
+    c.swap_iq = int(bool(swap_iq))
+    c.offset = int(offset)
+    c.volume = int(float(np.float32(volume)) * 256 + 0.5)
+    c.invert_video = int(bool(invert_video))
+    return c
+
+
+class Tables:
+    """Host-only table generation (no GPU needed) - htv_tables_* in the C-ABI."""
+
+    def __init__(self, conf: Config, sample_rate: int):
+        self._L = lib()
+        self._t = self._L.htv_tables_create(C.byref(conf), sample_rate)
+        if not self._t:
+            raise RuntimeError("htv_tables_create failed")
+
+    def get(self, name: str):
+        n = C.c_int(0)
+        p = self._L.htv_tables_get(self._t, name.encode(), C.byref(n))
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def close(self):
+        if self._t:
+            self._L.htv_tables_free(self._t)
+            self._t = None
+
+    def __del__(self):
+        self.close()
+
+
+class Encoder:
+    """htv_t: one RF channel on the current CUDA device."""
+
+    def __init__(self, mode, sample_rate: int = 16_000_000, **overrides):
+        self._L = lib()
+        self.conf = mode if isinstance(mode, Config) else mode_config(mode, **overrides)
+        h = C.c_void_p()
+        r = self._L.htv_init(C.byref(h), sample_rate, 0, C.byref(self.conf))
+        if r != HTV_OK or not h:
+            raise RuntimeError(f"htv_init failed ({r}): no CUDA device or unsupported configuration")
+        self._h = h
+        self.width = self._L.htv_samples_per_line(h)
+        self.lines = self._L.htv_lines_per_frame(h)
+        self.active_width = self._L.htv_active_width(h)
+        self.active_lines = self._L.htv_active_lines(h)
+        self.complex = bool(self._L.htv_is_complex(h))
+        self.bytes_per_sample = self._L.htv_bytes_per_sample(h)
+        self.sample_rate = sample_rate
+        self._keep = []
+
+    # ---- sources -------------------------------------------------------
+    def open_test_source(self):
+        r = self._L.htv_av_test_open(self._L.htv_av(self._h))
+        if r != HTV_OK:
+            raise RuntimeError("htv_av_test_open failed")
+
+    def set_source(self, frames: np.ndarray | None, audio: np.ndarray | None, *, audio_block: int = 0,
+                   static_video: bool = False):
+        """Install numpy-backed callbacks: frames uint32 [n, active_lines, active_width] used
+        cyclically one per video frame, audio int16 [n, 2] (32 kHz stereo) used cyclically."""
+        av = self._L.htv_av(self._h).contents
+        state = {"f": 0, "a": 0}
+        if frames is not None:
+            frames = np.ascontiguousarray(frames, dtype=np.uint32)
+            assert frames.shape[1:] == (self.active_lines, self.active_width), frames.shape
+
+            def read_video(ctx, fr):
+                i = state["f"] % frames.shape[0]
+                fr.contents.width = self.active_width
+                fr.contents.height = self.active_lines
+                fr.contents.framebuffer = frames[i].ctypes.data
+                fr.contents.serial = 1 if static_video else state["f"] + 1
+                state["f"] += 1
+                return HTV_OK
+            cb = _READ_VIDEO(read_video)
+            av.read_video = cb
+            self._keep += [cb, frames]
+        if audio is not None:
+            audio = np.ascontiguousarray(audio, dtype=np.int16)
+            assert audio.ndim == 2 and audio.shape[1] == 2
+            blk = audio_block or audio.shape[0]
+
+            def read_audio(ctx, samples, n):
+                at = state["a"]
+                m = min(blk, audio.shape[0] - at)
+                samples[0] = audio[at:].ctypes.data
+                n[0] = m
+                state["a"] = (at + m) % audio.shape[0]
+                return HTV_OK
+            cb = _READ_AUDIO(read_audio)
+            av.read_audio = cb
+            self._keep += [cb, audio]
+
+    # ---- rendering -----------------------------------------------------
+    def render(self, nlines: int, device_ptr: int, stream: int = 0) -> int:
+        """htv_render: next nlines into DEVICE memory, asynchronous on `stream`."""
+        n = C.c_size_t(0)
+        r = self._L.htv_render(self._h, nlines, C.c_void_p(device_ptr), C.byref(n), C.c_void_p(stream))
+        if r != HTV_OK:
+            raise RuntimeError(f"htv_render failed ({r})")
+        return n.value
+
+    def render_host(self, nlines: int, out: np.ndarray | None = None) -> np.ndarray:
+        """htv_render_host: next nlines into host memory (what `-o file` would hold)."""
+        per = 2 if self.complex else 1
+        if out is None:
+            out = np.empty(nlines * self.width * per, dtype=np.int16)
+        assert out.dtype == np.int16 and out.size >= nlines * self.width * per
+        r = self._L.htv_render_host(self._h, nlines, C.c_void_p(out.ctypes.data), None)
+        if r != HTV_OK:
+            raise RuntimeError(f"htv_render_host failed ({r})")
+        return out
+
+    def render_host_ptr(self, nlines: int, host_ptr: int):
+        r = self._L.htv_render_host(self._h, nlines, C.c_void_p(host_ptr), None)
+        if r != HTV_OK:
+            raise RuntimeError(f"htv_render_host failed ({r})")
+
+    def next_line(self):
+        p = self._L.htv_next_line(self._h)
+        if not p:
+            return None
+        l = p.contents
+        return np.ctypeslib.as_array(l.output, shape=(l.width * 2,)).copy(), l.frame, l.line
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.htv_kernel_launches(self._h))
+
+    def set_kernel_timing(self, on: bool):
+        self._L.htv_set_kernel_timing(self._h, int(on))
+
+    def last_line_kernel_ms(self) -> float:
+        return float(self._L.htv_last_line_kernel_ms(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.htv_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def test_pattern(width: int, height: int) -> np.ndarray:
+    out = np.zeros((height, width), dtype=np.uint32)
+    lib().htv_test_pattern(width, height, C.c_void_p(out.ctypes.data))
+    return out
+
+
+def test_tone() -> np.ndarray:
+    n = lib().htv_test_tone_pairs()
+    out = np.zeros((n, 2), dtype=np.int16)
+    lib().htv_test_tone(C.c_void_p(out.ctypes.data))
+    return out

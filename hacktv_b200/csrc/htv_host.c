@@ -1,0 +1,347 @@
+/* hacktv_b200 - C host layer: the encoder object behind the C-ABI.
+ *
+ * Mirrors the reference's vid_t life cycle (ref video.c:3812-4952, hacktv.c:1440-1601):
+ * init -> caller installs an AV source -> pull lines -> free. The per-line pthread
+ * pipeline of the reference is replaced by batched device launches: a call renders N
+ * scan lines; htv_next_line() is a view over a pinned host buffer refilled one frame
+ * at a time.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "htv_internal.h"
+
+#define MAX_FRAME_SLOTS 8
+#define MAX_CHUNK_SECONDS 4.0
+
+struct htv_t {
+	htv_tables_t *tab;
+	htv_dev_t *dev;
+	htv_av_t av;
+
+	int W, lines, complex, bps;
+
+	/* stream position */
+	int64_t next_line;            /* next scan line to render (0 = frame 1 line 1) */
+
+	/* video frames */
+	int64_t cur_frame;            /* 0-based index of the last frame pulled, -1 none */
+	int cur_slot;                 /* its slot, -1 = no picture (black) */
+	uint64_t cur_serial;
+	int have_serial;
+	int next_slot;
+
+	/* audio */
+	int64_t audio_have;           /* source pairs uploaded so far (absolute count) */
+	int16_t *zeros;
+
+	/* htv_render_host staging */
+	int16_t *d_stage;
+	size_t d_stage_bytes;
+
+	/* htv_next_line view */
+	int16_t *h_frame;             /* pinned, one frame of output */
+	int h_lines;                  /* lines held */
+	int h_pos;                    /* next line to hand out */
+	int64_t h_first_line;
+	int16_t *h_iq;                /* interleaved scratch for real modes */
+	htv_line_t line;
+};
+
+const char *htv_version(void) { return("hacktv_b200 0.1 (sm_100a)"); }
+
+const htv_config_t *htv_find_mode(const char *id)
+{
+	const htv_mode_t *m;
+	if(!id) return(NULL);
+	for(m = htv_modes; m->id; m++) if(strcmp(m->id, id) == 0) return(m->conf);
+	return(NULL);
+}
+
+size_t htv_config_size(void) { return(sizeof(htv_config_t)); }
+
+int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf)
+{
+	htv_t *s;
+	char err[256];
+
+	if(!out) return(HTV_ERROR);
+	*out = NULL;
+	if(pixel_rate != 0 && pixel_rate != sample_rate)
+	{
+		fprintf(stderr, "hacktv_b200: --pixelrate resampling is not on the accelerated path\n");
+		return(HTV_ERROR);
+	}
+	s = calloc(1, sizeof(htv_t));
+	if(!s) return(HTV_OUT_OF_MEMORY);
+
+	s->tab = htv_tables_create(conf, sample_rate);
+	if(!s->tab) { free(s); return(HTV_ERROR); }
+
+	/* No GPU, no encoder: there is deliberately no CPU fallback */
+	s->dev = htv_dev_create(s->tab, MAX_FRAME_SLOTS, err, sizeof(err));
+	if(!s->dev)
+	{
+		fprintf(stderr, "hacktv_b200: cannot initialise the CUDA encoder: %s\n", err);
+		htv_tables_free(s->tab);
+		free(s);
+		return(HTV_ERROR);
+	}
+
+	s->W = s->tab->dp.W;
+	s->lines = s->tab->dp.lines;
+	s->complex = s->tab->dp.complex_out;
+	s->bps = s->complex ? 4 : 2;
+	s->cur_frame = -1;
+	s->cur_slot = -1;
+	s->av.width = s->tab->dp.active_width;
+	s->av.height = s->tab->dp.active_lines;
+	s->zeros = calloc(65536, 2 * sizeof(int16_t));
+	*out = s;
+	return(HTV_OK);
+}
+
+void htv_av_close(htv_av_t *av)
+{
+	if(av && av->close) av->close(av->ctx);
+	if(av) { av->ctx = NULL; av->read_video = NULL; av->read_audio = NULL; av->close = NULL; }
+}
+
+void htv_free(htv_t *s)
+{
+	if(!s) return;
+	htv_av_close(&s->av);
+	if(s->dev)
+	{
+		htv_dev_free(s->dev, s->d_stage);
+		htv_dev_destroy(s->dev);
+	}
+	htv_dev_free_pinned(s->h_frame);
+	free(s->h_iq);
+	free(s->zeros);
+	htv_tables_free(s->tab);
+	free(s);
+}
+
+void htv_info(htv_t *s)
+{
+	const htv_config_t *c = &s->tab->conf;
+	fprintf(stderr, "Video: %dx%d %.2f fps (full frame %dx%d)\n",
+		s->tab->dp.active_width, c->active_lines,
+		(double) c->frame_rate_num / c->frame_rate_den, s->W, c->lines);
+	fprintf(stderr, "Sample rate: %d\n", (int) s->tab->rate);
+}
+
+size_t htv_get_framebuffer_length(htv_t *s)
+{
+	return(sizeof(uint32_t) * s->tab->dp.active_width * s->tab->conf.active_lines);
+}
+
+htv_av_t *htv_av(htv_t *s) { return(&s->av); }
+int htv_samples_per_line(const htv_t *s) { return(s->W); }
+int htv_active_width(const htv_t *s) { return(s->tab->dp.active_width); }
+int htv_active_lines(const htv_t *s) { return(s->tab->dp.active_lines); }
+int htv_lines_per_frame(const htv_t *s) { return(s->lines); }
+int htv_sample_rate(const htv_t *s) { return((int) s->tab->rate); }
+int htv_is_complex(const htv_t *s) { return(s->complex); }
+int htv_bytes_per_sample(const htv_t *s) { return(s->bps); }
+int64_t htv_lines_rendered(const htv_t *s) { return(s->next_line); }
+uint64_t htv_kernel_launches(const htv_t *s) { return(htv_dev_launches(s->dev)); }
+void htv_set_kernel_timing(htv_t *s, int on) { htv_dev_set_timing(s->dev, on); }
+float htv_last_line_kernel_ms(htv_t *s) { return(htv_dev_last_line_ms(s->dev)); }
+
+/* audio fetches completed up to and including audio-clock sample m (ref video.c:3273-3276) */
+static int64_t fetches_by(int64_t m, unsigned int rate)
+{
+	return((int64_t) (((unsigned long long) (m + 1) * HTV_AUDIO_RATE) / rate));
+}
+
+/* Make source audio available on the device up to pair index `need` (exclusive) */
+static int pull_audio(htv_t *s, int64_t need, void *stream)
+{
+	while(s->audio_have < need)
+	{
+		const int16_t *pcm = NULL;
+		size_t n = 0;
+		int r = HTV_OK;
+
+		if(s->av.read_audio)
+		{
+			r = s->av.read_audio(s->av.ctx, &pcm, &n);
+			if(r != HTV_OK) { s->av.read_audio = NULL; pcm = NULL; n = 0; }
+		}
+		if(!pcm || n == 0)
+		{
+			/* no audio from the source: silence (ref video.c:3298-3303) */
+			pcm = s->zeros;
+			n = (size_t) (need - s->audio_have);
+			if(n > 65536) n = 65536;
+		}
+		if(n > htv_dev_audio_ring_pairs() / 4)
+		{
+			/* hand it over in pieces the ring can hold */
+			n = htv_dev_audio_ring_pairs() / 4;
+		}
+		r = htv_dev_upload_audio(s->dev, s->audio_have, pcm, n, stream);
+		if(r != HTV_OK) return(r);
+		s->audio_have += n;
+	}
+	return(HTV_OK);
+}
+
+/* One device launch sequence for lines [L0, L0 + n): at most MAX_FRAME_SLOTS - 1 new pictures */
+static int render_chunk(htv_t *s, int *pn, int16_t *d_out, void *stream)
+{
+	int n = *pn, nnew = 0;
+	const htv_dparams_t *dp = &s->tab->dp;
+	const int64_t L0 = s->next_line;
+	const int64_t f0 = L0 / s->lines, f1 = (L0 + n - 1) / s->lines;
+	int32_t map[4096];
+	int64_t f;
+	int r, nmap = 0;
+
+	if(f1 - f0 + 1 > 4096) return(HTV_ERROR);
+
+	/* pictures: one pull per frame, at its first line (ref video.c:4873-4881) */
+	for(f = f0; f <= f1; f++)
+	{
+		if(f > s->cur_frame)
+		{
+			htv_frame_t fr;
+			if(nnew >= MAX_FRAME_SLOTS - 1)
+			{
+				/* every free picture slot is in use by this launch: stop at this frame boundary */
+				n = (int) (f * s->lines - L0);
+				break;
+			}
+			memset(&fr, 0, sizeof(fr));
+			s->cur_frame = f;
+			if(s->av.read_video && s->av.read_video(s->av.ctx, &fr) == HTV_OK && fr.framebuffer)
+			{
+				if(fr.width != dp->active_width || fr.height != dp->active_lines)
+				{
+					fprintf(stderr, "hacktv_b200: source frame is %dx%d, the raster needs %dx%d\n",
+						fr.width, fr.height, dp->active_width, dp->active_lines);
+					return(HTV_ERROR);
+				}
+				if(!s->have_serial || fr.serial != s->cur_serial || s->cur_slot < 0)
+				{
+					s->cur_slot = s->next_slot;
+					s->next_slot = (s->next_slot + 1) % MAX_FRAME_SLOTS;
+					r = htv_dev_upload_frame(s->dev, s->cur_slot, fr.framebuffer, stream);
+					if(r != HTV_OK) return(r);
+					s->cur_serial = fr.serial;
+					s->have_serial = 1;
+					nnew++;
+				}
+			}
+			else
+			{
+				if(s->av.read_video) s->av.read_video = NULL;
+				s->cur_slot = -1;
+			}
+		}
+		map[nmap++] = s->cur_slot;
+	}
+	r = htv_dev_set_frame_map(s->dev, map, nmap, f0, stream);
+	if(r != HTV_OK) return(r);
+
+	/* sound: everything the audio clock reaches inside this run */
+	if(dp->have_fm || dp->have_am || dp->have_nicam)
+	{
+		const int64_t m0 = L0 * s->W + dp->shift, m1 = (L0 + n) * (int64_t) s->W + dp->shift;
+		int64_t mm0 = m0;
+		if(L0 == 0) mm0 = 0;      /* the audio clock starts `shift` samples before the first emitted sample */
+		r = pull_audio(s, fetches_by(m1 - 1, s->tab->rate), stream);
+		if(r != HTV_OK) return(r);
+		r = htv_dev_audio_prepass(s->dev, mm0, m1, stream);
+		if(r != HTV_OK) return(r);
+	}
+
+	r = htv_dev_render_lines(s->dev, L0, n, d_out, stream);
+	if(r != HTV_OK) return(r);
+	s->next_line += n;
+	*pn = n;
+	return(HTV_OK);
+}
+
+static int max_chunk_lines(const htv_t *s)
+{
+	/* bounded by the device-side audio / NICAM rings (htv_kernels.cu) */
+	double lines_per_s = (double) s->tab->rate / s->W;
+	int n = (int) (lines_per_s * MAX_CHUNK_SECONDS);
+	return(n < 1 ? 1 : n);
+}
+
+int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream)
+{
+	int done = 0, r, cap;
+	if(!s || nlines < 0 || !d_out) return(HTV_ERROR);
+	cap = max_chunk_lines(s);
+	while(done < nlines)
+	{
+		int n = nlines - done;
+		if(n > cap) n = cap;
+		r = render_chunk(s, &n, d_out + (size_t) done * s->W * (s->complex ? 2 : 1), cuda_stream);
+		if(r != HTV_OK) return(r);
+		done += n;
+	}
+	if(nsamples) *nsamples = (size_t) nlines * s->W;
+	return(HTV_OK);
+}
+
+int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
+{
+	size_t bytes;
+	int r;
+	if(!s || nlines < 0 || !h_out) return(HTV_ERROR);
+	bytes = (size_t) nlines * s->W * s->bps;
+	if(bytes > s->d_stage_bytes)
+	{
+		htv_dev_free(s->dev, s->d_stage);
+		s->d_stage = htv_dev_alloc(s->dev, bytes);
+		s->d_stage_bytes = s->d_stage ? bytes : 0;
+		if(!s->d_stage) return(HTV_OUT_OF_MEMORY);
+	}
+	r = htv_render(s, nlines, s->d_stage, nsamples, NULL);
+	if(r != HTV_OK) return(r);
+	r = htv_dev_memcpy_d2h(s->dev, h_out, s->d_stage, bytes, NULL);
+	if(r != HTV_OK) return(r);
+	return(htv_dev_sync(s->dev, NULL));
+}
+
+htv_line_t *htv_next_line(htv_t *s)
+{
+	if(!s) return(NULL);
+	if(s->h_pos >= s->h_lines)
+	{
+		/* refill: the rest of the current frame (a whole frame in steady state) */
+		int n = s->lines - (int) (s->next_line % s->lines);
+		if(!s->h_frame)
+		{
+			s->h_frame = htv_dev_alloc_pinned((size_t) s->lines * s->W * s->bps);
+			s->h_iq = malloc(sizeof(int16_t) * 2 * s->W);
+			if(!s->h_frame || !s->h_iq) return(NULL);
+		}
+		s->h_first_line = s->next_line;
+		if(htv_render_host(s, n, s->h_frame, NULL) != HTV_OK) return(NULL);
+		s->h_lines = n;
+		s->h_pos = 0;
+	}
+	{
+		const int64_t L = s->h_first_line + s->h_pos;
+		int16_t *src = s->h_frame + (size_t) s->h_pos * s->W * (s->complex ? 2 : 1);
+		if(s->complex) s->line.output = src;
+		else
+		{
+			int x;
+			for(x = 0; x < s->W; x++) { s->h_iq[x * 2] = src[x]; s->h_iq[x * 2 + 1] = 0; }
+			s->line.output = s->h_iq;
+		}
+		s->line.width = s->W;
+		s->line.frame = (int) (L / s->lines) + 1;
+		s->line.line = (int) (L % s->lines) + 1;
+		s->h_pos++;
+	}
+	return(&s->line);
+}

@@ -1,0 +1,145 @@
+/* hacktv_b200 internal definitions shared by the C host layer and the CUDA
+ * translation unit. Not part of the public C-ABI (include/hacktv_b200.h). */
+#ifndef HTV_INTERNAL_H
+#define HTV_INTERNAL_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "hacktv_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int16_t i, q; } htv_c16_t;
+typedef struct { int32_t i, q; } htv_c32_t;
+
+#define HTV_VF_NTAPS   51      /* ref video.c:3671,3744 */
+#define HTV_MAX_CTAPS  31      /* chroma Gaussian LPF taps we accept (13 @16M, 15 @20M, 11 @13.5M) */
+#define HTV_AUDIO_RATE 32000   /* ref hacktv.h:30 */
+#define HTV_NICAM_SYMBOL_RATE 364000
+#define HTV_LIM_W      21      /* limiter width, ref video.c:4447 */
+#define HTV_AFIR_N     65      /* audio FIR taps, ref video.c:2118 */
+#define HTV_J17_N      83      /* ref nicam728.h:48 */
+
+/* Line code bits (one uint16 per line number, ref video.c:2447-2810 restated as a table) */
+#define HTV_LC_SYNC_MASK  0x001F   /* 5-bit pulse mask fed to the sync renderer */
+#define HTV_LC_BURST_SHIFT 5       /* 0 never, 1 always, 2 even frames ('1'), 3 odd frames ('2') */
+#define HTV_LC_BURST_MASK (3 << HTV_LC_BURST_SHIFT)
+#define HTV_LC_LEFT_ACTIVE  (1 << 7)
+#define HTV_LC_RIGHT_ACTIVE (1 << 8)
+
+/* Everything the kernels need by value. Passed as a __grid_constant__ kernel
+ * parameter (constant bank): uniform reads of taps cost no registers. */
+typedef struct {
+	/* geometry */
+	int32_t W, half_width, lines, hline;
+	int32_t active_left, active_width, active_lines;
+	int32_t raster, colour_mode, complex_out, interlaced;
+	int32_t blank, black_y, black_u, black_v;
+
+	/* sync pulses: values live in tables, here only the placement */
+	int32_t pulse_off[5], pulse_len[5], pulse_pos[5];
+
+	/* RGB -> YUV (ref video.c:3912-3959), evaluated in fp64 on the device */
+	double rw, gw, bw, eu, ev;
+	double black_level, white_minus_black, vlevel, uv_scale;
+
+	/* PAL/NTSC chroma */
+	int32_t chroma_ntaps;
+	int32_t chroma_taps[HTV_MAX_CTAPS + 1];
+	int32_t burst_left, burst_width, burst_i, burst_q;
+	uint32_t clut_width;
+
+	/* video filter */
+	int32_t vf_type;               /* 0 none, 1 real low-pass, 3 real->complex (VSB) */
+	int32_t vf_i[HTV_VF_NTAPS], vf_q[HTV_VF_NTAPS];
+
+	/* audio subcarriers */
+	int32_t rate;
+	int32_t shift;                 /* audio-clock lead over the emitted stream, in samples (W with a filter) */
+	int32_t volume;
+	int32_t have_fm, fm_level, have_lim;
+	int32_t have_am, am_level;
+	uint64_t am_ang;               /* carrier step, turns * 2^64 */
+	int32_t have_nicam, nicam_ntaps, nicam_F, nicam_D, nicam_cc_len, nicam_pad;
+
+	/* SECAM */
+	int32_t secam_level, secam_dmin[2], secam_dmax[2], secam_pad;
+	int32_t secam_lpf[15], secam_notch[51];
+	double iir_a1, iir_b0, iir_b1;
+
+	/* post mixers */
+	int32_t swap_iq, have_offset;
+	uint64_t offset_ang;           /* turns * 2^64 per sample */
+	uint64_t offset_phase0;        /* phase after the first renormalisation (see htv_tables.c) */
+} htv_dparams_t;
+
+/* Host-built tables (ref video.c:3812-4704, restated). All arrays are owned. */
+struct htv_tables_t {
+	htv_config_t conf;
+	unsigned int rate;
+	htv_dparams_t dp;
+
+	uint16_t *codes;        int ncodes;           /* lines + 1 */
+	int16_t *pulse_values;  int npulse_values;
+	double glut[256];
+	htv_c16_t *clut;        size_t clut_len;      /* clut_width + W */
+	int16_t *burst_win;     int burst_width;
+
+	uint64_t *fm_ang;                              /* 65536: effective angle of each FM LUT entry, turns * 2^64 */
+	int32_t afir_v[HTV_AFIR_N], afir_f[HTV_AFIR_N]; /* audio FIR taps in application order */
+	int16_t lim_shape[HTV_LIM_W];
+
+	int16_t *nicam_taps;    int nicam_ntaps;
+	htv_c16_t *nicam_cc;    int nicam_cc_len;
+	uint8_t nicam_prn[90];
+
+	htv_c32_t *secam_fm_lut;                       /* 65536 */
+	htv_c16_t *secam_bell;                         /* 65536 */
+
+	uint8_t *offset_start;  int offset_start_len;  /* start-up quirk, 2 bits/sample packed 1 byte/sample */
+
+	int32_t *scratch;                              /* htv_tables_get */
+};
+
+/* ---- device layer (htv_kernels.cu), all C linkage ---------------------- */
+
+typedef struct htv_dev_t htv_dev_t;
+
+/* Per-launch description of a run of consecutive scan lines */
+typedef struct {
+	int64_t line0;          /* global index of the first line (0 = frame 1 line 1) */
+	int32_t nlines;
+	int32_t frame_slot0;    /* frame slot table index of the frame containing line0 */
+} htv_run_t;
+
+extern int htv_dev_count(void);
+extern htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen);
+extern void htv_dev_destroy(htv_dev_t *d);
+/* frame slot <- host RGB (active_width x active_lines), async on stream */
+extern int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream);
+/* slot_of_frame[i] = slot holding frame (first_frame + i) for this launch */
+extern int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream);
+/* raw audio ring <- host PCM pairs for absolute indices [j0, j0 + n) */
+extern int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm, size_t npairs, void *stream);
+/* audio-rate pre-pass for the absolute audio-clock sample range [m0, m1) */
+extern int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *stream);
+/* the line kernel(s): render lines [line0, line0 + nlines) to d_out (device) */
+extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out, void *stream);
+extern int htv_dev_sync(htv_dev_t *d, void *stream);
+extern int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream);
+extern void *htv_dev_alloc(htv_dev_t *d, size_t bytes);
+extern void htv_dev_free(htv_dev_t *d, void *p);
+extern void *htv_dev_alloc_pinned(size_t bytes);
+extern void htv_dev_free_pinned(void *p);
+extern uint64_t htv_dev_launches(const htv_dev_t *d);
+extern void htv_dev_set_timing(htv_dev_t *d, int on);
+extern float htv_dev_last_line_ms(htv_dev_t *d);
+extern size_t htv_dev_audio_ring_pairs(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

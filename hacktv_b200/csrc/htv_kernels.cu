@@ -1,0 +1,1129 @@
+// hacktv_b200 - CUDA kernels (sm_100a) and the device layer behind the C-ABI.
+//
+// One CTA renders one scan line; a launch covers a run of lines (a field, a
+// frame, or many frames). Every piece of state the reference carries from
+// sample to sample (ref = fsphil/hacktv src/) is expressed as a closed form of
+// the global sample index so lines are independent:
+//
+//   - raster (sync / blank / luma / PAL-NTSC chroma)   ref video.c:2864-3066
+//   - VSB / low-pass video filter as a centred FIR     ref video.c:3235-3248, fir.c:304-355, 564-615
+//   - FM / AM sound carriers: integer phase = prefix sum of exact per-sample
+//     angles (audio-rate pre-pass), amplitude model of the Q31 recurrence   ref video.c:2259-2276, 2359-2378
+//   - NICAM-728: frames encoded per millisecond in a pre-pass, pulse shaping by
+//     direct evaluation of the <= 6 overlapping symbols per sample          ref nicam728.c:140-411
+//   - frequency-offset mixer / IQ swap                  ref video.c:3466-3515
+//
+// No tensor cores: the path has no dense contraction. The output is written once,
+// with 128-bit streaming stores; all tables are L2/L1/shared resident.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include "htv_internal.h"
+
+#define HALO 25                       // (HTV_VF_NTAPS - 1) / 2
+#define RA_BITS 20
+#define RA (1 << RA_BITS)             // audio ring: pairs / processed samples / phase prefix
+#define RS_BITS 23
+#define RS (1 << RS_BITS)             // NICAM symbol ring
+#define RF_BITS 14
+#define RF (1 << RF_BITS)             // NICAM frame ring
+#define MAX_SEG 8                     // audio samples overlapping one scan line (+1)
+#define MAX_NSYM 64                   // NICAM symbols overlapping one scan line
+
+#define CK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { \
+	fprintf(stderr, "hacktv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return(HTV_ERROR); } } while(0)
+
+struct DevTables {
+	const uint16_t *codes;
+	const int16_t *pulse_values;
+	const double *glut;
+	const htv_c16_t *clut;
+	const int16_t *burst_win;
+	const uint64_t *fm_ang;
+	const int32_t *afir_v, *afir_f;
+	const int16_t *lim_shape;
+	const int16_t *nicam_taps;
+	const htv_c16_t *nicam_cc;
+	const uint8_t *nicam_prn;
+	const uint8_t *offset_start;
+	// frames
+	const uint32_t *frames;           // slot-major, active_width * active_lines each
+	const int32_t *frame_map;         // slot of frame (first_frame + i)
+	int64_t frame_map_first;          // 0-based frame index of frame_map[0]
+	int32_t frame_map_len;
+	// audio state rings
+	const int16_t *pcm;               // RA stereo pairs, index j & (RA-1)
+	int32_t *lim_var, *lim_fix;       // RA, index j & (RA-1)
+	int16_t *fm_p;                    // RA, slot (j+1) & (RA-1): modulating sample in effect for audio index j
+	uint64_t *fm_B;                   // RA, same slot: phase accumulated before that segment starts
+	uint8_t *nic_local;               // RS: inclusive prefix (mod 4) of the DQPSK steps inside the symbol's frame
+	uint8_t *nic_ftot;                // RF: total step of frame k (mod 4)
+	uint8_t *nic_fstart;              // RF: differential symbol state before frame k
+};
+
+struct htv_dev_t {
+	int device;
+	htv_dparams_t dp;
+	DevTables dt;
+	size_t frame_pixels;
+	int max_slots;
+	void *alloc[32];
+	int nalloc;
+	uint32_t *d_frames;
+	int32_t *d_frame_map;
+	int frame_map_cap;
+	int16_t *d_pcm;
+	// carries
+	int64_t fm_jc;                    // last audio index whose fm_B entry is valid (-1 at start)
+	int64_t nic_kc;                   // first frame whose nic_fstart is valid for a restart
+	int have_run;
+	uint64_t launches;
+	int timing;
+	cudaEvent_t ev0, ev1;
+	int ev_pending;
+	int line_threads;
+	size_t line_smem;
+};
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ int sat16i(int a) { return(max(-32768, min(32767, a))); }
+__device__ __forceinline__ int wrap16i(int a) { return((int) (short) a); }
+
+// audio fetch count up to and including audio-clock sample m (ref video.c:3273-3276)
+__host__ __device__ __forceinline__ int64_t fetches_by(int64_t m, int rate)
+{
+	return((int64_t) (((unsigned long long) (m + 1) * HTV_AUDIO_RATE) / (unsigned long long) rate));
+}
+
+// first audio-clock sample at which q fetches have happened
+__host__ __device__ __forceinline__ int64_t first_with_fetches(int64_t q, int rate)
+{
+	if(q <= 0) return(0);
+	return((int64_t) (((unsigned long long) q * (unsigned long long) rate + HTV_AUDIO_RATE - 1) / HTV_AUDIO_RATE) - 1);
+}
+
+// first audio-clock sample of the segment during which audio index j (>= -1) is in effect
+__host__ __device__ __forceinline__ int64_t seg_start(int64_t j, int rate)
+{
+	return(j < 0 ? 0 : first_with_fetches(j + 1, rate));
+}
+
+// volume-scaled source sample (ref video.c:3291-3295); j < 0 -> silence
+__device__ __forceinline__ int pcm_vol(const DevTables &dt, int64_t j, int ch, int volume)
+{
+	if(j < 0) return(0);
+	int v = ((int) dt.pcm[((j & (RA - 1)) << 1) + ch] * volume + 128) >> 8;
+	return(sat16i(v));
+}
+
+__device__ __forceinline__ int pcm_mono(const DevTables &dt, int64_t j, int volume)
+{
+	// (L + R) / 2 with C truncation toward zero (ref video.c:3314,3319)
+	return((pcm_vol(dt, j, 0, volume) + pcm_vol(dt, j, 1, volume)) / 2);
+}
+
+// ---------------------------------------------------------------------------
+// Audio-rate pre-pass, FM path (ref video.c:3319-3327, fir.c:655-694, 818-870)
+// ---------------------------------------------------------------------------
+
+// var/fix inputs of the soft limiter for audio index u: two 65-tap int FIRs of the mono mix
+__global__ void k_fm_fir(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t u0, int64_t u1)
+{
+	int64_t u = u0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(u > u1) return;
+	long long av = 0, af = 0;
+	if(u >= 0)
+	{
+		for(int y = 0; y < HTV_AFIR_N; y++)
+		{
+			long long x = pcm_mono(dt, u - (HTV_AFIR_N - 1) + y, dp.volume);
+			av += x * dt.afir_v[y];
+			af += x * dt.afir_f[y];
+		}
+		av >>= 15; af >>= 15;
+		av = av < INT32_MIN ? INT32_MIN : (av > INT32_MAX ? INT32_MAX : av);
+		af = af < INT32_MIN ? INT32_MIN : (af > INT32_MAX ? INT32_MAX : af);
+		// hard-limit the fixed path, the variable path is the remainder (fir.c:836-841)
+		if(af < -32767) af = -32767; else if(af > 32767) af = 32767;
+		av -= af;
+	}
+	dt.lim_var[u & (RA - 1)] = (int) av;
+	dt.lim_fix[u & (RA - 1)] = (int) af;
+}
+
+__device__ __forceinline__ int lim_at(const int32_t *ring, int64_t u) { return(u < 0 ? 0 : ring[u & (RA - 1)]); }
+
+// limiter output = modulating sample for audio index j, and its phase increment
+__global__ void k_fm_limit(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t j0, int64_t j1)
+{
+	int64_t j = j0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(j > j1) return;
+	int p = 0;
+	if(j >= 0)
+	{
+		if(!dp.have_lim) p = pcm_mono(dt, j, dp.volume);
+		else
+		{
+			const int level = 32767;
+			int64_t t = j - (HTV_LIM_W - 1);                 // the sample leaving the look-ahead window
+			int att = 0;
+			for(int q = 0; q < HTV_LIM_W; q++)
+			{
+				int64_t u = t + q - HTV_LIM_W / 2;           // sample examined at call t + q
+				int var = lim_at(dt.lim_var, u), fix = lim_at(dt.lim_fix, u);
+				int a = abs(var + fix);
+				if(a > level)
+				{
+					a = 32767 - (int) ((unsigned) (level + abs(var) - a) * 32767u) / abs(var);
+					int b = (a * dt.lim_shape[HTV_LIM_W - 1 - q]) >> 15;
+					if(b > att) att = (short) b;
+				}
+			}
+			int var = lim_at(dt.lim_var, t), fix = lim_at(dt.lim_fix, t);
+			int a = fix + (int) (((long long) var * (32767 - att)) >> 15);
+			p = a < -level ? -level : (a > level ? level : a);
+		}
+	}
+	dt.fm_p[(j + 1) & (RA - 1)] = (short) p;
+}
+
+// phase prefix: B(j+1) = B(j) + cnt(j) * ang(p_j), sequential over <= a few 1e5 entries.
+// One block; each thread owns a contiguous chunk, block-wide exclusive scan of chunk sums.
+__global__ void k_fm_scan(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t jc, int64_t j1)
+{
+	__shared__ unsigned long long part[1024];
+	const int T = blockDim.x, t = threadIdx.x;
+	int64_t n = j1 - jc + 1;                                  // entries jc .. j1 contribute, B(jc) is the carry
+	int64_t per = (n + T - 1) / T;
+	int64_t a = jc + t * per, b = min(j1 + 1, a + per);
+	unsigned long long sum = 0;
+	for(int64_t j = a; j < b; j++)
+	{
+		unsigned long long cnt = (unsigned long long) (seg_start(j + 1, dp.rate) - seg_start(j, dp.rate));
+		sum += cnt * dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+	}
+	part[t] = sum;
+	__syncthreads();
+	if(t == 0)
+	{
+		unsigned long long acc = dt.fm_B[(jc + 1) & (RA - 1)];
+		for(int i = 0; i < T; i++) { unsigned long long s = part[i]; part[i] = acc; acc += s; }
+	}
+	__syncthreads();
+	unsigned long long acc = part[t];
+	for(int64_t j = a; j < b; j++)
+	{
+		dt.fm_B[(j + 1) & (RA - 1)] = acc;
+		unsigned long long cnt = (unsigned long long) (seg_start(j + 1, dp.rate) - seg_start(j, dp.rate));
+		acc += cnt * dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+	}
+	if(b == j1 + 1 && a <= j1) dt.fm_B[(j1 + 2) & (RA - 1)] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// NICAM-728 frame encoder pre-pass (ref nicam728.c:140-249), one CTA per 1 ms frame
+// ---------------------------------------------------------------------------
+
+__constant__ int c_j17[HTV_J17_N] = {
+	-1, 0, -1, -1, -1, -1, -1, -1, -1, -1, -2, -2, -3, -3, -3, -3, -5, -5,
+	-6, -7, -9, -10, -13, -14, -18, -21, -27, -32, -42, -51, -69, -86, -120,
+	-159, -233, -332, -524, -814, -1402, -2372, -4502, 25590, -4502, -2372,
+	-1402, -814, -524, -332, -233, -159, -120, -86, -69, -51, -42, -32, -27,
+	-21, -18, -14, -13, -10, -9, -7, -6, -5, -5, -3, -3, -3, -3, -2, -2, -1,
+	-1, -1, -1, -1, -1, -1, -1, 0, -1
+};
+// scale-factor code and shift per coding range (ref nicam728.c:59-68)
+__constant__ unsigned char c_nic_factor[8] = { 0, 1, 2, 4, 3, 5, 6, 7 };
+__constant__ unsigned char c_nic_shift[8]  = { 2, 2, 2, 2, 3, 4, 5, 6 };
+__constant__ unsigned char c_nic_step[4]   = { 0, 3, 1, 2 };   // ref nicam728.c:46
+
+// First audio-clock sample of NICAM symbol s: ceil(s * F / D) (ref nicam728.c:301-307, 399-407)
+__host__ __device__ __forceinline__ int64_t nic_sym_pos(int64_t s, int F, int D)
+{
+	return((int64_t) (((unsigned long long) s * (unsigned long long) F + (unsigned long long) D - 1) / (unsigned long long) D));
+}
+
+// Which 32-sample audio block frame k carries: the last block completed by the end of
+// the scan line in which the frame's first symbol starts (ref video.c:3352-3363 vs
+// 3435-3438); -1 = none yet (silence)
+__device__ __forceinline__ int64_t nic_block_of(int64_t k, const htv_dparams_t &dp)
+{
+	if(k < 0) return(-1);
+	int64_t p = nic_sym_pos(k * 364, dp.nicam_F, dp.nicam_D);
+	int64_t line_end = (p / dp.W + 1) * dp.W - 1;
+	return(fetches_by(line_end, dp.rate) / 32 - 1);
+}
+
+__global__ void __launch_bounds__(64) k_nicam_frames(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t k0)
+{
+	__shared__ int64_t blk[4];
+	__shared__ int rng[2];
+	__shared__ unsigned int bits[23];          // 728 bits, MSB-first within bytes, packed big-endian
+	__shared__ unsigned char steps[364];
+	const int x = threadIdx.x;                 // sample slot: channel = x & 1, n = x >> 1
+	const int64_t k = k0 + blockIdx.x;
+
+	if(x < 4) blk[x] = nic_block_of(k - x, dp);
+	if(x < 2) rng[x] = 1;
+	if(x < 23) bits[x] = 0;
+	__syncthreads();
+
+	// J.17 pre-emphasis over the sequence of encoded blocks; history spans 3 earlier frames
+	int acc = 0;
+	{
+		const int ch = x & 1, n = x >> 1;
+		for(int xi = 0; xi < HTV_J17_N; xi++)
+		{
+			int t = n - (HTV_J17_N - 1) + xi;          // sample index relative to this frame's block
+			int f = 0;
+			while(t < 0) { t += 32; f++; }
+			int64_t b = blk[f];
+			int v = b < 0 ? 0 : pcm_vol(dt, b * 32 + t, ch, dp.volume);
+			acc += v * c_j17[xi];
+		}
+	}
+	int d = (short) (acc >> 15);
+
+	// coding range per channel: smallest b in 1..7 with |d| < 2^(b+8) (ref nicam728.c:70-94)
+	{
+		int s = d < 0 ? ~d : d;
+		int need = 32 - __clz(s) - 8;
+		need = need < 1 ? 1 : (need > 7 ? 7 : need);
+		atomicMax(&rng[x & 1], need);
+	}
+	__syncthreads();
+	{
+		const int r = rng[x & 1];
+		int v = (d >> c_nic_shift[r]) & 0x3FF;
+		v |= (__popc(v >> 4) & 1) << 10;
+		if(x < 54) v ^= ((c_nic_factor[r] >> (2 - (x / 2 % 3))) & 1) << 10;
+		// 11 bits LSB first into the 16 x 44 interleaver (ref nicam728.c:220-239)
+		for(int b = 0; b < 11; b++)
+		{
+			if((v >> b) & 1)
+			{
+				int q = x * 11 + b;
+				int pos = 24 + 16 * (q % 44) + q / 44;
+				atomicOr(&bits[pos >> 5], 0x80000000u >> (pos & 31));
+			}
+		}
+	}
+	__syncthreads();
+	if(x < 23)
+	{
+		// header: FAW, C0 (toggles every 8 frames), mode 0, reserve flag 1; then the PRN
+		unsigned int w = bits[x], prn = 0;
+		if(x == 0) w |= (0x4Eu << 24) | ((((unsigned) (~k >> 3) & 1u) << 7 | (1u << 3)) << 16);
+		for(int b = 0; b < 4; b++)
+		{
+			int byte = x * 4 + b;
+			unsigned int pb = (byte >= 1 && byte <= 90) ? dt.nicam_prn[byte - 1] : 0;
+			prn |= pb << (24 - 8 * b);
+		}
+		bits[x] = w ^ prn;
+	}
+	__syncthreads();
+	for(int s = x; s < 364; s += 64)
+	{
+		int bit = 2 * s;
+		unsigned int dibit = (bits[bit >> 5] >> (30 - (bit & 31))) & 3;
+		steps[s] = c_nic_step[dibit];
+	}
+	__syncthreads();
+	if(x == 0)
+	{
+		int acc2 = 0;
+		const int64_t s0 = k * 364;
+		for(int s = 0; s < 364; s++)
+		{
+			acc2 = (acc2 + steps[s]) & 3;
+			dt.nic_local[(s0 + s) & (RS - 1)] = (unsigned char) acc2;
+		}
+		dt.nic_ftot[k & (RF - 1)] = (unsigned char) acc2;
+	}
+}
+
+__global__ void k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
+{
+	if(threadIdx.x != 0 || blockIdx.x != 0) return;
+	int acc = k0 == 0 ? 0 : dt.nic_fstart[k0 & (RF - 1)];
+	for(int64_t k = k0; k <= k1; k++)
+	{
+		dt.nic_fstart[k & (RF - 1)] = (unsigned char) acc;
+		acc = (acc + dt.nic_ftot[k & (RF - 1)]) & 3;
+	}
+	dt.nic_fstart[(k1 + 1) & (RF - 1)] = (unsigned char) acc;
+}
+
+// ---------------------------------------------------------------------------
+// The line kernel
+// ---------------------------------------------------------------------------
+
+struct LineInfo {
+	int64_t L;
+	int frame, line;                  // 1-based, as the reference counts
+	int code;
+	int pal;                          // 0 no chroma, +1 / -1 V-switch
+	int al, ar;                       // active sample range [al, ar), -1 if none
+	const uint32_t *row;              // source pixels of this line, or NULL for black
+	unsigned int clut_off;
+};
+
+struct __align__(16) LineShared {
+	LineInfo li[3];                   // previous, this, next
+	// audio
+	int nseg;
+	int seg_x[MAX_SEG + 1];           // first sample (relative to the line) of each segment
+	unsigned long long seg_phase[MAX_SEG];  // FM phase at the sample BEFORE relative sample 0 of ... (see setup)
+	unsigned long long seg_ang[MAX_SEG];
+	int seg_am[MAX_SEG];
+	int kk0;                          // (m0 mod 32767)
+	unsigned long long am_phase0;     // AM carrier phase before the line's first sample
+	unsigned long long off_phase0;
+	int64_t m0;
+	// NICAM
+	int nsym;
+	int sym_x[MAX_NSYM];              // first sample of each symbol relative to the line
+	unsigned char sym_v[MAX_NSYM];    // DQPSK state 0..3
+	int cc0;
+};
+
+__device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *glut, unsigned int rgb, int &y, int &u, int &v)
+{
+	// ref video.c:3912-3959, same operation order, no FMA contraction
+	const double r = glut[(rgb >> 16) & 0xFF], g = glut[(rgb >> 8) & 0xFF], b = glut[rgb & 0xFF];
+	double yy = __dadd_rn(__dadd_rn(__dmul_rn(r, dp.rw), __dmul_rn(g, dp.gw)), __dmul_rn(b, dp.bw));
+	double uu = __dmul_rn(__dadd_rn(b, -yy), dp.eu);
+	double vv = __dmul_rn(__dadd_rn(r, -yy), dp.ev);
+	yy = __dmul_rn(__dadd_rn(dp.black_level, __dmul_rn(yy, dp.white_minus_black)), dp.vlevel);
+	if(dp.colour_mode != HTV_SECAM)
+	{
+		uu = __dmul_rn(uu, dp.uv_scale);
+		vv = __dmul_rn(vv, dp.uv_scale);
+	}
+	else
+	{
+		uu = __ddiv_rn(__dadd_rn(__dadd_rn(uu, 4250000.0), -4328125.0), 1000e3);
+		vv = __ddiv_rn(__dadd_rn(__dadd_rn(vv, 4406250.0), -4328125.0), 1000e3);
+	}
+	yy = fmin(fmax(yy, -1.0), 1.0);
+	uu = fmin(fmax(uu, -1.0), 1.0);
+	vv = fmin(fmax(vv, -1.0), 1.0);
+	y = (int) (short) __double2int_rn(round(__dmul_rn(yy, 32767.0)));
+	u = (int) (short) __double2int_rn(round(__dmul_rn(uu, 32767.0)));
+	v = (int) (short) __double2int_rn(round(__dmul_rn(vv, 32767.0)));
+}
+
+__device__ void line_info(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineInfo &li)
+{
+	li.L = L;
+	if(L < 0) { li.frame = 0; li.line = 0; li.code = 0; li.pal = 0; li.al = li.ar = -1; li.row = NULL; li.clut_off = 0; return; }
+	const int64_t f0 = L / dp.lines;
+	li.frame = (int) (f0 + 1);
+	li.line = (int) (L - f0 * dp.lines) + 1;
+	li.code = dt.codes[li.line];
+	const int left = li.code & HTV_LC_LEFT_ACTIVE, right = li.code & HTV_LC_RIGHT_ACTIVE;
+	li.al = left ? dp.active_left : (right ? dp.half_width : -1);
+	li.ar = right ? dp.active_left + dp.active_width : (left ? dp.half_width : -1);
+
+	// source row (ref video.c:2812-2895): progressive source on an interlaced raster shifts down one row
+	int vy;
+	if(dp.raster == HTV_RASTER_625) vy = li.line < 313 ? (li.line - 23) * 2 : (li.line - 336) * 2 + 1;
+	else vy = li.line < 265 ? (li.line - 23) * 2 : (li.line - 286) * 2 + 1;
+	if(vy >= 0 && dp.interlaced != 0) vy += 1;
+	if(vy < 0 || vy >= dp.active_lines) vy = -1;
+	li.row = NULL;
+	if(vy >= 0 && dt.frames)
+	{
+		int64_t fi = f0 - dt.frame_map_first;
+		if(fi >= 0 && fi < dt.frame_map_len)
+		{
+			const int slot = dt.frame_map[fi];              // -1: the source has no picture (black)
+			if(slot >= 0) li.row = dt.frames + ((size_t) slot * dp.active_lines + vy) * (size_t) dp.active_width;
+		}
+	}
+
+	li.pal = 0;
+	li.clut_off = 0;
+	if(dp.colour_mode == HTV_PAL || dp.colour_mode == HTV_NTSC)
+	{
+		const int b = (li.code & HTV_LC_BURST_MASK) >> HTV_LC_BURST_SHIFT;
+		li.pal = b == 1 || (b == 2 && (li.frame & 1) == 0) || (b == 3 && (li.frame & 1) == 1);
+		if(dp.colour_mode == HTV_PAL && li.pal && ((li.frame + li.line) & 1)) li.pal = -1;
+		li.clut_off = (unsigned int) (((unsigned long long) L * (unsigned long long) dp.W) % dp.clut_width);
+	}
+}
+
+// Sum of the sync pulse samples landing on sample x of line `li` from the pulses of
+// line `src` displaced by `shift` samples (0 own line, +W previous line, -W next line)
+__device__ __forceinline__ int pulses_at(const htv_dparams_t &dp, const DevTables &dt, int mask, int x)
+{
+	int v = 0;
+	#pragma unroll
+	for(int b = 0; b < 5; b++)
+	{
+		if(mask & (1 << b))
+		{
+			int d = x - dp.pulse_off[b];
+			if(d >= 0 && d < dp.pulse_len[b]) v += dt.pulse_values[dp.pulse_pos[b] + d];
+		}
+	}
+	return(v);
+}
+
+// Unfiltered U,V at sample x of a line (0 outside the picture or on a colourless line)
+__device__ __forceinline__ void uv_at(const htv_dparams_t &dp, const DevTables &dt, const LineInfo &li, int x, int &u, int &v)
+{
+	u = v = 0;
+	if(!li.pal || x < li.al || x >= li.ar) return;
+	int y;
+	unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
+	yuv_of(dp, dt.glut, rgb, y, u, v);
+}
+
+// One composite sample from scratch (slow, exact): used for the 2 x 25 halo samples a
+// line needs from its neighbours. prev/next give the neighbours of `li`.
+__device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
+	const LineInfo &prev, const LineInfo &li, const LineInfo &next, int x)
+{
+	if(li.L < 0) return(0);            // before the stream: the filter window starts zeroed
+	int v = dp.blank;
+	const bool act = x >= li.al && x < li.ar;
+	if(act)
+	{
+		int y, u, w;
+		unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
+		yuv_of(dp, dt.glut, rgb, y, u, w);
+		v = y;
+	}
+	else
+	{
+		v += pulses_at(dp, dt, li.code & HTV_LC_SYNC_MASK, x);
+		if(prev.L >= 0) v += pulses_at(dp, dt, prev.code & HTV_LC_SYNC_MASK, x + dp.W);
+	}
+	v += pulses_at(dp, dt, next.code & HTV_LC_SYNC_MASK, x - dp.W);
+
+	if(li.pal)
+	{
+		int cu, cv;
+		if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
+		{
+			int w = dt.burst_win[x - dp.burst_left];
+			cu = (dp.burst_i * w) >> 15;
+			cv = (dp.burst_q * w) >> 15;
+		}
+		else
+		{
+			const int h = dp.chroma_ntaps / 2;
+			int au = 0, av = 0;
+			if(dp.chroma_ntaps == 0) uv_at(dp, dt, li, x, au, av);
+			else if(x + h >= li.al && x - h < li.ar)
+			{
+				for(int k = 0; k < dp.chroma_ntaps; k++)
+				{
+					int xx = x - h + k, u, w;
+					if(xx < 0 || xx >= dp.W) continue;
+					uv_at(dp, dt, li, xx, u, w);
+					au += u * dp.chroma_taps[k];
+					av += w * dp.chroma_taps[k];
+				}
+				au = sat16i(au >> 15);
+				av = sat16i(av >> 15);
+			}
+			cu = au; cv = av;
+		}
+		htv_c16_t c = dt.clut[li.clut_off + x];
+		v += ((int) c.i * cv * li.pal + (int) c.q * cu) >> 15;
+	}
+	return(wrap16i(v));
+}
+
+template<int SPT>
+__global__ void __launch_bounds__(384)
+k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t line0, int nlines, int16_t *out)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	LineShared &sh = *reinterpret_cast<LineShared *>(smem_raw);
+	const int W = dp.W;
+	const int CW = (W + 2 * HALO + 3) & ~3;                        // composite window, padded
+	int *comp = reinterpret_cast<int *>(smem_raw + ((sizeof(LineShared) + 15) & ~15));   // [CW], index = x + HALO
+	int *su = comp + CW;                                            // [W + 2*HC], index = x + HC
+	const int HC = HTV_MAX_CTAPS / 2 + 1;
+	int *sv = su + ((W + 2 * HC + 3) & ~3);
+	const int tid = threadIdx.x;
+	const int64_t L = line0 + blockIdx.x;
+
+	// ---- per-line setup --------------------------------------------------
+	if(tid < 3) line_info(dp, dt, L - 1 + tid, sh.li[tid]);
+	if(tid == 32)
+	{
+		const int64_t m0 = L * (int64_t) W + dp.shift;              // audio-clock index of the line's first sample
+		sh.m0 = m0;
+		sh.kk0 = (int) (m0 % 32767);
+		sh.cc0 = dp.have_nicam ? (int) (m0 % dp.nicam_cc_len) : 0;
+		sh.am_phase0 = dp.am_ang * (unsigned long long) m0;         // phase after m0 steps (mod 2^64)
+		// offset mixer: phase0 + (m - 32766) * ang for m >= 32767
+		sh.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
+		// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
+		int n = 0;
+		if(dp.have_fm || dp.have_am)
+		{
+			int64_t j = fetches_by(m0, dp.rate) - 1;
+			for(; n < MAX_SEG; n++, j++)
+			{
+				int64_t st = seg_start(j, dp.rate);
+				if(st >= m0 + W) break;
+				sh.seg_x[n] = (int) max((int64_t) 0, st - m0);
+				if(dp.have_fm)
+				{
+					unsigned long long ang = dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+					// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
+					sh.seg_ang[n] = ang;
+					sh.seg_phase[n] = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
+				}
+				sh.seg_am[n] = dp.have_am ? pcm_mono(dt, j, dp.volume) : 0;
+			}
+		}
+		sh.nseg = n;
+		sh.seg_x[n] = W;
+	}
+	if(tid >= 64 && tid < 64 + MAX_NSYM && dp.have_nicam)
+	{
+		const int i = tid - 64;
+		const int64_t m0 = L * (int64_t) W + dp.shift;
+		// symbols whose pulse can still reach this line: ntaps samples back
+		int64_t sfirst = (int64_t) (((unsigned long long) max((int64_t) 0, m0 - dp.nicam_ntaps) * dp.nicam_D) / dp.nicam_F);
+		int64_t slast = (int64_t) (((unsigned long long) (m0 + W - 1) * dp.nicam_D) / dp.nicam_F);
+		int64_t s = sfirst + i;
+		if(i == 0) sh.nsym = (int) min((int64_t) MAX_NSYM, slast - sfirst + 1);
+		if(s <= slast)
+		{
+			int64_t k = s / 364;
+			sh.sym_x[i] = (int) (nic_sym_pos(s, dp.nicam_F, dp.nicam_D) - m0);
+			sh.sym_v[i] = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
+		}
+	}
+	__syncthreads();
+
+	const LineInfo &li = sh.li[1];
+	const int x0 = tid * SPT;
+
+	// ---- phase 1: blanking / luma, unfiltered U,V -------------------------
+	for(int k = 0; k < SPT; k++)
+	{
+		const int x = x0 + k;
+		if(x >= W) break;
+		int y = dp.blank, u = 0, v = 0;
+		if(x >= li.al && x < li.ar)
+		{
+			unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
+			yuv_of(dp, dt.glut, rgb, y, u, v);
+			if(!li.pal) u = v = 0;
+		}
+		comp[x + HALO] = y;
+		su[x + HC] = u;
+		sv[x + HC] = v;
+	}
+	if(tid < 2 * HC)
+	{
+		const int i = tid < HC ? tid : W + tid;                      // [0,HC) and [W+HC, W+2HC)
+		su[i] = 0; sv[i] = 0;
+	}
+	// halo samples from the neighbouring lines (exact, from scratch)
+	if(dp.vf_type && tid >= blockDim.x - 2 * HALO)
+	{
+		const int h = tid - (blockDim.x - 2 * HALO);
+		if(h < HALO)
+		{
+			LineInfo pp; line_info(dp, dt, L - 2, pp);
+			comp[h] = comp_generic(dp, dt, pp, sh.li[0], sh.li[1], W - HALO + h);
+		}
+		else
+		{
+			LineInfo nn; line_info(dp, dt, L + 2, nn);
+			comp[W + h] = comp_generic(dp, dt, sh.li[1], sh.li[2], nn, h - HALO);
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: sync pulses (ref vbidata.c:186-239) ----------------------
+	{
+		// own pulses and the previous line's overrun are overwritten by luma inside the
+		// picture; the next line's leading edge (negative offsets) is added afterwards
+		const int masks[3] = { sh.li[0].L >= 0 ? (sh.li[0].code & HTV_LC_SYNC_MASK) : 0,
+		                       li.code & HTV_LC_SYNC_MASK, sh.li[2].code & HTV_LC_SYNC_MASK };
+		for(int s = 0; s < 3; s++)
+		{
+			for(int b = 0; b < 5; b++)
+			{
+				if(!(masks[s] & (1 << b))) continue;
+				const int base = dp.pulse_off[b] + (s - 1) * W;      // previous line: -W, own: 0, next line: +W
+				for(int i = tid; i < dp.pulse_len[b]; i += blockDim.x)
+				{
+					const int x = base + i;
+					if(x < 0 || x >= W) continue;
+					if(s != 2 && x >= li.al && x < li.ar) continue;
+					atomicAdd(&comp[x + HALO], (int) dt.pulse_values[dp.pulse_pos[b] + i]);
+				}
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 3: chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ----
+	if(li.pal)
+	{
+		const int nt = dp.chroma_ntaps, h = nt / 2;
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			if(x >= W) break;
+			int cu, cv;
+			if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
+			{
+				int w = dt.burst_win[x - dp.burst_left];
+				cu = (dp.burst_i * w) >> 15;
+				cv = (dp.burst_q * w) >> 15;
+			}
+			else if(nt == 0) { cu = su[x + HC]; cv = sv[x + HC]; }
+			else
+			{
+				int au = 0, av = 0;
+				for(int t = 0; t < nt; t++)
+				{
+					au += su[x + HC - h + t] * dp.chroma_taps[t];
+					av += sv[x + HC - h + t] * dp.chroma_taps[t];
+				}
+				cu = sat16i(au >> 15);
+				cv = sat16i(av >> 15);
+			}
+			htv_c16_t c = dt.clut[li.clut_off + x];
+			comp[x + HALO] = wrap16i(comp[x + HALO] + (((int) c.i * cv * li.pal + (int) c.q * cu) >> 15));
+		}
+	}
+	else
+	{
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			if(x < W) comp[x + HALO] = wrap16i(comp[x + HALO]);
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 4: video filter, sound carriers, mixers, store ---------------
+	int oi[SPT], oq[SPT];
+	if(dp.vf_type)
+	{
+		int c[SPT + 2 * HALO];
+		#pragma unroll
+		for(int k = 0; k < SPT + 2 * HALO; k++) c[k] = (x0 + k < CW) ? comp[x0 + k] : 0;
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			int ai = c[k + HALO] * dp.vf_i[HALO], aq = 0;
+			if(dp.vf_type == 3)
+			{
+				// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
+				#pragma unroll
+				for(int y = 0; y < HALO; y++)
+				{
+					ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
+					aq += (c[k + y] - c[k + 2 * HALO - y]) * dp.vf_q[y];
+				}
+			}
+			else
+			{
+				#pragma unroll
+				for(int y = 0; y < HALO; y++) ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
+			}
+			oi[k] = sat16i(ai >> 15);
+			oq[k] = dp.vf_type == 3 ? sat16i(aq >> 15) : 0;
+		}
+	}
+	else
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) { oi[k] = (x0 + k < W) ? comp[x0 + k + HALO] : 0; oq[k] = 0; }
+	}
+
+	if(dp.have_fm || dp.have_am || dp.have_nicam || dp.have_offset || dp.swap_iq)
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			if(x >= W) break;
+			int addi = 0, addq = 0;
+			if(dp.have_fm || dp.have_am)
+			{
+				int sg = 0;
+				while(sg + 1 < sh.nseg && x >= sh.seg_x[sg + 1]) sg++;
+				int kk = sh.kk0 + x; if(kk >= 32767) kk -= 32767;
+				// amplitude of the reference's Q31 phasor kk+1 multiplications after a renormalisation
+				const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
+				if(dp.have_fm)
+				{
+					unsigned long long ph = sh.seg_phase[sg] + sh.seg_ang[sg] * (unsigned long long) x;
+					float sn, cs;
+					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
+					int pi_ = (int) floorf(amp * cs), pq_ = (int) floorf(amp * sn);
+					addi += (pi_ * dp.fm_level) >> 15;
+					addq += (pq_ * dp.fm_level) >> 15;
+				}
+				if(dp.have_am)
+				{
+					unsigned long long ph = sh.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
+					float sn, cs;
+					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+					int pi_ = (int) floorf(amp * cs), pq_ = (int) floorf(amp * sn);
+					int smp = (sh.seg_am[sg] + 32768) / 2;
+					addi += (((pi_ * smp) >> 15) * dp.am_level) >> 15;
+					addq += (((pq_ * smp) >> 15) * dp.am_level) >> 15;
+				}
+			}
+			int vi = wrap16i(oi[k] + wrap16i(addi)), vq = wrap16i(oq[k] + wrap16i(addq));
+			if(dp.have_nicam)
+			{
+				// the symbol in progress: estimate from the mean spacing, then correct by one
+				int i = (int) ((float) (x - sh.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
+				i = max(0, min(sh.nsym - 1, i));
+				while(i + 1 < sh.nsym && sh.sym_x[i + 1] <= x) i++;
+				while(i > 0 && sh.sym_x[i] > x) i--;
+				int bi = 0, bq = 0;
+				for(; i >= 0; i--)
+				{
+					int d = x - sh.sym_x[i];
+					if(d < 0) continue;
+					if(d >= dp.nicam_ntaps) break;
+					int r = dt.nicam_taps[d];
+					// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I sign, bit1 -> Q sign
+					const int sy = sh.sym_v[i];
+					const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
+					bi += (code & 1) ? r : -r;
+					bq += (code & 2) ? r : -r;
+				}
+				bi = wrap16i(bi); bq = wrap16i(bq);
+				int ci = sh.cc0 + x; if(ci >= dp.nicam_cc_len) ci -= dp.nicam_cc_len; if(ci >= dp.nicam_cc_len) ci %= dp.nicam_cc_len;
+				htv_c16_t cc = dt.nicam_cc[ci];
+				vi = wrap16i(vi + ((bi * cc.i - bq * cc.q) >> 15));
+				vq = wrap16i(vq + ((bi * cc.q + bq * cc.i) >> 15));
+			}
+			if(dp.swap_iq) { int t = vi; vi = vq; vq = t; }
+			if(dp.have_offset)
+			{
+				const int64_t m = sh.m0 + x;
+				int bi, bq;
+				if(m < 32767)
+				{
+					unsigned char st = dt.offset_start[m];
+					bi = -(st & 1); bq = -((st >> 1) & 1);
+				}
+				else
+				{
+					int kk = (int) (m % 32767);
+					const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
+					unsigned long long ph = sh.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
+					float sn, cs;
+					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+					bi = (int) floorf(amp * cs); bq = (int) floorf(amp * sn);
+				}
+				int ri = (vi * bi - vq * bq) >> 15, rq = (vi * bq + vq * bi) >> 15;
+				vi = wrap16i(ri); vq = wrap16i(rq);
+			}
+			oi[k] = vi; oq[k] = vq;
+		}
+	}
+
+	// ---- store (ref rf_file.c:97-116, 226-233 layout) ------------------------
+	const size_t lbase = (size_t) blockIdx.x * (size_t) W;
+	if(dp.complex_out)
+	{
+		int16_t *o = out + (lbase + x0) * 2;
+		if(SPT == 4 && (W & 3) == 0 && x0 + 3 < W)
+		{
+			int4 pk;
+			pk.x = (oi[0] & 0xFFFF) | (oq[0] << 16);
+			pk.y = (oi[1] & 0xFFFF) | (oq[1] << 16);
+			pk.z = (oi[2] & 0xFFFF) | (oq[2] << 16);
+			pk.w = (oi[3] & 0xFFFF) | (oq[3] << 16);
+			__stcs(reinterpret_cast<int4 *>(o), pk);
+		}
+		else
+		{
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				if(x0 + k < W) __stcs(reinterpret_cast<int *>(o) + k, (oi[k] & 0xFFFF) | (oq[k] << 16));
+			}
+		}
+	}
+	else
+	{
+		int16_t *o = out + lbase + x0;
+		if(SPT == 4 && (W & 3) == 0 && x0 + 3 < W)
+		{
+			int2 pk;
+			pk.x = (oi[0] & 0xFFFF) | (oi[1] << 16);
+			pk.y = (oi[2] & 0xFFFF) | (oi[3] << 16);
+			__stcs(reinterpret_cast<int2 *>(o), pk);
+		}
+		else
+		{
+			#pragma unroll
+			for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) oi[k];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Device layer (C linkage)
+// ---------------------------------------------------------------------------
+
+static void *dev_copy(htv_dev_t *d, const void *src, size_t bytes)
+{
+	void *p = NULL;
+	if(!src || !bytes) return(NULL);
+	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
+	cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+	d->alloc[d->nalloc++] = p;
+	return(p);
+}
+
+static void *dev_zero(htv_dev_t *d, size_t bytes)
+{
+	void *p = NULL;
+	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
+	cudaMemset(p, 0, bytes);
+	d->alloc[d->nalloc++] = p;
+	return(p);
+}
+
+extern "C" int htv_dev_count(void)
+{
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess) return(0);
+	return(n);
+}
+
+extern "C" size_t htv_dev_audio_ring_pairs(void) { return(RA); }
+
+extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess || n < 1)
+	{
+		snprintf(err, errlen, "no CUDA device available (%s)", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+		return(NULL);
+	}
+	htv_dev_t *d = (htv_dev_t *) calloc(1, sizeof(htv_dev_t));
+	if(!d) { snprintf(err, errlen, "out of memory"); return(NULL); }
+	cudaGetDevice(&d->device);
+	d->dp = t->dp;
+	const htv_dparams_t &dp = d->dp;
+	DevTables &dt = d->dt;
+
+	dt.codes = (const uint16_t *) dev_copy(d, t->codes, sizeof(uint16_t) * t->ncodes);
+	dt.pulse_values = (const int16_t *) dev_copy(d, t->pulse_values, sizeof(int16_t) * (t->npulse_values + 8));
+	dt.glut = (const double *) dev_copy(d, t->glut, sizeof(t->glut));
+	dt.clut = (const htv_c16_t *) dev_copy(d, t->clut, sizeof(htv_c16_t) * t->clut_len);
+	dt.burst_win = (const int16_t *) dev_copy(d, t->burst_win, sizeof(int16_t) * (t->burst_width + 1));
+	dt.fm_ang = (const uint64_t *) dev_copy(d, t->fm_ang, t->fm_ang ? sizeof(uint64_t) * 65536 : 0);
+	dt.afir_v = (const int32_t *) dev_copy(d, t->afir_v, sizeof(t->afir_v));
+	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
+	dt.lim_shape = (const int16_t *) dev_copy(d, t->lim_shape, sizeof(t->lim_shape));
+	dt.nicam_taps = (const int16_t *) dev_copy(d, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
+	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, sizeof(htv_c16_t) * t->nicam_cc_len);
+	dt.nicam_prn = (const uint8_t *) dev_copy(d, t->nicam_prn, sizeof(t->nicam_prn));
+	dt.offset_start = (const uint8_t *) dev_copy(d, t->offset_start, t->offset_start ? 32768 : 0);
+
+	d->frame_pixels = (size_t) dp.active_width * dp.active_lines;
+	d->max_slots = max_frame_slots < 1 ? 1 : max_frame_slots;
+	d->d_frames = (uint32_t *) dev_zero(d, d->frame_pixels * 4 * d->max_slots);
+	d->frame_map_cap = 4096;
+	d->d_frame_map = (int32_t *) dev_zero(d, sizeof(int32_t) * d->frame_map_cap);
+	d->d_pcm = (int16_t *) dev_zero(d, sizeof(int16_t) * 2 * RA);
+	dt.frames = d->d_frames;
+	dt.frame_map = d->d_frame_map;
+	dt.pcm = d->d_pcm;
+	if(dp.have_fm)
+	{
+		dt.lim_var = (int32_t *) dev_zero(d, sizeof(int32_t) * RA);
+		dt.lim_fix = (int32_t *) dev_zero(d, sizeof(int32_t) * RA);
+		dt.fm_p = (int16_t *) dev_zero(d, sizeof(int16_t) * RA);
+		dt.fm_B = (uint64_t *) dev_zero(d, sizeof(uint64_t) * RA);
+	}
+	if(dp.have_nicam)
+	{
+		dt.nic_local = (uint8_t *) dev_zero(d, RS);
+		dt.nic_ftot = (uint8_t *) dev_zero(d, RF);
+		dt.nic_fstart = (uint8_t *) dev_zero(d, RF);
+	}
+	if(!d->d_frames || !d->d_pcm || !dt.codes || cudaGetLastError() != cudaSuccess)
+	{
+		snprintf(err, errlen, "device allocation failed");
+		htv_dev_destroy(d);
+		return(NULL);
+	}
+	d->fm_jc = -1;
+	d->nic_kc = 0;
+
+	const int W = dp.W;
+	int threads = (W + 3) / 4;
+	threads = (threads + 31) & ~31;
+	if(threads < 2 * HALO + 128) threads = 2 * HALO + 128;
+	d->line_threads = threads;
+	const int HC = HTV_MAX_CTAPS / 2 + 1;
+	d->line_smem = ((sizeof(LineShared) + 15) & ~15) + sizeof(int) * (((W + 2 * HALO + 3) & ~3) + 2 * ((W + 2 * HC + 3) & ~3));
+	if(threads > 384)
+	{
+		snprintf(err, errlen, "line width %d exceeds the kernel's 1536-sample limit", W);
+		htv_dev_destroy(d);
+		return(NULL);
+	}
+	cudaFuncSetAttribute(k_lines<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
+	cudaEventCreate(&d->ev0);
+	cudaEventCreate(&d->ev1);
+	return(d);
+}
+
+extern "C" void htv_dev_destroy(htv_dev_t *d)
+{
+	if(!d) return;
+	cudaSetDevice(d->device);
+	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
+	if(d->ev0) cudaEventDestroy(d->ev0);
+	if(d->ev1) cudaEventDestroy(d->ev1);
+	free(d);
+}
+
+extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream)
+{
+	if(slot < 0 || slot >= d->max_slots) return(HTV_ERROR);
+	CK(cudaMemcpyAsync(d->d_frames + (size_t) slot * d->frame_pixels, rgb, d->frame_pixels * 4,
+		cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream)
+{
+	if(n > d->frame_map_cap) return(HTV_ERROR);
+	CK(cudaMemcpyAsync(d->d_frame_map, slot_of_frame, sizeof(int32_t) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	d->dt.frame_map_first = first_frame;
+	d->dt.frame_map_len = n;
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm, size_t npairs, void *stream)
+{
+	while(npairs)
+	{
+		size_t at = (size_t) (j0 & (RA - 1)), n = npairs;
+		if(at + n > RA) n = RA - at;
+		CK(cudaMemcpyAsync(d->d_pcm + at * 2, pcm, n * 4, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+		pcm += n * 2; j0 += n; npairs -= n;
+	}
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *stream)
+{
+	const htv_dparams_t &dp = d->dp;
+	cudaStream_t st = (cudaStream_t) stream;
+	if(m1 <= m0) return(HTV_OK);
+	if(dp.have_fm)
+	{
+		const int64_t jA = d->fm_jc;                               // restart from the last valid prefix entry
+		const int64_t jB = fetches_by(m1 - 1, dp.rate) - 1;
+		if(jB - jA + 64 + HTV_LIM_W + HTV_AFIR_N >= RA / 2) return(HTV_ERROR);
+		if(jB >= jA)
+		{
+			if(dp.have_lim)
+			{
+				const int64_t u0 = jA - 2 * HTV_LIM_W, n = jB - u0 + 1;
+				k_fm_fir<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(dp, d->dt, u0, jB);
+				d->launches++;
+			}
+			const int64_t n = jB - jA + 1;
+			k_fm_limit<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(dp, d->dt, jA, jB);
+			k_fm_scan<<<1, 1024, 0, st>>>(dp, d->dt, jA, jB);
+			d->launches += 2;
+			d->fm_jc = jB;
+		}
+	}
+	if(dp.have_nicam)
+	{
+		const int64_t s_lo = (int64_t) (((unsigned long long) (m0 > dp.nicam_ntaps ? m0 - dp.nicam_ntaps : 0) * dp.nicam_D) / dp.nicam_F);
+		const int64_t s_hi = (int64_t) (((unsigned long long) (m1 - 1) * dp.nicam_D) / dp.nicam_F);
+		int64_t k_lo = s_lo / 364, k_hi = s_hi / 364;
+		if(k_lo > d->nic_kc) k_lo = d->nic_kc;                     // keep the frame-start chain contiguous
+		if(k_hi - k_lo + 2 >= RF / 2 || (k_hi - k_lo + 2) * 364 >= RS / 2) return(HTV_ERROR);
+		k_nicam_frames<<<(unsigned) (k_hi - k_lo + 1), 64, 0, st>>>(dp, d->dt, k_lo);
+		k_nicam_scan<<<1, 32, 0, st>>>(d->dt, k_lo, k_hi);
+		d->launches += 2;
+		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
+	}
+	CK(cudaGetLastError());
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out, void *stream)
+{
+	cudaStream_t st = (cudaStream_t) stream;
+	if(nlines <= 0) return(HTV_OK);
+	if(d->timing) cudaEventRecord(d->ev0, st);
+	k_lines<4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
+	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
+	d->launches++;
+	CK(cudaGetLastError());
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_sync(htv_dev_t *d, void *stream)
+{
+	CK(cudaStreamSynchronize((cudaStream_t) stream));
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream)
+{
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	return(HTV_OK);
+}
+
+extern "C" void *htv_dev_alloc(htv_dev_t *d, size_t bytes)
+{
+	void *p = NULL;
+	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
+	return(p);
+}
+
+extern "C" void htv_dev_free(htv_dev_t *d, void *p) { if(p) cudaFree(p); }
+
+extern "C" void *htv_dev_alloc_pinned(size_t bytes)
+{
+	void *p = NULL;
+	if(cudaMallocHost(&p, bytes) != cudaSuccess) return(NULL);
+	return(p);
+}
+
+extern "C" void htv_dev_free_pinned(void *p) { if(p) cudaFreeHost(p); }
+
+extern "C" uint64_t htv_dev_launches(const htv_dev_t *d) { return(d->launches); }
+extern "C" void htv_dev_set_timing(htv_dev_t *d, int on) { d->timing = on; }
+
+extern "C" float htv_dev_last_line_ms(htv_dev_t *d)
+{
+	float ms = 0;
+	if(!d->ev_pending) return(0);
+	if(cudaEventSynchronize(d->ev1) != cudaSuccess) return(0);
+	cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+	return(ms);
+}
