@@ -62,7 +62,7 @@ typedef struct {
 	int32_t have_fm, fm_level, have_lim;
 	int32_t have_am, am_level;
 	uint64_t am_ang;               /* carrier step, turns * 2^64 */
-	int32_t have_nicam, nicam_ntaps, nicam_F, nicam_D, nicam_cc_len, nicam_pad;
+	int32_t have_nicam, nicam_ntaps, nicam_F, nicam_D, nicam_cc_len, nicam_tpad_len;
 
 	/* SECAM */
 	int32_t secam_level, secam_dmin[2], secam_dmax[2], secam_pad;

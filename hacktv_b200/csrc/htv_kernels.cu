@@ -365,6 +365,12 @@ __global__ void k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
 // The line kernel
 // ---------------------------------------------------------------------------
 
+#define SPT 4                         // samples per thread: one 128-bit store of 4 complex int16 samples
+#define HCP 16                        // chroma window padding (>= taps / 2, multiple of 4)
+#define NIC_CAND 7                    // NICAM symbols that can overlap 4 consecutive samples
+#define NIC_TPAD 8                    // zero entries in front of the padded NICAM pulse table
+#define MAX_ENT 6                     // sync pulses that can touch one line (2 own + 2 previous + 2 next)
+
 struct LineInfo {
 	int64_t L;
 	int frame, line;                  // 1-based, as the reference counts
@@ -377,26 +383,39 @@ struct LineInfo {
 
 struct __align__(16) LineShared {
 	LineInfo li[3];                   // previous, this, next
-	// audio
+	// sync pulse pieces landing on this line
+	int nent;
+	int ent_base[MAX_ENT], ent_len[MAX_ENT], ent_pos[MAX_ENT], ent_keep[MAX_ENT];
+	// sound carriers
 	int nseg;
-	int seg_x[MAX_SEG + 1];           // first sample (relative to the line) of each segment
-	unsigned long long seg_phase[MAX_SEG];  // FM phase at the sample BEFORE relative sample 0 of ... (see setup)
+	int seg_x[MAX_SEG + 1];           // first sample (relative to the line) of each audio segment
+	unsigned long long seg_phase[MAX_SEG];  // FM phase "before relative sample 0" on that segment
 	unsigned long long seg_ang[MAX_SEG];
 	int seg_am[MAX_SEG];
-	int kk0;                          // (m0 mod 32767)
-	unsigned long long am_phase0;     // AM carrier phase before the line's first sample
-	unsigned long long off_phase0;
+	int kk0;                          // audio-clock index of the line start, mod 32767
+	unsigned long long am_phase0, off_phase0;
 	int64_t m0;
 	// NICAM
 	int nsym;
 	int sym_x[MAX_NSYM];              // first sample of each symbol relative to the line
-	unsigned char sym_v[MAX_NSYM];    // DQPSK state 0..3
+	signed char sym_si[MAX_NSYM], sym_sq[MAX_NSYM];   // +-1 pulse polarity on I and Q
 	int cc0;
 };
 
+__device__ __forceinline__ int round_away(double v)
+{
+	// round() (half away from zero) from the round-to-nearest-even conversion
+	int r = __double2int_rn(v);
+	double t = __dadd_rn(v, -(double) r);
+	r += (t == 0.5 && v > 0.0) ? 1 : 0;
+	r -= (t == -0.5 && v < 0.0) ? 1 : 0;
+	return(r);
+}
+
 __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *glut, unsigned int rgb, int &y, int &u, int &v)
 {
-	// ref video.c:3912-3959, same operation order, no FMA contraction
+	// ref video.c:3912-3959, same operation order, no FMA contraction. The reference clamps
+	// to [-1, 1] before scaling; clamping the rounded integer to +-32767 is the same thing.
 	const double r = glut[(rgb >> 16) & 0xFF], g = glut[(rgb >> 8) & 0xFF], b = glut[rgb & 0xFF];
 	double yy = __dadd_rn(__dadd_rn(__dmul_rn(r, dp.rw), __dmul_rn(g, dp.gw)), __dmul_rn(b, dp.bw));
 	double uu = __dmul_rn(__dadd_rn(b, -yy), dp.eu);
@@ -412,12 +431,9 @@ __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *gl
 		uu = __ddiv_rn(__dadd_rn(__dadd_rn(uu, 4250000.0), -4328125.0), 1000e3);
 		vv = __ddiv_rn(__dadd_rn(__dadd_rn(vv, 4406250.0), -4328125.0), 1000e3);
 	}
-	yy = fmin(fmax(yy, -1.0), 1.0);
-	uu = fmin(fmax(uu, -1.0), 1.0);
-	vv = fmin(fmax(vv, -1.0), 1.0);
-	y = (int) (short) __double2int_rn(round(__dmul_rn(yy, 32767.0)));
-	u = (int) (short) __double2int_rn(round(__dmul_rn(uu, 32767.0)));
-	v = (int) (short) __double2int_rn(round(__dmul_rn(vv, 32767.0)));
+	y = max(-32767, min(32767, round_away(__dmul_rn(yy, 32767.0))));
+	u = max(-32767, min(32767, round_away(__dmul_rn(uu, 32767.0))));
+	v = max(-32767, min(32767, round_away(__dmul_rn(vv, 32767.0))));
 }
 
 __device__ void line_info(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineInfo &li)
@@ -460,8 +476,7 @@ __device__ void line_info(const htv_dparams_t &dp, const DevTables &dt, int64_t 
 	}
 }
 
-// Sum of the sync pulse samples landing on sample x of line `li` from the pulses of
-// line `src` displaced by `shift` samples (0 own line, +W previous line, -W next line)
+// Sum of the sync pulse samples of pulse set `mask` at position x of the pulses' own line
 __device__ __forceinline__ int pulses_at(const htv_dparams_t &dp, const DevTables &dt, int mask, int x)
 {
 	int v = 0;
@@ -478,18 +493,18 @@ __device__ __forceinline__ int pulses_at(const htv_dparams_t &dp, const DevTable
 }
 
 // Unfiltered U,V at sample x of a line (0 outside the picture or on a colourless line)
-__device__ __forceinline__ void uv_at(const htv_dparams_t &dp, const DevTables &dt, const LineInfo &li, int x, int &u, int &v)
+__device__ __forceinline__ void uv_at(const htv_dparams_t &dp, const double *glut, const LineInfo &li, int x, int &u, int &v)
 {
 	u = v = 0;
 	if(!li.pal || x < li.al || x >= li.ar) return;
 	int y;
 	unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
-	yuv_of(dp, dt.glut, rgb, y, u, v);
+	yuv_of(dp, glut, rgb, y, u, v);
 }
 
 // One composite sample from scratch (slow, exact): used for the 2 x 25 halo samples a
-// line needs from its neighbours. prev/next give the neighbours of `li`.
-__device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
+// line needs from its neighbours. prev/next are the neighbours of `li`.
+__device__ __noinline__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt, const double *glut,
 	const LineInfo &prev, const LineInfo &li, const LineInfo &next, int x)
 {
 	if(li.L < 0) return(0);            // before the stream: the filter window starts zeroed
@@ -499,7 +514,7 @@ __device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
 	{
 		int y, u, w;
 		unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
-		yuv_of(dp, dt.glut, rgb, y, u, w);
+		yuv_of(dp, glut, rgb, y, u, w);
 		v = y;
 	}
 	else
@@ -511,7 +526,7 @@ __device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
 
 	if(li.pal)
 	{
-		int cu, cv;
+		int cu = 0, cv = 0;
 		if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
 		{
 			int w = dt.burst_win[x - dp.burst_left];
@@ -521,22 +536,21 @@ __device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
 		else
 		{
 			const int h = dp.chroma_ntaps / 2;
-			int au = 0, av = 0;
-			if(dp.chroma_ntaps == 0) uv_at(dp, dt, li, x, au, av);
+			if(dp.chroma_ntaps == 0) uv_at(dp, glut, li, x, cu, cv);
 			else if(x + h >= li.al && x - h < li.ar)
 			{
+				int au = 0, av = 0;
 				for(int k = 0; k < dp.chroma_ntaps; k++)
 				{
 					int xx = x - h + k, u, w;
 					if(xx < 0 || xx >= dp.W) continue;
-					uv_at(dp, dt, li, xx, u, w);
+					uv_at(dp, glut, li, xx, u, w);
 					au += u * dp.chroma_taps[k];
 					av += w * dp.chroma_taps[k];
 				}
-				au = sat16i(au >> 15);
-				av = sat16i(av >> 15);
+				cu = sat16i(au >> 15);
+				cv = sat16i(av >> 15);
 			}
-			cu = au; cv = av;
 		}
 		htv_c16_t c = dt.clut[li.clut_off + x];
 		v += ((int) c.i * cv * li.pal + (int) c.q * cu) >> 15;
@@ -544,22 +558,56 @@ __device__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt,
 	return(wrap16i(v));
 }
 
-template<int SPT>
-__global__ void __launch_bounds__(384)
+// Chroma low-pass for 4 consecutive samples with a compile-time tap count: the window is
+// read with aligned 128-bit shared loads and the symmetric taps are folded.
+template<int NT>
+__device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *su, const int *sv, int x0, int cu[4], int cv[4])
+{
+	constexpr int H = NT / 2;
+	static_assert(H <= 8, "window below assumes at most 17 taps");
+	int wu[20], wv[20];
+	const int4 *pu = reinterpret_cast<const int4 *>(su + x0 + HCP - 8);
+	const int4 *pv = reinterpret_cast<const int4 *>(sv + x0 + HCP - 8);
+	#pragma unroll
+	for(int i = 0; i < 5; i++)
+	{
+		int4 a = pu[i], b = pv[i];
+		wu[4 * i] = a.x; wu[4 * i + 1] = a.y; wu[4 * i + 2] = a.z; wu[4 * i + 3] = a.w;
+		wv[4 * i] = b.x; wv[4 * i + 1] = b.y; wv[4 * i + 2] = b.z; wv[4 * i + 3] = b.w;
+	}
+	#pragma unroll
+	for(int k = 0; k < 4; k++)
+	{
+		int au = wu[k + 8] * dp.chroma_taps[H], av = wv[k + 8] * dp.chroma_taps[H];
+		#pragma unroll
+		for(int t = 0; t < H; t++)
+		{
+			au += (wu[k + 8 - H + t] + wu[k + 8 + H - t]) * dp.chroma_taps[t];
+			av += (wv[k + 8 - H + t] + wv[k + 8 + H - t]) * dp.chroma_taps[t];
+		}
+		cu[k] = sat16i(au >> 15);
+		cv[k] = sat16i(av >> 15);
+	}
+}
+
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t line0, int nlines, int16_t *out)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	LineShared &sh = *reinterpret_cast<LineShared *>(smem_raw);
 	const int W = dp.W;
-	const int CW = (W + 2 * HALO + 3) & ~3;                        // composite window, padded
-	int *comp = reinterpret_cast<int *>(smem_raw + ((sizeof(LineShared) + 15) & ~15));   // [CW], index = x + HALO
-	int *su = comp + CW;                                            // [W + 2*HC], index = x + HC
-	const int HC = HTV_MAX_CTAPS / 2 + 1;
-	int *sv = su + ((W + 2 * HC + 3) & ~3);
+	const int CW = ((W + 2 * HALO + 3) & ~3) + 8;                   // composite window incl. read-ahead padding
+	const int UW = (W + 2 * HCP + 3) & ~3;
+	double *glut = reinterpret_cast<double *>(smem_raw + ((sizeof(LineShared) + 15) & ~15));
+	int *comp = reinterpret_cast<int *>(glut + 256);                // [CW], index = x + HALO
+	int *su = comp + CW;                                            // [UW], index = x + HCP
+	int *sv = su + UW;
+	short *ntp = reinterpret_cast<short *>(sv + UW);                // padded NICAM pulse table
 	const int tid = threadIdx.x;
 	const int64_t L = line0 + blockIdx.x;
 
-	// ---- per-line setup --------------------------------------------------
+	// ---- per-line setup (a few threads), table staging (all threads) ----------
 	if(tid < 3) line_info(dp, dt, L - 1 + tid, sh.li[tid]);
 	if(tid == 32)
 	{
@@ -567,8 +615,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		sh.m0 = m0;
 		sh.kk0 = (int) (m0 % 32767);
 		sh.cc0 = dp.have_nicam ? (int) (m0 % dp.nicam_cc_len) : 0;
-		sh.am_phase0 = dp.am_ang * (unsigned long long) m0;         // phase after m0 steps (mod 2^64)
-		// offset mixer: phase0 + (m - 32766) * ang for m >= 32767
+		sh.am_phase0 = dp.am_ang * (unsigned long long) m0;
 		sh.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
 		// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
 		int n = 0;
@@ -591,7 +638,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 			}
 		}
 		sh.nseg = n;
-		sh.seg_x[n] = W;
+		for(; n <= MAX_SEG; n++) sh.seg_x[n] = 0x7FFFFFFF;
 	}
 	if(tid >= 64 && tid < 64 + MAX_NSYM && dp.have_nicam)
 	{
@@ -605,35 +652,90 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		if(s <= slast)
 		{
 			int64_t k = s / 364;
+			const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
+			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
+			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
 			sh.sym_x[i] = (int) (nic_sym_pos(s, dp.nicam_F, dp.nicam_D) - m0);
-			sh.sym_v[i] = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
+			sh.sym_si[i] = (code & 1) ? 1 : -1;
+			sh.sym_sq[i] = (code & 2) ? 1 : -1;
 		}
+	}
+	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
+	if(dp.have_nicam)
+	{
+		for(int i = tid; i < dp.nicam_tpad_len; i += blockDim.x)
+		{
+			const int d = i - NIC_TPAD;
+			ntp[i] = (d >= 0 && d < dp.nicam_ntaps) ? dt.nicam_taps[d] : (short) 0;
+		}
+	}
+	__syncthreads();
+
+	if(tid == 0)
+	{
+		// which sync pulses touch this line: the previous line's overrun, its own, and the
+		// next line's leading edge (ref vbidata.c:186-239). Only the last adds inside the picture.
+		int n = 0;
+		for(int s = 0; s < 3; s++)
+		{
+			if(sh.li[s].L < 0) continue;
+			const int mask = sh.li[s].code & HTV_LC_SYNC_MASK;
+			for(int b = 0; b < 5; b++)
+			{
+				if(!(mask & (1 << b))) continue;
+				const int base = dp.pulse_off[b] + (s - 1) * W;
+				if(base + dp.pulse_len[b] <= 0 || base >= W || n >= MAX_ENT) continue;
+				sh.ent_base[n] = base; sh.ent_len[n] = dp.pulse_len[b];
+				sh.ent_pos[n] = dp.pulse_pos[b]; sh.ent_keep[n] = s == 2;
+				n++;
+			}
+		}
+		sh.nent = n;
 	}
 	__syncthreads();
 
 	const LineInfo &li = sh.li[1];
 	const int x0 = tid * SPT;
 
-	// ---- phase 1: blanking / luma, unfiltered U,V -------------------------
-	for(int k = 0; k < SPT; k++)
+	// ---- phase 1: blanking / sync / luma, unfiltered U,V ---------------------
+	if(x0 < W)
 	{
-		const int x = x0 + k;
-		if(x >= W) break;
-		int y = dp.blank, u = 0, v = 0;
-		if(x >= li.al && x < li.ar)
+		int val[SPT], uu[SPT], vv[SPT];
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
 		{
-			unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
-			yuv_of(dp, dt.glut, rgb, y, u, v);
-			if(!li.pal) u = v = 0;
+			const int x = x0 + k;
+			val[k] = dp.blank; uu[k] = 0; vv[k] = 0;
+			if(x >= li.al && x < li.ar)
+			{
+				unsigned int rgb = li.row ? (__ldg(li.row + (x - dp.active_left)) & 0xFFFFFF) : 0;
+				yuv_of(dp, glut, rgb, val[k], uu[k], vv[k]);
+				if(!li.pal) uu[k] = vv[k] = 0;
+			}
 		}
-		comp[x + HALO] = y;
-		su[x + HC] = u;
-		sv[x + HC] = v;
+		for(int e = 0; e < sh.nent; e++)
+		{
+			const int d0 = x0 - sh.ent_base[e];
+			if(d0 + SPT - 1 < 0 || d0 >= sh.ent_len[e]) continue;
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int d = d0 + k, x = x0 + k;
+				if(d < 0 || d >= sh.ent_len[e]) continue;
+				if(!sh.ent_keep[e] && x >= li.al && x < li.ar) continue;   // overwritten by the picture
+				val[k] += __ldg(dt.pulse_values + sh.ent_pos[e] + d);
+			}
+		}
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) if(x0 + k < W) comp[x0 + k + HALO] = wrap16i(val[k]);
+		*reinterpret_cast<int4 *>(su + x0 + HCP) = make_int4(uu[0], uu[1], uu[2], uu[3]);
+		*reinterpret_cast<int4 *>(sv + x0 + HCP) = make_int4(vv[0], vv[1], vv[2], vv[3]);
 	}
-	if(tid < 2 * HC)
+	if(tid < 2 * HCP)
 	{
-		const int i = tid < HC ? tid : W + tid;                      // [0,HC) and [W+HC, W+2HC)
-		su[i] = 0; sv[i] = 0;
+		// zero padding either side of the chroma window (samples outside the line are 0)
+		const int j = tid < HCP ? tid : ((W + 3) & ~3) + tid;
+		if(j < UW) { su[j] = 0; sv[j] = 0; }
 	}
 	// halo samples from the neighbouring lines (exact, from scratch)
 	if(dp.vf_type && tid >= blockDim.x - 2 * HALO)
@@ -642,88 +744,81 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		if(h < HALO)
 		{
 			LineInfo pp; line_info(dp, dt, L - 2, pp);
-			comp[h] = comp_generic(dp, dt, pp, sh.li[0], sh.li[1], W - HALO + h);
+			comp[h] = comp_generic(dp, dt, glut, pp, sh.li[0], sh.li[1], W - HALO + h);
 		}
 		else
 		{
 			LineInfo nn; line_info(dp, dt, L + 2, nn);
-			comp[W + h] = comp_generic(dp, dt, sh.li[1], sh.li[2], nn, h - HALO);
+			comp[W + h] = comp_generic(dp, dt, glut, sh.li[1], sh.li[2], nn, h - HALO);
 		}
 	}
 	__syncthreads();
 
-	// ---- phase 2: sync pulses (ref vbidata.c:186-239) ----------------------
+	// ---- phase 2: chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ----
+	if(li.pal && x0 < W)
 	{
-		// own pulses and the previous line's overrun are overwritten by luma inside the
-		// picture; the next line's leading edge (negative offsets) is added afterwards
-		const int masks[3] = { sh.li[0].L >= 0 ? (sh.li[0].code & HTV_LC_SYNC_MASK) : 0,
-		                       li.code & HTV_LC_SYNC_MASK, sh.li[2].code & HTV_LC_SYNC_MASK };
-		for(int s = 0; s < 3; s++)
+		const int h = dp.chroma_ntaps / 2;
+		const bool near_pic = x0 + SPT - 1 + h >= li.al && x0 - h < li.ar;
+		const bool near_burst = x0 + SPT - 1 >= dp.burst_left && x0 < dp.burst_left + dp.burst_width;
+		if(near_pic || near_burst)
 		{
-			for(int b = 0; b < 5; b++)
+			int cu[SPT] = { 0, 0, 0, 0 }, cv[SPT] = { 0, 0, 0, 0 };
+			if(near_pic)
 			{
-				if(!(masks[s] & (1 << b))) continue;
-				const int base = dp.pulse_off[b] + (s - 1) * W;      // previous line: -W, own: 0, next line: +W
-				for(int i = tid; i < dp.pulse_len[b]; i += blockDim.x)
+				switch(dp.chroma_ntaps)
 				{
-					const int x = base + i;
-					if(x < 0 || x >= W) continue;
-					if(s != 2 && x >= li.al && x < li.ar) continue;
-					atomicAdd(&comp[x + HALO], (int) dt.pulse_values[dp.pulse_pos[b] + i]);
+				case 11: chroma_fir4<11>(dp, su, sv, x0, cu, cv); break;
+				case 13: chroma_fir4<13>(dp, su, sv, x0, cu, cv); break;
+				case 15: chroma_fir4<15>(dp, su, sv, x0, cu, cv); break;
+				case 17: chroma_fir4<17>(dp, su, sv, x0, cu, cv); break;
+				case 0:
+					for(int k = 0; k < SPT; k++) { cu[k] = su[x0 + k + HCP]; cv[k] = sv[x0 + k + HCP]; }
+					break;
+				default:
+					for(int k = 0; k < SPT; k++)
+					{
+						int au = 0, av = 0;
+						for(int t = 0; t < dp.chroma_ntaps; t++)
+						{
+							au += su[x0 + k + HCP - h + t] * dp.chroma_taps[t];
+							av += sv[x0 + k + HCP - h + t] * dp.chroma_taps[t];
+						}
+						cu[k] = sat16i(au >> 15); cv[k] = sat16i(av >> 15);
+					}
 				}
 			}
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 3: chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ----
-	if(li.pal)
-	{
-		const int nt = dp.chroma_ntaps, h = nt / 2;
-		for(int k = 0; k < SPT; k++)
-		{
-			const int x = x0 + k;
-			if(x >= W) break;
-			int cu, cv;
-			if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
 			{
-				int w = dt.burst_win[x - dp.burst_left];
-				cu = (dp.burst_i * w) >> 15;
-				cv = (dp.burst_q * w) >> 15;
-			}
-			else if(nt == 0) { cu = su[x + HC]; cv = sv[x + HC]; }
-			else
-			{
-				int au = 0, av = 0;
-				for(int t = 0; t < nt; t++)
+				const int x = x0 + k;
+				if(x >= W) break;
+				if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
 				{
-					au += su[x + HC - h + t] * dp.chroma_taps[t];
-					av += sv[x + HC - h + t] * dp.chroma_taps[t];
+					const int w = dt.burst_win[x - dp.burst_left];
+					cu[k] = (dp.burst_i * w) >> 15;
+					cv[k] = (dp.burst_q * w) >> 15;
 				}
-				cu = sat16i(au >> 15);
-				cv = sat16i(av >> 15);
+				const htv_c16_t c = dt.clut[li.clut_off + x];
+				comp[x + HALO] = wrap16i(comp[x + HALO] + (((int) c.i * cv[k] * li.pal + (int) c.q * cu[k]) >> 15));
 			}
-			htv_c16_t c = dt.clut[li.clut_off + x];
-			comp[x + HALO] = wrap16i(comp[x + HALO] + (((int) c.i * cv * li.pal + (int) c.q * cu) >> 15));
-		}
-	}
-	else
-	{
-		for(int k = 0; k < SPT; k++)
-		{
-			const int x = x0 + k;
-			if(x < W) comp[x + HALO] = wrap16i(comp[x + HALO]);
 		}
 	}
 	__syncthreads();
 
-	// ---- phase 4: video filter, sound carriers, mixers, store ---------------
+	if(x0 >= W) return;
+
+	// ---- phase 3: video filter, sound carriers, mixers, store -----------------
 	int oi[SPT], oq[SPT];
 	if(dp.vf_type)
 	{
-		int c[SPT + 2 * HALO];
+		int c[SPT + 2 * HALO + 2];
+		const int4 *pc = reinterpret_cast<const int4 *>(comp + x0);
 		#pragma unroll
-		for(int k = 0; k < SPT + 2 * HALO; k++) c[k] = (x0 + k < CW) ? comp[x0 + k] : 0;
+		for(int i = 0; i < (SPT + 2 * HALO + 2) / 4; i++)
+		{
+			int4 a = pc[i];
+			c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
+		}
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
@@ -750,94 +845,116 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 	else
 	{
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) { oi[k] = (x0 + k < W) ? comp[x0 + k + HALO] : 0; oq[k] = 0; }
+		for(int k = 0; k < SPT; k++) { oi[k] = comp[x0 + k + HALO]; oq[k] = 0; }
 	}
 
-	if(dp.have_fm || dp.have_am || dp.have_nicam || dp.have_offset || dp.swap_iq)
+	if(dp.have_fm || dp.have_am)
 	{
+		// at most one audio-sample boundary falls inside 4 consecutive samples
+		int sg0 = 0;
+		while(sh.seg_x[sg0 + 1] <= x0) sg0++;
+		const int nb = sh.seg_x[sg0 + 1];
+		const int sg1 = min(sg0 + 1, MAX_SEG - 1);
+		int kk = sh.kk0 + x0; if(kk >= 32767) kk -= 32767;
+		#pragma unroll
+		for(int k = 0; k < SPT; k++, kk++)
+		{
+			const int x = x0 + k;
+			const int sg = x >= nb ? sg1 : sg0;
+			if(kk >= 32767) kk -= 32767;
+			// amplitude of the reference's Q31 phasor kk+1 multiplications after a renormalisation
+			const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
+			int addi = 0, addq = 0;
+			if(dp.have_fm)
+			{
+				const unsigned long long ph = sh.seg_phase[sg] + sh.seg_ang[sg] * (unsigned long long) x;
+				float sn, cs;
+				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
+				addi += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
+				addq += ((int) floorf(amp * sn) * dp.fm_level) >> 15;
+			}
+			if(dp.have_am)
+			{
+				const unsigned long long ph = sh.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
+				float sn, cs;
+				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+				const int smp = (sh.seg_am[sg] + 32768) / 2;
+				addi += ((((int) floorf(amp * cs) * smp) >> 15) * dp.am_level) >> 15;
+				addq += ((((int) floorf(amp * sn) * smp) >> 15) * dp.am_level) >> 15;
+			}
+			oi[k] = wrap16i(oi[k] + wrap16i(addi));
+			oq[k] = wrap16i(oq[k] + wrap16i(addq));
+		}
+	}
+
+	if(dp.have_nicam)
+	{
+		// the newest symbol started at or before the thread's last sample: estimate from the
+		// mean spacing, correct by one; then NIC_CAND symbols back cover all four samples
+		const int xl = x0 + SPT - 1;
+		int i3 = (int) ((float) (xl - sh.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
+		i3 = max(0, min(sh.nsym - 1, i3));
+		while(i3 + 1 < sh.nsym && sh.sym_x[i3 + 1] <= xl) i3++;
+		while(i3 > 0 && sh.sym_x[i3] > xl) i3--;
+		int bi[SPT] = { 0, 0, 0, 0 }, bq[SPT] = { 0, 0, 0, 0 };
+		#pragma unroll
+		for(int cnd = 0; cnd < NIC_CAND; cnd++)
+		{
+			const int i = i3 - cnd;
+			if(i < 0) break;
+			const int d0 = x0 - sh.sym_x[i] + NIC_TPAD;        // >= NIC_TPAD - 3 - (spacing); table is zero outside the pulse
+			if(d0 < 0) continue;                                // symbol starts after these samples (only the newest can)
+			const int si = sh.sym_si[i], sq = sh.sym_sq[i];
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int r = ntp[d0 + k];
+				bi[k] += r * si;
+				bq[k] += r * sq;
+			}
+		}
+		int ci = sh.cc0 + x0;
+		ci %= dp.nicam_cc_len;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
+			const htv_c16_t cc = dt.nicam_cc[ci];
+			if(++ci == dp.nicam_cc_len) ci = 0;
+			const int b0 = wrap16i(bi[k]), b1 = wrap16i(bq[k]);
+			oi[k] = wrap16i(oi[k] + ((b0 * cc.i - b1 * cc.q) >> 15));
+			oq[k] = wrap16i(oq[k] + ((b0 * cc.q + b1 * cc.i) >> 15));
+		}
+	}
+
+	if(dp.swap_iq)
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) { int t = oi[k]; oi[k] = oq[k]; oq[k] = t; }
+	}
+
+	if(dp.have_offset)
+	{
+		for(int k = 0; k < SPT; k++)
+		{
 			const int x = x0 + k;
-			if(x >= W) break;
-			int addi = 0, addq = 0;
-			if(dp.have_fm || dp.have_am)
+			const int64_t m = sh.m0 + x;
+			int bi, bq;
+			if(m < 32767)
 			{
-				int sg = 0;
-				while(sg + 1 < sh.nseg && x >= sh.seg_x[sg + 1]) sg++;
-				int kk = sh.kk0 + x; if(kk >= 32767) kk -= 32767;
-				// amplitude of the reference's Q31 phasor kk+1 multiplications after a renormalisation
+				const unsigned char st = dt.offset_start[m];
+				bi = -(st & 1); bq = -((st >> 1) & 1);
+			}
+			else
+			{
+				const int kk = (int) (m % 32767);
 				const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
-				if(dp.have_fm)
-				{
-					unsigned long long ph = sh.seg_phase[sg] + sh.seg_ang[sg] * (unsigned long long) x;
-					float sn, cs;
-					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
-					int pi_ = (int) floorf(amp * cs), pq_ = (int) floorf(amp * sn);
-					addi += (pi_ * dp.fm_level) >> 15;
-					addq += (pq_ * dp.fm_level) >> 15;
-				}
-				if(dp.have_am)
-				{
-					unsigned long long ph = sh.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
-					float sn, cs;
-					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
-					int pi_ = (int) floorf(amp * cs), pq_ = (int) floorf(amp * sn);
-					int smp = (sh.seg_am[sg] + 32768) / 2;
-					addi += (((pi_ * smp) >> 15) * dp.am_level) >> 15;
-					addq += (((pq_ * smp) >> 15) * dp.am_level) >> 15;
-				}
+				const unsigned long long ph = sh.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
+				float sn, cs;
+				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+				bi = (int) floorf(amp * cs); bq = (int) floorf(amp * sn);
 			}
-			int vi = wrap16i(oi[k] + wrap16i(addi)), vq = wrap16i(oq[k] + wrap16i(addq));
-			if(dp.have_nicam)
-			{
-				// the symbol in progress: estimate from the mean spacing, then correct by one
-				int i = (int) ((float) (x - sh.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
-				i = max(0, min(sh.nsym - 1, i));
-				while(i + 1 < sh.nsym && sh.sym_x[i + 1] <= x) i++;
-				while(i > 0 && sh.sym_x[i] > x) i--;
-				int bi = 0, bq = 0;
-				for(; i >= 0; i--)
-				{
-					int d = x - sh.sym_x[i];
-					if(d < 0) continue;
-					if(d >= dp.nicam_ntaps) break;
-					int r = dt.nicam_taps[d];
-					// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I sign, bit1 -> Q sign
-					const int sy = sh.sym_v[i];
-					const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
-					bi += (code & 1) ? r : -r;
-					bq += (code & 2) ? r : -r;
-				}
-				bi = wrap16i(bi); bq = wrap16i(bq);
-				int ci = sh.cc0 + x; if(ci >= dp.nicam_cc_len) ci -= dp.nicam_cc_len; if(ci >= dp.nicam_cc_len) ci %= dp.nicam_cc_len;
-				htv_c16_t cc = dt.nicam_cc[ci];
-				vi = wrap16i(vi + ((bi * cc.i - bq * cc.q) >> 15));
-				vq = wrap16i(vq + ((bi * cc.q + bq * cc.i) >> 15));
-			}
-			if(dp.swap_iq) { int t = vi; vi = vq; vq = t; }
-			if(dp.have_offset)
-			{
-				const int64_t m = sh.m0 + x;
-				int bi, bq;
-				if(m < 32767)
-				{
-					unsigned char st = dt.offset_start[m];
-					bi = -(st & 1); bq = -((st >> 1) & 1);
-				}
-				else
-				{
-					int kk = (int) (m % 32767);
-					const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
-					unsigned long long ph = sh.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
-					float sn, cs;
-					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
-					bi = (int) floorf(amp * cs); bq = (int) floorf(amp * sn);
-				}
-				int ri = (vi * bi - vq * bq) >> 15, rq = (vi * bq + vq * bi) >> 15;
-				vi = wrap16i(ri); vq = wrap16i(rq);
-			}
-			oi[k] = vi; oq[k] = vq;
+			const int ri = (oi[k] * bi - oq[k] * bq) >> 15, rq = (oi[k] * bq + oq[k] * bi) >> 15;
+			oi[k] = wrap16i(ri); oq[k] = wrap16i(rq);
 		}
 	}
 
@@ -846,7 +963,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 	if(dp.complex_out)
 	{
 		int16_t *o = out + (lbase + x0) * 2;
-		if(SPT == 4 && (W & 3) == 0 && x0 + 3 < W)
+		if((W & 3) == 0)
 		{
 			int4 pk;
 			pk.x = (oi[0] & 0xFFFF) | (oq[0] << 16);
@@ -867,7 +984,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 	else
 	{
 		int16_t *o = out + lbase + x0;
-		if(SPT == 4 && (W & 3) == 0 && x0 + 3 < W)
+		if((W & 3) == 0)
 		{
 			int2 pk;
 			pk.x = (oi[0] & 0xFFFF) | (oi[1] << 16);
@@ -881,6 +998,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		}
 	}
 }
+
 
 // ---------------------------------------------------------------------------
 // Device layer (C linkage)
@@ -980,15 +1098,17 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	threads = (threads + 31) & ~31;
 	if(threads < 2 * HALO + 128) threads = 2 * HALO + 128;
 	d->line_threads = threads;
-	const int HC = HTV_MAX_CTAPS / 2 + 1;
-	d->line_smem = ((sizeof(LineShared) + 15) & ~15) + sizeof(int) * (((W + 2 * HALO + 3) & ~3) + 2 * ((W + 2 * HC + 3) & ~3));
+	d->line_smem = ((sizeof(LineShared) + 15) & ~15) + 256 * sizeof(double)
+		+ sizeof(int) * ((((W + 2 * HALO + 3) & ~3) + 8) + 2 * ((W + 2 * HCP + 3) & ~3))
+		+ sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
 	if(threads > 384)
 	{
 		snprintf(err, errlen, "line width %d exceeds the kernel's 1536-sample limit", W);
 		htv_dev_destroy(d);
 		return(NULL);
 	}
-	cudaFuncSetAttribute(k_lines<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
+	cudaFuncSetAttribute(k_lines<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
+	cudaFuncSetAttribute(k_lines<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
 	return(d);
@@ -1079,7 +1199,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
 	if(d->timing) cudaEventRecord(d->ev0, st);
-	k_lines<4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
+	if(d->line_threads <= 256) k_lines<256, 4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
+	else k_lines<384, 2><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
 	d->launches++;
 	CK(cudaGetLastError());

@@ -583,6 +583,10 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		g = gcd64(sample_rate, HTV_NICAM_SYMBOL_RATE);
 		dp->nicam_F = sample_rate / g;         /* samples per ...            */
 		dp->nicam_D = HTV_NICAM_SYMBOL_RATE / g; /* ... this many symbols      */
+		/* padded pulse table the kernel stages in shared memory: 8 zeros, the pulse, zeros
+		 * out to the farthest offset 7 overlapping symbols + 4 samples can ask for */
+		dp->nicam_tpad_len = 8 + 8 * (int) ((sample_rate + HTV_NICAM_SYMBOL_RATE - 1) / HTV_NICAM_SYMBOL_RATE) + 8;
+		if(dp->nicam_tpad_len < 8 + dp->nicam_ntaps + 8) dp->nicam_tpad_len = 8 + dp->nicam_ntaps + 8;
 		g = gcd64(sample_rate, freq);
 		t->nicam_cc_len = dp->nicam_cc_len = sample_rate / g;
 		t->nicam_cc = malloc(sizeof(htv_c16_t) * t->nicam_cc_len);
