@@ -86,6 +86,8 @@ struct htv_dev_t {
 	int ev_pending;
 	int line_threads;
 	size_t line_smem;
+	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
+	int desc_cap;
 };
 
 // ---------------------------------------------------------------------------
@@ -362,56 +364,182 @@ __global__ void k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
 }
 
 // ---------------------------------------------------------------------------
-// The line kernel
+// Per-line descriptors (one thread per scan line) and the line kernel
 // ---------------------------------------------------------------------------
 
 #define SPT 4                         // samples per thread: one 128-bit store of 4 complex int16 samples
-#define HCP 16                        // chroma window padding (>= taps / 2, multiple of 4)
+#define EXT 32                        // neighbour samples rendered either side of a line (>= 25 + chroma half-width)
+#define COFF (EXT + 1)                // composite window index = x + COFF: makes the filter's 128-bit loads aligned
+#define UOFF (EXT + 8)                // chroma window index = x + UOFF
 #define NIC_CAND 7                    // NICAM symbols that can overlap 4 consecutive samples
 #define NIC_TPAD 8                    // zero entries in front of the padded NICAM pulse table
-#define MAX_ENT 6                     // sync pulses that can touch one line (2 own + 2 previous + 2 next)
+#define MAX_ENT 6                     // sync pulse pieces that can land on one line (2 previous + 2 own + 2 next)
+#define MAX_CENT 12                   // ... and on a line plus its two 32-sample margins
+#define MAX_SEGS 6                    // audio samples overlapping one scan line (+1)
+#define MAX_SYMS 48                   // NICAM symbols overlapping one scan line
 
-struct LineInfo {
-	int64_t L;
-	int frame, line;                  // 1-based, as the reference counts
-	int code;
+// What the raster needs to know about a line (also read for the two neighbours)
+struct __align__(16) LineRaster {
+	int valid;                        // 0: before the stream (the filter window starts zeroed)
+	int frame, line, code;            // 1-based, as the reference counts
 	int pal;                          // 0 no chroma, +1 / -1 V-switch
 	int al, ar;                       // active sample range [al, ar), -1 if none
-	const uint32_t *row;              // source pixels of this line, or NULL for black
 	unsigned int clut_off;
+	long long row_off;                // pixel offset of the source row in the frame store, -1 = black
+	int nent, pad0;
+	int ent_base[MAX_ENT], ent_len[MAX_ENT], ent_pos[MAX_ENT], ent_keep[MAX_ENT];
 };
 
-struct __align__(16) LineShared {
-	LineInfo li[3];                   // previous, this, next
-	// sync pulse pieces landing on this line
-	int nent;
-	int ent_base[MAX_ENT], ent_len[MAX_ENT], ent_pos[MAX_ENT], ent_keep[MAX_ENT];
-	// sound carriers
-	int nseg;
-	int seg_x[MAX_SEG + 1];           // first sample (relative to the line) of each audio segment
-	unsigned long long seg_phase[MAX_SEG];  // FM phase "before relative sample 0" on that segment
-	unsigned long long seg_ang[MAX_SEG];
-	int seg_am[MAX_SEG];
-	int kk0;                          // audio-clock index of the line start, mod 32767
+// Sound-carrier state at the start of a line
+struct __align__(16) LineAudio {
+	long long m0;                     // audio-clock index of the line's first sample
 	unsigned long long am_phase0, off_phase0;
-	int64_t m0;
-	// NICAM
-	int nsym;
-	int sym_x[MAX_NSYM];              // first sample of each symbol relative to the line
-	signed char sym_si[MAX_NSYM], sym_sq[MAX_NSYM];   // +-1 pulse polarity on I and Q
-	int cc0;
+	unsigned long long seg_phase[MAX_SEGS], seg_ang[MAX_SEGS];
+	int seg_x[MAX_SEGS + 1];          // first sample (relative to the line) of each audio segment
+	int seg_am[MAX_SEGS];
+	int nseg, kk0, cc0, nsym;
+	short sym_x[MAX_SYMS];            // first sample of each symbol relative to the line
+	signed char sym_si[MAX_SYMS], sym_sq[MAX_SYMS];   // +-1 pulse polarity on I and Q
+	int pad1[2];
 };
+
+struct LineDescs { LineRaster *r; LineAudio *a; };
+static_assert(sizeof(LineRaster) % 16 == 0 && sizeof(LineAudio) % 16 == 0, "descriptors are copied as int4");
+
+__device__ void line_raster(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineRaster &li)
+{
+	li.valid = L >= 0;
+	li.nent = 0;
+	if(L < 0) { li.frame = li.line = li.code = li.pal = 0; li.al = li.ar = -1; li.row_off = -1; li.clut_off = 0; return; }
+	const int64_t f0 = L / dp.lines;
+	li.frame = (int) (f0 + 1);
+	li.line = (int) (L - f0 * dp.lines) + 1;
+	li.code = dt.codes[li.line];
+	const int left = li.code & HTV_LC_LEFT_ACTIVE, right = li.code & HTV_LC_RIGHT_ACTIVE;
+	li.al = left ? dp.active_left : (right ? dp.half_width : -1);
+	li.ar = right ? dp.active_left + dp.active_width : (left ? dp.half_width : -1);
+
+	// source row (ref video.c:2812-2895): a progressive source on an interlaced raster shifts down one row
+	int vy;
+	if(dp.raster == HTV_RASTER_625) vy = li.line < 313 ? (li.line - 23) * 2 : (li.line - 336) * 2 + 1;
+	else vy = li.line < 265 ? (li.line - 23) * 2 : (li.line - 286) * 2 + 1;
+	if(vy >= 0 && dp.interlaced != 0) vy += 1;
+	if(vy < 0 || vy >= dp.active_lines) vy = -1;
+	li.row_off = -1;
+	if(vy >= 0 && dt.frames)
+	{
+		const int64_t fi = f0 - dt.frame_map_first;
+		if(fi >= 0 && fi < dt.frame_map_len)
+		{
+			const int slot = dt.frame_map[fi];              // -1: the source has no picture (black)
+			if(slot >= 0) li.row_off = ((long long) slot * dp.active_lines + vy) * (long long) dp.active_width;
+		}
+	}
+
+	li.pal = 0;
+	li.clut_off = 0;
+	if(dp.colour_mode == HTV_PAL || dp.colour_mode == HTV_NTSC)
+	{
+		const int b = (li.code & HTV_LC_BURST_MASK) >> HTV_LC_BURST_SHIFT;
+		li.pal = b == 1 || (b == 2 && (li.frame & 1) == 0) || (b == 3 && (li.frame & 1) == 1);
+		if(dp.colour_mode == HTV_PAL && li.pal && ((li.frame + li.line) & 1)) li.pal = -1;
+		li.clut_off = (unsigned int) (((unsigned long long) L * (unsigned long long) dp.W) % dp.clut_width);
+	}
+
+	// sync pulse pieces landing on this line: the previous line's overrun, its own pulses, and
+	// the next line's leading edge (ref vbidata.c:186-239). Only the last adds inside the picture.
+	int n = 0;
+	for(int s = -1; s <= 1; s++)
+	{
+		const int64_t S = L + s;
+		if(S < 0) continue;
+		const int mask = dt.codes[(int) (S % dp.lines) + 1] & HTV_LC_SYNC_MASK;
+		for(int b = 0; b < 5; b++)
+		{
+			if(!(mask & (1 << b))) continue;
+			const int base = dp.pulse_off[b] + s * dp.W;
+			if(base + dp.pulse_len[b] <= 0 || base >= dp.W || n >= MAX_ENT) continue;
+			li.ent_base[n] = base; li.ent_len[n] = dp.pulse_len[b];
+			li.ent_pos[n] = dp.pulse_pos[b]; li.ent_keep[n] = s == 1;
+			n++;
+		}
+	}
+	li.nent = n;
+}
+
+__device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineAudio &la)
+{
+	const int W = dp.W;
+	const int64_t m0 = L * (int64_t) W + dp.shift;
+	la.m0 = m0;
+	la.kk0 = (int) (m0 % 32767);
+	la.cc0 = dp.have_nicam ? (int) (m0 % dp.nicam_cc_len) : 0;
+	la.am_phase0 = dp.am_ang * (unsigned long long) m0;
+	la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
+	// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
+	int n = 0;
+	if(dp.have_fm || dp.have_am)
+	{
+		int64_t j = fetches_by(m0, dp.rate) - 1;
+		for(; n < MAX_SEGS; n++, j++)
+		{
+			const int64_t st = seg_start(j, dp.rate);
+			if(st >= m0 + W) break;
+			la.seg_x[n] = (int) max((int64_t) 0, st - m0);
+			la.seg_phase[n] = 0; la.seg_ang[n] = 0;
+			if(dp.have_fm)
+			{
+				const unsigned long long ang = dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+				// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
+				la.seg_ang[n] = ang;
+				la.seg_phase[n] = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
+			}
+			la.seg_am[n] = dp.have_am ? pcm_mono(dt, j, dp.volume) : 0;
+		}
+	}
+	la.nseg = n;
+	for(int i = n; i <= MAX_SEGS; i++) la.seg_x[i] = 0x7FFFFFFF;
+	la.nsym = 0;
+	if(dp.have_nicam)
+	{
+		// symbols whose pulse can still reach this line: ntaps samples back
+		const int64_t sfirst = (int64_t) (((unsigned long long) max((int64_t) 0, m0 - dp.nicam_ntaps) * dp.nicam_D) / dp.nicam_F);
+		const int64_t slast = (int64_t) (((unsigned long long) (m0 + W - 1) * dp.nicam_D) / dp.nicam_F);
+		const int ns = (int) min((int64_t) MAX_SYMS, slast - sfirst + 1);
+		for(int i = 0; i < ns; i++)
+		{
+			const int64_t s = sfirst + i, k = s / 364;
+			const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
+			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
+			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
+			la.sym_x[i] = (short) (nic_sym_pos(s, dp.nicam_F, dp.nicam_D) - m0);
+			la.sym_si[i] = (code & 1) ? 1 : -1;
+			la.sym_sq[i] = (code & 2) ? 1 : -1;
+		}
+		la.nsym = ns;
+	}
+}
+
+// descriptors for lines line0-1 .. line0+nlines (raster) and line0 .. line0+nlines-1 (audio)
+__global__ void k_line_desc(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= nlines + 2) return;
+	line_raster(dp, dt, line0 - 1 + i, ld.r[i]);
+	if(i >= 1 && i <= nlines) line_audio(dp, dt, line0 - 1 + i, ld.a[i - 1]);
+}
 
 __device__ __forceinline__ int round_away(double v)
 {
 	// round() (half away from zero) from the round-to-nearest-even conversion
 	int r = __double2int_rn(v);
-	double t = __dadd_rn(v, -(double) r);
+	const double t = __dadd_rn(v, -(double) r);
 	r += (t == 0.5 && v > 0.0) ? 1 : 0;
 	r -= (t == -0.5 && v < 0.0) ? 1 : 0;
 	return(r);
 }
 
+template<bool SECAM>
 __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *glut, unsigned int rgb, int &y, int &u, int &v)
 {
 	// ref video.c:3912-3959, same operation order, no FMA contraction. The reference clamps
@@ -421,7 +549,7 @@ __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *gl
 	double uu = __dmul_rn(__dadd_rn(b, -yy), dp.eu);
 	double vv = __dmul_rn(__dadd_rn(r, -yy), dp.ev);
 	yy = __dmul_rn(__dadd_rn(dp.black_level, __dmul_rn(yy, dp.white_minus_black)), dp.vlevel);
-	if(dp.colour_mode != HTV_SECAM)
+	if(!SECAM)
 	{
 		uu = __dmul_rn(uu, dp.uv_scale);
 		vv = __dmul_rn(vv, dp.uv_scale);
@@ -436,128 +564,6 @@ __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *gl
 	v = max(-32767, min(32767, round_away(__dmul_rn(vv, 32767.0))));
 }
 
-__device__ void line_info(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineInfo &li)
-{
-	li.L = L;
-	if(L < 0) { li.frame = 0; li.line = 0; li.code = 0; li.pal = 0; li.al = li.ar = -1; li.row = NULL; li.clut_off = 0; return; }
-	const int64_t f0 = L / dp.lines;
-	li.frame = (int) (f0 + 1);
-	li.line = (int) (L - f0 * dp.lines) + 1;
-	li.code = dt.codes[li.line];
-	const int left = li.code & HTV_LC_LEFT_ACTIVE, right = li.code & HTV_LC_RIGHT_ACTIVE;
-	li.al = left ? dp.active_left : (right ? dp.half_width : -1);
-	li.ar = right ? dp.active_left + dp.active_width : (left ? dp.half_width : -1);
-
-	// source row (ref video.c:2812-2895): progressive source on an interlaced raster shifts down one row
-	int vy;
-	if(dp.raster == HTV_RASTER_625) vy = li.line < 313 ? (li.line - 23) * 2 : (li.line - 336) * 2 + 1;
-	else vy = li.line < 265 ? (li.line - 23) * 2 : (li.line - 286) * 2 + 1;
-	if(vy >= 0 && dp.interlaced != 0) vy += 1;
-	if(vy < 0 || vy >= dp.active_lines) vy = -1;
-	li.row = NULL;
-	if(vy >= 0 && dt.frames)
-	{
-		int64_t fi = f0 - dt.frame_map_first;
-		if(fi >= 0 && fi < dt.frame_map_len)
-		{
-			const int slot = dt.frame_map[fi];              // -1: the source has no picture (black)
-			if(slot >= 0) li.row = dt.frames + ((size_t) slot * dp.active_lines + vy) * (size_t) dp.active_width;
-		}
-	}
-
-	li.pal = 0;
-	li.clut_off = 0;
-	if(dp.colour_mode == HTV_PAL || dp.colour_mode == HTV_NTSC)
-	{
-		const int b = (li.code & HTV_LC_BURST_MASK) >> HTV_LC_BURST_SHIFT;
-		li.pal = b == 1 || (b == 2 && (li.frame & 1) == 0) || (b == 3 && (li.frame & 1) == 1);
-		if(dp.colour_mode == HTV_PAL && li.pal && ((li.frame + li.line) & 1)) li.pal = -1;
-		li.clut_off = (unsigned int) (((unsigned long long) L * (unsigned long long) dp.W) % dp.clut_width);
-	}
-}
-
-// Sum of the sync pulse samples of pulse set `mask` at position x of the pulses' own line
-__device__ __forceinline__ int pulses_at(const htv_dparams_t &dp, const DevTables &dt, int mask, int x)
-{
-	int v = 0;
-	#pragma unroll
-	for(int b = 0; b < 5; b++)
-	{
-		if(mask & (1 << b))
-		{
-			int d = x - dp.pulse_off[b];
-			if(d >= 0 && d < dp.pulse_len[b]) v += dt.pulse_values[dp.pulse_pos[b] + d];
-		}
-	}
-	return(v);
-}
-
-// Unfiltered U,V at sample x of a line (0 outside the picture or on a colourless line)
-__device__ __forceinline__ void uv_at(const htv_dparams_t &dp, const double *glut, const LineInfo &li, int x, int &u, int &v)
-{
-	u = v = 0;
-	if(!li.pal || x < li.al || x >= li.ar) return;
-	int y;
-	unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
-	yuv_of(dp, glut, rgb, y, u, v);
-}
-
-// One composite sample from scratch (slow, exact): used for the 2 x 25 halo samples a
-// line needs from its neighbours. prev/next are the neighbours of `li`.
-__device__ __noinline__ int comp_generic(const htv_dparams_t &dp, const DevTables &dt, const double *glut,
-	const LineInfo &prev, const LineInfo &li, const LineInfo &next, int x)
-{
-	if(li.L < 0) return(0);            // before the stream: the filter window starts zeroed
-	int v = dp.blank;
-	const bool act = x >= li.al && x < li.ar;
-	if(act)
-	{
-		int y, u, w;
-		unsigned int rgb = li.row ? (li.row[x - dp.active_left] & 0xFFFFFF) : 0;
-		yuv_of(dp, glut, rgb, y, u, w);
-		v = y;
-	}
-	else
-	{
-		v += pulses_at(dp, dt, li.code & HTV_LC_SYNC_MASK, x);
-		if(prev.L >= 0) v += pulses_at(dp, dt, prev.code & HTV_LC_SYNC_MASK, x + dp.W);
-	}
-	v += pulses_at(dp, dt, next.code & HTV_LC_SYNC_MASK, x - dp.W);
-
-	if(li.pal)
-	{
-		int cu = 0, cv = 0;
-		if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
-		{
-			int w = dt.burst_win[x - dp.burst_left];
-			cu = (dp.burst_i * w) >> 15;
-			cv = (dp.burst_q * w) >> 15;
-		}
-		else
-		{
-			const int h = dp.chroma_ntaps / 2;
-			if(dp.chroma_ntaps == 0) uv_at(dp, glut, li, x, cu, cv);
-			else if(x + h >= li.al && x - h < li.ar)
-			{
-				int au = 0, av = 0;
-				for(int k = 0; k < dp.chroma_ntaps; k++)
-				{
-					int xx = x - h + k, u, w;
-					if(xx < 0 || xx >= dp.W) continue;
-					uv_at(dp, glut, li, xx, u, w);
-					au += u * dp.chroma_taps[k];
-					av += w * dp.chroma_taps[k];
-				}
-				cu = sat16i(au >> 15);
-				cv = sat16i(av >> 15);
-			}
-		}
-		htv_c16_t c = dt.clut[li.clut_off + x];
-		v += ((int) c.i * cv * li.pal + (int) c.q * cu) >> 15;
-	}
-	return(wrap16i(v));
-}
-
 // Chroma low-pass for 4 consecutive samples with a compile-time tap count: the window is
 // read with aligned 128-bit shared loads and the symmetric taps are folded.
 template<int NT>
@@ -566,12 +572,12 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 	constexpr int H = NT / 2;
 	static_assert(H <= 8, "window below assumes at most 17 taps");
 	int wu[20], wv[20];
-	const int4 *pu = reinterpret_cast<const int4 *>(su + x0 + HCP - 8);
-	const int4 *pv = reinterpret_cast<const int4 *>(sv + x0 + HCP - 8);
+	const int4 *pu = reinterpret_cast<const int4 *>(su + x0 + UOFF - 8);
+	const int4 *pv = reinterpret_cast<const int4 *>(sv + x0 + UOFF - 8);
 	#pragma unroll
 	for(int i = 0; i < 5; i++)
 	{
-		int4 a = pu[i], b = pv[i];
+		const int4 a = pu[i], b = pv[i];
 		wu[4 * i] = a.x; wu[4 * i + 1] = a.y; wu[4 * i + 2] = a.z; wu[4 * i + 3] = a.w;
 		wv[4 * i] = b.x; wv[4 * i + 1] = b.y; wv[4 * i + 2] = b.z; wv[4 * i + 3] = b.w;
 	}
@@ -590,75 +596,41 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 	}
 }
 
+struct __align__(16) LineShared {
+	LineRaster li[3];                 // previous, this, next
+	LineAudio la;
+	// sync pulse pieces in window coordinates (x relative to this line, may be < 0 or >= W)
+	int ncent;
+	int cent_base[MAX_CENT], cent_len[MAX_CENT], cent_pos[MAX_CENT];
+	int cent_al[MAX_CENT], cent_ar[MAX_CENT];   // picture range of the piece's line (pieces do not add inside it)
+	int cent_lo[MAX_CENT], cent_hi[MAX_CENT];   // the piece's own line: it adds nowhere else
+};
+
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t line0, int nlines, int16_t *out)
+k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineDescs ld, int64_t line0, int nlines, int16_t *out)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	LineShared &sh = *reinterpret_cast<LineShared *>(smem_raw);
 	const int W = dp.W;
-	const int CW = ((W + 2 * HALO + 3) & ~3) + 8;                   // composite window incl. read-ahead padding
-	const int UW = (W + 2 * HCP + 3) & ~3;
+	const int W4 = (W + 3) & ~3;
+	const int CW = W4 + 2 * EXT + 16;                               // composite window (+ read-ahead padding)
+	const int UW = W4 + 2 * EXT + 16;                               // chroma windows (+ 8 either side)
 	double *glut = reinterpret_cast<double *>(smem_raw + ((sizeof(LineShared) + 15) & ~15));
-	int *comp = reinterpret_cast<int *>(glut + 256);                // [CW], index = x + HALO
-	int *su = comp + CW;                                            // [UW], index = x + HCP
+	int *comp = reinterpret_cast<int *>(glut + 256);                // index = x + COFF
+	int *su = comp + CW;                                            // index = x + UOFF
 	int *sv = su + UW;
 	short *ntp = reinterpret_cast<short *>(sv + UW);                // padded NICAM pulse table
 	const int tid = threadIdx.x;
-	const int64_t L = line0 + blockIdx.x;
 
-	// ---- per-line setup (a few threads), table staging (all threads) ----------
-	if(tid < 3) line_info(dp, dt, L - 1 + tid, sh.li[tid]);
-	if(tid == 32)
+	// ---- stage descriptors and small tables -----------------------------------
 	{
-		const int64_t m0 = L * (int64_t) W + dp.shift;              // audio-clock index of the line's first sample
-		sh.m0 = m0;
-		sh.kk0 = (int) (m0 % 32767);
-		sh.cc0 = dp.have_nicam ? (int) (m0 % dp.nicam_cc_len) : 0;
-		sh.am_phase0 = dp.am_ang * (unsigned long long) m0;
-		sh.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
-		// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
-		int n = 0;
-		if(dp.have_fm || dp.have_am)
-		{
-			int64_t j = fetches_by(m0, dp.rate) - 1;
-			for(; n < MAX_SEG; n++, j++)
-			{
-				int64_t st = seg_start(j, dp.rate);
-				if(st >= m0 + W) break;
-				sh.seg_x[n] = (int) max((int64_t) 0, st - m0);
-				if(dp.have_fm)
-				{
-					unsigned long long ang = dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
-					// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
-					sh.seg_ang[n] = ang;
-					sh.seg_phase[n] = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
-				}
-				sh.seg_am[n] = dp.have_am ? pcm_mono(dt, j, dp.volume) : 0;
-			}
-		}
-		sh.nseg = n;
-		for(; n <= MAX_SEG; n++) sh.seg_x[n] = 0x7FFFFFFF;
-	}
-	if(tid >= 64 && tid < 64 + MAX_NSYM && dp.have_nicam)
-	{
-		const int i = tid - 64;
-		const int64_t m0 = L * (int64_t) W + dp.shift;
-		// symbols whose pulse can still reach this line: ntaps samples back
-		int64_t sfirst = (int64_t) (((unsigned long long) max((int64_t) 0, m0 - dp.nicam_ntaps) * dp.nicam_D) / dp.nicam_F);
-		int64_t slast = (int64_t) (((unsigned long long) (m0 + W - 1) * dp.nicam_D) / dp.nicam_F);
-		int64_t s = sfirst + i;
-		if(i == 0) sh.nsym = (int) min((int64_t) MAX_NSYM, slast - sfirst + 1);
-		if(s <= slast)
-		{
-			int64_t k = s / 364;
-			const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
-			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
-			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
-			sh.sym_x[i] = (int) (nic_sym_pos(s, dp.nicam_F, dp.nicam_D) - m0);
-			sh.sym_si[i] = (code & 1) ? 1 : -1;
-			sh.sym_sq[i] = (code & 2) ? 1 : -1;
-		}
+		const int4 *src = reinterpret_cast<const int4 *>(ld.r + blockIdx.x);
+		int4 *dst = reinterpret_cast<int4 *>(&sh.li[0]);
+		for(int i = tid; i < (int) (3 * sizeof(LineRaster) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+		const int4 *sa = reinterpret_cast<const int4 *>(ld.a + blockIdx.x);
+		int4 *da = reinterpret_cast<int4 *>(&sh.la);
+		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
 	}
 	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
 	if(dp.have_nicam)
@@ -669,193 +641,177 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 			ntp[i] = (d >= 0 && d < dp.nicam_ntaps) ? dt.nicam_taps[d] : (short) 0;
 		}
 	}
+	if(tid < 16)
+	{
+		// chroma windows: the 8 entries either side of [-EXT, W4 + EXT) read as zero
+		const int j = tid < 8 ? tid : UW - 16 + tid;
+		su[j] = 0; sv[j] = 0;
+	}
 	__syncthreads();
-
 	if(tid == 0)
 	{
-		// which sync pulses touch this line: the previous line's overrun, its own, and the
-		// next line's leading edge (ref vbidata.c:186-239). Only the last adds inside the picture.
+		// every sync pulse piece that lands in [-EXT, W4 + EXT), with the picture range of its line
 		int n = 0;
 		for(int s = 0; s < 3; s++)
 		{
-			if(sh.li[s].L < 0) continue;
-			const int mask = sh.li[s].code & HTV_LC_SYNC_MASK;
-			for(int b = 0; b < 5; b++)
+			const LineRaster &r = sh.li[s];
+			const int shift = (s - 1) * W;
+			for(int e = 0; e < r.nent; e++)
 			{
-				if(!(mask & (1 << b))) continue;
-				const int base = dp.pulse_off[b] + (s - 1) * W;
-				if(base + dp.pulse_len[b] <= 0 || base >= W || n >= MAX_ENT) continue;
-				sh.ent_base[n] = base; sh.ent_len[n] = dp.pulse_len[b];
-				sh.ent_pos[n] = dp.pulse_pos[b]; sh.ent_keep[n] = s == 2;
+				const int base = r.ent_base[e] + shift;
+				if(base + r.ent_len[e] <= -EXT || base >= W4 + EXT || n >= MAX_CENT) continue;
+				sh.cent_base[n] = base; sh.cent_len[n] = r.ent_len[e]; sh.cent_pos[n] = r.ent_pos[e];
+				// kept pieces (a next line's leading edge) add everywhere; others not inside the picture
+				sh.cent_al[n] = r.ent_keep[e] ? 0x7FFFFFFF : r.al + shift;
+				sh.cent_ar[n] = r.ent_keep[e] ? 0x7FFFFFFF : r.ar + shift;
+				sh.cent_lo[n] = shift; sh.cent_hi[n] = shift + W;
 				n++;
 			}
 		}
-		sh.nent = n;
+		sh.ncent = n;
 	}
 	__syncthreads();
 
-	const LineInfo &li = sh.li[1];
-	const int x0 = tid * SPT;
+	const int nquads = (W4 + 2 * EXT) / 4;
 
-	// ---- phase 1: blanking / sync / luma, unfiltered U,V ---------------------
-	if(x0 < W)
+	// ---- phase 1: blanking / sync / luma, unfiltered U,V over [-EXT, W4 + EXT) ----
+	for(int q = tid; q < nquads; q += blockDim.x)
 	{
+		const int xe0 = q * 4 - EXT;
 		int val[SPT], uu[SPT], vv[SPT];
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
-			const int x = x0 + k;
-			val[k] = dp.blank; uu[k] = 0; vv[k] = 0;
-			if(x >= li.al && x < li.ar)
+			const int xe = xe0 + k;
+			const int s = xe < 0 ? 0 : (xe < W ? 1 : 2);
+			const LineRaster &r = sh.li[s];
+			const int x = xe - (s - 1) * W;
+			val[k] = r.valid ? dp.blank : 0; uu[k] = 0; vv[k] = 0;
+			if(x >= r.al && x < r.ar)
 			{
-				unsigned int rgb = li.row ? (__ldg(li.row + (x - dp.active_left)) & 0xFFFFFF) : 0;
-				yuv_of(dp, glut, rgb, val[k], uu[k], vv[k]);
-				if(!li.pal) uu[k] = vv[k] = 0;
+				const unsigned int rgb = r.row_off >= 0 ? (__ldg(dt.frames + r.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
+				yuv_of<false>(dp, glut, rgb, val[k], uu[k], vv[k]);
+				if(!r.pal) uu[k] = vv[k] = 0;
 			}
 		}
-		for(int e = 0; e < sh.nent; e++)
+		for(int e = 0; e < sh.ncent; e++)
 		{
-			const int d0 = x0 - sh.ent_base[e];
-			if(d0 + SPT - 1 < 0 || d0 >= sh.ent_len[e]) continue;
+			const int d0 = xe0 - sh.cent_base[e];
+			if(d0 + SPT - 1 < 0 || d0 >= sh.cent_len[e]) continue;
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
-				const int d = d0 + k, x = x0 + k;
-				if(d < 0 || d >= sh.ent_len[e]) continue;
-				if(!sh.ent_keep[e] && x >= li.al && x < li.ar) continue;   // overwritten by the picture
-				val[k] += __ldg(dt.pulse_values + sh.ent_pos[e] + d);
+				const int d = d0 + k, xe = xe0 + k;
+				if(d < 0 || d >= sh.cent_len[e]) continue;
+				if(xe < sh.cent_lo[e] || xe >= sh.cent_hi[e]) continue;   // another line's sample
+				if(xe >= sh.cent_al[e] && xe < sh.cent_ar[e]) continue;   // overwritten by the picture
+				val[k] += __ldg(dt.pulse_values + sh.cent_pos[e] + d);
 			}
 		}
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) if(x0 + k < W) comp[x0 + k + HALO] = wrap16i(val[k]);
-		*reinterpret_cast<int4 *>(su + x0 + HCP) = make_int4(uu[0], uu[1], uu[2], uu[3]);
-		*reinterpret_cast<int4 *>(sv + x0 + HCP) = make_int4(vv[0], vv[1], vv[2], vv[3]);
-	}
-	if(tid < 2 * HCP)
-	{
-		// zero padding either side of the chroma window (samples outside the line are 0)
-		const int j = tid < HCP ? tid : ((W + 3) & ~3) + tid;
-		if(j < UW) { su[j] = 0; sv[j] = 0; }
-	}
-	// halo samples from the neighbouring lines (exact, from scratch)
-	if(dp.vf_type && tid >= blockDim.x - 2 * HALO)
-	{
-		const int h = tid - (blockDim.x - 2 * HALO);
-		if(h < HALO)
-		{
-			LineInfo pp; line_info(dp, dt, L - 2, pp);
-			comp[h] = comp_generic(dp, dt, glut, pp, sh.li[0], sh.li[1], W - HALO + h);
-		}
-		else
-		{
-			LineInfo nn; line_info(dp, dt, L + 2, nn);
-			comp[W + h] = comp_generic(dp, dt, glut, sh.li[1], sh.li[2], nn, h - HALO);
-		}
+		for(int k = 0; k < SPT; k++) comp[xe0 + k + COFF] = wrap16i(val[k]);
+		*reinterpret_cast<int4 *>(su + xe0 + UOFF) = make_int4(uu[0], uu[1], uu[2], uu[3]);
+		*reinterpret_cast<int4 *>(sv + xe0 + UOFF) = make_int4(vv[0], vv[1], vv[2], vv[3]);
 	}
 	__syncthreads();
 
 	// ---- phase 2: chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ----
-	if(li.pal && x0 < W)
+	if(sh.li[0].pal | sh.li[1].pal | sh.li[2].pal)
 	{
 		const int h = dp.chroma_ntaps / 2;
-		const bool near_pic = x0 + SPT - 1 + h >= li.al && x0 - h < li.ar;
-		const bool near_burst = x0 + SPT - 1 >= dp.burst_left && x0 < dp.burst_left + dp.burst_width;
-		if(near_pic || near_burst)
+		for(int q = tid; q < nquads; q += blockDim.x)
 		{
+			const int xe0 = q * 4 - EXT;
+			if(xe0 + SPT - 1 < -HALO || xe0 >= W + HALO) continue;     // not read by the video filter
+			// the line of the quad's first sample decides the fast path; mixed quads go per sample
+			const int s0 = xe0 < 0 ? 0 : (xe0 < W ? 1 : 2);
+			const int s3 = xe0 + 3 < 0 ? 0 : (xe0 + 3 < W ? 1 : 2);
+			const LineRaster &r0 = sh.li[s0], &r3 = sh.li[s3];
+			if(!(r0.pal | r3.pal)) continue;
+			const int x0 = xe0 - (s0 - 1) * W;
+			const bool near_pic = (x0 + SPT - 1 + h >= r0.al && x0 - h < r0.ar) || s0 != s3;
+			const bool near_burst = (x0 + SPT - 1 >= dp.burst_left && x0 < dp.burst_left + dp.burst_width) || s0 != s3;
+			if(!(near_pic || near_burst)) continue;
 			int cu[SPT] = { 0, 0, 0, 0 }, cv[SPT] = { 0, 0, 0, 0 };
 			if(near_pic)
 			{
 				switch(dp.chroma_ntaps)
 				{
-				case 11: chroma_fir4<11>(dp, su, sv, x0, cu, cv); break;
-				case 13: chroma_fir4<13>(dp, su, sv, x0, cu, cv); break;
-				case 15: chroma_fir4<15>(dp, su, sv, x0, cu, cv); break;
-				case 17: chroma_fir4<17>(dp, su, sv, x0, cu, cv); break;
-				case 0:
-					for(int k = 0; k < SPT; k++) { cu[k] = su[x0 + k + HCP]; cv[k] = sv[x0 + k + HCP]; }
-					break;
+				case 11: chroma_fir4<11>(dp, su, sv, xe0, cu, cv); break;
+				case 13: chroma_fir4<13>(dp, su, sv, xe0, cu, cv); break;
+				case 15: chroma_fir4<15>(dp, su, sv, xe0, cu, cv); break;
+				case 17: chroma_fir4<17>(dp, su, sv, xe0, cu, cv); break;
 				default:
-					for(int k = 0; k < SPT; k++)
-					{
-						int au = 0, av = 0;
-						for(int t = 0; t < dp.chroma_ntaps; t++)
-						{
-							au += su[x0 + k + HCP - h + t] * dp.chroma_taps[t];
-							av += sv[x0 + k + HCP - h + t] * dp.chroma_taps[t];
-						}
-						cu[k] = sat16i(au >> 15); cv[k] = sat16i(av >> 15);
-					}
+					for(int k = 0; k < SPT; k++) { cu[k] = su[xe0 + k + UOFF]; cv[k] = sv[xe0 + k + UOFF]; }
 				}
 			}
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
-				const int x = x0 + k;
-				if(x >= W) break;
+				const int xe = xe0 + k;
+				const int s = xe < 0 ? 0 : (xe < W ? 1 : 2);
+				const LineRaster &r = sh.li[s];
+				const int x = xe - (s - 1) * W;
+				if(!r.pal) continue;
 				if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
 				{
 					const int w = dt.burst_win[x - dp.burst_left];
 					cu[k] = (dp.burst_i * w) >> 15;
 					cv[k] = (dp.burst_q * w) >> 15;
 				}
-				const htv_c16_t c = dt.clut[li.clut_off + x];
-				comp[x + HALO] = wrap16i(comp[x + HALO] + (((int) c.i * cv[k] * li.pal + (int) c.q * cu[k]) >> 15));
+				const htv_c16_t c = dt.clut[r.clut_off + x];
+				comp[xe + COFF] = wrap16i(comp[xe + COFF] + (((int) c.i * cv[k] * r.pal + (int) c.q * cu[k]) >> 15));
 			}
 		}
 	}
 	__syncthreads();
 
+	const int x0 = tid * SPT;
 	if(x0 >= W) return;
+	const LineAudio &la = sh.la;
 
 	// ---- phase 3: video filter, sound carriers, mixers, store -----------------
 	int oi[SPT], oq[SPT];
 	if(dp.vf_type)
 	{
+		// c[j] = composite sample x0 - 25 + j
 		int c[SPT + 2 * HALO + 2];
-		const int4 *pc = reinterpret_cast<const int4 *>(comp + x0);
+		const int4 *pc = reinterpret_cast<const int4 *>(comp + x0 + COFF - HALO);
 		#pragma unroll
 		for(int i = 0; i < (SPT + 2 * HALO + 2) / 4; i++)
 		{
-			int4 a = pc[i];
+			const int4 a = pc[i];
 			c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
 		}
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
 			int ai = c[k + HALO] * dp.vf_i[HALO], aq = 0;
-			if(dp.vf_type == 3)
+			// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
+			#pragma unroll
+			for(int y = 0; y < HALO; y++)
 			{
-				// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
-				#pragma unroll
-				for(int y = 0; y < HALO; y++)
-				{
-					ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
-					aq += (c[k + y] - c[k + 2 * HALO - y]) * dp.vf_q[y];
-				}
-			}
-			else
-			{
-				#pragma unroll
-				for(int y = 0; y < HALO; y++) ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
+				ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
+				aq += (c[k + y] - c[k + 2 * HALO - y]) * dp.vf_q[y];
 			}
 			oi[k] = sat16i(ai >> 15);
-			oq[k] = dp.vf_type == 3 ? sat16i(aq >> 15) : 0;
+			oq[k] = sat16i(aq >> 15);                               // vf_q is all zero for the real low-pass
 		}
 	}
 	else
 	{
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) { oi[k] = comp[x0 + k + HALO]; oq[k] = 0; }
+		for(int k = 0; k < SPT; k++) { oi[k] = comp[x0 + k + COFF]; oq[k] = 0; }
 	}
 
 	if(dp.have_fm || dp.have_am)
 	{
 		// at most one audio-sample boundary falls inside 4 consecutive samples
 		int sg0 = 0;
-		while(sh.seg_x[sg0 + 1] <= x0) sg0++;
-		const int nb = sh.seg_x[sg0 + 1];
-		const int sg1 = min(sg0 + 1, MAX_SEG - 1);
-		int kk = sh.kk0 + x0; if(kk >= 32767) kk -= 32767;
+		while(la.seg_x[sg0 + 1] <= x0) sg0++;
+		const int nb = la.seg_x[sg0 + 1];
+		const int sg1 = min(sg0 + 1, MAX_SEGS - 1);
+		int kk = la.kk0 + x0; if(kk >= 32767) kk -= 32767;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++, kk++)
 		{
@@ -867,7 +823,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 			int addi = 0, addq = 0;
 			if(dp.have_fm)
 			{
-				const unsigned long long ph = sh.seg_phase[sg] + sh.seg_ang[sg] * (unsigned long long) x;
+				const unsigned long long ph = la.seg_phase[sg] + la.seg_ang[sg] * (unsigned long long) x;
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
 				addi += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
@@ -875,10 +831,10 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 			}
 			if(dp.have_am)
 			{
-				const unsigned long long ph = sh.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
+				const unsigned long long ph = la.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
-				const int smp = (sh.seg_am[sg] + 32768) / 2;
+				const int smp = (la.seg_am[sg] + 32768) / 2;
 				addi += ((((int) floorf(amp * cs) * smp) >> 15) * dp.am_level) >> 15;
 				addq += ((((int) floorf(amp * sn) * smp) >> 15) * dp.am_level) >> 15;
 			}
@@ -892,19 +848,19 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		// the newest symbol started at or before the thread's last sample: estimate from the
 		// mean spacing, correct by one; then NIC_CAND symbols back cover all four samples
 		const int xl = x0 + SPT - 1;
-		int i3 = (int) ((float) (xl - sh.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
-		i3 = max(0, min(sh.nsym - 1, i3));
-		while(i3 + 1 < sh.nsym && sh.sym_x[i3 + 1] <= xl) i3++;
-		while(i3 > 0 && sh.sym_x[i3] > xl) i3--;
+		int i3 = (int) ((float) (xl - la.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
+		i3 = max(0, min(la.nsym - 1, i3));
+		while(i3 + 1 < la.nsym && la.sym_x[i3 + 1] <= xl) i3++;
+		while(i3 > 0 && la.sym_x[i3] > xl) i3--;
 		int bi[SPT] = { 0, 0, 0, 0 }, bq[SPT] = { 0, 0, 0, 0 };
 		#pragma unroll
 		for(int cnd = 0; cnd < NIC_CAND; cnd++)
 		{
 			const int i = i3 - cnd;
 			if(i < 0) break;
-			const int d0 = x0 - sh.sym_x[i] + NIC_TPAD;        // >= NIC_TPAD - 3 - (spacing); table is zero outside the pulse
-			if(d0 < 0) continue;                                // symbol starts after these samples (only the newest can)
-			const int si = sh.sym_si[i], sq = sh.sym_sq[i];
+			const int d0 = x0 - la.sym_x[i] + NIC_TPAD;        // the table is zero outside the pulse
+			if(d0 < 0) continue;
+			const int si = la.sym_si[i], sq = la.sym_sq[i];
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
@@ -913,8 +869,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 				bq[k] += r * sq;
 			}
 		}
-		int ci = sh.cc0 + x0;
-		ci %= dp.nicam_cc_len;
+		int ci = (la.cc0 + x0) % dp.nicam_cc_len;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
@@ -929,7 +884,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 	if(dp.swap_iq)
 	{
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) { int t = oi[k]; oi[k] = oq[k]; oq[k] = t; }
+		for(int k = 0; k < SPT; k++) { const int t = oi[k]; oi[k] = oq[k]; oq[k] = t; }
 	}
 
 	if(dp.have_offset)
@@ -937,7 +892,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		for(int k = 0; k < SPT; k++)
 		{
 			const int x = x0 + k;
-			const int64_t m = sh.m0 + x;
+			const int64_t m = la.m0 + x;
 			int bi, bq;
 			if(m < 32767)
 			{
@@ -948,7 +903,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 			{
 				const int kk = (int) (m % 32767);
 				const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
-				const unsigned long long ph = sh.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
+				const unsigned long long ph = la.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
 				bi = (int) floorf(amp * cs); bq = (int) floorf(amp * sn);
@@ -998,7 +953,6 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t li
 		}
 	}
 }
-
 
 // ---------------------------------------------------------------------------
 // Device layer (C linkage)
@@ -1096,10 +1050,10 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	const int W = dp.W;
 	int threads = (W + 3) / 4;
 	threads = (threads + 31) & ~31;
-	if(threads < 2 * HALO + 128) threads = 2 * HALO + 128;
+	if(threads < 64) threads = 64;
 	d->line_threads = threads;
 	d->line_smem = ((sizeof(LineShared) + 15) & ~15) + 256 * sizeof(double)
-		+ sizeof(int) * ((((W + 2 * HALO + 3) & ~3) + 8) + 2 * ((W + 2 * HCP + 3) & ~3))
+		+ sizeof(int) * 3 * (((W + 3) & ~3) + 2 * EXT + 16)
 		+ sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
 	if(threads > 384)
 	{
@@ -1119,6 +1073,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	cudaSetDevice(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	free(d);
@@ -1198,9 +1153,22 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 {
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
+	if(nlines > d->desc_cap)
+	{
+		cudaStreamSynchronize(st);
+		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
+		d->d_desc_r = d->d_desc_a = NULL;
+		d->desc_cap = 0;
+		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 2)));
+		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * (size_t) nlines));
+		d->desc_cap = nlines;
+	}
+	LineDescs ld = { (LineRaster *) d->d_desc_r, (LineAudio *) d->d_desc_a };
+	k_line_desc<<<(nlines + 2 + 127) / 128, 128, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
+	d->launches++;
 	if(d->timing) cudaEventRecord(d->ev0, st);
-	if(d->line_threads <= 256) k_lines<256, 4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
-	else k_lines<384, 2><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, line0, nlines, d_out);
+	if(d->line_threads <= 256) k_lines<256, 4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, ld, line0, nlines, d_out);
+	else k_lines<384, 2><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, ld, line0, nlines, d_out);
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
 	d->launches++;
 	CK(cudaGetLastError());

@@ -415,6 +415,14 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 			gaussian(taps, n, sample_rate, c->colour_bw, 1);
 			quantise(dp->chroma_taps, taps, n, 1);
 			dp->chroma_ntaps = n;
+			/* the kernel filters U/V across line boundaries in one window; that equals the
+			 * reference's per-line zero padding as long as the picture keeps n/2 clear of both ends */
+			if(n > 17 || dp->active_left < n / 2 || dp->active_left + dp->active_width + n / 2 > dp->W)
+			{
+				fprintf(stderr, "hacktv_b200: chroma filter (%d taps) / picture geometry not supported\n", n);
+				htv_tables_free(t);
+				return(NULL);
+			}
 		}
 	}
 
