@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.htv_kernel_launches.restype = C.c_uint64; L.htv_kernel_launches.argtypes = [vp]
     L.htv_set_kernel_timing.restype = None; L.htv_set_kernel_timing.argtypes = [vp, C.c_int]
     L.htv_last_line_kernel_ms.restype = C.c_float; L.htv_last_line_kernel_ms.argtypes = [vp]
+    L.htv_last_line_kernel_lines.restype = C.c_int; L.htv_last_line_kernel_lines.argtypes = [vp]
     L.htv_tables_create.restype = vp; L.htv_tables_create.argtypes = [C.POINTER(Config), C.c_uint]
     L.htv_tables_free.restype = None; L.htv_tables_free.argtypes = [vp]
     L.htv_tables_get.restype = C.POINTER(C.c_int32); L.htv_tables_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
@@ -303,6 +304,9 @@ class Encoder:
 
     def last_line_kernel_ms(self) -> float:
         return float(self._L.htv_last_line_kernel_ms(self._h))
+
+    def last_line_kernel_lines(self) -> int:
+        return int(self._L.htv_last_line_kernel_lines(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -149,6 +149,7 @@ int64_t htv_lines_rendered(const htv_t *s) { return(s->next_line); }
 uint64_t htv_kernel_launches(const htv_t *s) { return(htv_dev_launches(s->dev)); }
 void htv_set_kernel_timing(htv_t *s, int on) { htv_dev_set_timing(s->dev, on); }
 float htv_last_line_kernel_ms(htv_t *s) { return(htv_dev_last_line_ms(s->dev)); }
+int htv_last_line_kernel_lines(const htv_t *s) { return(htv_dev_last_line_count(s->dev)); }
 
 /* audio fetches completed up to and including audio-clock sample m (ref video.c:3273-3276) */
 static int64_t fetches_by(int64_t m, unsigned int rate)

@@ -136,6 +136,7 @@ extern void htv_dev_free_pinned(void *p);
 extern uint64_t htv_dev_launches(const htv_dev_t *d);
 extern void htv_dev_set_timing(htv_dev_t *d, int on);
 extern float htv_dev_last_line_ms(htv_dev_t *d);
+extern int htv_dev_last_line_count(const htv_dev_t *d);
 extern size_t htv_dev_audio_ring_pairs(void);
 
 #ifdef __cplusplus

@@ -88,6 +88,10 @@ struct htv_dev_t {
 	size_t line_smem;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
 	int desc_cap;
+	int16_t *d_comp;                  // composite scratch, (sub + 2) lines, reused by every sub-batch (stays in L2)
+	int sub_lines;
+	size_t raster_smem, mod_smem;
+	int last_mod_lines;
 };
 
 // ---------------------------------------------------------------------------
@@ -368,13 +372,12 @@ __global__ void k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
 // ---------------------------------------------------------------------------
 
 #define SPT 4                         // samples per thread: one 128-bit store of 4 complex int16 samples
-#define EXT 32                        // neighbour samples rendered either side of a line (>= 25 + chroma half-width)
+#define EXT 32                        // composite samples staged either side of a line for the video filter (>= 25)
 #define COFF (EXT + 1)                // composite window index = x + COFF: makes the filter's 128-bit loads aligned
 #define UOFF (EXT + 8)                // chroma window index = x + UOFF
 #define NIC_CAND 7                    // NICAM symbols that can overlap 4 consecutive samples
 #define NIC_TPAD 8                    // zero entries in front of the padded NICAM pulse table
 #define MAX_ENT 6                     // sync pulse pieces that can land on one line (2 previous + 2 own + 2 next)
-#define MAX_CENT 12                   // ... and on a line plus its two 32-sample margins
 #define MAX_SEGS 6                    // audio samples overlapping one scan line (+1)
 #define MAX_SYMS 48                   // NICAM symbols overlapping one scan line
 
@@ -596,43 +599,163 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 	}
 }
 
-struct __align__(16) LineShared {
-	LineRaster li[3];                 // previous, this, next
-	LineAudio la;
-	// sync pulse pieces in window coordinates (x relative to this line, may be < 0 or >= W)
-	int ncent;
-	int cent_base[MAX_CENT], cent_len[MAX_CENT], cent_pos[MAX_CENT];
-	int cent_al[MAX_CENT], cent_ar[MAX_CENT];   // picture range of the piece's line (pieces do not add inside it)
-	int cent_lo[MAX_CENT], cent_hi[MAX_CENT];   // the piece's own line: it adds nowhere else
-};
+// ---------------------------------------------------------------------------
+// Raster kernel: one CTA per scan line, 4 samples per thread -> int16 composite stream
+// (ref video.c:2864-3066 _vid_next_line_raster, vbidata.c:186-239). Low register count
+// and high occupancy on purpose: the work is fp64 + gathers, i.e. latency bound.
+// Launch covers lines first-1 .. first+n (one extra either side for the filter halo);
+// line r of the launch lands at comp[r * W ..].
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(384, 4)
+k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int W4 = (W + 3) & ~3;
+	const int UW = W4 + 2 * UOFF;
+	double *glut = reinterpret_cast<double *>(smem_raw);
+	int *su = reinterpret_cast<int *>(glut + 256);                  // index = x + UOFF
+	int *sv = su + UW;
+	__shared__ LineRaster li;
+	const int tid = threadIdx.x;
+
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(lr + blockIdx.x);
+		int4 *dst = reinterpret_cast<int4 *>(&li);
+		if(tid < (int) (sizeof(LineRaster) / 16)) dst[tid] = __ldg(src + tid);
+	}
+	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
+	if(tid < 2 * UOFF)
+	{
+		// U,V outside the line read as zero (the reference filters each line on its own)
+		const int j = tid < UOFF ? tid : W4 + tid;
+		su[j] = 0; sv[j] = 0;
+	}
+	__syncthreads();
+
+	const int x0 = tid * SPT;
+	int val[SPT];
+	if(x0 < W)
+	{
+		// ---- blanking / luma, unfiltered U,V ----------------------------------
+		int uu[SPT], vv[SPT];
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			val[k] = li.valid ? dp.blank : 0; uu[k] = 0; vv[k] = 0;
+			if(x >= li.al && x < li.ar)
+			{
+				const unsigned int rgb = li.row_off >= 0 ? (__ldg(dt.frames + li.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
+				yuv_of<false>(dp, glut, rgb, val[k], uu[k], vv[k]);
+				if(!li.pal) uu[k] = vv[k] = 0;
+			}
+		}
+		// ---- sync pulse pieces landing on this line -----------------------------
+		for(int e = 0; e < li.nent; e++)
+		{
+			const int d0 = x0 - li.ent_base[e];
+			if(d0 + SPT - 1 < 0 || d0 >= li.ent_len[e]) continue;
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int d = d0 + k, x = x0 + k;
+				if(d < 0 || d >= li.ent_len[e] || x >= W) continue;
+				if(!li.ent_keep[e] && x >= li.al && x < li.ar) continue;   // overwritten by the picture
+				val[k] += __ldg(dt.pulse_values + li.ent_pos[e] + d);
+			}
+		}
+		if(li.pal)
+		{
+			*reinterpret_cast<int4 *>(su + x0 + UOFF) = make_int4(uu[0], uu[1], uu[2], uu[3]);
+			*reinterpret_cast<int4 *>(sv + x0 + UOFF) = make_int4(vv[0], vv[1], vv[2], vv[3]);
+		}
+	}
+	if(li.pal)
+	{
+		__syncthreads();
+		// ---- chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ------------
+		if(x0 < W)
+		{
+			const int h = dp.chroma_ntaps / 2;
+			const bool near_pic = x0 + SPT - 1 + h >= li.al && x0 - h < li.ar;
+			const bool near_burst = x0 + SPT - 1 >= dp.burst_left && x0 < dp.burst_left + dp.burst_width;
+			if(near_pic || near_burst)
+			{
+				int cu[SPT] = { 0, 0, 0, 0 }, cv[SPT] = { 0, 0, 0, 0 };
+				if(near_pic)
+				{
+					switch(dp.chroma_ntaps)
+					{
+					case 11: chroma_fir4<11>(dp, su, sv, x0, cu, cv); break;
+					case 13: chroma_fir4<13>(dp, su, sv, x0, cu, cv); break;
+					case 15: chroma_fir4<15>(dp, su, sv, x0, cu, cv); break;
+					case 17: chroma_fir4<17>(dp, su, sv, x0, cu, cv); break;
+					default:
+						for(int k = 0; k < SPT; k++) { cu[k] = su[x0 + k + UOFF]; cv[k] = sv[x0 + k + UOFF]; }
+					}
+				}
+				#pragma unroll
+				for(int k = 0; k < SPT; k++)
+				{
+					const int x = x0 + k;
+					if(x >= W) break;
+					if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
+					{
+						const int w = dt.burst_win[x - dp.burst_left];
+						cu[k] = (dp.burst_i * w) >> 15;
+						cv[k] = (dp.burst_q * w) >> 15;
+					}
+					const htv_c16_t c = dt.clut[li.clut_off + x];
+					val[k] += ((int) c.i * cv[k] * li.pal + (int) c.q * cu[k]) >> 15;
+				}
+			}
+		}
+	}
+	if(x0 >= W) return;
+	int16_t *o = comp + (size_t) blockIdx.x * W + x0;
+	if((W & 3) == 0)
+	{
+		int2 pk;
+		pk.x = (val[0] & 0xFFFF) | (val[1] << 16);
+		pk.y = (val[2] & 0xFFFF) | (val[3] << 16);
+		*reinterpret_cast<int2 *>(o) = pk;
+	}
+	else
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) val[k];
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Modulator kernel: one CTA per scan line, 4 samples per thread. Stages the line's
+// composite samples (+-32 from the contiguous stream, so neighbours need no special
+// case) in shared memory, applies the video filter as a centred 51-tap FIR (ref
+// video.c:3235-3248, fir.c:304-355/564-615), adds the sound carriers (ref
+// video.c:3261-3450, nicam728.c:342-411), the optional mixers (ref video.c:3466-3515)
+// and writes int16 IQ with 128-bit streaming stores.
+// ---------------------------------------------------------------------------
 
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineDescs ld, int64_t line0, int nlines, int16_t *out)
+k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, int16_t *out)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	LineShared &sh = *reinterpret_cast<LineShared *>(smem_raw);
 	const int W = dp.W;
 	const int W4 = (W + 3) & ~3;
-	const int CW = W4 + 2 * EXT + 16;                               // composite window (+ read-ahead padding)
-	const int UW = W4 + 2 * EXT + 16;                               // chroma windows (+ 8 either side)
-	double *glut = reinterpret_cast<double *>(smem_raw + ((sizeof(LineShared) + 15) & ~15));
-	int *comp = reinterpret_cast<int *>(glut + 256);                // index = x + COFF
-	int *su = comp + CW;                                            // index = x + UOFF
-	int *sv = su + UW;
-	short *ntp = reinterpret_cast<short *>(sv + UW);                // padded NICAM pulse table
+	const int CW = W4 + 2 * EXT + 16;
+	int *cw = reinterpret_cast<int *>(smem_raw);                    // index = x + COFF
+	short *ntp = reinterpret_cast<short *>(cw + CW);                // padded NICAM pulse table
+	__shared__ LineAudio la;
 	const int tid = threadIdx.x;
 
-	// ---- stage descriptors and small tables -----------------------------------
 	{
-		const int4 *src = reinterpret_cast<const int4 *>(ld.r + blockIdx.x);
-		int4 *dst = reinterpret_cast<int4 *>(&sh.li[0]);
-		for(int i = tid; i < (int) (3 * sizeof(LineRaster) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-		const int4 *sa = reinterpret_cast<const int4 *>(ld.a + blockIdx.x);
-		int4 *da = reinterpret_cast<int4 *>(&sh.la);
+		const int4 *sa = reinterpret_cast<const int4 *>(lap + blockIdx.x);
+		int4 *da = reinterpret_cast<int4 *>(&la);
 		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
 	}
-	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
 	if(dp.have_nicam)
 	{
 		for(int i = tid; i < dp.nicam_tpad_len; i += blockDim.x)
@@ -641,142 +764,39 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Line
 			ntp[i] = (d >= 0 && d < dp.nicam_ntaps) ? dt.nicam_taps[d] : (short) 0;
 		}
 	}
-	if(tid < 16)
 	{
-		// chroma windows: the 8 entries either side of [-EXT, W4 + EXT) read as zero
-		const int j = tid < 8 ? tid : UW - 16 + tid;
-		su[j] = 0; sv[j] = 0;
-	}
-	__syncthreads();
-	if(tid == 0)
-	{
-		// every sync pulse piece that lands in [-EXT, W4 + EXT), with the picture range of its line
-		int n = 0;
-		for(int s = 0; s < 3; s++)
-		{
-			const LineRaster &r = sh.li[s];
-			const int shift = (s - 1) * W;
-			for(int e = 0; e < r.nent; e++)
-			{
-				const int base = r.ent_base[e] + shift;
-				if(base + r.ent_len[e] <= -EXT || base >= W4 + EXT || n >= MAX_CENT) continue;
-				sh.cent_base[n] = base; sh.cent_len[n] = r.ent_len[e]; sh.cent_pos[n] = r.ent_pos[e];
-				// kept pieces (a next line's leading edge) add everywhere; others not inside the picture
-				sh.cent_al[n] = r.ent_keep[e] ? 0x7FFFFFFF : r.al + shift;
-				sh.cent_ar[n] = r.ent_keep[e] ? 0x7FFFFFFF : r.ar + shift;
-				sh.cent_lo[n] = shift; sh.cent_hi[n] = shift + W;
-				n++;
-			}
-		}
-		sh.ncent = n;
-	}
-	__syncthreads();
-
-	const int nquads = (W4 + 2 * EXT) / 4;
-
-	// ---- phase 1: blanking / sync / luma, unfiltered U,V over [-EXT, W4 + EXT) ----
-	for(int q = tid; q < nquads; q += blockDim.x)
-	{
-		const int xe0 = q * 4 - EXT;
-		int val[SPT], uu[SPT], vv[SPT];
-		#pragma unroll
-		for(int k = 0; k < SPT; k++)
-		{
-			const int xe = xe0 + k;
-			const int s = xe < 0 ? 0 : (xe < W ? 1 : 2);
-			const LineRaster &r = sh.li[s];
-			const int x = xe - (s - 1) * W;
-			val[k] = r.valid ? dp.blank : 0; uu[k] = 0; vv[k] = 0;
-			if(x >= r.al && x < r.ar)
-			{
-				const unsigned int rgb = r.row_off >= 0 ? (__ldg(dt.frames + r.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
-				yuv_of<false>(dp, glut, rgb, val[k], uu[k], vv[k]);
-				if(!r.pal) uu[k] = vv[k] = 0;
-			}
-		}
-		for(int e = 0; e < sh.ncent; e++)
-		{
-			const int d0 = xe0 - sh.cent_base[e];
-			if(d0 + SPT - 1 < 0 || d0 >= sh.cent_len[e]) continue;
-			#pragma unroll
-			for(int k = 0; k < SPT; k++)
-			{
-				const int d = d0 + k, xe = xe0 + k;
-				if(d < 0 || d >= sh.cent_len[e]) continue;
-				if(xe < sh.cent_lo[e] || xe >= sh.cent_hi[e]) continue;   // another line's sample
-				if(xe >= sh.cent_al[e] && xe < sh.cent_ar[e]) continue;   // overwritten by the picture
-				val[k] += __ldg(dt.pulse_values + sh.cent_pos[e] + d);
-			}
-		}
-		#pragma unroll
-		for(int k = 0; k < SPT; k++) comp[xe0 + k + COFF] = wrap16i(val[k]);
-		*reinterpret_cast<int4 *>(su + xe0 + UOFF) = make_int4(uu[0], uu[1], uu[2], uu[3]);
-		*reinterpret_cast<int4 *>(sv + xe0 + UOFF) = make_int4(vv[0], vv[1], vv[2], vv[3]);
-	}
-	__syncthreads();
-
-	// ---- phase 2: chroma low-pass, burst, subcarrier (ref video.c:3011-3040) ----
-	if(sh.li[0].pal | sh.li[1].pal | sh.li[2].pal)
-	{
-		const int h = dp.chroma_ntaps / 2;
+		// the launch's composite stream starts one line early: this line begins at (b + 1) * W
+		const int16_t *cs = comp + ((size_t) blockIdx.x + 1) * W;
+		const int nquads = (W4 + 2 * EXT) / 4;
 		for(int q = tid; q < nquads; q += blockDim.x)
 		{
 			const int xe0 = q * 4 - EXT;
-			if(xe0 + SPT - 1 < -HALO || xe0 >= W + HALO) continue;     // not read by the video filter
-			// the line of the quad's first sample decides the fast path; mixed quads go per sample
-			const int s0 = xe0 < 0 ? 0 : (xe0 < W ? 1 : 2);
-			const int s3 = xe0 + 3 < 0 ? 0 : (xe0 + 3 < W ? 1 : 2);
-			const LineRaster &r0 = sh.li[s0], &r3 = sh.li[s3];
-			if(!(r0.pal | r3.pal)) continue;
-			const int x0 = xe0 - (s0 - 1) * W;
-			const bool near_pic = (x0 + SPT - 1 + h >= r0.al && x0 - h < r0.ar) || s0 != s3;
-			const bool near_burst = (x0 + SPT - 1 >= dp.burst_left && x0 < dp.burst_left + dp.burst_width) || s0 != s3;
-			if(!(near_pic || near_burst)) continue;
-			int cu[SPT] = { 0, 0, 0, 0 }, cv[SPT] = { 0, 0, 0, 0 };
-			if(near_pic)
+			int v[4];
+			if((W & 3) == 0)
 			{
-				switch(dp.chroma_ntaps)
-				{
-				case 11: chroma_fir4<11>(dp, su, sv, xe0, cu, cv); break;
-				case 13: chroma_fir4<13>(dp, su, sv, xe0, cu, cv); break;
-				case 15: chroma_fir4<15>(dp, su, sv, xe0, cu, cv); break;
-				case 17: chroma_fir4<17>(dp, su, sv, xe0, cu, cv); break;
-				default:
-					for(int k = 0; k < SPT; k++) { cu[k] = su[xe0 + k + UOFF]; cv[k] = sv[xe0 + k + UOFF]; }
-				}
+				const int2 p = __ldg(reinterpret_cast<const int2 *>(cs + xe0));
+				v[0] = (int) (short) p.x; v[1] = p.x >> 16; v[2] = (int) (short) p.y; v[3] = p.y >> 16;
+			}
+			else
+			{
+				#pragma unroll
+				for(int k = 0; k < 4; k++) v[k] = __ldg(cs + xe0 + k);
 			}
 			#pragma unroll
-			for(int k = 0; k < SPT; k++)
-			{
-				const int xe = xe0 + k;
-				const int s = xe < 0 ? 0 : (xe < W ? 1 : 2);
-				const LineRaster &r = sh.li[s];
-				const int x = xe - (s - 1) * W;
-				if(!r.pal) continue;
-				if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
-				{
-					const int w = dt.burst_win[x - dp.burst_left];
-					cu[k] = (dp.burst_i * w) >> 15;
-					cv[k] = (dp.burst_q * w) >> 15;
-				}
-				const htv_c16_t c = dt.clut[r.clut_off + x];
-				comp[xe + COFF] = wrap16i(comp[xe + COFF] + (((int) c.i * cv[k] * r.pal + (int) c.q * cu[k]) >> 15));
-			}
+			for(int k = 0; k < 4; k++) cw[xe0 + k + COFF] = v[k];
 		}
 	}
 	__syncthreads();
 
 	const int x0 = tid * SPT;
 	if(x0 >= W) return;
-	const LineAudio &la = sh.la;
 
-	// ---- phase 3: video filter, sound carriers, mixers, store -----------------
 	int oi[SPT], oq[SPT];
 	if(dp.vf_type)
 	{
 		// c[j] = composite sample x0 - 25 + j
 		int c[SPT + 2 * HALO + 2];
-		const int4 *pc = reinterpret_cast<const int4 *>(comp + x0 + COFF - HALO);
+		const int4 *pc = reinterpret_cast<const int4 *>(cw + x0 + COFF - HALO);
 		#pragma unroll
 		for(int i = 0; i < (SPT + 2 * HALO + 2) / 4; i++)
 		{
@@ -801,7 +821,7 @@ k_lines(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Line
 	else
 	{
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) { oi[k] = comp[x0 + k + COFF]; oq[k] = 0; }
+		for(int k = 0; k < SPT; k++) { oi[k] = cw[x0 + k + COFF]; oq[k] = 0; }
 	}
 
 	if(dp.have_fm || dp.have_am)
@@ -1052,17 +1072,27 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	threads = (threads + 31) & ~31;
 	if(threads < 64) threads = 64;
 	d->line_threads = threads;
-	d->line_smem = ((sizeof(LineShared) + 15) & ~15) + 256 * sizeof(double)
-		+ sizeof(int) * 3 * (((W + 3) & ~3) + 2 * EXT + 16)
-		+ sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
+	const int W4 = (W + 3) & ~3;
+	d->raster_smem = 256 * sizeof(double) + sizeof(int) * 2 * (W4 + 2 * UOFF);
+	d->mod_smem = sizeof(int) * (W4 + 2 * EXT + 16) + sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
 	if(threads > 384)
 	{
-		snprintf(err, errlen, "line width %d exceeds the kernel's 1536-sample limit", W);
+		snprintf(err, errlen, "line width %d exceeds the kernels' 1536-sample limit", W);
 		htv_dev_destroy(d);
 		return(NULL);
 	}
-	cudaFuncSetAttribute(k_lines<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
-	cudaFuncSetAttribute(k_lines<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->line_smem);
+	cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->raster_smem);
+	cudaFuncSetAttribute(k_mod<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->mod_smem);
+	cudaFuncSetAttribute(k_mod<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->mod_smem);
+	// sub-batches keep the int16 composite scratch (2 B/sample) resident in the 126 MB L2
+	d->sub_lines = (16 * 1024 * 1024) / (W * 2);
+	if(d->sub_lines < 64) d->sub_lines = 64;
+	if(cudaMalloc((void **) &d->d_comp, sizeof(int16_t) * ((size_t) d->sub_lines + 2) * W + 256) != cudaSuccess)
+	{
+		snprintf(err, errlen, "device allocation failed");
+		htv_dev_destroy(d);
+		return(NULL);
+	}
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
 	return(d);
@@ -1073,7 +1103,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	cudaSetDevice(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	free(d);
@@ -1166,11 +1196,20 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	LineDescs ld = { (LineRaster *) d->d_desc_r, (LineAudio *) d->d_desc_a };
 	k_line_desc<<<(nlines + 2 + 127) / 128, 128, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
 	d->launches++;
-	if(d->timing) cudaEventRecord(d->ev0, st);
-	if(d->line_threads <= 256) k_lines<256, 4><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, ld, line0, nlines, d_out);
-	else k_lines<384, 2><<<nlines, d->line_threads, d->line_smem, st>>>(d->dp, d->dt, ld, line0, nlines, d_out);
+	for(int done = 0; done < nlines; done += d->sub_lines)
+	{
+		const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
+		const bool last = done + n >= nlines;
+		// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
+		k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp);
+		if(d->timing && last) cudaEventRecord(d->ev0, st);
+		int16_t *o = d_out + (size_t) done * d->dp.W * (d->dp.complex_out ? 2 : 1);
+		if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp, o);
+		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp, o);
+		if(last) d->last_mod_lines = n;
+		d->launches += 2;
+	}
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
-	d->launches++;
 	CK(cudaGetLastError());
 	return(HTV_OK);
 }
@@ -1207,6 +1246,8 @@ extern "C" void htv_dev_free_pinned(void *p) { if(p) cudaFreeHost(p); }
 
 extern "C" uint64_t htv_dev_launches(const htv_dev_t *d) { return(d->launches); }
 extern "C" void htv_dev_set_timing(htv_dev_t *d, int on) { d->timing = on; }
+
+extern "C" int htv_dev_last_line_count(const htv_dev_t *d) { return(d->last_mod_lines); }
 
 extern "C" float htv_dev_last_line_ms(htv_dev_t *d)
 {

@@ -201,10 +201,11 @@ extern int htv_bytes_per_sample(const htv_t *s);   /* 4 complex, 2 real */
 extern int64_t htv_lines_rendered(const htv_t *s);
 /* Kernel launches issued by this encoder since htv_init (for bench accounting) */
 extern uint64_t htv_kernel_launches(const htv_t *s);
-/* Duration of the dominant kernel's most recent launch, measured with CUDA
- * events on the stream it ran on; 0 if timing is off. */
+/* Duration of the dominant kernel's (k_mod) most recent launch, measured with CUDA
+ * events on the stream it ran on (0 if timing is off), and the scan lines that launch covered. */
 extern void htv_set_kernel_timing(htv_t *s, int on);
 extern float htv_last_line_kernel_ms(htv_t *s);
+extern int htv_last_line_kernel_lines(const htv_t *s);
 
 /* ---- host-only table generation (no GPU needed; used by htv_init) ------ */
 
