@@ -59,6 +59,8 @@ struct DevTables {
 	int32_t *lim_var, *lim_fix;       // RA, index j & (RA-1)
 	int16_t *fm_p;                    // RA, slot (j+1) & (RA-1): modulating sample in effect for audio index j
 	uint64_t *fm_B;                   // RA, same slot: phase accumulated before that segment starts
+	uint64_t *fm_inc;                 // RA, same slot: phase advance over the whole segment
+	unsigned long long *scan_carry, *scan_tot;   // scratch of the two-pass phase scan
 	uint8_t *nic_local;               // RS: inclusive prefix (mod 4) of the DQPSK steps inside the symbol's frame
 	uint8_t *nic_ftot;                // RF: total step of frame k (mod 4)
 	uint8_t *nic_fstart;              // RF: differential symbol state before frame k
@@ -70,7 +72,7 @@ struct htv_dev_t {
 	DevTables dt;
 	size_t frame_pixels;
 	int max_slots;
-	void *alloc[32];
+	void *alloc[48];
 	int nalloc;
 	uint32_t *d_frames;
 	int32_t *d_frame_map;
@@ -197,39 +199,70 @@ __global__ void k_fm_limit(const __grid_constant__ htv_dparams_t dp, const DevTa
 		}
 	}
 	dt.fm_p[(j + 1) & (RA - 1)] = (short) p;
+	// phase advance over the whole segment during which audio index j is in effect
+	const unsigned long long cnt = (unsigned long long) (seg_start(j + 1, dp.rate) - seg_start(j, dp.rate));
+	dt.fm_inc[(j + 1) & (RA - 1)] = cnt * dt.fm_ang[p + 32768];
 }
 
-// phase prefix: B(j+1) = B(j) + cnt(j) * ang(p_j), sequential over <= a few 1e5 entries.
-// One block; each thread owns a contiguous chunk, block-wide exclusive scan of chunk sums.
-__global__ void k_fm_scan(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t jc, int64_t j1)
+// Phase prefix B(j+1) = B(j) + inc(j) over entries jc .. j1 (B(jc) is the carry from the
+// previous batch). Two passes: per-block inclusive scans + block totals, then offsets.
+#define SCAN_T 256
+#define SCAN_PER 8
+#define SCAN_BLK (SCAN_T * SCAN_PER)
+
+__global__ void __launch_bounds__(SCAN_T) k_fm_scan_local(const DevTables dt, int64_t jc, int64_t j1)
 {
-	__shared__ unsigned long long part[1024];
-	const int T = blockDim.x, t = threadIdx.x;
-	int64_t n = j1 - jc + 1;                                  // entries jc .. j1 contribute, B(jc) is the carry
-	int64_t per = (n + T - 1) / T;
-	int64_t a = jc + t * per, b = min(j1 + 1, a + per);
-	unsigned long long sum = 0;
-	for(int64_t j = a; j < b; j++)
+	__shared__ unsigned long long part[SCAN_T];
+	const int t = threadIdx.x;
+	const int64_t a = jc + (int64_t) blockIdx.x * SCAN_BLK + t * SCAN_PER;
+	unsigned long long v[SCAN_PER], sum = 0;
+	if(blockIdx.x == 0 && t == 0) dt.scan_carry[0] = dt.fm_B[(jc + 1) & (RA - 1)];
+	#pragma unroll
+	for(int i = 0; i < SCAN_PER; i++)
 	{
-		unsigned long long cnt = (unsigned long long) (seg_start(j + 1, dp.rate) - seg_start(j, dp.rate));
-		sum += cnt * dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+		const int64_t j = a + i;
+		v[i] = j <= j1 ? dt.fm_inc[(j + 1) & (RA - 1)] : 0ull;
+		sum += v[i];
 	}
 	part[t] = sum;
 	__syncthreads();
+	for(int o = 1; o < SCAN_T; o <<= 1)
+	{
+		const unsigned long long add = t >= o ? part[t - o] : 0ull;
+		__syncthreads();
+		part[t] += add;
+		__syncthreads();
+	}
+	unsigned long long acc = part[t] - sum;                     // exclusive prefix of this thread's chunk
+	#pragma unroll
+	for(int i = 0; i < SCAN_PER; i++)
+	{
+		const int64_t j = a + i;
+		if(j <= j1) dt.fm_B[(j + 1) & (RA - 1)] = acc;          // local value; k_fm_scan_fix adds the block offset
+		acc += v[i];
+	}
+	if(t == SCAN_T - 1) dt.scan_tot[blockIdx.x] = part[t];
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_fm_scan_fix(const DevTables dt, int64_t jc, int64_t j1)
+{
+	__shared__ unsigned long long off;
+	const int t = threadIdx.x;
 	if(t == 0)
 	{
-		unsigned long long acc = dt.fm_B[(jc + 1) & (RA - 1)];
-		for(int i = 0; i < T; i++) { unsigned long long s = part[i]; part[i] = acc; acc += s; }
+		unsigned long long o = dt.scan_carry[0];
+		for(unsigned int b = 0; b < blockIdx.x; b++) o += dt.scan_tot[b];
+		off = o;
+		if(blockIdx.x == gridDim.x - 1) dt.fm_B[(j1 + 2) & (RA - 1)] = o + dt.scan_tot[blockIdx.x];   // B(j1 + 1)
 	}
 	__syncthreads();
-	unsigned long long acc = part[t];
-	for(int64_t j = a; j < b; j++)
+	const int64_t a = jc + (int64_t) blockIdx.x * SCAN_BLK + t * SCAN_PER;
+	#pragma unroll
+	for(int i = 0; i < SCAN_PER; i++)
 	{
-		dt.fm_B[(j + 1) & (RA - 1)] = acc;
-		unsigned long long cnt = (unsigned long long) (seg_start(j + 1, dp.rate) - seg_start(j, dp.rate));
-		acc += cnt * dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+		const int64_t j = a + i;
+		if(j <= j1) dt.fm_B[(j + 1) & (RA - 1)] += off;
 	}
-	if(b == j1 + 1 && a <= j1) dt.fm_B[(j1 + 2) & (RA - 1)] = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -287,8 +320,8 @@ __global__ void __launch_bounds__(64) k_nicam_frames(const __grid_constant__ htv
 		for(int xi = 0; xi < HTV_J17_N; xi++)
 		{
 			int t = n - (HTV_J17_N - 1) + xi;          // sample index relative to this frame's block
-			int f = 0;
-			while(t < 0) { t += 32; f++; }
+			const int f = t < 0 ? (31 - t) >> 5 : 0;    // how many frames back
+			t += f << 5;
 			int64_t b = blk[f];
 			int v = b < 0 ? 0 : pcm_vol(dt, b * 32 + t, ch, dp.volume);
 			acc += v * c_j17[xi];
@@ -342,29 +375,65 @@ __global__ void __launch_bounds__(64) k_nicam_frames(const __grid_constant__ htv
 		steps[s] = c_nic_step[dibit];
 	}
 	__syncthreads();
-	if(x == 0)
 	{
-		int acc2 = 0;
+		// inclusive prefix (mod 4) of the 364 steps: 6 symbols per thread, then across the 64 threads
+		__shared__ int wsum[2];
 		const int64_t s0 = k * 364;
-		for(int s = 0; s < 364; s++)
+		int loc[6], sum = 0;
+		#pragma unroll
+		for(int i = 0; i < 6; i++)
 		{
-			acc2 = (acc2 + steps[s]) & 3;
-			dt.nic_local[(s0 + s) & (RS - 1)] = (unsigned char) acc2;
+			const int s = x * 6 + i;
+			sum += s < 364 ? steps[s] : 0;
+			loc[i] = sum;
 		}
-		dt.nic_ftot[k & (RF - 1)] = (unsigned char) acc2;
+		int inc = sum;
+		#pragma unroll
+		for(int o = 1; o < 32; o <<= 1)
+		{
+			const int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+			if((x & 31) >= o) inc += v;
+		}
+		if((x & 31) == 31) wsum[x >> 5] = inc;
+		__syncthreads();
+		const int base = inc - sum + (x >= 32 ? wsum[0] : 0);
+		#pragma unroll
+		for(int i = 0; i < 6; i++)
+		{
+			const int s = x * 6 + i;
+			if(s < 364) dt.nic_local[(s0 + s) & (RS - 1)] = (unsigned char) ((base + loc[i]) & 3);
+		}
+		if(x == 63) dt.nic_ftot[k & (RF - 1)] = (unsigned char) ((wsum[0] + inc) & 3);
 	}
 }
 
-__global__ void k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
+// DQPSK state before each frame: exclusive prefix (mod 4) of the frame totals k0 .. k1,
+// seeded with the state before k0 (valid from the previous batch, 0 at the stream start)
+__global__ void __launch_bounds__(1024) k_nicam_scan(const DevTables dt, int64_t k0, int64_t k1)
 {
-	if(threadIdx.x != 0 || blockIdx.x != 0) return;
-	int acc = k0 == 0 ? 0 : dt.nic_fstart[k0 & (RF - 1)];
-	for(int64_t k = k0; k <= k1; k++)
+	__shared__ int part[1024];
+	const int t = threadIdx.x;
+	const int64_t n = k1 - k0 + 1, per = (n + 1023) / 1024;
+	const int64_t a = k0 + t * per, b = min(k1 + 1, a + per);
+	const int seed = k0 == 0 ? 0 : dt.nic_fstart[k0 & (RF - 1)];
+	int sum = 0;
+	for(int64_t k = a; k < b; k++) sum += dt.nic_ftot[k & (RF - 1)];
+	part[t] = sum;
+	__syncthreads();
+	for(int o = 1; o < 1024; o <<= 1)
 	{
-		dt.nic_fstart[k & (RF - 1)] = (unsigned char) acc;
-		acc = (acc + dt.nic_ftot[k & (RF - 1)]) & 3;
+		const int add = t >= o ? part[t - o] : 0;
+		__syncthreads();
+		part[t] += add;
+		__syncthreads();
 	}
-	dt.nic_fstart[(k1 + 1) & (RF - 1)] = (unsigned char) acc;
+	int acc = seed + part[t] - sum;
+	for(int64_t k = a; k < b; k++)
+	{
+		dt.nic_fstart[k & (RF - 1)] = (unsigned char) (acc & 3);
+		acc += dt.nic_ftot[k & (RF - 1)];
+	}
+	if(t == 1023) dt.nic_fstart[(k1 + 1) & (RF - 1)] = (unsigned char) ((seed + part[1023]) & 3);
 }
 
 // ---------------------------------------------------------------------------
@@ -509,15 +578,23 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 		const int64_t sfirst = (int64_t) (((unsigned long long) max((int64_t) 0, m0 - dp.nicam_ntaps) * dp.nicam_D) / dp.nicam_F);
 		const int64_t slast = (int64_t) (((unsigned long long) (m0 + W - 1) * dp.nicam_D) / dp.nicam_F);
 		const int ns = (int) min((int64_t) MAX_SYMS, slast - sfirst + 1);
+		// walk the symbols incrementally: pos = ceil(s * F / D), rem = pos * D - s * F
+		int64_t s = sfirst, k = s / 364, pos = nic_sym_pos(s, dp.nicam_F, dp.nicam_D);
+		int ks = (int) (s - k * 364);
+		int rem = (int) (pos * dp.nicam_D - s * dp.nicam_F);
+		int fst = dt.nic_fstart[k & (RF - 1)];
 		for(int i = 0; i < ns; i++)
 		{
-			const int64_t s = sfirst + i, k = s / 364;
-			const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[s & (RS - 1)]) & 3;
+			const int sy = (fst + dt.nic_local[s & (RS - 1)]) & 3;
 			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
 			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
-			la.sym_x[i] = (short) (nic_sym_pos(s, dp.nicam_F, dp.nicam_D) - m0);
+			la.sym_x[i] = (short) (pos - m0);
 			la.sym_si[i] = (code & 1) ? 1 : -1;
 			la.sym_sq[i] = (code & 2) ? 1 : -1;
+			const int adv = (dp.nicam_F - rem + dp.nicam_D - 1) / dp.nicam_D;
+			pos += adv; rem += adv * dp.nicam_D - dp.nicam_F;
+			s++;
+			if(++ks == 364) { ks = 0; k++; fst = dt.nic_fstart[k & (RF - 1)]; }
 		}
 		la.nsym = ns;
 	}
@@ -1051,6 +1128,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		dt.lim_fix = (int32_t *) dev_zero(d, sizeof(int32_t) * RA);
 		dt.fm_p = (int16_t *) dev_zero(d, sizeof(int16_t) * RA);
 		dt.fm_B = (uint64_t *) dev_zero(d, sizeof(uint64_t) * RA);
+		dt.fm_inc = (uint64_t *) dev_zero(d, sizeof(uint64_t) * RA);
+		dt.scan_carry = (unsigned long long *) dev_zero(d, sizeof(unsigned long long) * 8);
+		dt.scan_tot = (unsigned long long *) dev_zero(d, sizeof(unsigned long long) * (RA / SCAN_BLK + 8));
 	}
 	if(dp.have_nicam)
 	{
@@ -1158,8 +1238,10 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 			}
 			const int64_t n = jB - jA + 1;
 			k_fm_limit<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(dp, d->dt, jA, jB);
-			k_fm_scan<<<1, 1024, 0, st>>>(dp, d->dt, jA, jB);
-			d->launches += 2;
+			const unsigned nb = (unsigned) ((n + SCAN_BLK - 1) / SCAN_BLK);
+			k_fm_scan_local<<<nb, SCAN_T, 0, st>>>(d->dt, jA, jB);
+			k_fm_scan_fix<<<nb, SCAN_T, 0, st>>>(d->dt, jA, jB);
+			d->launches += 3;
 			d->fm_jc = jB;
 		}
 	}
@@ -1171,7 +1253,7 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		if(k_lo > d->nic_kc) k_lo = d->nic_kc;                     // keep the frame-start chain contiguous
 		if(k_hi - k_lo + 2 >= RF / 2 || (k_hi - k_lo + 2) * 364 >= RS / 2) return(HTV_ERROR);
 		k_nicam_frames<<<(unsigned) (k_hi - k_lo + 1), 64, 0, st>>>(dp, d->dt, k_lo);
-		k_nicam_scan<<<1, 32, 0, st>>>(d->dt, k_lo, k_hi);
+		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
 	}
@@ -1194,7 +1276,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r, (LineAudio *) d->d_desc_a };
-	k_line_desc<<<(nlines + 2 + 127) / 128, 128, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
+	k_line_desc<<<(nlines + 2 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
 	d->launches++;
 	for(int done = 0; done < nlines; done += d->sub_lines)
 	{
