@@ -346,6 +346,9 @@ struct orc_t {
 	pulse_t syncs[5];
 
 	double glut[256];
+	/* memo of the per-colour result (the reference keeps a full 2^24-entry table) */
+	uint32_t yuv_key[4096];
+	int16_t yuv_val[4096][3];
 
 	/* PAL/NTSC chroma: ref video.c:3961-4048 */
 	unsigned int clut_width;
@@ -435,9 +438,16 @@ static double dlimit(double v, double min, double max)
 	return(v);
 }
 
-void orc_yuv(const orc_t *o, uint32_t c, int16_t yuv[3])
+void orc_yuv(const orc_t *oc, uint32_t c, int16_t yuv[3])
 {
+	orc_t *o = (orc_t *) oc;
 	const orc_params_t *p = &o->p;
+	const unsigned int slot = (c ^ (c >> 12)) & 4095;
+	if(o->yuv_key[slot] == (c | 0x80000000u))
+	{
+		yuv[0] = o->yuv_val[slot][0]; yuv[1] = o->yuv_val[slot][1]; yuv[2] = o->yuv_val[slot][2];
+		return;
+	}
 	double level = o->vlevel;
 	double r = o->glut[(c & 0xFF0000) >> 16];
 	double g = o->glut[(c & 0x00FF00) >> 8];
@@ -466,6 +476,8 @@ void orc_yuv(const orc_t *o, uint32_t c, int16_t yuv[3])
 	yuv[0] = round(dlimit(y, -1, 1) * I16MAX);
 	yuv[1] = round(dlimit(u, -1, 1) * I16MAX);
 	yuv[2] = round(dlimit(v, -1, 1) * I16MAX);
+	o->yuv_key[slot] = c | 0x80000000u;
+	o->yuv_val[slot][0] = yuv[0]; o->yuv_val[slot][1] = yuv[1]; o->yuv_val[slot][2] = yuv[2];
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1525,22 +1537,20 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 			/* video.c:3235-3248 + fir.c:304-355/564-615 as a centred FIR over
 			 * the stream; samples before the first are zero (calloc'd window) */
 			int h = o->vf_ntaps / 2;
+			int32_t *win = malloc(sizeof(int32_t) * (W + 2 * h));
+			for(x = 0; x < h; x++) win[x] = (t == 0) ? 0 : prev[W - h + x];
+			for(x = 0; x < W; x++) win[h + x] = cur[x];
+			for(x = 0; x < h; x++) win[h + W + x] = next[x];
 			for(x = 0; x < W; x++)
 			{
 				int32_t ai = 0, aq = 0;
-				for(y = 0; y < o->vf_ntaps; y++)
-				{
-					int xx = x - h + y;
-					int32_t v;
-					if(xx < 0) v = (t == 0) ? 0 : prev[W + xx];
-					else if(xx >= W) v = next[xx - W];
-					else v = cur[xx];
-					ai += v * o->vf_itaps[y];
-					if(o->vf_qtaps) aq += v * o->vf_qtaps[y];
-				}
+				const int32_t *w = win + x;
+				for(y = 0; y < o->vf_ntaps; y++) ai += w[y] * o->vf_itaps[y];
+				if(o->vf_qtaps) for(y = 0; y < o->vf_ntaps; y++) aq += w[y] * o->vf_qtaps[y];
 				iq[x * 2 + 0] = sat16(ai >> 15);
 				iq[x * 2 + 1] = o->vf_qtaps ? sat16(aq >> 15) : 0;
 			}
+			free(win);
 		}
 		else
 		{

@@ -1,0 +1,72 @@
+"""The oracle against the reference itself (oracle/_ref/ref_harness, the unmodified
+fsphil/hacktv sources compiled in place): bit-exact, incl. inputs and options the golden
+fixtures do not cover. Skipped where the prebuilt reference is absent."""
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+
+CASES = [
+    ("pal", 16000000, 700, False, ()),
+    ("i", 16000000, 700, True, ()),
+    ("i", 16000000, 700, True, ("--nonicam",)),
+    ("i", 16000000, 700, True, ("--noaudio", "--nocolour")),
+    ("m", 13500000, 600, True, ()),
+    ("l", 16000000, 700, True, ()),
+    ("l", 16000000, 700, False, ()),
+    ("i", 20000000, 400, True, ()),
+    ("secam", 16000000, 700, False, ()),
+    ("ntsc", 13500000, 600, False, ()),
+    ("b", 16000000, 400, True, ()),
+    ("pal-m", 13500000, 400, True, ()),
+    ("d", 16000000, 400, True, ()),
+    ("i", 16000000, 700, True, ("--offset", "2000000")),
+    ("i", 16000000, 400, True, ("--swap-iq",)),
+    ("pal", 16000000, 400, True, ()),
+]
+
+
+def _conf(H, mode, filt, extra):
+    kw = dict(vfilter=filt)
+    it = iter(extra)
+    for e in it:
+        if e == "--nonicam": kw["nonicam"] = True
+        elif e == "--noaudio": kw["noaudio"] = True
+        elif e == "--nocolour": kw["nocolour"] = True
+        elif e == "--swap-iq": kw["swap_iq"] = True
+        elif e == "--offset": kw["offset"] = int(next(it))
+    return H.mode_config(mode, **kw)
+
+
+@pytest.mark.parametrize("mode,rate,nlines,filt,extra", CASES)
+def test_oracle_equals_reference(built, mode, rate, nlines, filt, extra):
+    o = orc.Oracle(_conf(built, mode, filt, extra), rate)
+    o.open_test_source()
+    got = o.render(nlines)
+    o.close()
+    want = orc.run_ref(mode, rate, nlines, vfilter=filt, extra=extra)
+    assert got.size == want.size
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+
+
+def test_oracle_equals_reference_on_random_input(built):
+    rng = np.random.default_rng(7)
+    conf = built.mode_config("i", vfilter=True)
+    o = orc.Oracle(conf, 16000000)
+    frames = rng.integers(0, 1 << 24, size=(2, o.active_lines, o.active_width), dtype=np.uint32)
+    audio = rng.integers(-32768, 32767, size=(30000, 2), dtype=np.int16)
+    o.set_source(frames, audio)
+    got = o.render(1400)
+    o.close()
+    want = orc.run_ref("i", 16000000, 1400, vfilter=True, frames=frames, audio=audio, audio_block=4000)
+    assert np.array_equal(got, want)
+
+
+def test_unpatched_heap_differs_only_near_line_ends():
+    """The stock allocator lets the chroma FIR read past its buffer: the
+    masked comparison - everything further than 32 samples from a line boundary - is exact."""
+    a = orc.run_ref("i", 16000000, 700, vfilter=True).reshape(700, 1024, 2)
+    b = orc.run_ref("i", 16000000, 700, vfilter=True, rawheap=True).reshape(700, 1024, 2)
+    assert np.array_equal(a[:, 32:-32], b[:, 32:-32])
