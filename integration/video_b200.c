@@ -1,0 +1,173 @@
+/* video_b200.c - the reference-side binding: hacktv's video.h entry points implemented
+ * on top of the hacktv_b200 C-ABI (include/hacktv_b200.h).
+ *
+ * This file is what a hacktv maintainer adds to src/. It is compiled AGAINST THE
+ * REFERENCE'S OWN HEADERS (video.h, av.h, rf.h - unmodified) and exports the symbols the
+ * rest of hacktv links to: vid_init, vid_next_line, vid_free, vid_info,
+ * vid_get_framebuffer_length (ref video.h:512-516). hacktv.c, av*.c, rf*.c stay untouched;
+ * the stock encoder in video.c is kept as the fallback for every configuration the GPU
+ * path does not cover (teletext, scramblers, MAC, FM video, ...) by building it with
+ *     -Dvid_init=cpu_vid_init -Dvid_next_line=cpu_vid_next_line -Dvid_free=cpu_vid_free
+ *     -Dvid_info=cpu_vid_info -Dvid_get_framebuffer_length=cpu_vid_get_framebuffer_length
+ * (see oracle/Makefile target `dropin`, which does exactly that without touching a source).
+ *
+ * It cannot be built outside a hacktv source tree and is not part of libhacktv_b200.so.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "video.h"
+#include "hacktv_b200.h"
+
+/* the stock CPU encoder, renamed at compile time */
+extern int cpu_vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const vid_config_t * const conf);
+extern void cpu_vid_free(vid_t *s);
+extern void cpu_vid_info(vid_t *s);
+extern size_t cpu_vid_get_framebuffer_length(vid_t *s);
+extern vid_line_t *cpu_vid_next_line(vid_t *s);
+
+#define MAX_ENCODERS 16
+static struct { vid_t *vid; htv_t *htv; vid_line_t line; uint32_t *packed; uint64_t serial; } _enc[MAX_ENCODERS];
+
+static int _find(vid_t *s)
+{
+	int i;
+	for(i = 0; i < MAX_ENCODERS; i++) if(_enc[i].vid == s) return(i);
+	return(-1);
+}
+
+/* Can the accelerated path render this configuration bit for bit? */
+static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigned int pixel_rate)
+{
+	if(getenv("HACKTV_NO_B200")) return(0);
+	if(c->type != VID_RASTER_625 && c->type != VID_RASTER_525) return(0);
+	if(c->modulation == VID_FM) return(0);
+	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC) return(0);
+	if(pixel_rate && pixel_rate != sample_rate) return(0);
+	if(c->teletext || c->wss || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
+	   c->d11 || c->systercnr || c->acp || c->vits || c->vitc || c->cc608 || c->sis || c->eurocrypt) return(0);
+	if(c->raw_bb_file || c->passthru || c->a2stereo || c->s_video || c->secam_field_id) return(0);
+	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
+	if(c->interlace || c->frame_orientation) return(0);
+	return(1);
+}
+
+static void _translate(htv_config_t *h, const vid_config_t *c)
+{
+	memset(h, 0, sizeof(*h));
+#define CP(f) h->f = c->f
+	CP(output_type); CP(modulation); CP(video_bw); CP(vsb_upper_bw); CP(vsb_lower_bw); CP(level);
+	CP(swap_iq); CP(invert_video); CP(offset); CP(video_level); CP(fm_mono_level); CP(am_audio_level);
+	CP(nicam_level); CP(type); CP(lines); CP(hline); CP(interlaced); CP(active_lines); CP(vfilter);
+	CP(hsync_width); CP(vsync_short_width); CP(vsync_long_width); CP(sync_rise);
+	CP(white_level); CP(black_level); CP(blanking_level); CP(sync_level); CP(active_width); CP(active_left);
+	CP(gamma); CP(rw_co); CP(gw_co); CP(bw_co); CP(colour_mode); CP(volume); CP(colour_bw);
+	CP(burst_width); CP(burst_left); CP(burst_level); CP(burst_rise); CP(ev_co); CP(eu_co);
+	CP(fm_mono_carrier); CP(fm_mono_deviation); CP(fm_mono_preemph); CP(nicam_carrier); CP(nicam_beta);
+	CP(am_mono_carrier);
+#undef CP
+	h->frame_rate_num = c->frame_rate.num; h->frame_rate_den = c->frame_rate.den;
+	h->colour_carrier_num = c->colour_carrier.num; h->colour_carrier_den = c->colour_carrier.den;
+}
+
+/* htv_av_t callbacks -> the reference's av_t (which hacktv.c fills in s->vid.av) */
+static int _read_video(void *ctx, htv_frame_t *out)
+{
+	int i = _find((vid_t *) ctx), x, y;
+	vid_t *s = ctx;
+	av_frame_t f;
+	if(i < 0 || av_read_video(&s->av, &f) != AV_OK || !f.framebuffer) return(HTV_ERROR);
+	out->width = f.width; out->height = f.height;
+	out->serial = ++_enc[i].serial;                 /* a pulled frame may have changed: always upload */
+	if(f.pixel_stride == 1 && f.line_stride == f.width) { out->framebuffer = f.framebuffer; return(HTV_OK); }
+	if(!_enc[i].packed) _enc[i].packed = malloc(sizeof(uint32_t) * f.width * f.height);
+	for(y = 0; y < f.height; y++)
+		for(x = 0; x < f.width; x++)
+			_enc[i].packed[y * f.width + x] = f.framebuffer[y * f.line_stride + x * f.pixel_stride];
+	out->framebuffer = _enc[i].packed;
+	return(HTV_OK);
+}
+
+static int _read_audio(void *ctx, const int16_t **samples, size_t *npairs)
+{
+	vid_t *s = ctx;
+	int16_t *p = NULL;
+	int r = av_read_audio(&s->av, &p, npairs);
+	*samples = p;
+	return(r == AV_OK ? HTV_OK : HTV_ERROR);
+}
+
+int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const vid_config_t * const conf)
+{
+	htv_config_t hc;
+	htv_t *h = NULL;
+	int i;
+
+	if(!_accelerated(conf, sample_rate, pixel_rate)) return(cpu_vid_init(s, sample_rate, pixel_rate, conf));
+	_translate(&hc, conf);
+	if(htv_init(&h, sample_rate, pixel_rate, &hc) != HTV_OK)
+	{
+		/* an in-scope configuration never silently drops to the CPU: set HACKTV_NO_B200=1 to ask for it */
+		fprintf(stderr, "video_b200: the GPU encoder could not be initialised\n");
+		return(VID_ERROR);
+	}
+	i = _find(NULL);
+	if(i < 0) { htv_free(h); return(VID_ERROR); }
+
+	/* the fields hacktv.c and the sinks read (ref hacktv.c:1447-1526) */
+	memset(s, 0, sizeof(vid_t));
+	s->conf = *conf;
+	s->sample_rate = sample_rate;
+	s->pixel_rate = pixel_rate ? pixel_rate : sample_rate;
+	s->width = s->max_width = htv_samples_per_line(h);
+	s->active_width = htv_active_width(h);
+	s->thread_abort = 1;                             /* no CPU stage threads to join */
+	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
+	htv_av(h)->ctx = s;
+	htv_av(h)->read_video = _read_video;
+	htv_av(h)->read_audio = _read_audio;
+	return(VID_OK);
+}
+
+vid_line_t *vid_next_line(vid_t *s)
+{
+	int i = _find(s);
+	htv_line_t *l;
+	if(i < 0) return(cpu_vid_next_line(s));
+	if(av_eof(&s->av)) return(NULL);
+	l = htv_next_line(_enc[i].htv);
+	if(!l) return(NULL);
+	memset(&_enc[i].line, 0, sizeof(vid_line_t));
+	_enc[i].line.output = l->output;
+	_enc[i].line.width = l->width;
+	_enc[i].line.frame = s->frame = l->frame;
+	_enc[i].line.line = s->line = l->line;
+	return(&_enc[i].line);
+}
+
+void vid_free(vid_t *s)
+{
+	int i = _find(s);
+	if(i < 0) { cpu_vid_free(s); return; }
+	av_close(&s->av);
+	htv_av(_enc[i].htv)->close = NULL;
+	htv_free(_enc[i].htv);
+	free(_enc[i].packed);
+	memset(&_enc[i], 0, sizeof(_enc[i]));
+	memset(s, 0, sizeof(vid_t));
+}
+
+void vid_info(vid_t *s)
+{
+	int i = _find(s);
+	if(i < 0) { cpu_vid_info(s); return; }
+	htv_info(_enc[i].htv);
+	fprintf(stderr, "Encoder: %s\n", htv_version());
+}
+
+size_t vid_get_framebuffer_length(vid_t *s)
+{
+	int i = _find(s);
+	if(i < 0) return(cpu_vid_get_framebuffer_length(s));
+	return(htv_get_framebuffer_length(_enc[i].htv));
+}

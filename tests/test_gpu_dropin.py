@@ -1,0 +1,38 @@
+"""hacktv's own, unmodified front end (hacktv.c + av_test.c + rf_file.c compiled in place from
+the reference tree) linked against integration/video_b200.c + libhacktv_b200.so, run next to
+the stock build: same command line, same bytes (within the +-1 LSB the sound carriers allow).
+Both binaries are prebuilt by `make -C oracle ref dropin` and travel to the GPU box."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "hacktv_b200_dropin")
+STOCK = os.path.join(ROOT, "oracle", "_ref", "hacktv_ref")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(STOCK)), reason="drop-in demo not built")]
+
+
+def _run(binary, args, nbytes):
+    cmd = f"timeout 120 {binary} {args} -o - test 2>/dev/null | head -c {nbytes}"
+    out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=180).stdout
+    assert len(out) == nbytes, f"{binary}: got {len(out)} of {nbytes} bytes"
+    return np.frombuffer(out, dtype=np.int16)
+
+
+@pytest.mark.parametrize("args,per,tol", [
+    ("-m pal -s 16000000", 2, 0),
+    ("-m i -s 16000000 --filter --noaudio", 4, 0),
+    ("-m i -s 16000000 --filter", 4, 1),
+    ("-m m -s 13500000 --filter", 4, 1),
+])
+def test_same_cli_same_bytes(args, per, tol):
+    w = 858 if "13500000" in args else 1024
+    lines = 1300 if w == 1024 else 1100
+    a = _run(DROPIN, args, lines * w * per)
+    b = _run(STOCK, args, lines * w * per)
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    assert d.max() <= tol, f"max |diff| {d.max()}"
