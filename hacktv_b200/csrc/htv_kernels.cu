@@ -49,6 +49,8 @@ struct DevTables {
 	const htv_c16_t *nicam_cc;
 	const uint8_t *nicam_prn;
 	const uint8_t *offset_start;
+	const htv_c32_t *secam_fm_lut;
+	const htv_c16_t *secam_bell;
 	// frames
 	const uint32_t *frames;           // slot-major, active_width * active_lines each
 	const int32_t *frame_map;         // slot of frame (first_frame + i)
@@ -64,6 +66,27 @@ struct DevTables {
 	uint8_t *nic_local;               // RS: inclusive prefix (mod 4) of the DQPSK steps inside the symbol's frame
 	uint8_t *nic_ftot;                // RF: total step of frame k (mod 4)
 	uint8_t *nic_fstart;              // RF: differential symbol state before frame k
+};
+
+#define LOFF 33                       // luma window index = x + LOFF (aligned 128-bit loads at x0 - 25)
+#define SEC_TAIL 8                    // low-pass outputs that see the two aliased words (7 used)
+
+struct __align__(16) SecState {
+	int A, B;                         // chrominance_buffer[W], [W + 1]
+	int pad0, pad1;
+	double ix, iy;                    // iir_int16_t state (ref fir.c:721-735)
+};
+
+struct SecScratch {
+	int16_t *cb;                      // [lines][W]   low-passed baseband without the aliased-tail terms
+	int *tail;                        // [lines][SEC_TAIL] raw sums of the last outputs
+	int16_t *y;                       // [lines][W + 2] after IIR + clamp (FM input)
+	int16_t *add;                     // [lines][W]   subcarrier samples to add to the composite
+	SecState *st[2];                  // [lines] outgoing state, ping-pong between passes
+	SecState *used;                   // [lines] the incoming state the line was last computed from
+	SecState *carry;                  // state before the first line of the chain
+	int *flags;                       // [0] outgoing states changed in the last pass, [2] lines recomputed
+	int *claim;                       // [lines] last pass that rendered the line
 };
 
 struct htv_dev_t {
@@ -90,7 +113,9 @@ struct htv_dev_t {
 	size_t line_smem;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
 	int desc_cap;
-	int16_t *d_comp;                  // composite scratch, (sub + 2) lines, reused by every sub-batch (stays in L2)
+	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
+	int sec_passes;
+	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
 	int sub_lines;
 	size_t raster_smem, mod_smem;
 	int last_mod_lines;
@@ -460,6 +485,17 @@ struct __align__(16) LineRaster {
 	long long row_off;                // pixel offset of the source row in the frame store, -1 = black
 	int nent, pad0;
 	int ent_base[MAX_ENT], ent_len[MAX_ENT], ent_pos[MAX_ENT], ent_keep[MAX_ENT];
+	// SECAM (ref video.c:3068-3233)
+	int sec_proc;                     // the line carries a chroma subcarrier
+	int sec_dr;                       // 1: D'r line (uses v), 0: D'b (uses u)
+	int sec_sign;                     // subcarrier phase reset: +1 / -1
+	int sec_sr;                       // end of the modulated range (start is burst_left)
+	int sec_clear;                    // the line-average store is cleared at this line (line 1 / hline)
+	int sec_prev_kind;                // what the store holds: 0 zeros, 1 black, 2 a picture row
+	int sec_prev_comp;                // ... and which component of it: 1 u, 2 v
+	int pad1;
+	long long sec_prev_row;           // pixel offset of that row
+	long long pad2;
 };
 
 // Sound-carrier state at the start of a line
@@ -478,10 +514,68 @@ struct __align__(16) LineAudio {
 struct LineDescs { LineRaster *r; LineAudio *a; };
 static_assert(sizeof(LineRaster) % 16 == 0 && sizeof(LineAudio) % 16 == 0, "descriptors are copied as int4");
 
+// frame / line / picture row of scan line L; L < 0 are the pipeline-fill lines the reference's
+// SECAM stage sees before line 1 (frame 1, line 0: an all-black active line, ref video.c:4665-4667)
+__device__ __forceinline__ void line_numbers(const htv_dparams_t &dp, const DevTables &dt, int64_t L,
+	int &frame, int &line, int &code, long long &row_off)
+{
+	row_off = -1;
+	if(L < 0) { frame = 1; line = 0; code = dt.codes[0]; return; }
+	const int64_t f0 = L / dp.lines;
+	frame = (int) (f0 + 1);
+	line = (int) (L - f0 * dp.lines) + 1;
+	code = dt.codes[line];
+	int vy;
+	if(dp.raster == HTV_RASTER_625) vy = line < 313 ? (line - 23) * 2 : (line - 336) * 2 + 1;
+	else vy = line < 265 ? (line - 23) * 2 : (line - 286) * 2 + 1;
+	if(vy >= 0 && dp.interlaced != 0) vy += 1;
+	if(vy < 0 || vy >= dp.active_lines) vy = -1;
+	if(vy >= 0 && dt.frames)
+	{
+		const int64_t fi = f0 - dt.frame_map_first;
+		if(fi >= 0 && fi < dt.frame_map_len)
+		{
+			const int slot = dt.frame_map[fi];              // -1: the source has no picture (black)
+			if(slot >= 0) row_off = ((long long) slot * dp.active_lines + vy) * (long long) dp.active_width;
+		}
+	}
+}
+
+__device__ void line_secam(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineRaster &li)
+{
+	int frame, line, code; long long row;
+	line_numbers(dp, dt, L, frame, line, code, row);
+	li.sec_proc = (code & (HTV_LC_LEFT_ACTIVE | HTV_LC_RIGHT_ACTIVE)) != 0;
+	li.sec_dr = ((frame * dp.lines) + line) & 1;
+	li.sec_sign = ((frame * dp.lines) + line) % 3 == 0 ? 1 : -1;
+	li.sec_sr = (code & HTV_LC_RIGHT_ACTIVE) ? dp.burst_left + dp.burst_width : dp.half_width;
+	li.sec_clear = L >= 0 && (line == 1 || line == dp.hline);
+	li.sec_prev_kind = 0; li.sec_prev_comp = 1; li.sec_prev_row = -1;
+	// what the vertical-average store holds when this line reads it (ref video.c:3149-3196):
+	// the other component of the last processed line, unless a clearing line came in between
+	for(int64_t M = L; M >= L - dp.lines; M--)
+	{
+		int f2, l2, c2; long long r2;
+		line_numbers(dp, dt, M, f2, l2, c2, r2);
+		if(M >= 0 && (l2 == 1 || l2 == dp.hline)) break;       // cleared at the start of line M
+		if(M - 1 < -2) break;                                   // stream start: the store is zeroed
+		line_numbers(dp, dt, M - 1, f2, l2, c2, r2);
+		if(c2 & (HTV_LC_LEFT_ACTIVE | HTV_LC_RIGHT_ACTIVE))
+		{
+			li.sec_prev_kind = r2 >= 0 ? 2 : 1;
+			li.sec_prev_row = r2;
+			li.sec_prev_comp = (((f2 * dp.lines) + l2) & 1) ? 1 : 2;   // a D'r line stores u, a D'b line v
+			break;
+		}
+	}
+}
+
 __device__ void line_raster(const htv_dparams_t &dp, const DevTables &dt, int64_t L, LineRaster &li)
 {
 	li.valid = L >= 0;
 	li.nent = 0;
+	li.sec_proc = 0;
+	if(dp.colour_mode == HTV_SECAM) line_secam(dp, dt, L, li);
 	if(L < 0) { li.frame = li.line = li.code = li.pal = 0; li.al = li.ar = -1; li.row_off = -1; li.clut_off = 0; return; }
 	const int64_t f0 = L / dp.lines;
 	li.frame = (int) (f0 + 1);
@@ -604,9 +698,10 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 __global__ void k_line_desc(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= nlines + 2) return;
-	line_raster(dp, dt, line0 - 1 + i, ld.r[i]);
-	if(i >= 1 && i <= nlines) line_audio(dp, dt, line0 - 1 + i, ld.a[i - 1]);
+	if(i >= nlines + 3) return;
+	// raster descriptor index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
+	line_raster(dp, dt, line0 - 2 + i, ld.r[i - 1]);
+	if(i >= 2 && i <= nlines + 1) line_audio(dp, dt, line0 - 2 + i, ld.a[i - 2]);
 }
 
 __device__ __forceinline__ int round_away(double v)
@@ -807,6 +902,281 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 }
 
 // ---------------------------------------------------------------------------
+// SECAM (ref video.c:3068-3233). Three parts:
+//   k_raster_secam  one CTA per line: luma / sync as k_raster, the luma notch FIR, the
+//                   line's colour-difference baseband (vertical average with the previous
+//                   line) and its 15-tap low-pass - everything that is parallel in x.
+//   k_secam_seq     one THREAD per line: the sample-serial tail of the reference - the
+//                   double-precision pre-emphasis IIR and the Q31 FM recurrence with the
+//                   bell-filter gain - exactly as the reference computes them.
+//   cross-line state (IIR state; the two words at chrominance_buffer[W], [W+1] that the
+//                   reference's FM loop overruns into and the next line's low-pass reads
+//                   back) is resolved by iteration: every line is computed from a guess of
+//                   its predecessor's state and recomputed while that guess was wrong. The
+//                   chain is contracting, so a handful of passes reaches the fixed point,
+//                   which is the sequential result bit for bit.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ bool sec_same(const SecState &a, const SecState &b)
+{
+	return(a.A == b.A && a.B == b.B && __double_as_longlong(a.ix) == __double_as_longlong(b.ix) &&
+	       __double_as_longlong(a.iy) == __double_as_longlong(b.iy));
+}
+
+__global__ void __launch_bounds__(384, 3)
+k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, SecScratch ss)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int W4 = (W + 3) & ~3;
+	const int LW = W4 + 2 * LOFF + 14;
+	double *glut = reinterpret_cast<double *>(smem_raw);
+	int *line = reinterpret_cast<int *>(glut + 256);                // index = x + LOFF
+	int *cbin = line + ((LW + 3) & ~3);                             // index = x + 8
+	__shared__ LineRaster li;
+	const int tid = threadIdx.x;
+
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(lr + blockIdx.x);
+		int4 *dst = reinterpret_cast<int4 *>(&li);
+		if(tid < (int) (sizeof(LineRaster) / 16)) dst[tid] = __ldg(src + tid);
+	}
+	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
+	for(int i = tid; i < LOFF; i += blockDim.x) { line[i] = 0; line[W4 + LOFF + i] = 0; }
+	if(tid < 16) { cbin[tid < 8 ? tid : W4 + tid] = 0; }
+	__syncthreads();
+
+	const int x0 = tid * SPT;
+	const int cur = li.sec_dr ? 2 : 1;                              // 1: u, 2: v
+	if(x0 < W4)
+	{
+		int val[SPT], cbv[SPT];
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			val[k] = li.valid ? dp.blank : 0;
+			cbv[k] = cur == 1 ? dp.black_u : dp.black_v;
+			int y = 0, u = 0, v = 0;
+			const bool inpic = x >= dp.active_left && x < dp.active_left + dp.active_width;
+			if((x >= li.al && x < li.ar) || (li.sec_proc && inpic))
+			{
+				const unsigned int rgb = li.row_off >= 0 ? (__ldg(dt.frames + li.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
+				yuv_of<true>(dp, glut, rgb, y, u, v);
+			}
+			if(x >= li.al && x < li.ar) val[k] = y;
+			if(li.sec_proc && inpic)
+			{
+				// average with what the previous line left in the store (C division: toward zero)
+				int st = 0;
+				if(li.sec_prev_kind == 1) st = li.sec_prev_comp == 1 ? dp.black_u : dp.black_v;
+				else if(li.sec_prev_kind == 2)
+				{
+					int y2, u2, v2;
+					const unsigned int rgb2 = __ldg(dt.frames + li.sec_prev_row + (x - dp.active_left)) & 0xFFFFFF;
+					yuv_of<true>(dp, glut, rgb2, y2, u2, v2);
+					st = li.sec_prev_comp == 1 ? u2 : v2;
+				}
+				cbv[k] = ((cur == 1 ? u : v) + st) / 2;
+			}
+		}
+		for(int e = 0; e < li.nent; e++)
+		{
+			const int d0 = x0 - li.ent_base[e];
+			if(d0 + SPT - 1 < 0 || d0 >= li.ent_len[e]) continue;
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int d = d0 + k, x = x0 + k;
+				if(d < 0 || d >= li.ent_len[e] || x >= W) continue;
+				if(!li.ent_keep[e] && x >= li.al && x < li.ar) continue;
+				val[k] += __ldg(dt.pulse_values + li.ent_pos[e] + d);
+			}
+		}
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			line[x + LOFF] = x < W ? wrap16i(val[k]) : 0;
+			cbin[x + 8] = x < W ? cbv[k] : 0;
+		}
+	}
+	__syncthreads();
+	if(x0 >= W) return;
+
+	int outv[SPT];
+	#pragma unroll
+	for(int k = 0; k < SPT; k++) outv[k] = line[x0 + k + LOFF];
+	if(li.sec_proc)
+	{
+		// luma notch over the picture region; samples left of it read as zero (ref fir.c:357-375)
+		const int a0 = dp.active_left, a1 = dp.active_left + dp.active_width;
+		if(x0 + SPT - 1 >= a0 && x0 < a1)
+		{
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int x = x0 + k;
+				if(x < a0 || x >= a1) continue;
+				int acc = 0;
+				for(int t = 0; t < 51; t++)
+				{
+					const int j = x - 25 + t;
+					acc += (j >= a0 ? line[j + LOFF] : 0) * dp.secam_notch[t];
+				}
+				outv[k] = sat16i(acc >> 15);
+			}
+		}
+		// 15-tap low-pass of the colour-difference baseband; the two aliased words past the
+		// end of the line are added by k_secam_seq, so the last 7 outputs are kept as raw sums
+		const size_t row = (size_t) blockIdx.x;
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			if(x >= W) break;
+			int acc = 0;
+			#pragma unroll
+			for(int t = 0; t < 15; t++) acc += cbin[x - 7 + t + 8] * dp.secam_lpf[t];
+			ss.cb[row * W + x] = (int16_t) sat16i(acc >> 15);
+			if(x >= W - 7) ss.tail[row * SEC_TAIL + (x - (W - 7))] = acc;
+		}
+	}
+	const size_t o = (size_t) blockIdx.x * W + x0;
+	#pragma unroll
+	for(int k = 0; k < SPT; k++)
+	{
+		if(x0 + k < W) { comp[o + k] = (int16_t) outv[k]; ss.add[o + k] = 0; }
+	}
+}
+
+// The sample-serial part of one line: incoming state -> outgoing state; when `commit` is set
+// the subcarrier samples are written to the line's row of ss.add.
+__device__ __noinline__ SecState secam_line(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
+	const SecScratch &ss, int c, const SecState &in, bool commit, int16_t *y)
+{
+	const int W = dp.W;
+	SecState out = in;
+	if(li.sec_clear) { out.A = 0; out.B = 0; }
+	if(!li.sec_proc) return(out);
+
+	const int A = out.A, B = out.B;
+	const int16_t *cb = ss.cb + (size_t) c * W;
+	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
+	// pre-emphasis IIR in double, separately rounded operations (ref fir.c:721-735)
+	double ix = out.ix, iy = out.iy;
+	for(int x = 0; x < W; x++)
+	{
+		int v = cb[x];
+		if(x >= W - 7)
+		{
+			// finish the low-pass: taps reaching chrominance_buffer[W] and [W + 1]
+			int acc = tail[x - (W - 7)];
+			const int kA = W - x + 7, kB = W + 1 - x + 7;
+			if(kA <= 14) acc += A * dp.secam_lpf[kA];
+			if(kB <= 14) acc += B * dp.secam_lpf[kB];
+			v = sat16i(acc >> 15);
+		}
+		const double xin = (double) v;
+		iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
+		ix = xin;
+		const double cl = iy < -32768.0 ? -32768.0 : (iy > 32767.0 ? 32767.0 : iy);
+		y[x] = (int16_t) round_away(cl);
+	}
+	out.ix = ix; out.iy = iy;
+	y[W] = (int16_t) A; y[W + 1] = (int16_t) B;
+
+	// FM modulator: Q31 phasor reset every line, exact recurrence (ref video.c:2278-2297, 3211-3228)
+	const int sl = dp.burst_left, sr = li.sec_sr;
+	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+	int16_t *add = ss.add + (size_t) c * W;
+	for(int x = sl; x < sr; x++)
+	{
+		int s = y[x];
+		s = s < dmin ? dmin : (s > dmax ? dmax : s);
+		const htv_c32_t m = dt.secam_fm_lut[s + 32768];
+		const htv_c16_t g = dt.secam_bell[(unsigned short) s];
+		const long long ni = (long long) pi * m.i - (long long) pq * m.q;
+		const long long nq = (long long) pi * m.q + (long long) pq * m.i;
+		pi = (int) (ni >> 31); pq = (int) (nq >> 31);
+		const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
+		                     - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
+		if(x < W) { if(commit && li.valid) add[x] = (int16_t) ((o * dt.burst_win[x - sl]) >> 15); }   // fill lines are never emitted
+		else if(x == W) out.A = o;
+		else if(x == W + 1) out.B = o;
+	}
+	return(out);
+}
+
+#define SEC_MAXW 1536
+#define SEC_RUN 8                     // lines a thread renders in sequence in the first pass ...
+#define SEC_WARM 4                    // ... after this many warm-up lines (state only, nothing written)
+
+// Pass 0: each thread walks a run of consecutive lines, so the state it hands from line to line
+// is exact inside the run; only the run's starting state is a guess, tightened by a few warm-up
+// lines (the dependence on the incoming state contracts by roughly 10x per line).
+__global__ void __launch_bounds__(64)
+k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const int c0 = r * SEC_RUN;
+	if(c0 >= n) return;
+	int16_t y[SEC_MAXW + 2];
+	SecState st;
+	int c = c0 - SEC_WARM;
+	if(c <= 0) { c = 0; st = *ss.carry; }
+	else { st.A = st.B = st.pad0 = st.pad1 = 0; st.ix = st.iy = 0.0; }
+	const int c1 = min(n, c0 + SEC_RUN);
+	for(; c < c1; c++)
+	{
+		const bool mine = c >= c0;
+		if(mine) ss.used[c] = st;
+		st = secam_line(dp, dt, lr[c], ss, c, st, mine, y);
+		if(mine) ss.st[0][c] = st;
+	}
+}
+
+// Later passes, one thread per line: recompute a line only if the state its predecessor now
+// hands over differs from the one it was computed from - and keep walking down the following
+// lines while the outgoing state keeps changing, so a correction front is absorbed in one pass
+// instead of one line per pass. ss.claim makes sure a line has one writer per pass. dst was
+// preset to src by the host (device-to-device copy), so untouched lines keep their state.
+#define SEC_WALK 256
+__global__ void __launch_bounds__(64)
+k_secam_seq(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n) return;
+	const SecState *src = ss.st[(pass + 1) & 1];
+	SecState *dst = ss.st[pass & 1];
+	SecState in = c == 0 ? *ss.carry : src[c - 1];
+	if(sec_same(in, ss.used[c])) return;
+	int16_t y[SEC_MAXW + 2];
+	for(int steps = 0; steps < SEC_WALK && c < n; steps++, c++)
+	{
+		if(atomicMax(ss.claim + c, pass) >= pass) break;            // another thread has this line in this pass
+		ss.used[c] = in;
+		atomicAdd(ss.flags + 2, 1);
+		const SecState out = secam_line(dp, dt, lr[c], ss, c, in, true, y);
+		const bool changed = !sec_same(out, src[c]);
+		dst[c] = out;
+		if(!changed) break;
+		atomicAdd(ss.flags, 1);                                     // the successor is stale unless we fix it now
+		in = out;
+	}
+}
+
+// carry for the next launch: the state after chain line `idx` of the final pass
+__global__ void k_secam_carry(SecScratch ss, int idx, int pass_final)
+{
+	if(threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		*ss.carry = ss.st[pass_final & 1][idx];
+	}
+}
+
+// ---------------------------------------------------------------------------
 // Modulator kernel: one CTA per scan line, 4 samples per thread. Stages the line's
 // composite samples (+-32 from the contiguous stream, so neighbours need no special
 // case) in shared memory, applies the video filter as a centred 51-tap FIR (ref
@@ -817,7 +1187,7 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, int16_t *out)
+k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int16_t *out)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -858,6 +1228,13 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 			{
 				#pragma unroll
 				for(int k = 0; k < 4; k++) v[k] = __ldg(cs + xe0 + k);
+			}
+			if(sadd)
+			{
+				// SECAM: the subcarrier samples k_secam_seq produced for the same stream positions
+				const int16_t *sa = sadd + ((size_t) blockIdx.x + 1) * W + xe0;
+				#pragma unroll
+				for(int k = 0; k < 4; k++) v[k] = wrap16i(v[k] + __ldg(sa + k));
 			}
 			#pragma unroll
 			for(int k = 0; k < 4; k++) cw[xe0 + k + COFF] = v[k];
@@ -1112,6 +1489,8 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, sizeof(htv_c16_t) * t->nicam_cc_len);
 	dt.nicam_prn = (const uint8_t *) dev_copy(d, t->nicam_prn, sizeof(t->nicam_prn));
 	dt.offset_start = (const uint8_t *) dev_copy(d, t->offset_start, t->offset_start ? 32768 : 0);
+	dt.secam_fm_lut = (const htv_c32_t *) dev_copy(d, t->secam_fm_lut, t->secam_fm_lut ? sizeof(htv_c32_t) * 65536 : 0);
+	dt.secam_bell = (const htv_c16_t *) dev_copy(d, t->secam_bell, t->secam_bell ? sizeof(htv_c16_t) * 65536 : 0);
 
 	d->frame_pixels = (size_t) dp.active_width * dp.active_lines;
 	d->max_slots = max_frame_slots < 1 ? 1 : max_frame_slots;
@@ -1165,13 +1544,39 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaFuncSetAttribute(k_mod<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->mod_smem);
 	cudaFuncSetAttribute(k_mod<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->mod_smem);
 	// sub-batches keep the int16 composite scratch (2 B/sample) resident in the 126 MB L2
-	d->sub_lines = (16 * 1024 * 1024) / (W * 2);
+	const bool secam = dp.colour_mode == HTV_SECAM;
+	d->sub_lines = ((secam ? 32 : 16) * 1024 * 1024) / (W * 2);
 	if(d->sub_lines < 64) d->sub_lines = 64;
-	if(cudaMalloc((void **) &d->d_comp, sizeof(int16_t) * ((size_t) d->sub_lines + 2) * W + 256) != cudaSuccess)
+	if(cudaMalloc((void **) &d->d_comp, sizeof(int16_t) * ((size_t) d->sub_lines + 3) * W + 256) != cudaSuccess)
 	{
 		snprintf(err, errlen, "device allocation failed");
 		htv_dev_destroy(d);
 		return(NULL);
+	}
+	if(secam)
+	{
+		const size_t rows = (size_t) d->sub_lines + 3;
+		d->sec.cb = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W);
+		d->sec.tail = (int *) dev_zero(d, sizeof(int) * rows * SEC_TAIL);
+		d->sec.y = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * (W + 2));
+		d->sec.add = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W + 256);
+		d->sec.st[0] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
+		d->sec.st[1] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
+		d->sec.used = (SecState *) dev_zero(d, sizeof(SecState) * rows);
+		d->sec.carry = (SecState *) dev_zero(d, sizeof(SecState));
+		d->sec.flags = (int *) dev_zero(d, sizeof(int) * 4);
+		d->sec.claim = (int *) dev_zero(d, sizeof(int) * rows);
+		d->sec_passes = 64;
+		if(!d->sec.cb || !d->sec.y || !d->sec.add || !d->sec.flags)
+		{
+			snprintf(err, errlen, "device allocation failed");
+			htv_dev_destroy(d);
+			return(NULL);
+		}
+		const int W4s = (W + 3) & ~3;
+		const size_t sm = 256 * sizeof(double) + sizeof(int) * ((((W4s + 2 * LOFF + 14) + 3) & ~3) + W4s + 32);
+		d->raster_smem = sm > d->raster_smem ? sm : d->raster_smem;
+		cudaFuncSetAttribute(k_raster_secam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->raster_smem);
 	}
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
@@ -1271,25 +1676,65 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
 		d->d_desc_r = d->d_desc_a = NULL;
 		d->desc_cap = 0;
-		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 2)));
+		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
 		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * (size_t) nlines));
 		d->desc_cap = nlines;
 	}
-	LineDescs ld = { (LineRaster *) d->d_desc_r, (LineAudio *) d->d_desc_a };
-	k_line_desc<<<(nlines + 2 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
+	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
+	k_line_desc<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
 	d->launches++;
 	for(int done = 0; done < nlines; done += d->sub_lines)
 	{
 		const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
 		const bool last = done + n >= nlines;
-		// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
-		k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp);
-		if(d->timing && last) cudaEventRecord(d->ev0, st);
 		int16_t *o = d_out + (size_t) done * d->dp.W * (d->dp.complex_out ? 2 : 1);
-		if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp, o);
-		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp, o);
+		const int16_t *sadd = NULL;
+		const int16_t *cstream = d->d_comp;
+		if(d->dp.colour_mode == HTV_SECAM)
+		{
+			// rows 0 .. n+2 <-> lines first-2 .. first+n; the chain covers rows 0 .. n+1
+			const LineRaster *lr = ld.r + done - 1;
+			k_raster_secam<<<n + 3, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec);
+			// pass 0 in runs, then per-line passes until no line's outgoing state changes: at that
+			// fixed point every line was computed from its true predecessor state = the sequential
+			// result. The loop needs the change count on the host, so SECAM launches synchronise.
+			const int nch = n + 2;
+			cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
+			k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+			d->launches += 2;
+			int pass = 1, changed = 1;
+			for(; pass <= d->sec_passes && changed; pass++)
+			{
+				int fl[4];
+				cudaMemsetAsync(d->sec.flags, 0, sizeof(int) * 4, st);
+				cudaMemcpyAsync(d->sec.st[pass & 1], d->sec.st[(pass + 1) & 1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
+				k_secam_seq<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+				d->launches++;
+				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				changed = fl[0];
+				if(getenv("HTV_DEBUG")) fprintf(stderr, "secam pass %d: recomputed %d, output changed %d\n", pass, fl[2], fl[0]);
+			}
+			if(changed)
+			{
+				fprintf(stderr, "hacktv_b200: SECAM cross-line state did not converge in %d passes\n", d->sec_passes);
+				return(HTV_ERROR);
+			}
+			k_secam_carry<<<1, 32, 0, st>>>(d->sec, n - 1, pass - 1);
+			cstream = d->d_comp + d->dp.W;          // k_mod's line b sits at row b + 2
+			sadd = d->sec.add + d->dp.W;
+		}
+		else
+		{
+			// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
+			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp);
+			d->launches++;
+		}
+		if(d->timing && last) cudaEventRecord(d->ev0, st);
+		if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
+		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
+		d->launches++;
 		if(last) d->last_mod_lines = n;
-		d->launches += 2;
 	}
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
 	CK(cudaGetLastError());

@@ -50,6 +50,11 @@ CASES = [
     ("b", 16000000, 700, dict(vfilter=True), 1),
     ("pal-m", 13500000, 600, dict(vfilter=True), 1),
     ("pal-n", 16000000, 700, dict(vfilter=True), 1),
+    ("l", 16000000, 1300, dict(vfilter=True), 1),                         # config 4: SECAM-L, AM sound + NICAM
+    ("l", 16000000, 1300, dict(vfilter=True, noaudio=True), 0),           # SECAM chroma is exact
+    ("secam", 16000000, 1300, dict(), 0),
+    ("d", 16000000, 700, dict(vfilter=True), 1),
+    ("secam-i", 16000000, 700, dict(vfilter=True, nonicam=True), 1),
 ]
 
 
@@ -112,3 +117,21 @@ def test_next_line_view_matches_batches(built):
         assert frame == k // 625 + 1 and line == k % 625 + 1
         assert np.array_equal(iq[0::2], ref[k]) and not iq[1::2].any()
     b.close()
+
+
+def test_secam_random_pictures_exact(built):
+    """SECAM chroma on random pictures (a new one every frame), rendered in uneven pieces so
+    the cross-line state (IIR state, the two aliased buffer words) crosses launch boundaries."""
+    H = built
+    rng = np.random.default_rng(99)
+    conf = H.mode_config("l", vfilter=True, noaudio=True)
+    enc = H.Encoder(conf, 16000000)
+    frames = rng.integers(0, 1 << 24, size=(3, enc.active_lines, enc.active_width), dtype=np.uint32)
+    enc.set_source(frames, None)
+    got = np.concatenate([enc.render_host(n) for n in (1, 2, 23, 300, 625, 949)])
+    enc.close()
+    o = orc.Oracle(conf, 16000000)
+    o.set_source(frames, None)
+    want = o.render(1900)
+    o.close()
+    assert _diff(got, want).max() == 0
