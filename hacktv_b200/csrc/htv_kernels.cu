@@ -115,6 +115,7 @@ struct htv_dev_t {
 	int desc_cap;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
+	size_t sec_smem;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
 	int sub_lines;
 	size_t raster_smem, mod_smem;
@@ -1050,12 +1051,22 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 	}
 }
 
-// The sample-serial part of one line: incoming state -> outgoing state; when `commit` is set
-// the subcarrier samples are written to the line's row of ss.add.
-__device__ __noinline__ SecState secam_line(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
-	const SecScratch &ss, int c, const SecState &in, bool commit, int16_t *y)
+// The sample-serial part of one line, run by ONE WARP: lane 0 walks the two recurrences, all
+// lanes do the memory work around it (coalesced row load, table gathers, row store) through
+// shared memory. Incoming state -> outgoing state; when `commit` is set the subcarrier samples
+// are written to the line's row of ss.add.
+struct SecSmem {
+	short *cbS;                       // [W]     low-passed baseband
+	short *yS;                        // [W + 2] FM input (after IIR + clamp), then the two aliased words
+	htv_c32_t *mS;                    // [n]     FM phasor steps for the modulated range
+	htv_c16_t *gS;                    // [n]     bell-filter gains
+	short *oS;                        // [n]     modulator output
+};
+
+__device__ __forceinline__ SecState secam_line_warp(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
+	const SecScratch &ss, int c, const SecState &in, bool commit, const SecSmem &sm)
 {
-	const int W = dp.W;
+	const int W = dp.W, lane = threadIdx.x & 31;
 	SecState out = in;
 	if(li.sec_clear) { out.A = 0; out.B = 0; }
 	if(!li.sec_proc) return(out);
@@ -1063,9 +1074,7 @@ __device__ __noinline__ SecState secam_line(const htv_dparams_t &dp, const DevTa
 	const int A = out.A, B = out.B;
 	const int16_t *cb = ss.cb + (size_t) c * W;
 	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
-	// pre-emphasis IIR in double, separately rounded operations (ref fir.c:721-735)
-	double ix = out.ix, iy = out.iy;
-	for(int x = 0; x < W; x++)
+	for(int x = lane; x < W; x += 32)
 	{
 		int v = cb[x];
 		if(x >= W - 7)
@@ -1077,52 +1086,93 @@ __device__ __noinline__ SecState secam_line(const htv_dparams_t &dp, const DevTa
 			if(kB <= 14) acc += B * dp.secam_lpf[kB];
 			v = sat16i(acc >> 15);
 		}
-		const double xin = (double) v;
-		iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
-		ix = xin;
-		const double cl = iy < -32768.0 ? -32768.0 : (iy > 32767.0 ? 32767.0 : iy);
-		y[x] = (int16_t) round_away(cl);
+		sm.cbS[x] = (short) v;
 	}
+	__syncwarp();
+	// pre-emphasis IIR in double, separately rounded operations (ref fir.c:721-735)
+	double ix = out.ix, iy = out.iy;
+	if(lane == 0)
+	{
+		#pragma unroll 4
+		for(int x = 0; x < W; x++)
+		{
+			const double xin = (double) sm.cbS[x];
+			iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
+			ix = xin;
+			const double cl = iy < -32768.0 ? -32768.0 : (iy > 32767.0 ? 32767.0 : iy);
+			sm.yS[x] = (short) round_away(cl);
+		}
+		sm.yS[W] = (short) A; sm.yS[W + 1] = (short) B;
+	}
+	ix = __shfl_sync(0xFFFFFFFFu, ix, 0); iy = __shfl_sync(0xFFFFFFFFu, iy, 0);
 	out.ix = ix; out.iy = iy;
-	y[W] = (int16_t) A; y[W + 1] = (int16_t) B;
+	__syncwarp();
 
 	// FM modulator: Q31 phasor reset every line, exact recurrence (ref video.c:2278-2297, 3211-3228)
-	const int sl = dp.burst_left, sr = li.sec_sr;
+	const int sl = dp.burst_left, sr = li.sec_sr, n = sr - sl;
 	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
-	int16_t *add = ss.add + (size_t) c * W;
-	for(int x = sl; x < sr; x++)
+	for(int i = lane; i < n; i += 32)
 	{
-		int s = y[x];
+		int s = sm.yS[sl + i];
 		s = s < dmin ? dmin : (s > dmax ? dmax : s);
-		const htv_c32_t m = dt.secam_fm_lut[s + 32768];
-		const htv_c16_t g = dt.secam_bell[(unsigned short) s];
-		const long long ni = (long long) pi * m.i - (long long) pq * m.q;
-		const long long nq = (long long) pi * m.q + (long long) pq * m.i;
-		pi = (int) (ni >> 31); pq = (int) (nq >> 31);
-		const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
-		                     - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
-		if(x < W) { if(commit && li.valid) add[x] = (int16_t) ((o * dt.burst_win[x - sl]) >> 15); }   // fill lines are never emitted
-		else if(x == W) out.A = o;
-		else if(x == W + 1) out.B = o;
+		sm.mS[i] = dt.secam_fm_lut[s + 32768];
+		sm.gS[i] = dt.secam_bell[(unsigned short) s];
 	}
+	__syncwarp();
+	if(lane == 0)
+	{
+		int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+		#pragma unroll 4
+		for(int i = 0; i < n; i++)
+		{
+			const htv_c32_t m = sm.mS[i];
+			const htv_c16_t g = sm.gS[i];
+			const long long ni = (long long) pi * m.i - (long long) pq * m.q;
+			const long long nq = (long long) pi * m.q + (long long) pq * m.i;
+			pi = (int) (ni >> 31); pq = (int) (nq >> 31);
+			sm.oS[i] = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
+			                  - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
+		}
+	}
+	__syncwarp();
+	if(sr > W) out.A = sm.oS[W - sl];
+	if(sr > W + 1) out.B = sm.oS[W + 1 - sl];
+	if(commit && li.valid)                                          // fill lines are never emitted
+	{
+		int16_t *add = ss.add + (size_t) c * W;
+		const int top = min(sr, W);
+		for(int x = sl + lane; x < top; x += 32) add[x] = (int16_t) (((int) sm.oS[x - sl] * dt.burst_win[x - sl]) >> 15);
+	}
+	__syncwarp();
 	return(out);
 }
 
-#define SEC_MAXW 1536
-#define SEC_RUN 8                     // lines a thread renders in sequence in the first pass ...
-#define SEC_WARM 4                    // ... after this many warm-up lines (state only, nothing written)
+__device__ __forceinline__ SecSmem sec_smem(const htv_dparams_t &dp, unsigned char *base)
+{
+	const int W = dp.W, n = dp.burst_width + 2;
+	SecSmem sm;
+	sm.mS = reinterpret_cast<htv_c32_t *>(base);
+	sm.gS = reinterpret_cast<htv_c16_t *>(sm.mS + n);
+	sm.cbS = reinterpret_cast<short *>(sm.gS + n);
+	sm.yS = sm.cbS + ((W + 7) & ~7);
+	sm.oS = sm.yS + ((W + 2 + 7) & ~7);
+	return(sm);
+}
 
-// Pass 0: each thread walks a run of consecutive lines, so the state it hands from line to line
-// is exact inside the run; only the run's starting state is a guess, tightened by a few warm-up
-// lines (the dependence on the incoming state contracts by roughly 10x per line).
-__global__ void __launch_bounds__(64)
+#define SEC_RUN 8                     // lines a warp renders in sequence in the first pass ...
+#define SEC_WARM 8                    // ... after this many warm-up lines (state only, nothing written)
+
+// Pass 0: each warp walks a run of consecutive lines, so the state it hands from line to line
+// is exact inside the run; only the run's starting state is a guess, tightened by warm-up
+// lines (the dependence on the incoming state contracts by roughly 3x per line).
+__global__ void __launch_bounds__(32)
 k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
 {
-	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const SecSmem sm = sec_smem(dp, smem_raw);
+	const int r = blockIdx.x;
 	const int c0 = r * SEC_RUN;
 	if(c0 >= n) return;
-	int16_t y[SEC_MAXW + 2];
 	SecState st;
 	int c = c0 - SEC_WARM;
 	if(c <= 0) { c = 0; st = *ss.carry; }
@@ -1131,38 +1181,41 @@ k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 	for(; c < c1; c++)
 	{
 		const bool mine = c >= c0;
-		if(mine) ss.used[c] = st;
-		st = secam_line(dp, dt, lr[c], ss, c, st, mine, y);
-		if(mine) ss.st[0][c] = st;
+		if(mine && threadIdx.x == 0) ss.used[c] = st;
+		st = secam_line_warp(dp, dt, lr[c], ss, c, st, mine, sm);
+		if(mine && threadIdx.x == 0) ss.st[0][c] = st;
 	}
 }
 
-// Later passes, one thread per line: recompute a line only if the state its predecessor now
+// Later passes, one warp per line: recompute a line only if the state its predecessor now
 // hands over differs from the one it was computed from - and keep walking down the following
 // lines while the outgoing state keeps changing, so a correction front is absorbed in one pass
 // instead of one line per pass. ss.claim makes sure a line has one writer per pass. dst was
 // preset to src by the host (device-to-device copy), so untouched lines keep their state.
 #define SEC_WALK 256
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
 k_secam_seq(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
 {
-	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	int c = blockIdx.x;
 	if(c >= n) return;
 	const SecState *src = ss.st[(pass + 1) & 1];
 	SecState *dst = ss.st[pass & 1];
 	SecState in = c == 0 ? *ss.carry : src[c - 1];
 	if(sec_same(in, ss.used[c])) return;
-	int16_t y[SEC_MAXW + 2];
+	const SecSmem sm = sec_smem(dp, smem_raw);
 	for(int steps = 0; steps < SEC_WALK && c < n; steps++, c++)
 	{
-		if(atomicMax(ss.claim + c, pass) >= pass) break;            // another thread has this line in this pass
-		ss.used[c] = in;
-		atomicAdd(ss.flags + 2, 1);
-		const SecState out = secam_line(dp, dt, lr[c], ss, c, in, true, y);
+		int got = 0;
+		if(threadIdx.x == 0) got = atomicMax(ss.claim + c, pass) < pass;
+		got = __shfl_sync(0xFFFFFFFFu, got, 0);
+		if(!got) break;                                             // another warp has this line in this pass
+		if(threadIdx.x == 0) { ss.used[c] = in; atomicAdd(ss.flags + 2, 1); }
+		const SecState out = secam_line_warp(dp, dt, lr[c], ss, c, in, true, sm);
 		const bool changed = !sec_same(out, src[c]);
-		dst[c] = out;
+		if(threadIdx.x == 0) dst[c] = out;
 		if(!changed) break;
-		atomicAdd(ss.flags, 1);                                     // the successor is stale unless we fix it now
+		if(threadIdx.x == 0) atomicAdd(ss.flags, 1);                // the successor is stale unless we fix it now
 		in = out;
 	}
 }
@@ -1567,6 +1620,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		d->sec.flags = (int *) dev_zero(d, sizeof(int) * 4);
 		d->sec.claim = (int *) dev_zero(d, sizeof(int) * rows);
 		d->sec_passes = 64;
+		d->sec_smem = (size_t) (dp.burst_width + 2) * 12 + 2 * (((W + 7) & ~7) + ((W + 2 + 7) & ~7) + ((dp.burst_width + 2 + 7) & ~7)) + 64;
+		cudaFuncSetAttribute(k_secam_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
+		cudaFuncSetAttribute(k_secam_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
 		if(!d->sec.cb || !d->sec.y || !d->sec.add || !d->sec.flags)
 		{
 			snprintf(err, errlen, "device allocation failed");
@@ -1700,7 +1756,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			// result. The loop needs the change count on the host, so SECAM launches synchronise.
 			const int nch = n + 2;
 			cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
-			k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+			k_secam_runs<<<(nch + SEC_RUN - 1) / SEC_RUN, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch);
 			d->launches += 2;
 			int pass = 1, changed = 1;
 			for(; pass <= d->sec_passes && changed; pass++)
@@ -1708,7 +1764,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				int fl[4];
 				cudaMemsetAsync(d->sec.flags, 0, sizeof(int) * 4, st);
 				cudaMemcpyAsync(d->sec.st[pass & 1], d->sec.st[(pass + 1) & 1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
-				k_secam_seq<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+				k_secam_seq<<<nch, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
 				d->launches++;
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
