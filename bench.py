@@ -50,25 +50,46 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through
+    NVML at ~1 kHz (the region is only milliseconds long; spawning nvidia-smi is too slow).
+    Falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index):
         self.index, self.rows, self._stop = index, [], threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.t0 = self.t1 = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # torch device index -> NVML handle (respects CUDA_VISIBLE_DEVICES through the UUID)
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        nv = self._nv
         while not self._stop.is_set():
             try:
-                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                p = [x.strip() for x in r.stdout.strip().split(",")]
-                if len(p) >= 6:
-                    self.rows.append(p)
+                if nv:
+                    clk = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    self.rows.append((time.perf_counter(), clk, self._max, rs))
+                else:
+                    q = "clocks.sm,clocks.max.sm"
+                    r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5)
+                    p = [x.strip() for x in r.stdout.strip().split(",")]
+                    self.rows.append((time.perf_counter(), int(p[0]), int(p[1]), 0))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.001 if nv else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -79,12 +100,20 @@ class ClockSampler:
         self._t.join(timeout=3)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        rows = [r for r in self.rows if self.t0 is None or (self.t0 <= r[0] <= self.t1)] or self.rows
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
+        nv = self._nv
+        if nv:
+            names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                     "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+            for r in rows:
+                for k, attr in names.items():
+                    bit = getattr(nv, attr, None) or getattr(nv, attr.replace("Event", "Throttle"), 0)
+                    if bit and (r[3] & bit):
+                        reasons.add(k)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvml" if nv else "nvidia-smi"}
 
 
 def run_reference_instances(ninst, frames, timeout=900):
@@ -193,11 +222,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
     with ClockSampler(local) as clk:
+        time.sleep(0.005)
+        clk.t0 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
             enc.render(nlines, out.data_ptr(), stream)
         ev1.record()
         barrier()
+        clk.t1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     launches = enc.kernel_launches - l0
     clocks = clk.summary()
