@@ -92,6 +92,7 @@ struct htv_tables_t {
 	int16_t lim_shape[HTV_LIM_W];
 
 	int16_t *nicam_taps;    int nicam_ntaps;
+	int16_t *nicam_tpad;                           /* 8 zeros, the pulse, zeros up to dp.nicam_tpad_len (multiple of 8) */
 	htv_c16_t *nicam_cc;    int nicam_cc_len;
 	uint8_t nicam_prn[90];
 

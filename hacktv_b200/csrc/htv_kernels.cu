@@ -46,6 +46,7 @@ struct DevTables {
 	const int32_t *afir_v, *afir_f;
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
+	const int16_t *nicam_tpad;
 	const htv_c16_t *nicam_cc;
 	const uint8_t *nicam_prn;
 	const uint8_t *offset_start;
@@ -507,8 +508,7 @@ struct __align__(16) LineAudio {
 	int seg_x[MAX_SEGS + 1];          // first sample (relative to the line) of each audio segment
 	int seg_am[MAX_SEGS];
 	int nseg, kk0, cc0, nsym;
-	short sym_x[MAX_SYMS];            // first sample of each symbol relative to the line
-	signed char sym_si[MAX_SYMS], sym_sq[MAX_SYMS];   // +-1 pulse polarity on I and Q
+	int sym[MAX_SYMS];                // per symbol: first sample relative to the line (x4, arithmetic), bit 0: I polarity +, bit 1: Q polarity +
 	int pad1[2];
 };
 
@@ -683,9 +683,7 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 			const int sy = (fst + dt.nic_local[s & (RS - 1)]) & 3;
 			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
 			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
-			la.sym_x[i] = (short) (pos - m0);
-			la.sym_si[i] = (code & 1) ? 1 : -1;
-			la.sym_sq[i] = (code & 2) ? 1 : -1;
+			la.sym[i] = (int) ((pos - m0) * 4) | (code & 3);
 			const int adv = (dp.nicam_F - rem + dp.nicam_D - 1) / dp.nicam_D;
 			pos += adv; rem += adv * dp.nicam_D - dp.nicam_F;
 			s++;
@@ -798,7 +796,7 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 		int4 *dst = reinterpret_cast<int4 *>(&li);
 		if(tid < (int) (sizeof(LineRaster) / 16)) dst[tid] = __ldg(src + tid);
 	}
-	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
+	if(tid < 128) reinterpret_cast<int4 *>(glut)[tid] = __ldg(reinterpret_cast<const int4 *>(dt.glut) + tid);
 	if(tid < 2 * UOFF)
 	{
 		// U,V outside the line read as zero (the reference filters each line on its own)
@@ -1258,11 +1256,10 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 	}
 	if(dp.have_nicam)
 	{
-		for(int i = tid; i < dp.nicam_tpad_len; i += blockDim.x)
-		{
-			const int d = i - NIC_TPAD;
-			ntp[i] = (d >= 0 && d < dp.nicam_ntaps) ? dt.nicam_taps[d] : (short) 0;
-		}
+		// the zero-padded pulse table (8 zeros, the pulse, zeros) is prepared on the host
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
 	{
 		// the launch's composite stream starts one line early: this line begins at (b + 1) * W
@@ -1338,35 +1335,37 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 		while(la.seg_x[sg0 + 1] <= x0) sg0++;
 		const int nb = la.seg_x[sg0 + 1];
 		const int sg1 = min(sg0 + 1, MAX_SEGS - 1);
+		const unsigned long long angA = la.seg_ang[sg0], angB = la.seg_ang[sg1];
+		unsigned long long phA = la.seg_phase[sg0] + angA * (unsigned long long) x0;
+		unsigned long long phB = la.seg_phase[sg1] + angB * (unsigned long long) x0;
+		unsigned long long phM = la.am_phase0 + dp.am_ang * (unsigned long long) (x0 + 1);
+		const int amA = (la.seg_am[sg0] + 32768) / 2, amB = (la.seg_am[sg1] + 32768) / 2;
 		int kk = la.kk0 + x0; if(kk >= 32767) kk -= 32767;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++, kk++)
 		{
-			const int x = x0 + k;
-			const int sg = x >= nb ? sg1 : sg0;
+			const bool second = x0 + k >= nb;
 			if(kk >= 32767) kk -= 32767;
 			// amplitude of the reference's Q31 phasor kk+1 multiplications after a renormalisation
 			const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
-			int addi = 0, addq = 0;
 			if(dp.have_fm)
 			{
-				const unsigned long long ph = la.seg_phase[sg] + la.seg_ang[sg] * (unsigned long long) x;
+				const unsigned long long ph = second ? phB : phA;
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
-				addi += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
-				addq += ((int) floorf(amp * sn) * dp.fm_level) >> 15;
+				oi[k] += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
+				oq[k] += ((int) floorf(amp * sn) * dp.fm_level) >> 15;
+				phA += angA; phB += angB;
 			}
 			if(dp.have_am)
 			{
-				const unsigned long long ph = la.am_phase0 + dp.am_ang * (unsigned long long) (x + 1);
 				float sn, cs;
-				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
-				const int smp = (la.seg_am[sg] + 32768) / 2;
-				addi += ((((int) floorf(amp * cs) * smp) >> 15) * dp.am_level) >> 15;
-				addq += ((((int) floorf(amp * sn) * smp) >> 15) * dp.am_level) >> 15;
+				__sincosf((float) (int) (phM >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+				const int smp = second ? amB : amA;
+				oi[k] += ((((int) floorf(amp * cs) * smp) >> 15) * dp.am_level) >> 15;
+				oq[k] += ((((int) floorf(amp * sn) * smp) >> 15) * dp.am_level) >> 15;
+				phM += dp.am_ang;
 			}
-			oi[k] = wrap16i(oi[k] + wrap16i(addi));
-			oq[k] = wrap16i(oq[k] + wrap16i(addq));
 		}
 	}
 
@@ -1375,19 +1374,20 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 		// the newest symbol started at or before the thread's last sample: estimate from the
 		// mean spacing, correct by one; then NIC_CAND symbols back cover all four samples
 		const int xl = x0 + SPT - 1;
-		int i3 = (int) ((float) (xl - la.sym_x[0]) * ((float) dp.nicam_D / (float) dp.nicam_F));
+		int i3 = (int) ((float) (xl - (la.sym[0] >> 2)) * ((float) dp.nicam_D / (float) dp.nicam_F));
 		i3 = max(0, min(la.nsym - 1, i3));
-		while(i3 + 1 < la.nsym && la.sym_x[i3 + 1] <= xl) i3++;
-		while(i3 > 0 && la.sym_x[i3] > xl) i3--;
+		while(i3 + 1 < la.nsym && (la.sym[i3 + 1] >> 2) <= xl) i3++;
+		while(i3 > 0 && (la.sym[i3] >> 2) > xl) i3--;
 		int bi[SPT] = { 0, 0, 0, 0 }, bq[SPT] = { 0, 0, 0, 0 };
 		#pragma unroll
 		for(int cnd = 0; cnd < NIC_CAND; cnd++)
 		{
 			const int i = i3 - cnd;
 			if(i < 0) break;
-			const int d0 = x0 - la.sym_x[i] + NIC_TPAD;        // the table is zero outside the pulse
+			const int sy = la.sym[i];
+			const int d0 = x0 - (sy >> 2) + NIC_TPAD;           // the table is zero outside the pulse
 			if(d0 < 0) continue;
-			const int si = la.sym_si[i], sq = la.sym_sq[i];
+			const int si = (sy & 1) ? 1 : -1, sq = (sy & 2) ? 1 : -1;
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
@@ -1396,16 +1396,24 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 				bq[k] += r * sq;
 			}
 		}
-		int ci = (la.cc0 + x0) % dp.nicam_cc_len;
+		int ci = la.cc0 + x0;
+		while(ci >= dp.nicam_cc_len) ci -= dp.nicam_cc_len;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
 			const htv_c16_t cc = dt.nicam_cc[ci];
 			if(++ci == dp.nicam_cc_len) ci = 0;
-			const int b0 = wrap16i(bi[k]), b1 = wrap16i(bq[k]);
-			oi[k] = wrap16i(oi[k] + ((b0 * cc.i - b1 * cc.q) >> 15));
-			oq[k] = wrap16i(oq[k] + ((b0 * cc.q + b1 * cc.i) >> 15));
+			// the overlap-add ring holds at most 7 pulses of < 2^11: it never wraps an int16
+			oi[k] += (bi[k] * cc.i - bq[k] * cc.q) >> 15;
+			oq[k] += (bi[k] * cc.q + bq[k] * cc.i) >> 15;
 		}
+	}
+
+	// every addition above is an int16 wrap-around addition in the reference; wrapping once is the same
+	if(dp.swap_iq || dp.have_offset)
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) { oi[k] = wrap16i(oi[k]); oq[k] = wrap16i(oq[k]); }
 	}
 
 	if(dp.swap_iq)
@@ -1539,6 +1547,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
 	dt.lim_shape = (const int16_t *) dev_copy(d, t->lim_shape, sizeof(t->lim_shape));
 	dt.nicam_taps = (const int16_t *) dev_copy(d, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
+	dt.nicam_tpad = (const int16_t *) dev_copy(d, t->nicam_tpad, t->nicam_tpad ? sizeof(int16_t) * ((t->dp.nicam_tpad_len + 7) & ~7) : 0);
 	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, sizeof(htv_c16_t) * t->nicam_cc_len);
 	dt.nicam_prn = (const uint8_t *) dev_copy(d, t->nicam_prn, sizeof(t->nicam_prn));
 	dt.offset_start = (const uint8_t *) dev_copy(d, t->offset_start, t->offset_start ? 32768 : 0);

@@ -595,6 +595,9 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		 * out to the farthest offset 7 overlapping symbols + 4 samples can ask for */
 		dp->nicam_tpad_len = 8 + 8 * (int) ((sample_rate + HTV_NICAM_SYMBOL_RATE - 1) / HTV_NICAM_SYMBOL_RATE) + 8;
 		if(dp->nicam_tpad_len < 8 + dp->nicam_ntaps + 8) dp->nicam_tpad_len = 8 + dp->nicam_ntaps + 8;
+		dp->nicam_tpad_len = (dp->nicam_tpad_len + 7) & ~7;
+		t->nicam_tpad = calloc(dp->nicam_tpad_len, sizeof(int16_t));
+		memcpy(t->nicam_tpad + 8, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
 		g = gcd64(sample_rate, freq);
 		t->nicam_cc_len = dp->nicam_cc_len = sample_rate / g;
 		t->nicam_cc = malloc(sizeof(htv_c16_t) * t->nicam_cc_len);
@@ -654,7 +657,7 @@ void htv_tables_free(htv_tables_t *t)
 {
 	if(!t) return;
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
-	free(t->fm_ang); free(t->nicam_taps); free(t->nicam_cc);
+	free(t->fm_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
 	free(t);
 }
