@@ -63,6 +63,7 @@ typedef struct {
 	int32_t have_am, am_level;
 	uint64_t am_ang;               /* carrier step, turns * 2^64 */
 	int32_t have_nicam, nicam_ntaps, nicam_F, nicam_D, nicam_cc_len, nicam_tpad_len;
+	int32_t nicam_sps, nicam_minor_short, nicam_lut_ok, nicam_pad2;
 
 	/* SECAM */
 	int32_t secam_level, secam_dmin[2], secam_dmax[2], secam_pad;
@@ -92,6 +93,7 @@ struct htv_tables_t {
 	int16_t lim_shape[HTV_LIM_W];
 
 	int16_t *nicam_taps;    int nicam_ntaps;
+	int16_t *nicam_lut;     int nicam_lut_len;     /* pulse-shaping table, see htv_tables.c */
 	int16_t *nicam_tpad;                           /* 8 zeros, the pulse, zeros up to dp.nicam_tpad_len (multiple of 8) */
 	htv_c16_t *nicam_cc;    int nicam_cc_len;
 	uint8_t nicam_prn[90];

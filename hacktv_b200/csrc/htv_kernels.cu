@@ -47,6 +47,7 @@ struct DevTables {
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
 	const int16_t *nicam_tpad;
+	const int16_t *nicam_lut;
 	const htv_c16_t *nicam_cc;
 	const uint8_t *nicam_prn;
 	const uint8_t *offset_start;
@@ -508,6 +509,7 @@ struct __align__(16) LineAudio {
 	int seg_x[MAX_SEGS + 1];          // first sample (relative to the line) of each audio segment
 	int seg_am[MAX_SEGS];
 	int nseg, kk0, cc0, nsym;
+	int symrow[MAX_SYMS];             // pulse-table rows: I row | Q row << 16, or -1 (use the generic sum)
 	int sym[MAX_SYMS];                // per symbol: first sample relative to the line (x4, arithmetic), bit 0: I polarity +, bit 1: Q polarity +
 	int pad1[2];
 };
@@ -673,19 +675,40 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 		const int64_t sfirst = (int64_t) (((unsigned long long) max((int64_t) 0, m0 - dp.nicam_ntaps) * dp.nicam_D) / dp.nicam_F);
 		const int64_t slast = (int64_t) (((unsigned long long) (m0 + W - 1) * dp.nicam_D) / dp.nicam_F);
 		const int ns = (int) min((int64_t) MAX_SYMS, slast - sfirst + 1);
-		// walk the symbols incrementally: pos = ceil(s * F / D), rem = pos * D - s * F
-		int64_t s = sfirst, k = s / 364, pos = nic_sym_pos(s, dp.nicam_F, dp.nicam_D);
+		// walk the symbols incrementally: pos = ceil(s * F / D), rem = pos * D - s * F. Start 5
+		// symbols early to know the polarities / spacings behind the first listed one.
+		const int lead = (int) min((int64_t) 5, sfirst);
+		int64_t s = sfirst - lead, k = s / 364, pos = nic_sym_pos(s, dp.nicam_F, dp.nicam_D);
 		int ks = (int) (s - k * 364);
 		int rem = (int) (pos * dp.nicam_D - s * dp.nicam_F);
 		int fst = dt.nic_fstart[k & (RF - 1)];
-		for(int i = 0; i < ns; i++)
+		int patI = 0, patQ = 0, gaps = 0, prev_adv = 0;
+		for(int i = -lead; i < ns; i++)
 		{
 			const int sy = (fst + dt.nic_local[s & (RS - 1)]) & 3;
 			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
 			const int code = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
-			la.sym[i] = (int) ((pos - m0) * 4) | (code & 3);
+			patI = ((patI << 1) | (code & 1)) & 63;
+			patQ = ((patQ << 1) | ((code >> 1) & 1)) & 63;
+			if(i > -lead || s > 0)
+			{
+				const int minor = dp.nicam_minor_short ? prev_adv == dp.nicam_sps - 1 : prev_adv == dp.nicam_sps;
+				gaps = ((gaps << 1) | (s > 0 ? minor : 0)) & 31;
+			}
+			if(i >= 0)
+			{
+				la.sym[i] = (int) ((pos - m0) * 4) | (code & 3);
+				int row = -1;
+				if(dp.nicam_lut_ok && s >= 5 && __popc(gaps) <= 1)
+				{
+					const int g = gaps ? 1 + (31 - __clz(gaps & -gaps)) : 0;   // which gap (1 = newest) has the rarer spacing
+					row = (g * 64 + patI) | ((g * 64 + patQ) << 16);
+				}
+				la.symrow[i] = row;
+			}
 			const int adv = (dp.nicam_F - rem + dp.nicam_D - 1) / dp.nicam_D;
 			pos += adv; rem += adv * dp.nicam_D - dp.nicam_F;
+			prev_adv = adv;
 			s++;
 			if(++ks == 364) { ks = 0; k++; fst = dt.nic_fstart[k & (RF - 1)]; }
 		}
@@ -1372,28 +1395,51 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 	if(dp.have_nicam)
 	{
 		// the newest symbol started at or before the thread's last sample: estimate from the
-		// mean spacing, correct by one; then NIC_CAND symbols back cover all four samples
+		// mean spacing, correct by one
 		const int xl = x0 + SPT - 1;
 		int i3 = (int) ((float) (xl - (la.sym[0] >> 2)) * ((float) dp.nicam_D / (float) dp.nicam_F));
 		i3 = max(0, min(la.nsym - 1, i3));
 		while(i3 + 1 < la.nsym && (la.sym[i3 + 1] >> 2) <= xl) i3++;
 		while(i3 > 0 && (la.sym[i3] >> 2) > xl) i3--;
-		int bi[SPT] = { 0, 0, 0, 0 }, bq[SPT] = { 0, 0, 0, 0 };
-		#pragma unroll
-		for(int cnd = 0; cnd < NIC_CAND; cnd++)
+		const int sx3 = la.sym[i3] >> 2;
+		const int i2 = max(i3 - 1, 0);
+		const int r3 = la.symrow[i3], r2 = la.symrow[i2];
+		int bi[SPT], bq[SPT];
+		if((r3 | r2) >= 0)
 		{
-			const int i = i3 - cnd;
-			if(i < 0) break;
-			const int sy = la.sym[i];
-			const int d0 = x0 - (sy >> 2) + NIC_TPAD;           // the table is zero outside the pulse
-			if(d0 < 0) continue;
-			const int si = (sy & 1) ? 1 : -1, sq = (sy & 2) ? 1 : -1;
+			// pulse-shaping table: one entry per sample and channel (htv_tables.c)
+			const int sx2 = la.sym[i2] >> 2;
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
-				const int r = ntp[d0 + k];
-				bi[k] += r * si;
-				bq[k] += r * sq;
+				const int x = x0 + k;
+				const bool cur = x >= sx3;
+				const int rows = cur ? r3 : r2;
+				const int phi = x - (cur ? sx3 : sx2);
+				bi[k] = __ldg(dt.nicam_lut + (rows & 0xFFFF) * dp.nicam_sps + phi);
+				bq[k] = __ldg(dt.nicam_lut + (rows >> 16) * dp.nicam_sps + phi);
+			}
+		}
+		else
+		{
+			// generic sum over the symbols whose pulse covers the samples (stream start, unusual rates)
+			#pragma unroll
+			for(int k = 0; k < SPT; k++) { bi[k] = 0; bq[k] = 0; }
+			for(int cnd = 0; cnd < NIC_CAND; cnd++)
+			{
+				const int i = i3 - cnd;
+				if(i < 0) break;
+				const int sy = la.sym[i];
+				const int d0 = x0 - (sy >> 2) + NIC_TPAD;           // the table is zero outside the pulse
+				if(d0 < 0) continue;
+				const int si = (sy & 1) ? 1 : -1, sq = (sy & 2) ? 1 : -1;
+				#pragma unroll
+				for(int k = 0; k < SPT; k++)
+				{
+					const int r = ntp[d0 + k];
+					bi[k] += r * si;
+					bq[k] += r * sq;
+				}
 			}
 		}
 		int ci = la.cc0 + x0;
@@ -1547,6 +1593,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
 	dt.lim_shape = (const int16_t *) dev_copy(d, t->lim_shape, sizeof(t->lim_shape));
 	dt.nicam_taps = (const int16_t *) dev_copy(d, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
+	dt.nicam_lut = (const int16_t *) dev_copy(d, t->nicam_lut, t->nicam_lut ? sizeof(int16_t) * (t->nicam_lut_len + 8) : 0);
 	dt.nicam_tpad = (const int16_t *) dev_copy(d, t->nicam_tpad, t->nicam_tpad ? sizeof(int16_t) * ((t->dp.nicam_tpad_len + 7) & ~7) : 0);
 	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, sizeof(htv_c16_t) * t->nicam_cc_len);
 	dt.nicam_prn = (const uint8_t *) dev_copy(d, t->nicam_prn, sizeof(t->nicam_prn));

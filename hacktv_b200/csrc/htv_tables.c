@@ -595,6 +595,40 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		 * out to the farthest offset 7 overlapping symbols + 4 samples can ask for */
 		dp->nicam_tpad_len = 8 + 8 * (int) ((sample_rate + HTV_NICAM_SYMBOL_RATE - 1) / HTV_NICAM_SYMBOL_RATE) + 8;
 		if(dp->nicam_tpad_len < 8 + dp->nicam_ntaps + 8) dp->nicam_tpad_len = 8 + dp->nicam_ntaps + 8;
+		{
+			/* Pulse-shaping table. Symbols start every sps or sps-1 samples (ref nicam728.c:399-407)
+			 * and the pulse spans < 6 symbol periods, so a sample's baseband value is decided by
+			 * its offset into the current symbol, the polarities of the 6 latest symbols and where
+			 * (if anywhere) the rarer of the two spacings occurs among the 5 gaps between them:
+			 *   lut[(g * 64 + pattern) * sps + phi],  g = 0 none, 1..5 = that gap (1 = newest)
+			 * pattern bit j = polarity of the j-th latest symbol (1 = +). Exact integers. */
+			const int sps_i = (int) ((sample_rate + HTV_NICAM_SYMBOL_RATE - 1) / HTV_NICAM_SYMBOL_RATE);
+			const int64_t gg = gcd64(sample_rate, HTV_NICAM_SYMBOL_RATE);
+			const int D = (int) (HTV_NICAM_SYMBOL_RATE / gg), F = (int) (sample_rate / gg);
+			const int nshort = sps_i * D - F;              /* gaps of sps-1 per D symbols */
+			const int minor_is_short = nshort * 2 <= D;
+			const int nminor = minor_is_short ? nshort : D - nshort;
+			dp->nicam_sps = sps_i;
+			dp->nicam_minor_short = minor_is_short;
+			dp->nicam_lut_ok = nminor * 5 < D && t->nicam_ntaps <= 6 * (sps_i - 1) && sps_i >= 8;
+			if(dp->nicam_lut_ok)
+			{
+				const int major = minor_is_short ? sps_i : sps_i - 1, minor = minor_is_short ? sps_i - 1 : sps_i;
+				int gi, pat, phi, j;
+				t->nicam_lut_len = 6 * 64 * sps_i;
+				t->nicam_lut = calloc(t->nicam_lut_len + 8, sizeof(int16_t));
+				for(gi = 0; gi < 6; gi++) for(pat = 0; pat < 64; pat++) for(phi = 0; phi < sps_i; phi++)
+				{
+					int off = 0, v = 0;
+					for(j = 0; j < 6; j++)
+					{
+						if(j > 0) off += (gi == j) ? minor : major;
+						if(phi + off < t->nicam_ntaps) v += ((pat >> j) & 1) ? t->nicam_taps[phi + off] : -t->nicam_taps[phi + off];
+					}
+					t->nicam_lut[(gi * 64 + pat) * sps_i + phi] = (int16_t) v;
+				}
+			}
+		}
 		dp->nicam_tpad_len = (dp->nicam_tpad_len + 7) & ~7;
 		t->nicam_tpad = calloc(dp->nicam_tpad_len, sizeof(int16_t));
 		memcpy(t->nicam_tpad + 8, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
@@ -657,7 +691,7 @@ void htv_tables_free(htv_tables_t *t)
 {
 	if(!t) return;
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
-	free(t->fm_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_cc);
+	free(t->fm_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
 	free(t);
 }
