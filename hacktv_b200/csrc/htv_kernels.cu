@@ -118,6 +118,9 @@ struct htv_dev_t {
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
 	size_t sec_smem;
+	int *d_comp32;                    // int32 composite scratch for the TMA-fed modulator (4 | W, not SECAM)
+	size_t modt_smem;
+	int mod_grid;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
 	int sub_lines;
 	size_t raster_smem, mod_smem;
@@ -802,7 +805,7 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 // ---------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(384, 4)
-k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp)
+k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int *comp32)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -908,6 +911,13 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 		}
 	}
 	if(x0 >= W) return;
+	if(comp32)
+	{
+		// int32 stream for the TMA-fed modulator (values are int16-wrapped as the reference's buffer is)
+		*reinterpret_cast<int4 *>(comp32 + (size_t) blockIdx.x * W + x0) =
+			make_int4(wrap16i(val[0]), wrap16i(val[1]), wrap16i(val[2]), wrap16i(val[3]));
+		return;
+	}
 	int16_t *o = comp + (size_t) blockIdx.x * W + x0;
 	if((W & 3) == 0)
 	{
@@ -1259,73 +1269,21 @@ __global__ void k_secam_carry(SecScratch ss, int idx, int pass_final)
 // and writes int16 IQ with 128-bit streaming stores.
 // ---------------------------------------------------------------------------
 
-template<int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int16_t *out)
+// Everything k_mod does for 4 consecutive samples once the composite window is in shared
+// memory. cwin[j] = composite sample x0 - 25 - CSKEW + j (16-byte aligned).
+template<int CSKEW>
+__device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
+	const int *cwin, const short *ntp, int x0, int row, int16_t *out)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
-	const int W4 = (W + 3) & ~3;
-	const int CW = W4 + 2 * EXT + 16;
-	int *cw = reinterpret_cast<int *>(smem_raw);                    // index = x + COFF
-	short *ntp = reinterpret_cast<short *>(cw + CW);                // padded NICAM pulse table
-	__shared__ LineAudio la;
-	const int tid = threadIdx.x;
-
-	{
-		const int4 *sa = reinterpret_cast<const int4 *>(lap + blockIdx.x);
-		int4 *da = reinterpret_cast<int4 *>(&la);
-		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
-	}
-	if(dp.have_nicam)
-	{
-		// the zero-padded pulse table (8 zeros, the pulse, zeros) is prepared on the host
-		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
-		int4 *dst = reinterpret_cast<int4 *>(ntp);
-		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
-	}
-	{
-		// the launch's composite stream starts one line early: this line begins at (b + 1) * W
-		const int16_t *cs = comp + ((size_t) blockIdx.x + 1) * W;
-		const int nquads = (W4 + 2 * EXT) / 4;
-		for(int q = tid; q < nquads; q += blockDim.x)
-		{
-			const int xe0 = q * 4 - EXT;
-			int v[4];
-			if((W & 3) == 0)
-			{
-				const int2 p = __ldg(reinterpret_cast<const int2 *>(cs + xe0));
-				v[0] = (int) (short) p.x; v[1] = p.x >> 16; v[2] = (int) (short) p.y; v[3] = p.y >> 16;
-			}
-			else
-			{
-				#pragma unroll
-				for(int k = 0; k < 4; k++) v[k] = __ldg(cs + xe0 + k);
-			}
-			if(sadd)
-			{
-				// SECAM: the subcarrier samples k_secam_seq produced for the same stream positions
-				const int16_t *sa = sadd + ((size_t) blockIdx.x + 1) * W + xe0;
-				#pragma unroll
-				for(int k = 0; k < 4; k++) v[k] = wrap16i(v[k] + __ldg(sa + k));
-			}
-			#pragma unroll
-			for(int k = 0; k < 4; k++) cw[xe0 + k + COFF] = v[k];
-		}
-	}
-	__syncthreads();
-
-	const int x0 = tid * SPT;
-	if(x0 >= W) return;
-
 	int oi[SPT], oq[SPT];
 	if(dp.vf_type)
 	{
 		// c[j] = composite sample x0 - 25 + j
-		int c[SPT + 2 * HALO + 2];
-		const int4 *pc = reinterpret_cast<const int4 *>(cw + x0 + COFF - HALO);
+		int c[(SPT + 2 * HALO + 2 + CSKEW + 3) / 4 * 4];
+		const int4 *pc = reinterpret_cast<const int4 *>(cwin);
 		#pragma unroll
-		for(int i = 0; i < (SPT + 2 * HALO + 2) / 4; i++)
+		for(int i = 0; i < (SPT + 2 * HALO + 2 + CSKEW + 3) / 4; i++)
 		{
 			const int4 a = pc[i];
 			c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
@@ -1333,13 +1291,13 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
-			int ai = c[k + HALO] * dp.vf_i[HALO], aq = 0;
+			int ai = c[k + HALO + CSKEW] * dp.vf_i[HALO], aq = 0;
 			// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
 			#pragma unroll
 			for(int y = 0; y < HALO; y++)
 			{
-				ai += (c[k + y] + c[k + 2 * HALO - y]) * dp.vf_i[y];
-				aq += (c[k + y] - c[k + 2 * HALO - y]) * dp.vf_q[y];
+				ai += (c[k + y + CSKEW] + c[k + 2 * HALO - y + CSKEW]) * dp.vf_i[y];
+				aq += (c[k + y + CSKEW] - c[k + 2 * HALO - y + CSKEW]) * dp.vf_q[y];
 			}
 			oi[k] = sat16i(ai >> 15);
 			oq[k] = sat16i(aq >> 15);                               // vf_q is all zero for the real low-pass
@@ -1348,7 +1306,7 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 	else
 	{
 		#pragma unroll
-		for(int k = 0; k < SPT; k++) { oi[k] = cw[x0 + k + COFF]; oq[k] = 0; }
+		for(int k = 0; k < SPT; k++) { oi[k] = cwin[k + HALO + CSKEW]; oq[k] = 0; }
 	}
 
 	if(dp.have_fm || dp.have_am)
@@ -1495,7 +1453,7 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 	}
 
 	// ---- store (ref rf_file.c:97-116, 226-233 layout) ------------------------
-	const size_t lbase = (size_t) blockIdx.x * (size_t) W;
+	const size_t lbase = (size_t) row * (size_t) W;
 	if(dp.complex_out)
 	{
 		int16_t *o = out + (lbase + x0) * 2;
@@ -1532,6 +1490,158 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 			#pragma unroll
 			for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) oi[k];
 		}
+	}
+}
+
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int16_t *out)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int W4 = (W + 3) & ~3;
+	const int CW = W4 + 2 * EXT + 16;
+	int *cw = reinterpret_cast<int *>(smem_raw);                    // index = x + COFF
+	short *ntp = reinterpret_cast<short *>(cw + CW);                // padded NICAM pulse table
+	__shared__ LineAudio la;
+	const int tid = threadIdx.x;
+
+	{
+		const int4 *sa = reinterpret_cast<const int4 *>(lap + blockIdx.x);
+		int4 *da = reinterpret_cast<int4 *>(&la);
+		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
+	}
+	if(dp.have_nicam)
+	{
+		// the zero-padded pulse table (8 zeros, the pulse, zeros) is prepared on the host
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	{
+		// the launch's composite stream starts one line early: this line begins at (b + 1) * W
+		const int16_t *cs = comp + ((size_t) blockIdx.x + 1) * W;
+		const int nquads = (W4 + 2 * EXT) / 4;
+		for(int q = tid; q < nquads; q += blockDim.x)
+		{
+			const int xe0 = q * 4 - EXT;
+			int v[4];
+			if((W & 3) == 0)
+			{
+				const int2 p = __ldg(reinterpret_cast<const int2 *>(cs + xe0));
+				v[0] = (int) (short) p.x; v[1] = p.x >> 16; v[2] = (int) (short) p.y; v[3] = p.y >> 16;
+			}
+			else
+			{
+				#pragma unroll
+				for(int k = 0; k < 4; k++) v[k] = __ldg(cs + xe0 + k);
+			}
+			if(sadd)
+			{
+				// SECAM: the subcarrier samples k_secam_seq produced for the same stream positions
+				const int16_t *sa = sadd + ((size_t) blockIdx.x + 1) * W + xe0;
+				#pragma unroll
+				for(int k = 0; k < 4; k++) v[k] = wrap16i(v[k] + __ldg(sa + k));
+			}
+			#pragma unroll
+			for(int k = 0; k < 4; k++) cw[xe0 + k + COFF] = v[k];
+		}
+	}
+	__syncthreads();
+
+	const int x0 = tid * SPT;
+	if(x0 >= W) return;
+
+	mod_body<0>(dp, dt, la, cw + x0 + COFF - HALO, ntp, x0, (int) blockIdx.x, out);
+}
+
+// ---------------------------------------------------------------------------
+// Persistent modulator: one CTA per SM slot loops over scan lines; the next line's composite
+// window (int32, written by k_raster) and its LineAudio descriptor are fetched by the TMA
+// (cp.async.bulk global -> shared, mbarrier completion) into the other half of a double
+// buffer while the current line is computed, so no thread spends instructions on staging
+// and the load latency is hidden. Used whenever 4 | W (16-byte alignment of every window).
+// ---------------------------------------------------------------------------
+
+#define TOFF 28                       // window index = x + TOFF; the filter reads from x0 + (TOFF - 25 - 3)
+#define TWIN(W) ((W) + 2 * TOFF + 4)  // ints per window (multiple of 4)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return((unsigned) __cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void tma_load(void *dst_smem, const void *src_gmem, unsigned bytes, void *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}"
+		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int *comp32, int nlines, int16_t *out)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int NW = TWIN(W);
+	int *cwb[2];
+	LineAudio *lab[2];
+	cwb[0] = reinterpret_cast<int *>(smem_raw);
+	cwb[1] = cwb[0] + NW;
+	lab[0] = reinterpret_cast<LineAudio *>(cwb[1] + NW);
+	lab[1] = lab[0] + 1;
+	short *ntp = reinterpret_cast<short *>(lab[1] + 1);
+	__shared__ __align__(8) unsigned long long bar[2];
+	const int tid = threadIdx.x;
+	const unsigned bytes = (unsigned) (NW * sizeof(int) + sizeof(LineAudio));
+
+	if(dp.have_nicam)
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	if(tid == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[0])));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[1])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	int row = blockIdx.x;
+	if(tid == 0 && row < nlines)
+	{
+		// the launch's composite stream starts one line early: line `row` begins at (row + 1) * W
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(bytes) : "memory");
+		tma_load(cwb[0], comp32 + ((size_t) row + 1) * W - TOFF, NW * sizeof(int), &bar[0]);
+		tma_load(lab[0], lap + row, sizeof(LineAudio), &bar[0]);
+	}
+	unsigned phase[2] = { 0, 0 };
+	for(int it = 0; row < nlines; it++, row += gridDim.x)
+	{
+		const int cb = it & 1, nb = cb ^ 1;
+		const int nrow = row + gridDim.x;
+		if(tid == 0 && nrow < nlines)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(bytes) : "memory");
+			tma_load(cwb[nb], comp32 + ((size_t) nrow + 1) * W - TOFF, NW * sizeof(int), &bar[nb]);
+			tma_load(lab[nb], lap + nrow, sizeof(LineAudio), &bar[nb]);
+		}
+		mbar_wait(&bar[cb], phase[cb]);
+		phase[cb] ^= 1;
+		const int x0 = tid * SPT;
+		if(x0 < W) mod_body<3>(dp, dt, *lab[cb], cwb[cb] + x0, ntp, x0, row, out);
+		__syncthreads();                                            // everyone is done with this half before it is refilled
 	}
 }
 
@@ -1662,6 +1772,22 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		htv_dev_destroy(d);
 		return(NULL);
 	}
+	if(!secam && (W & 3) == 0)
+	{
+		int nsm = 148;
+		cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+		d->modt_smem = sizeof(int) * 2 * TWIN(W) + 2 * sizeof(LineAudio) + sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
+		if(cudaMalloc((void **) &d->d_comp32, sizeof(int) * (((size_t) d->sub_lines + 3) * W + 256)) != cudaSuccess)
+		{
+			snprintf(err, errlen, "device allocation failed");
+			htv_dev_destroy(d);
+			return(NULL);
+		}
+		cudaMemset(d->d_comp32, 0, sizeof(int) * (((size_t) d->sub_lines + 3) * W + 256));
+		cudaFuncSetAttribute(k_mod_tma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
+		cudaFuncSetAttribute(k_mod_tma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
+		d->mod_grid = nsm * (d->line_threads <= 256 ? 4 : 2);
+	}
 	if(secam)
 	{
 		const size_t rows = (size_t) d->sub_lines + 3;
@@ -1700,7 +1826,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	cudaSetDevice(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	free(d);
@@ -1839,11 +1965,17 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else
 		{
 			// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
-			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp);
+			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32);
 			d->launches++;
 		}
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
-		if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
+		if(d->d_comp32)
+		{
+			const int grid = n < d->mod_grid ? n : d->mod_grid;
+			if(d->line_threads <= 256) k_mod_tma<256, 4><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o);
+			else k_mod_tma<384, 2><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o);
+		}
+		else if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
 		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
 		d->launches++;
 		if(last) d->last_mod_lines = n;
