@@ -1190,20 +1190,124 @@ __device__ __forceinline__ SecSmem sec_smem(const htv_dparams_t &dp, unsigned ch
 	return(sm);
 }
 
-#define SEC_RUN 8                     // lines a warp renders in sequence in the first pass ...
+#define SEC_RUN 4                     // lines a thread renders in sequence in the first pass ...
 #define SEC_WARM 8                    // ... after this many warm-up lines (state only, nothing written)
+#define SEC_MAXW 1536
 
-// Pass 0: each warp walks a run of consecutive lines, so the state it hands from line to line
-// is exact inside the run; only the run's starting state is a guess, tightened by warm-up
-// lines (the dependence on the incoming state contracts by roughly 3x per line).
+// The same line computation for ONE THREAD (one line per lane): used by pass 0, where 32 runs
+// advance in lock-step per warp. Written for instruction-level parallelism - the only serial
+// parts are the two recurrences (2 dependent fp64 ops, resp. a 64-bit multiply-add, per sample);
+// conversions, rounding, table gathers and output scaling of neighbouring samples overlap them.
+__device__ __noinline__ SecState secam_line_lane(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
+	const SecScratch &ss, int c, const SecState &in, bool commit, short *y)
+{
+	const int W = dp.W;
+	SecState out = in;
+	if(li.sec_clear) { out.A = 0; out.B = 0; }
+	if(!li.sec_proc) return(out);
+
+	const int A = out.A, B = out.B;
+	const int16_t *cb = ss.cb + (size_t) c * W;
+	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
+	double ix = out.ix, iy = out.iy;
+	const int Wm = (W - 8) & ~3;                                     // the last outputs need the aliased words
+	for(int x = 0; x < Wm; x += 4)
+	{
+		const short2 p0 = *reinterpret_cast<const short2 *>(cb + x), p1 = *reinterpret_cast<const short2 *>(cb + x + 2);
+		const double x0 = (double) p0.x, x1 = (double) p0.y, x2 = (double) p1.x, x3 = (double) p1.y;
+		const double t0 = __dadd_rn(__dmul_rn(x0, dp.iir_b0), __dmul_rn(ix, dp.iir_b1));
+		const double t1 = __dadd_rn(__dmul_rn(x1, dp.iir_b0), __dmul_rn(x0, dp.iir_b1));
+		const double t2 = __dadd_rn(__dmul_rn(x2, dp.iir_b0), __dmul_rn(x1, dp.iir_b1));
+		const double t3 = __dadd_rn(__dmul_rn(x3, dp.iir_b0), __dmul_rn(x2, dp.iir_b1));
+		const double y0 = __dadd_rn(t0, -__dmul_rn(iy, dp.iir_a1));
+		const double y1 = __dadd_rn(t1, -__dmul_rn(y0, dp.iir_a1));
+		const double y2 = __dadd_rn(t2, -__dmul_rn(y1, dp.iir_a1));
+		const double y3 = __dadd_rn(t3, -__dmul_rn(y2, dp.iir_a1));
+		iy = y3; ix = x3;
+		y[x + 0] = (short) round_away(fmin(fmax(y0, -32768.0), 32767.0));
+		y[x + 1] = (short) round_away(fmin(fmax(y1, -32768.0), 32767.0));
+		y[x + 2] = (short) round_away(fmin(fmax(y2, -32768.0), 32767.0));
+		y[x + 3] = (short) round_away(fmin(fmax(y3, -32768.0), 32767.0));
+	}
+	for(int x = Wm; x < W; x++)
+	{
+		int v = cb[x];
+		if(x >= W - 7)
+		{
+			int acc = tail[x - (W - 7)];
+			const int kA = W - x + 7, kB = W + 1 - x + 7;
+			if(kA <= 14) acc += A * dp.secam_lpf[kA];
+			if(kB <= 14) acc += B * dp.secam_lpf[kB];
+			v = sat16i(acc >> 15);
+		}
+		const double xin = (double) v;
+		iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
+		ix = xin;
+		y[x] = (short) round_away(fmin(fmax(iy, -32768.0), 32767.0));
+	}
+	out.ix = ix; out.iy = iy;
+	y[W] = (short) A; y[W + 1] = (short) B;
+
+	const int sl = dp.burst_left, sr = li.sec_sr;
+	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+	int16_t *add = ss.add + (size_t) c * W;
+	const bool wr = commit && li.valid;
+	htv_c32_t m[8];
+	htv_c16_t g[8];
+	#pragma unroll
+	for(int k = 0; k < 8; k++)
+	{
+		int sv = sl + k < sr ? y[sl + k] : 0;
+		sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
+		m[k] = dt.secam_fm_lut[sv + 32768];
+		g[k] = dt.secam_bell[(unsigned short) sv];
+	}
+	for(int xb = sl; xb < sr; xb += 8)
+	{
+		htv_c32_t mn[8];
+		htv_c16_t gn[8];
+		#pragma unroll
+		for(int k = 0; k < 8; k++)                                  // gathers of the next block fly while this one is computed
+		{
+			int sv = xb + 8 + k < sr ? y[xb + 8 + k] : 0;
+			sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
+			mn[k] = dt.secam_fm_lut[sv + 32768];
+			gn[k] = dt.secam_bell[(unsigned short) sv];
+		}
+		#pragma unroll
+		for(int k = 0; k < 8; k++)
+		{
+			const int x = xb + k;
+			if(x < sr)
+			{
+				const long long ni = (long long) pi * m[k].i - (long long) pq * m[k].q;
+				const long long nq = (long long) pi * m[k].q + (long long) pq * m[k].i;
+				pi = (int) (ni >> 31); pq = (int) (nq >> 31);
+				const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g[k].i) >> 15)
+				                     - (((((pq >> 16) * dp.secam_level) >> 15) * g[k].q) >> 15));
+				if(x < W) { if(wr) add[x] = (int16_t) ((o * dt.burst_win[x - sl]) >> 15); }
+				else if(x == W) out.A = o;
+				else if(x == W + 1) out.B = o;
+			}
+		}
+		#pragma unroll
+		for(int k = 0; k < 8; k++) { m[k] = mn[k]; g[k] = gn[k]; }
+	}
+	return(out);
+}
+
+// Pass 0: each THREAD walks a run of consecutive lines (32 runs per warp in lock-step), so the
+// state handed from line to line is exact inside the run; only the run's starting state is a
+// guess, tightened by warm-up lines (the dependence on the incoming state contracts by roughly
+// 3x per line).
 __global__ void __launch_bounds__(32)
 k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const SecSmem sm = sec_smem(dp, smem_raw);
-	const int r = blockIdx.x;
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	const int c0 = r * SEC_RUN;
 	if(c0 >= n) return;
+	short y[SEC_MAXW + 16];
 	SecState st;
 	int c = c0 - SEC_WARM;
 	if(c <= 0) { c = 0; st = *ss.carry; }
@@ -1212,9 +1316,9 @@ k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 	for(; c < c1; c++)
 	{
 		const bool mine = c >= c0;
-		if(mine && threadIdx.x == 0) ss.used[c] = st;
-		st = secam_line_warp(dp, dt, lr[c], ss, c, st, mine, sm);
-		if(mine && threadIdx.x == 0) ss.st[0][c] = st;
+		if(mine) ss.used[c] = st;
+		st = secam_line_lane(dp, dt, lr[c], ss, c, st, mine, y);
+		if(mine) ss.st[0][c] = st;
 	}
 }
 
@@ -1764,7 +1868,8 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaFuncSetAttribute(k_mod<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->mod_smem);
 	// sub-batches keep the int16 composite scratch (2 B/sample) resident in the 126 MB L2
 	const bool secam = dp.colour_mode == HTV_SECAM;
-	d->sub_lines = ((secam ? 32 : 16) * 1024 * 1024) / (W * 2);
+	// SECAM: the cross-line chain is latency bound per launch, so one launch should cover the whole call
+	d->sub_lines = ((secam ? 160 : 16) * 1024 * 1024) / (W * 2);
 	if(d->sub_lines < 64) d->sub_lines = 64;
 	if(cudaMalloc((void **) &d->d_comp, sizeof(int16_t) * ((size_t) d->sub_lines + 3) * W + 256) != cudaSuccess)
 	{
@@ -1803,7 +1908,6 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		d->sec.claim = (int *) dev_zero(d, sizeof(int) * rows);
 		d->sec_passes = 64;
 		d->sec_smem = (size_t) (dp.burst_width + 2) * 12 + 2 * (((W + 7) & ~7) + ((W + 2 + 7) & ~7) + ((dp.burst_width + 2 + 7) & ~7)) + 64;
-		cudaFuncSetAttribute(k_secam_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
 		cudaFuncSetAttribute(k_secam_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
 		if(!d->sec.cb || !d->sec.y || !d->sec.add || !d->sec.flags)
 		{
@@ -1937,9 +2041,18 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			// fixed point every line was computed from its true predecessor state = the sequential
 			// result. The loop needs the change count on the host, so SECAM launches synchronise.
 			const int nch = n + 2;
+			cudaEvent_t dbg0 = NULL, dbg1 = NULL;
+			const bool dbg = getenv("HTV_DEBUG") != NULL;
+			if(dbg) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, st); }
 			cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
-			k_secam_runs<<<(nch + SEC_RUN - 1) / SEC_RUN, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch);
+			k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 31) / 32, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
 			d->launches += 2;
+			if(dbg)
+			{
+				float ms = 0;
+				cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1); cudaEventElapsedTime(&ms, dbg0, dbg1);
+				fprintf(stderr, "secam raster+pass0 for %d lines: %.3f ms\n", nch, ms);
+			}
 			int pass = 1, changed = 1;
 			for(; pass <= d->sec_passes && changed; pass++)
 			{
@@ -1951,7 +2064,12 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
 				changed = fl[0];
-				if(getenv("HTV_DEBUG")) fprintf(stderr, "secam pass %d: recomputed %d, output changed %d\n", pass, fl[2], fl[0]);
+				if(dbg)
+				{
+					float ms = 0;
+					cudaEventRecord(dbg0, st); cudaEventSynchronize(dbg0); cudaEventElapsedTime(&ms, dbg1, dbg0);
+					fprintf(stderr, "secam pass %d: recomputed %d, output changed %d, cumulative %.3f ms\n", pass, fl[2], fl[0], ms);
+				}
 			}
 			if(changed)
 			{
