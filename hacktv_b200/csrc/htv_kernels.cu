@@ -110,6 +110,9 @@ struct htv_dev_t {
 	uint64_t launches;
 	int timing;
 	cudaEvent_t ev0, ev1;
+	cudaStream_t side;                // audio-rate pre-pass + sound descriptors run here, beside the raster
+	cudaEvent_t ev_in, ev_audio;
+	int side_armed;
 	int ev_pending;
 	int line_threads;
 	size_t line_smem;
@@ -719,14 +722,20 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 	}
 }
 
-// descriptors for lines line0-1 .. line0+nlines (raster) and line0 .. line0+nlines-1 (audio)
-__global__ void k_line_desc(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
+// raster descriptors: index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
+__global__ void k_line_desc_r(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= nlines + 3) return;
-	// raster descriptor index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
 	line_raster(dp, dt, line0 - 2 + i, ld.r[i - 1]);
-	if(i >= 2 && i <= nlines + 1) line_audio(dp, dt, line0 - 2 + i, ld.a[i - 2]);
+}
+
+// sound-carrier descriptors for lines line0 .. line0+nlines-1 (needs the audio pre-pass results)
+__global__ void k_line_desc_a(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= nlines) return;
+	line_audio(dp, dt, line0 + i, ld.a[i]);
 }
 
 __device__ __forceinline__ int round_away(double v)
@@ -1922,6 +1931,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	}
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
+	cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
 	return(d);
 }
 
@@ -1933,6 +1945,9 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
+	if(d->ev_in) cudaEventDestroy(d->ev_in);
+	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
+	if(d->side) cudaStreamDestroy(d->side);
 	free(d);
 }
 
@@ -1968,8 +1983,13 @@ extern "C" int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm
 extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *stream)
 {
 	const htv_dparams_t &dp = d->dp;
-	cudaStream_t st = (cudaStream_t) stream;
 	if(m1 <= m0) return(HTV_OK);
+	// everything the caller queued so far (PCM uploads) precedes the pre-pass, which runs on the
+	// side stream so that it overlaps the raster kernels of the same call
+	CK(cudaEventRecord(d->ev_in, (cudaStream_t) stream));
+	CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+	d->side_armed = 1;
+	cudaStream_t st = d->side;
 	if(dp.have_fm)
 	{
 		const int64_t jA = d->fm_jc;                               // restart from the last valid prefix entry
@@ -2015,6 +2035,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	if(nlines > d->desc_cap)
 	{
 		cudaStreamSynchronize(st);
+		cudaStreamSynchronize(d->side);
 		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
 		d->d_desc_r = d->d_desc_a = NULL;
 		d->desc_cap = 0;
@@ -2023,8 +2044,17 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
-	k_line_desc<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
-	d->launches++;
+	k_line_desc_r<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
+	if(!d->side_armed)
+	{
+		CK(cudaEventRecord(d->ev_in, st));
+		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+	}
+	k_line_desc_a<<<(nlines + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0, nlines);
+	CK(cudaEventRecord(d->ev_audio, d->side));
+	d->side_armed = 0;
+	bool joined = false;
+	d->launches += 2;
 	for(int done = 0; done < nlines; done += d->sub_lines)
 	{
 		const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
@@ -2086,6 +2116,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32);
 			d->launches++;
 		}
+		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
 		if(d->d_comp32)
 		{

@@ -55,6 +55,9 @@ CASES = [
     ("secam", 16000000, 1300, dict(), 0),
     ("d", 16000000, 700, dict(vfilter=True), 1),
     ("secam-i", 16000000, 700, dict(vfilter=True, nonicam=True), 1),
+    ("i", 16000000, 700, dict(vfilter=True, swap_iq=True), 1),
+    ("i", 16000000, 700, dict(vfilter=True, invert_video=True, noaudio=True), 0),
+    ("i", 16000000, 700, dict(vfilter=True, level=0.7, volume=2.0), 1),
 ]
 
 
@@ -135,3 +138,14 @@ def test_secam_random_pictures_exact(built):
     want = o.render(1900)
     o.close()
     assert _diff(got, want).max() == 0
+
+
+def test_offset_mixer(built):
+    """--offset: the complex NCO multiply of ref video.c:3482-3515 incl. its INT16_MAX start-up
+    (the first 32767 samples are scaled to ~0). Closed-form NCO: +-1 LSB on top of the sound carriers'."""
+    got, want = _pair(built, "i", 16000000, 700, vfilter=True, offset=2000000)
+    d = _diff(got, want)
+    assert d.max() <= 2, f"max |diff| = {d.max()}"
+    assert (d <= 1).mean() > 0.999
+    got, want = _pair(built, "i", 16000000, 700, vfilter=True, offset=-3500000, noaudio=True)
+    assert _diff(got, want).max() <= 1
