@@ -244,7 +244,7 @@ def main():
     # ---- end to end through the C-ABI with host buffers ("e2e") -----------------
     e2e = None
     if not args.no_e2e:
-        e2e_frames = min(args.frames, 16)
+        e2e_frames = args.frames
         e2e_lines = e2e_frames * enc.lines
         enc2 = H.Encoder(conf, RATE)
         pic = torch.from_numpy(H.test_pattern(enc2.active_width, enc2.active_lines).astype(np.int32)).pin_memory()

@@ -35,9 +35,12 @@ struct htv_t {
 	int64_t audio_have;           /* source pairs uploaded so far (absolute count) */
 	int16_t *zeros;
 
-	/* htv_render_host staging */
-	int16_t *d_stage;
+	/* htv_render_host: two device staging buffers, rendering of one piece overlaps the
+	 * device-to-host copy of the previous one */
+	int16_t *d_stage[2];
 	size_t d_stage_bytes;
+	void *st_compute, *st_copy;
+	void *ev_rendered[2], *ev_copied[2];
 
 	/* htv_next_line view */
 	int16_t *h_frame;             /* pinned, one frame of output */
@@ -113,7 +116,11 @@ void htv_free(htv_t *s)
 	htv_av_close(&s->av);
 	if(s->dev)
 	{
-		htv_dev_free(s->dev, s->d_stage);
+		htv_dev_free(s->dev, s->d_stage[0]);
+		htv_dev_free(s->dev, s->d_stage[1]);
+		htv_dev_event_free(s->ev_rendered[0]); htv_dev_event_free(s->ev_rendered[1]);
+		htv_dev_event_free(s->ev_copied[0]); htv_dev_event_free(s->ev_copied[1]);
+		htv_dev_stream_free(s->st_compute); htv_dev_stream_free(s->st_copy);
 		htv_dev_destroy(s->dev);
 	}
 	htv_dev_free_pinned(s->h_frame);
@@ -291,24 +298,48 @@ int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cud
 	return(HTV_OK);
 }
 
+#define HOST_PIECE_BYTES (24u << 20)
+
 int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 {
-	size_t bytes;
-	int r;
+	const size_t line_bytes = (size_t) s->W * s->bps;
+	int piece = (int) (HOST_PIECE_BYTES / line_bytes), done = 0, p = 0, r, i;
 	if(!s || nlines < 0 || !h_out) return(HTV_ERROR);
-	bytes = (size_t) nlines * s->W * s->bps;
-	if(bytes > s->d_stage_bytes)
+	if(piece < 1) piece = 1;
+	if(piece > nlines) piece = nlines > 0 ? nlines : 1;
+	if((size_t) piece * line_bytes > s->d_stage_bytes)
 	{
-		htv_dev_free(s->dev, s->d_stage);
-		s->d_stage = htv_dev_alloc(s->dev, bytes);
-		s->d_stage_bytes = s->d_stage ? bytes : 0;
-		if(!s->d_stage) return(HTV_OUT_OF_MEMORY);
+		for(i = 0; i < 2; i++)
+		{
+			htv_dev_free(s->dev, s->d_stage[i]);
+			s->d_stage[i] = htv_dev_alloc(s->dev, (size_t) piece * line_bytes);
+			if(!s->d_stage[i]) { s->d_stage_bytes = 0; return(HTV_OUT_OF_MEMORY); }
+		}
+		s->d_stage_bytes = (size_t) piece * line_bytes;
 	}
-	r = htv_render(s, nlines, s->d_stage, nsamples, NULL);
+	if(!s->st_compute)
+	{
+		s->st_compute = htv_dev_stream_new();
+		s->st_copy = htv_dev_stream_new();
+		for(i = 0; i < 2; i++) { s->ev_rendered[i] = htv_dev_event_new(); s->ev_copied[i] = htv_dev_event_new(); }
+	}
+	for(; done < nlines; done += piece, p++)
+	{
+		const int n = nlines - done < piece ? nlines - done : piece, b = p & 1;
+		/* the staging buffer must have been copied out before it is rendered into again */
+		if(p >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(r);
+		r = htv_render(s, n, s->d_stage[b], NULL, s->st_compute);
+		if(r != HTV_OK) return(r);
+		if((r = htv_dev_event_record(s->ev_rendered[b], s->st_compute)) != HTV_OK) return(r);
+		if((r = htv_dev_stream_wait(s->st_copy, s->ev_rendered[b])) != HTV_OK) return(r);
+		r = htv_dev_memcpy_d2h(s->dev, (char *) h_out + (size_t) done * line_bytes, s->d_stage[b], (size_t) n * line_bytes, s->st_copy);
+		if(r != HTV_OK) return(r);
+		if((r = htv_dev_event_record(s->ev_copied[b], s->st_copy)) != HTV_OK) return(r);
+	}
+	if(nsamples) *nsamples = (size_t) nlines * s->W;
+	r = htv_dev_sync(s->dev, s->st_copy);
 	if(r != HTV_OK) return(r);
-	r = htv_dev_memcpy_d2h(s->dev, h_out, s->d_stage, bytes, NULL);
-	if(r != HTV_OK) return(r);
-	return(htv_dev_sync(s->dev, NULL));
+	return(htv_dev_sync(s->dev, s->st_compute));
 }
 
 htv_line_t *htv_next_line(htv_t *s)

@@ -141,6 +141,12 @@ extern void htv_dev_set_timing(htv_dev_t *d, int on);
 extern float htv_dev_last_line_ms(htv_dev_t *d);
 extern int htv_dev_last_line_count(const htv_dev_t *d);
 extern size_t htv_dev_audio_ring_pairs(void);
+extern void *htv_dev_stream_new(void);
+extern void htv_dev_stream_free(void *s);
+extern void *htv_dev_event_new(void);
+extern void htv_dev_event_free(void *e);
+extern int htv_dev_event_record(void *e, void *stream);
+extern int htv_dev_stream_wait(void *stream, void *e);
 
 #ifdef __cplusplus
 }

@@ -2146,6 +2146,14 @@ extern "C" int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size
 	return(HTV_OK);
 }
 
+// thin stream / event wrappers for the host layer's copy-compute pipeline
+extern "C" void *htv_dev_stream_new(void) { cudaStream_t s = NULL; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); return((void *) s); }
+extern "C" void htv_dev_stream_free(void *s) { if(s) cudaStreamDestroy((cudaStream_t) s); }
+extern "C" void *htv_dev_event_new(void) { cudaEvent_t e = NULL; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return((void *) e); }
+extern "C" void htv_dev_event_free(void *e) { if(e) cudaEventDestroy((cudaEvent_t) e); }
+extern "C" int htv_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return(HTV_OK); }
+extern "C" int htv_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return(HTV_OK); }
+
 extern "C" void *htv_dev_alloc(htv_dev_t *d, size_t bytes)
 {
 	void *p = NULL;
