@@ -11,7 +11,7 @@ RF channel on its own GPU (weak scaling, no collective on the data path); `value
 the sum over channels divided by the slowest rank's device time.
 
 Keys beyond the base contract:
-  roofline      HBM-write roofline of the dominant kernel (k_lines): algorithmic bytes
+  roofline      HBM-write roofline of the dominant kernel (k_mod_tma): algorithmic bytes
                 (4 B per complex sample) / CUDA-event duration of that kernel, vs the
                 measured copy bandwidth in MEASURED_PEAKS.json.
   e2e           the same metric through htv_render_host() with HOST buffers: every
@@ -39,6 +39,12 @@ MODE, RATE, FILTER = "i", 16_000_000, True
 WORKLOAD = "PAL-I (-m i) 16 Msps --filter: VSB + FM mono + NICAM-728 + colour, built-in test pattern"
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 REF_THREADS = 3          # main/raster + vfilter + audio (reference video.c:4692: 1 + nthreads)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_mod_tma launch (7 232 lines, 29.6 MB of IQ) from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_mod_raw.txt (38.48 MB read + 3.22 MB written: ncu
+# flushes L2 between replays, so the L2-resident composite scratch is re-read from HBM and most of the
+# output is still in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 41_701_120
+NCU_TRAFFIC_LINES = 7232
 
 
 def measured_peak_gbs():
@@ -299,7 +305,8 @@ def main():
                        "l2": f"each step writes {nsamp * 4 / 1e6:.0f} MB of IQ per GPU (> 126 MB L2); tables are L2-resident by design",
                        "realtime_x": round(value / world / (RATE / 1e6), 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
+                         "frac": round(achieved / peak, 4) if achieved else None,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if kern_lines == NCU_TRAFFIC_LINES else None,
                          "kernel": "k_mod (video filter + sound carriers + IQ store)", "kernel_ms": round(k_ms, 4),
                          "lines_per_launch": kern_lines, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_samples * 4,
