@@ -256,7 +256,7 @@ def main():
         pic = torch.from_numpy(H.test_pattern(enc2.active_width, enc2.active_lines).astype(np.int32)).pin_memory()
         tone = torch.from_numpy(H.test_tone()).pin_memory()
         # a live source: a new picture serial every frame -> one H2D upload per frame
-        enc2.set_source(pic.numpy().view(np.uint32)[None], tone.numpy(), audio_block=8192, static_video=False)
+        enc2.open_memory_source(pic.numpy().view(np.uint32)[None], tone.numpy(), audio_block=8192, static_video=False)
         host = torch.empty(e2e_lines * enc2.width * 2, dtype=torch.int16).pin_memory()
         for _ in range(max(1, args.warmup)):
             enc2.render_host_ptr(e2e_lines, host.data_ptr())
@@ -274,7 +274,7 @@ def main():
         e2e = {"value": round(world * e2e_samples * args.steps / tt.item() / 1e6, 2), "unit": "Msamples/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_samples * 4,
                "frames_per_step": e2e_frames, "checksum": int(host[:4096].to(torch.int32).sum().item()),
-               "api": "htv_render_host (C-ABI), pinned host buffers, one picture upload per frame"}
+               "api": "htv_av_memory_open + htv_render_host (C-ABI), pinned host buffers, one picture upload per frame"}
         enc2.close()
 
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")

@@ -71,6 +71,7 @@ class Frame(C.Structure):
 
 _READ_VIDEO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Frame))
 _READ_AUDIO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+_PASSTHRU_READ = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t)
 _CLOSE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
@@ -116,9 +117,15 @@ def lib() -> C.CDLL:
     L.htv_av.restype = C.POINTER(AV); L.htv_av.argtypes = [vp]
     L.htv_av_test_open.restype = C.c_int; L.htv_av_test_open.argtypes = [C.POINTER(AV)]
     L.htv_av_close.restype = None; L.htv_av_close.argtypes = [C.POINTER(AV)]
+    L.htv_av_memory_open.restype = C.c_int
+    L.htv_av_memory_open.argtypes = [C.POINTER(AV), vp, sz, vp, sz, sz, C.c_int]
     L.htv_next_line.restype = C.POINTER(Line); L.htv_next_line.argtypes = [vp]
     L.htv_render.restype = C.c_int; L.htv_render.argtypes = [vp, C.c_int, vp, C.POINTER(sz), vp]
     L.htv_render_host.restype = C.c_int; L.htv_render_host.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
+    L.htv_render_add.restype = C.c_int; L.htv_render_add.argtypes = [vp, C.c_int, vp, C.POINTER(sz), vp]
+    L.htv_mix_add.restype = C.c_int; L.htv_mix_add.argtypes = [vp, vp, sz, vp]
+    L.htv_set_passthru.restype = C.c_int; L.htv_set_passthru.argtypes = [vp, _PASSTHRU_READ, vp]
+    L.htv_passthru_delay_lines.restype = C.c_int; L.htv_passthru_delay_lines.argtypes = [vp]
     for f in ("htv_samples_per_line", "htv_active_width", "htv_active_lines", "htv_lines_per_frame",
               "htv_sample_rate", "htv_is_complex", "htv_bytes_per_sample"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
@@ -263,6 +270,24 @@ class Encoder:
             av.read_audio = cb
             self._keep += [cb, audio]
 
+    def open_memory_source(self, frames: np.ndarray | None, audio: np.ndarray | None, *, audio_block: int = 0,
+                           static_video: bool = False):
+        """htv_av_memory_open: the same as set_source but served by C code (no interpreter in the
+        per-frame path). Arrays must stay alive and unchanged in place; they are used as they are."""
+        fp, nf, ap, na = None, 0, None, 0
+        if frames is not None:
+            assert frames.dtype == np.uint32 and frames.flags["C_CONTIGUOUS"]
+            assert frames.shape[1:] == (self.active_lines, self.active_width), frames.shape
+            fp, nf = C.c_void_p(frames.ctypes.data), frames.shape[0]
+            self._keep.append(frames)
+        if audio is not None:
+            assert audio.dtype == np.int16 and audio.flags["C_CONTIGUOUS"] and audio.shape[1] == 2
+            ap, na = C.c_void_p(audio.ctypes.data), audio.shape[0]
+            self._keep.append(audio)
+        r = self._L.htv_av_memory_open(self._L.htv_av(self._h), fp, nf, ap, na, audio_block, int(static_video))
+        if r != HTV_OK:
+            raise RuntimeError("htv_av_memory_open failed")
+
     # ---- rendering -----------------------------------------------------
     def render(self, nlines: int, device_ptr: int, stream: int = 0) -> int:
         """htv_render: next nlines into DEVICE memory, asynchronous on `stream`."""
@@ -271,6 +296,36 @@ class Encoder:
         if r != HTV_OK:
             raise RuntimeError(f"htv_render failed ({r})")
         return n.value
+
+    def render_add(self, nlines: int, device_ptr: int, stream: int = 0) -> int:
+        """htv_render_add: next nlines ADDED (int16 wrap) into the stream already in DEVICE memory."""
+        n = C.c_size_t(0)
+        r = self._L.htv_render_add(self._h, nlines, C.c_void_p(device_ptr), C.byref(n), C.c_void_p(stream))
+        if r != HTV_OK:
+            raise RuntimeError(f"htv_render_add failed ({r})")
+        return n.value
+
+    def set_passthru(self, iq: np.ndarray):
+        """htv_set_passthru over an in-memory int16 [n, 2] stream (ref --passthru <file>)."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        assert iq.ndim == 2 and iq.shape[1] == 2
+        state = {"at": 0}
+
+        def read(ctx, dst, ncomplex):
+            n = min(int(ncomplex), iq.shape[0] - state["at"])
+            if n > 0:
+                C.memmove(dst, iq[state["at"]:].ctypes.data, n * 4)
+                state["at"] += n
+            return max(n, 0)
+        cb = _PASSTHRU_READ(read)
+        self._keep += [cb, iq]
+        r = self._L.htv_set_passthru(self._h, cb, None)
+        if r != HTV_OK:
+            raise RuntimeError("htv_set_passthru failed (it must precede the first rendered line)")
+
+    @property
+    def passthru_delay_lines(self) -> int:
+        return int(self._L.htv_passthru_delay_lines(self._h))
 
     def render_host(self, nlines: int, out: np.ndarray | None = None) -> np.ndarray:
         """htv_render_host: next nlines into host memory (what `-o file` would hold)."""
@@ -318,6 +373,13 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+
+def mix_add(acc_ptr: int, in_ptr: int, nvalues: int, stream: int = 0):
+    """htv_mix_add: acc[i] += in[i] (int16 wrap) over device memory."""
+    r = lib().htv_mix_add(C.c_void_p(acc_ptr), C.c_void_p(in_ptr), nvalues, C.c_void_p(stream))
+    if r != HTV_OK:
+        raise RuntimeError(f"htv_mix_add failed ({r})")
 
 
 def test_pattern(width: int, height: int) -> np.ndarray:

@@ -124,3 +124,63 @@ int htv_av_test_open(htv_av_t *av)
 	av->close = test_close;
 	return(HTV_OK);
 }
+
+/* ---- in-memory source ---------------------------------------------------
+ * Caller-owned pictures (RGBx, width x height each, used cyclically one per video frame)
+ * and 32 kHz stereo PCM (used cyclically, handed out `audio_block` pairs at a time).
+ * The C counterpart of what the tests install through Python callbacks; lets a host
+ * program (and bench.py's end-to-end leg) drive the encoder without an interpreter in
+ * the per-frame path. `static_video` keeps the picture serial constant (one upload). */
+typedef struct {
+	int width, height;
+	const uint32_t *frames;
+	size_t nframes, cur;
+	const int16_t *audio;
+	size_t audio_pairs, audio_block, audio_pos;
+	int static_video;
+	uint64_t serial;
+} mem_src_t;
+
+static int mem_read_video(void *ctx, htv_frame_t *frame)
+{
+	mem_src_t *s = ctx;
+	frame->width = s->width;
+	frame->height = s->height;
+	frame->framebuffer = s->frames + (size_t) s->width * s->height * s->cur;
+	s->cur = (s->cur + 1) % s->nframes;
+	frame->serial = s->static_video ? 1 : ++s->serial;
+	return(HTV_OK);
+}
+
+static int mem_read_audio(void *ctx, const int16_t **samples, size_t *npairs)
+{
+	mem_src_t *s = ctx;
+	size_t n = s->audio_block;
+	if(s->audio_pos + n > s->audio_pairs) n = s->audio_pairs - s->audio_pos;
+	*samples = s->audio + s->audio_pos * 2;
+	*npairs = n;
+	s->audio_pos += n;
+	if(s->audio_pos >= s->audio_pairs) s->audio_pos = 0;
+	return(HTV_OK);
+}
+
+static int mem_close(void *ctx) { free(ctx); return(HTV_OK); }
+
+int htv_av_memory_open(htv_av_t *av, const uint32_t *frames, size_t nframes,
+	const int16_t *audio, size_t audio_pairs, size_t audio_block, int static_video)
+{
+	mem_src_t *s;
+	if(!av || av->width < 1 || av->height < 1) return(HTV_ERROR);
+	s = calloc(1, sizeof(*s));
+	if(!s) return(HTV_OUT_OF_MEMORY);
+	s->width = av->width; s->height = av->height;
+	s->frames = frames; s->nframes = nframes;
+	s->audio = audio; s->audio_pairs = audio_pairs;
+	s->audio_block = audio_block && audio_block < audio_pairs ? audio_block : audio_pairs;
+	s->static_video = static_video;
+	av->ctx = s;
+	av->read_video = frames && nframes ? mem_read_video : NULL;
+	av->read_audio = audio && audio_pairs ? mem_read_audio : NULL;
+	av->close = mem_close;
+	return(HTV_OK);
+}

@@ -13,6 +13,7 @@
 
 #define MAX_FRAME_SLOTS 8
 #define MAX_CHUNK_SECONDS 4.0
+#define PT_MAX_LINES 4096
 
 struct htv_t {
 	htv_tables_t *tab;
@@ -34,6 +35,14 @@ struct htv_t {
 	/* audio */
 	int64_t audio_have;           /* source pairs uploaded so far (absolute count) */
 	int16_t *zeros;
+
+	/* channel combiner (ref --passthru, video.c:3517-3541, 4607-4634) */
+	htv_passthru_read_t pt_read;
+	void *pt_ctx;
+	int pt_started;
+	int16_t *pt_host;             /* pinned staging, PT_MAX_LINES lines in output layout */
+	int16_t *pt_dev;
+	int16_t *pt_tmp;              /* complex scratch for real-output modes */
 
 	/* htv_render_host: two device staging buffers, rendering of one piece overlaps the
 	 * device-to-host copy of the previous one */
@@ -118,12 +127,15 @@ void htv_free(htv_t *s)
 	{
 		htv_dev_free(s->dev, s->d_stage[0]);
 		htv_dev_free(s->dev, s->d_stage[1]);
+		htv_dev_free(s->dev, s->pt_dev);
 		htv_dev_event_free(s->ev_rendered[0]); htv_dev_event_free(s->ev_rendered[1]);
 		htv_dev_event_free(s->ev_copied[0]); htv_dev_event_free(s->ev_copied[1]);
 		htv_dev_stream_free(s->st_compute); htv_dev_stream_free(s->st_copy);
 		htv_dev_destroy(s->dev);
 	}
 	htv_dev_free_pinned(s->h_frame);
+	htv_dev_free_pinned(s->pt_host);
+	free(s->pt_tmp);
 	free(s->h_iq);
 	free(s->zeros);
 	htv_tables_free(s->tab);
@@ -197,8 +209,68 @@ static int pull_audio(htv_t *s, int64_t need, void *stream)
 	return(HTV_OK);
 }
 
+/* ---- channel combiner -----------------------------------------------------
+ * The reference adds an external int16 complex stream to its own output, line by line, as
+ * the last stage before the sink (ref _vid_passthru_process video.c:3517-3541). Because that
+ * stage also runs on the pipeline's fill lines, the first `delay` lines of the external
+ * stream are consumed and dropped with them: output line j receives external line j + delay,
+ * where delay = 1 with a video filter and 0 without (measured on the reference, see
+ * tests/test_oracle_vs_ref.py::test_passthru_alignment). A stream that ends adds whole lines
+ * only (the `fread() == 0 -> return` at video.c:3530). */
+int htv_passthru_delay_lines(const htv_t *s) { return(s->tab->dp.vf_type ? 1 : 0); }
+
+int htv_set_passthru(htv_t *s, htv_passthru_read_t read, void *ctx)
+{
+	if(!s) return(HTV_ERROR);
+	if(s->next_line != 0 && read) return(HTV_ERROR);      /* as in the reference: fixed at init */
+	s->pt_read = read;
+	s->pt_ctx = ctx;
+	s->pt_started = 0;
+	return(HTV_OK);
+}
+
+/* Stage the next n lines of the external stream on the device; returns whole lines available */
+static int pull_passthru(htv_t *s, int n, void *stream)
+{
+	const size_t W = (size_t) s->W;
+	size_t got;
+	int lines, r;
+
+	if(!s->pt_host)
+	{
+		s->pt_host = htv_dev_alloc_pinned(sizeof(int16_t) * 2 * W * PT_MAX_LINES);
+		s->pt_dev = htv_dev_alloc(s->dev, sizeof(int16_t) * 2 * W * PT_MAX_LINES);
+		if(!s->complex) s->pt_tmp = malloc(sizeof(int16_t) * 2 * W * PT_MAX_LINES);
+		if(!s->pt_host || !s->pt_dev || (!s->complex && !s->pt_tmp)) return(-1);
+	}
+	/* the staging buffer may still be in flight from the previous chunk */
+	if(htv_dev_sync(s->dev, stream) != HTV_OK) return(-1);
+	if(!s->pt_started)
+	{
+		size_t skip = (size_t) htv_passthru_delay_lines(s) * W;
+		s->pt_started = 1;
+		if(skip && s->pt_read(s->pt_ctx, s->pt_host, skip) < skip) { s->pt_read = NULL; return(0); }
+	}
+	if(s->complex) got = s->pt_read(s->pt_ctx, s->pt_host, (size_t) n * W);
+	else
+	{
+		/* real output carries I only (the file sink drops Q, ref rf_file.c:97-116) */
+		size_t i;
+		got = s->pt_read(s->pt_ctx, s->pt_tmp, (size_t) n * W);
+		for(i = 0; i < got; i++) s->pt_host[i] = s->pt_tmp[i * 2];
+	}
+	if(got < (size_t) n * W) s->pt_read = NULL;           /* end of the external stream */
+	lines = (int) (got / W);
+	if(lines > 0)
+	{
+		r = htv_dev_memcpy_h2d(s->dev, s->pt_dev, s->pt_host, (size_t) lines * W * s->bps, stream);
+		if(r != HTV_OK) return(-1);
+	}
+	return(lines);
+}
+
 /* One device launch sequence for lines [L0, L0 + n): at most MAX_FRAME_SLOTS - 1 new pictures */
-static int render_chunk(htv_t *s, int *pn, int16_t *d_out, void *stream)
+static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream)
 {
 	int n = *pn, nnew = 0;
 	const htv_dparams_t *dp = &s->tab->dp;
@@ -266,8 +338,19 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, void *stream)
 		if(r != HTV_OK) return(r);
 	}
 
-	r = htv_dev_render_lines(s->dev, L0, n, d_out, stream);
-	if(r != HTV_OK) return(r);
+	{
+		const int16_t *acc = add ? d_out : NULL;
+		int acc_lines = add ? n : 0;
+		if(s->pt_read)
+		{
+			if(add) return(HTV_ERROR);                        /* one combiner input at a time */
+			acc_lines = pull_passthru(s, n, stream);
+			if(acc_lines < 0) return(HTV_ERROR);
+			acc = s->pt_dev;
+		}
+		r = htv_dev_render_lines(s->dev, L0, n, d_out, acc, acc_lines, stream);
+		if(r != HTV_OK) return(r);
+	}
 	s->next_line += n;
 	*pn = n;
 	return(HTV_OK);
@@ -281,21 +364,38 @@ static int max_chunk_lines(const htv_t *s)
 	return(n < 1 ? 1 : n);
 }
 
-int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream)
+static int render_any(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, int add, void *cuda_stream)
 {
 	int done = 0, r, cap;
 	if(!s || nlines < 0 || !d_out) return(HTV_ERROR);
 	cap = max_chunk_lines(s);
+	if(s->pt_read && cap > PT_MAX_LINES) cap = PT_MAX_LINES;
 	while(done < nlines)
 	{
 		int n = nlines - done;
 		if(n > cap) n = cap;
-		r = render_chunk(s, &n, d_out + (size_t) done * s->W * (s->complex ? 2 : 1), cuda_stream);
+		if(s->pt_read && n > PT_MAX_LINES) n = PT_MAX_LINES;
+		r = render_chunk(s, &n, d_out + (size_t) done * s->W * (s->complex ? 2 : 1), add, cuda_stream);
 		if(r != HTV_OK) return(r);
 		done += n;
 	}
 	if(nsamples) *nsamples = (size_t) nlines * s->W;
 	return(HTV_OK);
+}
+
+int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream)
+{
+	return(render_any(s, nlines, d_out, nsamples, 0, cuda_stream));
+}
+
+int htv_render_add(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream)
+{
+	return(render_any(s, nlines, d_out, nsamples, 1, cuda_stream));
+}
+
+int htv_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *cuda_stream)
+{
+	return(htv_dev_mix_add(d_acc, d_in, nvalues, cuda_stream));
 }
 
 #define HOST_PIECE_BYTES (24u << 20)

@@ -129,7 +129,10 @@ extern int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm, si
 /* audio-rate pre-pass for the absolute audio-clock sample range [m0, m1) */
 extern int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *stream);
 /* the line kernel(s): render lines [line0, line0 + nlines) to d_out (device) */
-extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out, void *stream);
+extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out,
+	const int16_t *d_acc, int acc_lines, void *stream);
+extern int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *stream);
+extern int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream);
 extern int htv_dev_sync(htv_dev_t *d, void *stream);
 extern int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream);
 extern void *htv_dev_alloc(htv_dev_t *d, size_t bytes);

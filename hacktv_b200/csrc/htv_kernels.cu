@@ -1386,7 +1386,7 @@ __global__ void k_secam_carry(SecScratch ss, int idx, int pass_final)
 // memory. cwin[j] = composite sample x0 - 25 - CSKEW + j (16-byte aligned).
 template<int CSKEW>
 __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
-	const int *cwin, const short *ntp, int x0, int row, int16_t *out)
+	const int *cwin, const short *ntp, int x0, int row, int16_t *out, const int16_t *acc)
 {
 	const int W = dp.W;
 	int oi[SPT], oq[SPT];
@@ -1566,6 +1566,8 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 	}
 
 	// ---- store (ref rf_file.c:97-116, 226-233 layout) ------------------------
+	// `acc` (same layout as `out`, may alias it): the stream to add this one into, int16 wrap per
+	// component - ref _vid_passthru_process video.c:3536-3539, the channel combiner.
 	const size_t lbase = (size_t) row * (size_t) W;
 	if(dp.complex_out)
 	{
@@ -1577,6 +1579,11 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 			pk.y = (oi[1] & 0xFFFF) | (oq[1] << 16);
 			pk.z = (oi[2] & 0xFFFF) | (oq[2] << 16);
 			pk.w = (oi[3] & 0xFFFF) | (oq[3] << 16);
+			if(acc)
+			{
+				const int4 a = __ldcs(reinterpret_cast<const int4 *>(acc + (lbase + x0) * 2));
+				pk.x = __vadd2(pk.x, a.x); pk.y = __vadd2(pk.y, a.y); pk.z = __vadd2(pk.z, a.z); pk.w = __vadd2(pk.w, a.w);
+			}
 			__stcs(reinterpret_cast<int4 *>(o), pk);
 		}
 		else
@@ -1584,7 +1591,12 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 			#pragma unroll
 			for(int k = 0; k < SPT; k++)
 			{
-				if(x0 + k < W) __stcs(reinterpret_cast<int *>(o) + k, (oi[k] & 0xFFFF) | (oq[k] << 16));
+				if(x0 + k < W)
+				{
+					unsigned v = (oi[k] & 0xFFFF) | (oq[k] << 16);
+					if(acc) v = __vadd2(v, __ldcs(reinterpret_cast<const unsigned *>(acc + (lbase + x0) * 2) + k));
+					__stcs(reinterpret_cast<unsigned *>(o) + k, v);
+				}
 			}
 		}
 	}
@@ -1596,19 +1608,25 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 			int2 pk;
 			pk.x = (oi[0] & 0xFFFF) | (oi[1] << 16);
 			pk.y = (oi[2] & 0xFFFF) | (oi[3] << 16);
+			if(acc)
+			{
+				const int2 a = __ldcs(reinterpret_cast<const int2 *>(acc + lbase + x0));
+				pk.x = __vadd2(pk.x, a.x); pk.y = __vadd2(pk.y, a.y);
+			}
 			__stcs(reinterpret_cast<int2 *>(o), pk);
 		}
 		else
 		{
 			#pragma unroll
-			for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) oi[k];
+			for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) (oi[k] + (acc ? acc[lbase + x0 + k] : 0));
 		}
 	}
 }
 
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int16_t *out)
+k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int16_t *out,
+	const int16_t *acc, int acc_rows)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -1665,7 +1683,7 @@ k_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAu
 	const int x0 = tid * SPT;
 	if(x0 >= W) return;
 
-	mod_body<0>(dp, dt, la, cw + x0 + COFF - HALO, ntp, x0, (int) blockIdx.x, out);
+	mod_body<0>(dp, dt, la, cw + x0 + COFF - HALO, ntp, x0, (int) blockIdx.x, out, (int) blockIdx.x < acc_rows ? acc : NULL);
 }
 
 // ---------------------------------------------------------------------------
@@ -1701,7 +1719,8 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
 
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int *comp32, int nlines, int16_t *out)
+k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int *comp32, int nlines, int16_t *out,
+	const int16_t *acc, int acc_rows)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -1753,7 +1772,7 @@ k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 		mbar_wait(&bar[cb], phase[cb]);
 		phase[cb] ^= 1;
 		const int x0 = tid * SPT;
-		if(x0 < W) mod_body<3>(dp, dt, *lab[cb], cwb[cb] + x0, ntp, x0, row, out);
+		if(x0 < W) mod_body<3>(dp, dt, *lab[cb], cwb[cb] + x0, ntp, x0, row, out, row < acc_rows ? acc : NULL);
 		__syncthreads();                                            // everyone is done with this half before it is refilled
 	}
 }
@@ -2028,7 +2047,8 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	return(HTV_OK);
 }
 
-extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out, void *stream)
+extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out,
+	const int16_t *d_acc, int acc_lines, void *stream)
 {
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
@@ -2062,6 +2082,9 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		int16_t *o = d_out + (size_t) done * d->dp.W * (d->dp.complex_out ? 2 : 1);
 		const int16_t *sadd = NULL;
 		const int16_t *cstream = d->d_comp;
+		// the stream to sum into (channel combiner): its first acc_lines lines, laid out like d_out
+		const int16_t *acc = d_acc && acc_lines > done ? d_acc + (size_t) done * d->dp.W * (d->dp.complex_out ? 2 : 1) : NULL;
+		const int acc_rows = acc ? acc_lines - done : 0;
 		if(d->dp.colour_mode == HTV_SECAM)
 		{
 			// rows 0 .. n+2 <-> lines first-2 .. first+n; the chain covers rows 0 .. n+1
@@ -2121,15 +2144,50 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		if(d->d_comp32)
 		{
 			const int grid = n < d->mod_grid ? n : d->mod_grid;
-			if(d->line_threads <= 256) k_mod_tma<256, 4><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o);
-			else k_mod_tma<384, 2><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o);
+			if(d->line_threads <= 256) k_mod_tma<256, 4><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o, acc, acc_rows);
+			else k_mod_tma<384, 2><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o, acc, acc_rows);
 		}
-		else if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
-		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o);
+		else if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o, acc, acc_rows);
+		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, ld.a + done, cstream, sadd, o, acc, acc_rows);
 		d->launches++;
 		if(last) d->last_mod_lines = n;
 	}
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
+	CK(cudaGetLastError());
+	return(HTV_OK);
+}
+
+// Standalone channel combiner: acc[i] += in[i] with int16 wrap (ref video.c:3536-3539). Pure
+// streaming: 2 B read + 2 B read + 2 B written per value, HBM-bound. `in` may be peer memory.
+__global__ void __launch_bounds__(256) k_mix_add(int16_t *acc, const int16_t *in, size_t nvalues)
+{
+	const size_t n8 = nvalues / 8;
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for(size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride)
+	{
+		int4 a = __ldcs(reinterpret_cast<const int4 *>(acc) + i);
+		const int4 b = __ldcs(reinterpret_cast<const int4 *>(in) + i);
+		a.x = __vadd2(a.x, b.x); a.y = __vadd2(a.y, b.y); a.z = __vadd2(a.z, b.z); a.w = __vadd2(a.w, b.w);
+		__stcs(reinterpret_cast<int4 *>(acc) + i, a);
+	}
+	if(blockIdx.x == 0 && threadIdx.x < (nvalues & 7))
+	{
+		const size_t i = n8 * 8 + threadIdx.x;
+		acc[i] = (int16_t) (acc[i] + in[i]);
+	}
+}
+
+extern "C" int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *stream)
+{
+	if(!nvalues) return(HTV_OK);
+	if((((uintptr_t) d_acc) | ((uintptr_t) d_in)) & 15) return(HTV_ERROR);
+	int dev = 0, nsm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	size_t blocks = (nvalues / 8 + 255) / 256;
+	if(blocks > (size_t) nsm * 8) blocks = (size_t) nsm * 8;
+	if(blocks < 1) blocks = 1;
+	k_mix_add<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>(d_acc, d_in, nvalues);
 	CK(cudaGetLastError());
 	return(HTV_OK);
 }
@@ -2143,6 +2201,12 @@ extern "C" int htv_dev_sync(htv_dev_t *d, void *stream)
 extern "C" int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream)
 {
 	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream)
+{
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
 	return(HTV_OK);
 }
 

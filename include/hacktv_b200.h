@@ -173,6 +173,11 @@ extern size_t htv_get_framebuffer_length(htv_t *s);
 extern htv_av_t *htv_av(htv_t *s);
 extern int htv_av_test_open(htv_av_t *av);
 extern void htv_av_close(htv_av_t *av);
+/* In-memory source: caller-owned RGBx pictures (av->width x av->height each, one per video frame,
+ * cyclic) and 32 kHz stereo PCM (cyclic, `audio_block` pairs per read; 0 = all). `static_video`
+ * != 0 promises the pictures never change, so each is uploaded once. Pointers are borrowed. */
+extern int htv_av_memory_open(htv_av_t *av, const uint32_t *frames, size_t nframes,
+	const int16_t *audio, size_t audio_pairs, size_t audio_block, int static_video);
 
 extern htv_line_t *htv_next_line(htv_t *s);
 
@@ -189,6 +194,27 @@ extern htv_line_t *htv_next_line(htv_t *s);
  * I only for real modes. */
 extern int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream);
 extern int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples);
+
+/* Channel combiner - replaces the reference's `--passthru` stage (vid_config_t.passthru
+ * video.h:158; _vid_passthru_process video.c:3517-3541, set-up 4607-4634): an external int16
+ * stream is added to this encoder's output, component by component with int16 wrap, as the
+ * very last step (after --offset). Three forms:
+ *  htv_set_passthru: an fread-like source of int16 complex samples (I,Q interleaved, as the
+ *    reference reads them); `read` returns the complex samples delivered, a short count means
+ *    end of stream (only whole lines are added after that, as in the reference). Must be
+ *    installed before the first line is rendered. As in the reference the first
+ *    htv_passthru_delay_lines() lines of the external stream are consumed without being
+ *    used (they meet the pipeline's fill lines): output line j gets external line j + delay.
+ *  htv_render_add: like htv_render, but adds this encoder's lines INTO what `d_out` already
+ *    holds (same layout) - k channels with different --offset rendered into one wideband
+ *    buffer without the stream ever leaving HBM. The caller picks the alignment.
+ *  htv_mix_add: d_acc[i] += d_in[i] (int16 wrap) over nvalues int16 values, both device
+ *    (or peer-mapped) pointers, 16-byte aligned; for streams that already exist. */
+typedef size_t (*htv_passthru_read_t)(void *ctx, int16_t *iq, size_t ncomplex);
+extern int htv_set_passthru(htv_t *s, htv_passthru_read_t read, void *ctx);
+extern int htv_passthru_delay_lines(const htv_t *s);
+extern int htv_render_add(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream);
+extern int htv_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *cuda_stream);
 
 /* Geometry / state accessors (fields hacktv.c reads from vid_t, ref video.h:358-420) */
 extern int htv_samples_per_line(const htv_t *s);   /* vid_t.width */

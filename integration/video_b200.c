@@ -42,11 +42,11 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 	if(getenv("HACKTV_NO_B200")) return(0);
 	if(c->type != VID_RASTER_625 && c->type != VID_RASTER_525) return(0);
 	if(c->modulation == VID_FM) return(0);
-	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC) return(0);
+	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
 	if(pixel_rate && pixel_rate != sample_rate) return(0);
 	if(c->teletext || c->wss || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
 	   c->d11 || c->systercnr || c->acp || c->vits || c->vitc || c->cc608 || c->sis || c->eurocrypt) return(0);
-	if(c->raw_bb_file || c->passthru || c->a2stereo || c->s_video || c->secam_field_id) return(0);
+	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);
 	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
 	if(c->interlace || c->frame_orientation) return(0);
 	return(1);
@@ -97,10 +97,20 @@ static int _read_audio(void *ctx, const int16_t **samples, size_t *npairs)
 	return(r == AV_OK ? HTV_OK : HTV_ERROR);
 }
 
+/* --passthru: the external stream as the reference reads it (video.c:3527-3533) */
+static size_t _read_passthru(void *ctx, int16_t *iq, size_t ncomplex)
+{
+	FILE *f = ctx;
+	size_t x = 0, i;
+	while(x < ncomplex && (i = fread(iq + x * 2, sizeof(int16_t) * 2, ncomplex - x, f)) > 0) x += i;
+	return(x);
+}
+
 int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const vid_config_t * const conf)
 {
 	htv_config_t hc;
 	htv_t *h = NULL;
+	FILE *pt = NULL;
 	int i;
 
 	if(!_accelerated(conf, sample_rate, pixel_rate)) return(cpu_vid_init(s, sample_rate, pixel_rate, conf));
@@ -113,6 +123,13 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	}
 	i = _find(NULL);
 	if(i < 0) { htv_free(h); return(VID_ERROR); }
+	if(conf->passthru)
+	{
+		/* ref video.c:4607-4624 */
+		pt = strcmp(conf->passthru, "-") == 0 ? stdin : fopen(conf->passthru, "rb");
+		if(!pt) { perror(conf->passthru); htv_free(h); return(VID_ERROR); }
+		htv_set_passthru(h, _read_passthru, pt);
+	}
 
 	/* the fields hacktv.c and the sinks read (ref hacktv.c:1447-1526) */
 	memset(s, 0, sizeof(vid_t));
@@ -122,6 +139,7 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	s->width = s->max_width = htv_samples_per_line(h);
 	s->active_width = htv_active_width(h);
 	s->thread_abort = 1;                             /* no CPU stage threads to join */
+	s->passthru = pt;
 	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
 	htv_av(h)->ctx = s;
 	htv_av(h)->read_video = _read_video;
@@ -150,6 +168,7 @@ void vid_free(vid_t *s)
 	int i = _find(s);
 	if(i < 0) { cpu_vid_free(s); return; }
 	av_close(&s->av);
+	if(s->passthru) fclose(s->passthru);             /* ref video.c:4743-4746 */
 	htv_av(_enc[i].htv)->close = NULL;
 	htv_free(_enc[i].htv);
 	free(_enc[i].packed);

@@ -392,6 +392,7 @@ struct orc_t {
 	/* sources */
 	const uint32_t *frames; int nframes;
 	const int16_t *pcm; size_t pcm_pairs; size_t pcm_pos;
+	const int16_t *pt; size_t pt_len; size_t pt_pos;   /* passthru stream (complex samples) */
 
 	/* stream state */
 	int64_t next_raster;        /* next line index to raster */
@@ -1464,6 +1465,7 @@ void orc_close(orc_t *o)
 }
 
 void orc_set_frames(orc_t *o, const uint32_t *rgb, int nframes) { o->frames = rgb; o->nframes = nframes; }
+void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex) { o->pt = iq; o->pt_len = ncomplex; o->pt_pos = 0; }
 void orc_set_audio(orc_t *o, const int16_t *pcm, size_t npairs) { o->pcm = pcm; o->pcm_pairs = npairs; o->pcm_pos = 0; }
 
 int orc_width(const orc_t *o) { return(o->width); }
@@ -1507,6 +1509,8 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 			memset(iq, 0, sizeof(int16_t) * 2 * W);
 			audio_line(o, iq);
 			if(o->p.offset != 0) offset_line(o, iq);
+			/* ... and the passthru stage spends its first line on that buffer too */
+			if(o->pt) o->pt_pos = o->pt_len < (size_t) W ? o->pt_len : (size_t) W;
 		}
 	}
 
@@ -1574,6 +1578,15 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		}
 
 		if(o->p.offset != 0) offset_line(o, iq);
+
+		/* ref _vid_passthru_process video.c:3517-3541: the last stage before the sink adds
+		 * the external stream line by line, int16 wrap, whole lines only */
+		if(o->pt && o->pt_pos + (size_t) W <= o->pt_len)
+		{
+			const int16_t *pl = o->pt + o->pt_pos * 2;
+			for(x = 0; x < W * 2; x++) iq[x] = (int16_t) (iq[x] + pl[x]);
+			o->pt_pos += W;
+		}
 
 		if(o->complex)
 		{

@@ -121,6 +121,9 @@ extern void orc_close(orc_t *o);
  * 32 kHz stereo int16, used cyclically. Pointers are borrowed. */
 extern void orc_set_frames(orc_t *o, const uint32_t *rgb, int nframes);
 extern void orc_set_audio(orc_t *o, const int16_t *pcm, size_t npairs);
+/* External int16 complex stream added to the output (ref --passthru, video.c:3517-3541);
+ * borrowed pointer, set before the first orc_render */
+extern void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex);
 
 /* vid_next_line x nlines + the file sink (reference video.c:4936-4952,
  * rf_file.c:97-116,226-233): appends the next nlines scan lines of the emitted

@@ -92,7 +92,7 @@ static void _usage(void)
 {
 	fprintf(stderr,
 		"ref_harness -m MODE -s RATE [--pixelrate N] [--filter] [--noaudio] [--nonicam]\n"
-		"            [--nocolour] [--offset HZ] [--swap-iq] [--level F] [--volume F]\n"
+		"            [--nocolour] [--offset HZ] [--swap-iq] [--level F] [--volume F] [--passthru FILE]\n"
 		"            [--skip LINES] [--lines N] [-o FILE] [--bench] [--geometry]\n"
 		"            [--frames FILE.rgb32] [--audio FILE.s16le] [--audio-block N]\n");
 	exit(2);
@@ -103,7 +103,7 @@ int main(int argc, char **argv)
 	static hacktv_t s;
 	const vid_configs_t *vc;
 	vid_config_t conf;
-	const char *mode = "i", *out = NULL, *frames_fn = NULL, *audio_fn = NULL;
+	const char *mode = "i", *out = NULL, *frames_fn = NULL, *audio_fn = NULL, *passthru_fn = NULL;
 	unsigned int rate = 16000000, pixelrate = 0;
 	int filter = 0, noaudio = 0, nonicam = 0, nocolour = 0, swap_iq = 0, bench = 0, geometry = 0;
 	long long offset = 0, skip = 0, lines = 625;
@@ -137,6 +137,7 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "--frames") && i + 1 < argc) frames_fn = argv[++i];
 		else if(!strcmp(argv[i], "--audio") && i + 1 < argc) audio_fn = argv[++i];
 		else if(!strcmp(argv[i], "--audio-block") && i + 1 < argc) audio_block = strtoul(argv[++i], NULL, 10);
+		else if(!strcmp(argv[i], "--passthru") && i + 1 < argc) passthru_fn = argv[++i];
 		else _usage();
 	}
 
@@ -164,6 +165,7 @@ int main(int argc, char **argv)
 	if(filter) conf.vfilter = 1;
 	conf.swap_iq = swap_iq;
 	conf.offset = offset;
+	conf.passthru = (char *) passthru_fn;                 /* hacktv.c --passthru; video.c:4607-4634 */
 	conf.volume = (float) volume * 256 + 0.5;
 	conf.raw_bb_white_level = INT16_MAX;
 

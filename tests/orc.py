@@ -28,6 +28,7 @@ def lib():
         L.orc_close.restype = None; L.orc_close.argtypes = [vp]
         L.orc_set_frames.restype = None; L.orc_set_frames.argtypes = [vp, vp, C.c_int]
         L.orc_set_audio.restype = None; L.orc_set_audio.argtypes = [vp, vp, C.c_size_t]
+        L.orc_set_passthru.restype = None; L.orc_set_passthru.argtypes = [vp, vp, C.c_size_t]
         L.orc_render.restype = C.c_size_t; L.orc_render.argtypes = [vp, C.c_int, vp]
         for f in ("orc_width", "orc_active_width", "orc_active_lines", "orc_is_complex"):
             getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
@@ -67,6 +68,12 @@ class Oracle:
             audio = np.ascontiguousarray(audio, dtype=np.int16)
             self._L.orc_set_audio(self._o, audio.ctypes.data, audio.shape[0])
             self._keep.append(audio)
+
+    def set_passthru(self, iq):
+        """iq: int16 [n, 2] complex samples added to the output (ref --passthru)."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        self._L.orc_set_passthru(self._o, iq.ctypes.data, iq.shape[0])
+        self._keep.append(iq)
 
     def open_test_source(self):
         self.set_source(test_pattern(self.active_width, self.active_lines)[None], test_tone())

@@ -28,6 +28,7 @@ def _run(binary, args, nbytes):
     ("-m i -s 16000000 --filter --noaudio", 4, 0),
     ("-m i -s 16000000 --filter", 4, 1),
     ("-m m -s 13500000 --filter", 4, 1),
+    ("-m l -s 16000000 --filter", 4, 1),
 ])
 def test_same_cli_same_bytes(args, per, tol):
     w = 858 if "13500000" in args else 1024
@@ -36,3 +37,20 @@ def test_same_cli_same_bytes(args, per, tol):
     b = _run(STOCK, args, lines * w * per)
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert d.max() <= tol, f"max |diff| {d.max()}"
+
+
+def test_readme_two_channel_pipeline():
+    """README:89-90: one hacktv piped into another through --passthru; both stages on the GPU path
+    against both stages stock."""
+    def pipeline(binary, nbytes):
+        cmd = (f"timeout 120 {binary} -s 20000000 --offset -6750000 --level 0.5 --filter -o - test 2>/dev/null | "
+               f"timeout 120 {binary} -s 20000000 --offset 1250000 --level 0.5 --passthru /dev/stdin --filter -o - test "
+               f"2>/dev/null | head -c {nbytes}")
+        out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=300).stdout
+        assert len(out) == nbytes, f"{binary}: got {len(out)} of {nbytes} bytes"
+        return np.frombuffer(out, dtype=np.int16)
+    n = 700 * 1280 * 4
+    a = pipeline(DROPIN, n)
+    b = pipeline(STOCK, n)
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    assert d.max() <= 2, f"max |diff| {d.max()}"

@@ -149,3 +149,19 @@ def test_offset_mixer(built):
     assert (d <= 1).mean() > 0.999
     got, want = _pair(built, "i", 16000000, 700, vfilter=True, offset=-3500000, noaudio=True)
     assert _diff(got, want).max() <= 1
+
+
+def test_memory_source_equals_callback_source(built):
+    """htv_av_memory_open (C) and Python callbacks feed the same stream."""
+    H = built
+    rng = np.random.default_rng(5)
+    conf = H.mode_config("i", vfilter=True)
+    a = H.Encoder(conf, 16000000)
+    frames = rng.integers(0, 1 << 24, size=(2, a.active_lines, a.active_width), dtype=np.uint32)
+    audio = rng.integers(-8000, 8000, size=(5000, 2), dtype=np.int16)
+    a.set_source(frames, audio, audio_block=777)
+    x = a.render_host(1400); a.close()
+    b = H.Encoder(conf, 16000000)
+    b.open_memory_source(frames, audio, audio_block=1000)
+    y = b.render_host(1400); b.close()
+    assert np.array_equal(x, y)

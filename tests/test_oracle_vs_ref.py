@@ -51,6 +51,35 @@ def test_oracle_equals_reference(built, mode, rate, nlines, filt, extra):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
 
 
+PASSTHRU_CASES = [
+    ("pal", 16000000, False, (), 40),                    # real output: I only reaches the sink
+    ("i", 16000000, True, ("--offset", "1250000"), 40),  # the README's two-channel recipe (second stage)
+    ("l", 16000000, True, (), 40),
+    ("i", 16000000, False, ("--noaudio",), 40),
+    ("m", 13500000, True, (), 12),                       # external stream ends early, mid-line
+]
+
+
+@pytest.mark.parametrize("mode,rate,filt,extra,ext_lines", PASSTHRU_CASES)
+def test_passthru_alignment(built, tmp_path, mode, rate, filt, extra, ext_lines):
+    """ref _vid_passthru_process video.c:3517-3541: line alignment (the external stream's first
+    line is spent on the filter's fill line), int16 wrap, whole lines only at its end."""
+    rng = np.random.default_rng(11)
+    o = orc.Oracle(_conf(built, mode, filt, extra), rate)
+    W = o.width
+    ext = rng.integers(-32768, 32767, size=(ext_lines * W + W // 3, 2), dtype=np.int16)
+    o.open_test_source()
+    o.set_passthru(ext)
+    got = o.render(30)
+    o.close()
+    fn = tmp_path / "ext.iq"
+    ext.tofile(fn)
+    want = orc.run_ref(mode, rate, 30, vfilter=filt, extra=tuple(extra) + ("--passthru", str(fn)))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+    plain = orc.run_ref(mode, rate, 30, vfilter=filt, extra=extra)
+    assert not np.array_equal(plain, want)
+
+
 def test_oracle_equals_reference_on_random_input(built):
     rng = np.random.default_rng(7)
     conf = built.mode_config("i", vfilter=True)
