@@ -11,7 +11,11 @@
 #include <string.h>
 #include "htv_internal.h"
 
-#define MAX_FRAME_SLOTS 8
+/* Picture slots on the device and new pictures per launch sequence: with 16 slots and at most 7
+ * new pictures (+ 1 carried over) per chunk, the uploads of chunk c touch no slot chunk c-1 reads,
+ * so they may run (on the upload stream) while chunk c-1 is still computing. */
+#define MAX_FRAME_SLOTS 16
+#define MAX_NEW_FRAMES 7
 #define MAX_CHUNK_SECONDS 4.0
 #define PT_MAX_LINES 4096
 
@@ -108,7 +112,9 @@ int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, con
 	s->cur_slot = -1;
 	s->av.width = s->tab->dp.active_width;
 	s->av.height = s->tab->dp.active_lines;
-	s->zeros = calloc(65536, 2 * sizeof(int16_t));
+	s->zeros = htv_dev_alloc_pinned(65536 * 2 * sizeof(int16_t));    /* pinned: uploads stay asynchronous */
+	if(!s->zeros) { htv_free(s); return(HTV_OUT_OF_MEMORY); }
+	memset(s->zeros, 0, 65536 * 2 * sizeof(int16_t));
 	*out = s;
 	return(HTV_OK);
 }
@@ -137,7 +143,7 @@ void htv_free(htv_t *s)
 	htv_dev_free_pinned(s->pt_host);
 	free(s->pt_tmp);
 	free(s->h_iq);
-	free(s->zeros);
+	htv_dev_free_pinned(s->zeros);
 	htv_tables_free(s->tab);
 	free(s);
 }
@@ -269,7 +275,7 @@ static int pull_passthru(htv_t *s, int n, void *stream)
 	return(lines);
 }
 
-/* One device launch sequence for lines [L0, L0 + n): at most MAX_FRAME_SLOTS - 1 new pictures */
+/* One device launch sequence for lines [L0, L0 + n): at most MAX_NEW_FRAMES new pictures */
 static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream)
 {
 	int n = *pn, nnew = 0;
@@ -279,8 +285,13 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	int32_t map[4096];
 	int64_t f;
 	int r, nmap = 0;
+	void *up;
 
 	if(f1 - f0 + 1 > 4096) return(HTV_ERROR);
+
+	/* pictures and PCM go up on the encoder's own upload stream, ahead of the kernels queued on
+	 * `stream` for the previous chunk and beside the caller's device-to-host copies */
+	up = htv_dev_uploads_begin(s->dev);
 
 	/* pictures: one pull per frame, at its first line (ref video.c:4873-4881) */
 	for(f = f0; f <= f1; f++)
@@ -288,7 +299,7 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 		if(f > s->cur_frame)
 		{
 			htv_frame_t fr;
-			if(nnew >= MAX_FRAME_SLOTS - 1)
+			if(nnew >= MAX_NEW_FRAMES)
 			{
 				/* every free picture slot is in use by this launch: stop at this frame boundary */
 				n = (int) (f * s->lines - L0);
@@ -308,7 +319,7 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 				{
 					s->cur_slot = s->next_slot;
 					s->next_slot = (s->next_slot + 1) % MAX_FRAME_SLOTS;
-					r = htv_dev_upload_frame(s->dev, s->cur_slot, fr.framebuffer, stream);
+					r = htv_dev_upload_frame(s->dev, s->cur_slot, fr.framebuffer, up);
 					if(r != HTV_OK) return(r);
 					s->cur_serial = fr.serial;
 					s->have_serial = 1;
@@ -323,17 +334,24 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 		}
 		map[nmap++] = s->cur_slot;
 	}
+	/* sound: everything the audio clock reaches inside this run */
+	if(dp->have_fm || dp->have_am || dp->have_nicam)
+	{
+		const int64_t m1 = (L0 + n) * (int64_t) s->W + dp->shift;
+		r = pull_audio(s, fetches_by(m1 - 1, s->tab->rate), up);
+		if(r != HTV_OK) return(r);
+	}
+	r = htv_dev_uploads_end(s->dev, stream);
+	if(r != HTV_OK) return(r);
+
 	r = htv_dev_set_frame_map(s->dev, map, nmap, f0, stream);
 	if(r != HTV_OK) return(r);
 
-	/* sound: everything the audio clock reaches inside this run */
 	if(dp->have_fm || dp->have_am || dp->have_nicam)
 	{
 		const int64_t m0 = L0 * s->W + dp->shift, m1 = (L0 + n) * (int64_t) s->W + dp->shift;
 		int64_t mm0 = m0;
 		if(L0 == 0) mm0 = 0;      /* the audio clock starts `shift` samples before the first emitted sample */
-		r = pull_audio(s, fetches_by(m1 - 1, s->tab->rate), stream);
-		if(r != HTV_OK) return(r);
 		r = htv_dev_audio_prepass(s->dev, mm0, m1, stream);
 		if(r != HTV_OK) return(r);
 	}
@@ -398,7 +416,9 @@ int htv_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *cuda_
 	return(htv_dev_mix_add(d_acc, d_in, nvalues, cuda_stream));
 }
 
-#define HOST_PIECE_BYTES (24u << 20)
+/* copy-back granularity: small enough that the first render / last copy (which overlap nothing)
+ * stay short, large enough for full PCIe rate (measured on the B200 box: 4-48 MB within 10 %) */
+#define HOST_PIECE_BYTES (8u << 20)
 
 int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 {
@@ -423,18 +443,39 @@ int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 		s->st_copy = htv_dev_stream_new();
 		for(i = 0; i < 2; i++) { s->ev_rendered[i] = htv_dev_event_new(); s->ev_copied[i] = htv_dev_event_new(); }
 	}
+	void *dbg[64][4];
+	const int debug = getenv("HTV_DEBUG_PIPE") != NULL;
+	void *dbg0 = NULL;
+	if(debug) { dbg0 = htv_dev_event_new_timed(); htv_dev_event_record(dbg0, s->st_compute); }
 	for(; done < nlines; done += piece, p++)
 	{
 		const int n = nlines - done < piece ? nlines - done : piece, b = p & 1;
 		/* the staging buffer must have been copied out before it is rendered into again */
 		if(p >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(r);
+		if(debug && p < 64) { for(i = 0; i < 4; i++) dbg[p][i] = htv_dev_event_new_timed(); htv_dev_event_record(dbg[p][0], s->st_compute); }
 		r = htv_render(s, n, s->d_stage[b], NULL, s->st_compute);
 		if(r != HTV_OK) return(r);
+		if(debug && p < 64) htv_dev_event_record(dbg[p][1], s->st_compute);
 		if((r = htv_dev_event_record(s->ev_rendered[b], s->st_compute)) != HTV_OK) return(r);
 		if((r = htv_dev_stream_wait(s->st_copy, s->ev_rendered[b])) != HTV_OK) return(r);
+		if(debug && p < 64) htv_dev_event_record(dbg[p][2], s->st_copy);
 		r = htv_dev_memcpy_d2h(s->dev, (char *) h_out + (size_t) done * line_bytes, s->d_stage[b], (size_t) n * line_bytes, s->st_copy);
 		if(r != HTV_OK) return(r);
+		if(debug && p < 64) htv_dev_event_record(dbg[p][3], s->st_copy);
 		if((r = htv_dev_event_record(s->ev_copied[b], s->st_copy)) != HTV_OK) return(r);
+	}
+	if(debug)
+	{
+		int q;
+		htv_dev_sync(s->dev, s->st_copy);
+		for(q = 0; q < p && q < 64; q++)
+		{
+			fprintf(stderr, "piece %d: render %.3f..%.3f ms, copy %.3f..%.3f ms\n", q,
+				htv_dev_event_elapsed(dbg0, dbg[q][0]), htv_dev_event_elapsed(dbg0, dbg[q][1]),
+				htv_dev_event_elapsed(dbg0, dbg[q][2]), htv_dev_event_elapsed(dbg0, dbg[q][3]));
+			for(i = 0; i < 4; i++) htv_dev_event_free(dbg[q][i]);
+		}
+		htv_dev_event_free(dbg0);
 	}
 	if(nsamples) *nsamples = (size_t) nlines * s->W;
 	r = htv_dev_sync(s->dev, s->st_copy);

@@ -121,6 +121,8 @@ extern int htv_dev_count(void);
 extern htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen);
 extern void htv_dev_destroy(htv_dev_t *d);
 /* frame slot <- host RGB (active_width x active_lines), async on stream */
+extern void *htv_dev_uploads_begin(htv_dev_t *d);
+extern int htv_dev_uploads_end(htv_dev_t *d, void *stream);
 extern int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream);
 /* slot_of_frame[i] = slot holding frame (first_frame + i) for this launch */
 extern int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream);
@@ -131,6 +133,8 @@ extern int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *str
 /* the line kernel(s): render lines [line0, line0 + nlines) to d_out (device) */
 extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out,
 	const int16_t *d_acc, int acc_lines, void *stream);
+extern void *htv_dev_event_new_timed(void);
+extern float htv_dev_event_elapsed(void *e0, void *e1);
 extern int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *stream);
 extern int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream);
 extern int htv_dev_sync(htv_dev_t *d, void *stream);

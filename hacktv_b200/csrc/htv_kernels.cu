@@ -91,6 +91,8 @@ struct SecScratch {
 	int *claim;                       // [lines] last pass that rendered the line
 };
 
+#define MAPBUFS 16
+
 struct htv_dev_t {
 	int device;
 	htv_dparams_t dp;
@@ -102,6 +104,11 @@ struct htv_dev_t {
 	uint32_t *d_frames;
 	int32_t *d_frame_map;
 	int frame_map_cap;
+	// pinned staging for the frame map: a copy from pageable memory would make cudaMemcpyAsync
+	// drain the stream first and stall the host behind the uploads it has just queued
+	int32_t *h_map;
+	cudaEvent_t ev_map[MAPBUFS];
+	int map_i;
 	int16_t *d_pcm;
 	// carries
 	int64_t fm_jc;                    // last audio index whose fm_B entry is valid (-1 at start)
@@ -111,6 +118,9 @@ struct htv_dev_t {
 	int timing;
 	cudaEvent_t ev0, ev1;
 	cudaStream_t side;                // audio-rate pre-pass + sound descriptors run here, beside the raster
+	cudaStream_t up;                  // picture / PCM uploads: ahead of the previous chunk's kernels
+	cudaEvent_t ev_up, ev_chunk[2];
+	unsigned chunk_i;
 	cudaEvent_t ev_in, ev_audio;
 	int side_armed;
 	int ev_pending;
@@ -1848,6 +1858,8 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	d->d_frames = (uint32_t *) dev_zero(d, d->frame_pixels * 4 * d->max_slots);
 	d->frame_map_cap = 4096;
 	d->d_frame_map = (int32_t *) dev_zero(d, sizeof(int32_t) * d->frame_map_cap);
+	if(cudaMallocHost((void **) &d->h_map, sizeof(int32_t) * d->frame_map_cap * MAPBUFS) != cudaSuccess) d->h_map = NULL;
+	for(int i = 0; i < MAPBUFS; i++) cudaEventCreateWithFlags(&d->ev_map[i], cudaEventDisableTiming);
 	d->d_pcm = (int16_t *) dev_zero(d, sizeof(int16_t) * 2 * RA);
 	dt.frames = d->d_frames;
 	dt.frame_map = d->d_frame_map;
@@ -1868,7 +1880,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		dt.nic_ftot = (uint8_t *) dev_zero(d, RF);
 		dt.nic_fstart = (uint8_t *) dev_zero(d, RF);
 	}
-	if(!d->d_frames || !d->d_pcm || !dt.codes || cudaGetLastError() != cudaSuccess)
+	if(!d->d_frames || !d->d_pcm || !dt.codes || !d->h_map || cudaGetLastError() != cudaSuccess)
 	{
 		snprintf(err, errlen, "device allocation failed");
 		htv_dev_destroy(d);
@@ -1951,6 +1963,10 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
 	cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&d->up, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&d->ev_up, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_chunk[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
 	return(d);
@@ -1962,12 +1978,33 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	cudaSetDevice(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
 	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32);
+	if(d->h_map) cudaFreeHost(d->h_map);
+	for(int i = 0; i < MAPBUFS; i++) if(d->ev_map[i]) cudaEventDestroy(d->ev_map[i]);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
+	if(d->up) cudaStreamDestroy(d->up);
+	if(d->ev_up) cudaEventDestroy(d->ev_up);
+	if(d->ev_chunk[0]) cudaEventDestroy(d->ev_chunk[0]);
+	if(d->ev_chunk[1]) cudaEventDestroy(d->ev_chunk[1]);
 	free(d);
+}
+
+// Uploads of chunk c overwrite picture slots last read by chunk c-2 (see htv_host.c): wait for that
+// chunk's kernels, then run beside chunk c-1's. The compute stream joins at htv_dev_uploads_end.
+extern "C" void *htv_dev_uploads_begin(htv_dev_t *d)
+{
+	cudaStreamWaitEvent(d->up, d->ev_chunk[d->chunk_i & 1], 0);
+	return((void *) d->up);
+}
+
+extern "C" int htv_dev_uploads_end(htv_dev_t *d, void *stream)
+{
+	CK(cudaEventRecord(d->ev_up, d->up));
+	CK(cudaStreamWaitEvent((cudaStream_t) stream, d->ev_up, 0));
+	return(HTV_OK);
 }
 
 extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream)
@@ -1981,7 +2018,13 @@ extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb,
 extern "C" int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream)
 {
 	if(n > d->frame_map_cap) return(HTV_ERROR);
-	CK(cudaMemcpyAsync(d->d_frame_map, slot_of_frame, sizeof(int32_t) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	const int b = d->map_i;
+	d->map_i = (b + 1) % MAPBUFS;
+	int32_t *hm = d->h_map + (size_t) b * d->frame_map_cap;
+	CK(cudaEventSynchronize(d->ev_map[b]));                        // its previous use (MAPBUFS calls ago) has been consumed
+	memcpy(hm, slot_of_frame, sizeof(int32_t) * n);
+	CK(cudaMemcpyAsync(d->d_frame_map, hm, sizeof(int32_t) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	CK(cudaEventRecord(d->ev_map[b], (cudaStream_t) stream));
 	d->dt.frame_map_first = first_frame;
 	d->dt.frame_map_len = n;
 	return(HTV_OK);
@@ -2153,6 +2196,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		if(last) d->last_mod_lines = n;
 	}
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
+	CK(cudaEventRecord(d->ev_chunk[d->chunk_i & 1], st));
+	d->chunk_i++;
 	CK(cudaGetLastError());
 	return(HTV_OK);
 }
@@ -2214,6 +2259,8 @@ extern "C" int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size
 extern "C" void *htv_dev_stream_new(void) { cudaStream_t s = NULL; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); return((void *) s); }
 extern "C" void htv_dev_stream_free(void *s) { if(s) cudaStreamDestroy((cudaStream_t) s); }
 extern "C" void *htv_dev_event_new(void) { cudaEvent_t e = NULL; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return((void *) e); }
+extern "C" void *htv_dev_event_new_timed(void) { cudaEvent_t e = NULL; cudaEventCreate(&e); return((void *) e); }
+extern "C" float htv_dev_event_elapsed(void *e0, void *e1) { float ms = -1; cudaEventSynchronize((cudaEvent_t) e1); cudaEventElapsedTime(&ms, (cudaEvent_t) e0, (cudaEvent_t) e1); return(ms); }
 extern "C" void htv_dev_event_free(void *e) { if(e) cudaEventDestroy((cudaEvent_t) e); }
 extern "C" int htv_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return(HTV_OK); }
 extern "C" int htv_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return(HTV_OK); }

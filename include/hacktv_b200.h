@@ -152,6 +152,11 @@ typedef struct {
 	void *ctx;
 	htv_read_video_t read_video;  /* once per frame, at line 1 (ref video.c:4873-4881) */
 	htv_read_audio_t read_audio;  /* 32 kHz stereo int16, any block size (ref video.c:3280) */
+	/* Buffers handed out by the callbacks are read by cudaMemcpyAsync on the encoder's upload
+	 * stream. Pageable memory is staged before the callback's caller returns (reusable at once,
+	 * as with the reference); page-locked memory (cudaHostAlloc) is read asynchronously - full
+	 * PCIe rate, overlapped with the kernels and the copy back - and must stay unchanged until
+	 * the render call that pulled it has completed on its stream. */
 	htv_av_close_t close;
 } htv_av_t;
 

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 PASSTHRU = [
     ("pal", 16000000, 700, dict(), 800, 0),                                # real output: I only
     ("i", 16000000, 700, dict(vfilter=True, noaudio=True), 800, 0),        # delay 1 line, exact path
-    ("i", 20000000, 500, dict(vfilter=True, offset=1250000, level=0.5), 600, 1),   # README recipe, stage 2
+    ("i", 20000000, 500, dict(vfilter=True, offset=1250000, level=0.5), 600, 2),   # README recipe, stage 2:
+    #   +-1 LSB from the sound carriers, then +-1 from the offset NCO (as test_gpu_parity.test_offset_mixer)
     ("l", 16000000, 700, dict(vfilter=True), 800, 1),
     ("m", 13500000, 600, dict(vfilter=True), 100, 1),                      # external stream ends early
     ("i", 16000000, 9000, dict(vfilter=True, noaudio=True), 8500, 0),      # > one staging buffer (4096 lines)
