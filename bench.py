@@ -299,7 +299,7 @@ def main():
             "metric": "IQ Msamples/s", "value": round(value, 2), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int16 (int32 accumulate; fp64 RGB->YUV)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int16 (int32 accumulate; RGB->YUV table built in fp64 at init)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": args.frames, "lines_per_step": nlines,
                        "samples_per_step_per_gpu": nsamp, "parallelism": f"{world} independent RF channel(s), one per GPU, no collectives",
                        "l2": f"each step writes {nsamp * 4 / 1e6:.0f} MB of IQ per GPU (> 126 MB L2); tables are L2-resident by design",

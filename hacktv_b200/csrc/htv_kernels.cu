@@ -40,6 +40,7 @@ struct DevTables {
 	const uint16_t *codes;
 	const int16_t *pulse_values;
 	const double *glut;
+	const short4 *yuv_lut;            // [2^24] RGB -> (y, u, v, 0), the reference's yuv_level_lookup (video.c:3905-3960)
 	const htv_c16_t *clut;
 	const int16_t *burst_win;
 	const uint64_t *fm_ang;
@@ -99,7 +100,7 @@ struct htv_dev_t {
 	DevTables dt;
 	size_t frame_pixels;
 	int max_slots;
-	void *alloc[48];
+	void *alloc[64];
 	int nalloc;
 	uint32_t *d_frames;
 	int32_t *d_frame_map;
@@ -783,6 +784,27 @@ __device__ __forceinline__ void yuv_of(const htv_dparams_t &dp, const double *gl
 	v = max(-32767, min(32767, round_away(__dmul_rn(vv, 32767.0))));
 }
 
+// The reference converts every pixel through a 2^24-entry table built once in vid_init
+// (video.c:3905-3960, read at 2975-2992 / 3152-3190). Same here: 8 bytes per colour (134 MB of
+// HBM; what a picture actually uses stays in L2), built on the device by the exact fp64 code.
+template<bool SECAM>
+__global__ void __launch_bounds__(256) k_yuv_lut(const __grid_constant__ htv_dparams_t dp, const double *glut_g, short4 *lut)
+{
+	__shared__ double glut[256];
+	glut[threadIdx.x] = glut_g[threadIdx.x];
+	__syncthreads();
+	const unsigned int rgb = blockIdx.x * 256u + threadIdx.x;
+	int y, u, v;
+	yuv_of<SECAM>(dp, glut, rgb, y, u, v);
+	lut[rgb] = make_short4((short) y, (short) u, (short) v, 0);
+}
+
+__device__ __forceinline__ void yuv_lookup(const DevTables &dt, unsigned int rgb, int &y, int &u, int &v)
+{
+	const short4 e = __ldg(dt.yuv_lut + rgb);
+	y = e.x; u = e.y; v = e.z;
+}
+
 // Chroma low-pass for 4 consecutive samples with a compile-time tap count: the window is
 // read with aligned 128-bit shared loads and the symmetric taps are folded.
 template<int NT>
@@ -830,8 +852,7 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 	const int W = dp.W;
 	const int W4 = (W + 3) & ~3;
 	const int UW = W4 + 2 * UOFF;
-	double *glut = reinterpret_cast<double *>(smem_raw);
-	int *su = reinterpret_cast<int *>(glut + 256);                  // index = x + UOFF
+	int *su = reinterpret_cast<int *>(smem_raw);                    // index = x + UOFF
 	int *sv = su + UW;
 	__shared__ LineRaster li;
 	const int tid = threadIdx.x;
@@ -841,7 +862,6 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 		int4 *dst = reinterpret_cast<int4 *>(&li);
 		if(tid < (int) (sizeof(LineRaster) / 16)) dst[tid] = __ldg(src + tid);
 	}
-	if(tid < 128) reinterpret_cast<int4 *>(glut)[tid] = __ldg(reinterpret_cast<const int4 *>(dt.glut) + tid);
 	if(tid < 2 * UOFF)
 	{
 		// U,V outside the line read as zero (the reference filters each line on its own)
@@ -864,7 +884,7 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 			if(x >= li.al && x < li.ar)
 			{
 				const unsigned int rgb = li.row_off >= 0 ? (__ldg(dt.frames + li.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
-				yuv_of<false>(dp, glut, rgb, val[k], uu[k], vv[k]);
+				yuv_lookup(dt, rgb, val[k], uu[k], vv[k]);
 				if(!li.pal) uu[k] = vv[k] = 0;
 			}
 		}
@@ -981,8 +1001,7 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 	const int W = dp.W;
 	const int W4 = (W + 3) & ~3;
 	const int LW = W4 + 2 * LOFF + 14;
-	double *glut = reinterpret_cast<double *>(smem_raw);
-	int *line = reinterpret_cast<int *>(glut + 256);                // index = x + LOFF
+	int *line = reinterpret_cast<int *>(smem_raw);                  // index = x + LOFF
 	int *cbin = line + ((LW + 3) & ~3);                             // index = x + 8
 	__shared__ LineRaster li;
 	const int tid = threadIdx.x;
@@ -992,7 +1011,6 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 		int4 *dst = reinterpret_cast<int4 *>(&li);
 		if(tid < (int) (sizeof(LineRaster) / 16)) dst[tid] = __ldg(src + tid);
 	}
-	for(int i = tid; i < 256; i += blockDim.x) glut[i] = dt.glut[i];
 	for(int i = tid; i < LOFF; i += blockDim.x) { line[i] = 0; line[W4 + LOFF + i] = 0; }
 	if(tid < 16) { cbin[tid < 8 ? tid : W4 + tid] = 0; }
 	__syncthreads();
@@ -1013,7 +1031,7 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 			if((x >= li.al && x < li.ar) || (li.sec_proc && inpic))
 			{
 				const unsigned int rgb = li.row_off >= 0 ? (__ldg(dt.frames + li.row_off + (x - dp.active_left)) & 0xFFFFFF) : 0;
-				yuv_of<true>(dp, glut, rgb, y, u, v);
+				yuv_lookup(dt, rgb, y, u, v);
 			}
 			if(x >= li.al && x < li.ar) val[k] = y;
 			if(li.sec_proc && inpic)
@@ -1025,7 +1043,7 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 				{
 					int y2, u2, v2;
 					const unsigned int rgb2 = __ldg(dt.frames + li.sec_prev_row + (x - dp.active_left)) & 0xFFFFFF;
-					yuv_of<true>(dp, glut, rgb2, y2, u2, v2);
+					yuv_lookup(dt, rgb2, y2, u2, v2);
 					st = li.sec_prev_comp == 1 ? u2 : v2;
 				}
 				cbv[k] = ((cur == 1 ? u : v) + st) / 2;
@@ -1853,6 +1871,20 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.secam_fm_lut = (const htv_c32_t *) dev_copy(d, t->secam_fm_lut, t->secam_fm_lut ? sizeof(htv_c32_t) * 65536 : 0);
 	dt.secam_bell = (const htv_c16_t *) dev_copy(d, t->secam_bell, t->secam_bell ? sizeof(htv_c16_t) * 65536 : 0);
 
+	{
+		short4 *lut = NULL;
+		if(!dt.glut || cudaMalloc((void **) &lut, sizeof(short4) << 24) != cudaSuccess)
+		{
+			snprintf(err, errlen, "device allocation failed (RGB -> YUV table, 134 MB)");
+			htv_dev_destroy(d);
+			return(NULL);
+		}
+		d->alloc[d->nalloc++] = lut;
+		if(dp.colour_mode == HTV_SECAM) k_yuv_lut<true><<<65536, 256>>>(dp, dt.glut, lut);
+		else k_yuv_lut<false><<<65536, 256>>>(dp, dt.glut, lut);
+		dt.yuv_lut = lut;
+	}
+
 	d->frame_pixels = (size_t) dp.active_width * dp.active_lines;
 	d->max_slots = max_frame_slots < 1 ? 1 : max_frame_slots;
 	d->d_frames = (uint32_t *) dev_zero(d, d->frame_pixels * 4 * d->max_slots);
@@ -1895,7 +1927,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	if(threads < 64) threads = 64;
 	d->line_threads = threads;
 	const int W4 = (W + 3) & ~3;
-	d->raster_smem = 256 * sizeof(double) + sizeof(int) * 2 * (W4 + 2 * UOFF);
+	d->raster_smem = sizeof(int) * 2 * (W4 + 2 * UOFF);
 	d->mod_smem = sizeof(int) * (W4 + 2 * EXT + 16) + sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
 	if(threads > 384)
 	{
@@ -1956,7 +1988,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			return(NULL);
 		}
 		const int W4s = (W + 3) & ~3;
-		const size_t sm = 256 * sizeof(double) + sizeof(int) * ((((W4s + 2 * LOFF + 14) + 3) & ~3) + W4s + 32);
+		const size_t sm = sizeof(int) * ((((W4s + 2 * LOFF + 14) + 3) & ~3) + W4s + 32);
 		d->raster_smem = sm > d->raster_smem ? sm : d->raster_smem;
 		cudaFuncSetAttribute(k_raster_secam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->raster_smem);
 	}
@@ -1969,6 +2001,14 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
+	// the table build and the memsets above ran on the default stream, which the (non-blocking)
+	// streams the encoder works on do not wait for
+	if(cudaDeviceSynchronize() != cudaSuccess)
+	{
+		snprintf(err, errlen, "device initialisation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+		htv_dev_destroy(d);
+		return(NULL);
+	}
 	return(d);
 }
 
