@@ -53,6 +53,7 @@ class Config(C.Structure):
         ("fm_mono_carrier", C.c_double), ("fm_mono_deviation", C.c_double),
         ("fm_mono_preemph", C.c_int32), ("reserved0", C.c_int32),
         ("nicam_carrier", C.c_double), ("nicam_beta", C.c_double), ("am_mono_carrier", C.c_double),
+        ("fm_level", C.c_double), ("fm_deviation", C.c_double), ("fm_energy_dispersal", C.c_double),
     ]
 
     def copy(self) -> "Config":
@@ -158,7 +159,7 @@ def modes() -> dict:
 
 
 def mode_config(mode: str, *, vfilter=False, nocolour=False, noaudio=False, nonicam=False,
-                offset=0, swap_iq=False, level=1.0, volume=1.0, invert_video=False) -> Config:
+                offset=0, swap_iq=False, level=1.0, volume=1.0, invert_video=False, deviation=0.0) -> Config:
     """Mode lookup + the command-line overrides of reference hacktv.c:1107-1437 (in-scope options)."""
     p = lib().htv_find_mode(mode.encode())
     if not p:
@@ -179,6 +180,8 @@ def mode_config(mode: str, *, vfilter=False, nocolour=False, noaudio=False, noni
     c.offset = int(offset)
     c.volume = int(float(np.float32(volume)) * 256 + 0.5)
     c.invert_video = int(bool(invert_video))
+    if deviation > 0:
+        c.fm_deviation = float(deviation)            # -D / --deviation, hacktv.c:1109-1113
     return c
 
 

@@ -119,6 +119,11 @@ typedef struct {
 	double nicam_carrier;
 	double nicam_beta;
 	double am_mono_carrier;
+	/* FM video, modulation == HTV_FM (ref video.h:141-143, -D/--deviation hacktv.c:1109-1113).
+	 * fm_energy_dispersal must be 0: no mode in scope uses it */
+	double fm_level;
+	double fm_deviation;
+	double fm_energy_dispersal;
 } htv_config_t;
 
 typedef struct {

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <math.h>
 #include "htv_oracle.h"
+#include "fm_video_taps.h"
 
 #define I16MAX 32767
 #define I16MIN (-32768)
@@ -392,6 +393,7 @@ struct orc_t {
 	/* sources */
 	const uint32_t *frames; int nframes;
 	const int16_t *pcm; size_t pcm_pairs; size_t pcm_pos;
+	int have_fmv; fm_t fm_video;                       /* FM video modulator (video.c:2299-2335) */
 	const int16_t *pt; size_t pt_len; size_t pt_pos;   /* passthru stream (complex samples) */
 
 	/* stream state */
@@ -521,6 +523,21 @@ static inline void fm_add(fm_t *fm, int16_t *dst, int16_t sample)
 	dst[0] += ((fm->phase.i >> 16) * fm->level) >> 15;
 	dst[1] += ((fm->phase.q >> 16) * fm->level) >> 15;
 	nco_renorm(&fm->phase, &fm->counter);
+}
+
+/* ref video.c:2299-2335 without energy dispersal, 3452-3464: the line's I becomes the
+ * modulating signal, I and Q are replaced by the phasor */
+static void fmv_line(fm_t *fm, int16_t *iq, int W)
+{
+	int x;
+	for(x = 0; x < W; x++)
+	{
+		int16_t *d = iq + x * 2;
+		c32_mul(&fm->phase, &fm->phase, &fm->lut[d[0] - I16MIN]);
+		d[0] = ((fm->phase.i >> 16) * fm->level) >> 15;
+		d[1] = ((fm->phase.q >> 16) * fm->level) >> 15;
+		nco_renorm(&fm->phase, &fm->counter);
+	}
 }
 
 /* ref video.c:2278-2297 (SECAM only) */
@@ -1213,7 +1230,7 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	o->rate = sample_rate;
 
 	if(p->type != ORC_RASTER_625 && p->type != ORC_RASTER_525) { free(o); return(NULL); }
-	if(p->modulation == ORC_MOD_FM) { free(o); return(NULL); }
+	if(p->modulation == ORC_MOD_FM && p->fm_energy_dispersal != 0) { free(o); return(NULL); }
 
 	/* video.c:3832-3837 defaults */
 	if(p->hline <= 0 && p->interlaced != 0) p->hline = (p->lines + 1) / 2;
@@ -1233,7 +1250,7 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	if(o->active_width > o->width) o->active_width = o->width;
 
 	/* video.c:3855-3881 */
-	o->slevel = p->level; /* FM is out of scope */
+	o->slevel = p->modulation == ORC_MOD_FM ? 1.0 : p->level;
 	o->vlevel = p->video_level * o->slevel;
 
 	if(p->invert_video)
@@ -1390,6 +1407,29 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 			o->vf_itaps = quantise_taps(taps + 0, 51, 2);
 			o->vf_qtaps = quantise_taps(taps + 1, 51, 2);
 		}
+		else if(p->modulation == ORC_MOD_FM)
+		{
+			/* video.c:3678-3740: a fixed pre-emphasis table per line standard and sample rate */
+			const double *taps;
+			int ntaps;
+			#define FMT(t) do { taps = t; ntaps = sizeof(t) / sizeof(double); } while(0)
+			if(p->lines == 525)
+			{
+				if(o->rate == 18000000) FMT(orc_fm_525_18_taps);
+				else FMT(orc_fm_525_2025_taps);
+			}
+			else
+			{
+				if(o->rate == 14000000) FMT(orc_fm_625_14_taps);
+				else if(o->rate == 20000000) FMT(orc_fm_625_20_taps);
+				else if(o->rate == 28000000) FMT(orc_fm_625_28_taps);
+				else FMT(orc_fm_625_2025_taps);
+			}
+			#undef FMT
+			o->vf_type = 1;
+			o->vf_ntaps = ntaps;
+			o->vf_itaps = quantise_taps(taps, ntaps, 1);
+		}
 		else
 		{
 			double taps[51];
@@ -1422,6 +1462,13 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	{
 		o->have_am = 1;
 		am_init(&o->am_mono, o->rate, p->am_mono_carrier, p->am_audio_level * o->slevel);
+	}
+
+	if(p->modulation == ORC_MOD_FM)
+	{
+		/* video.c:4564-4585 */
+		o->have_fmv = 1;
+		fm_init(&o->fm_video, o->rate, 0, p->fm_deviation, p->fm_level * p->level);
 	}
 
 	if(p->offset != 0)
@@ -1507,7 +1554,28 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		if(o->vf_type)
 		{
 			memset(iq, 0, sizeof(int16_t) * 2 * W);
+			if(o->have_fmv)
+			{
+				/* the FM modulator integrates what is IN the fill line: the filter's output for
+				 * the line before the stream - zero history, with the first samples of line 1
+				 * reaching in through the taps ahead of centre */
+				int h = o->vf_ntaps / 2;
+				const int16_t *first;
+				while(o->next_raster <= 1) raster_line(o, o->next_raster++);
+				first = ring_line(o, 0);
+				for(x = W - h; x < W; x++)
+				{
+					int32_t a = 0;
+					for(y = 0; y < o->vf_ntaps; y++)
+					{
+						int j = x - h + y - W;             /* position in line 1 */
+						if(j >= 0) a += first[j] * o->vf_itaps[y];
+					}
+					iq[x * 2] = sat16(a >> 15);
+				}
+			}
 			audio_line(o, iq);
+			if(o->have_fmv) fmv_line(&o->fm_video, iq, W);
 			if(o->p.offset != 0) offset_line(o, iq);
 			/* ... and the passthru stage spends its first line on that buffer too */
 			if(o->pt) o->pt_pos = o->pt_len < (size_t) W ? o->pt_len : (size_t) W;
@@ -1566,6 +1634,8 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		}
 
 		if(o->have_fm || o->have_am || o->have_nicam) audio_line(o, iq);
+
+		if(o->have_fmv) fmv_line(&o->fm_video, iq, W);
 
 		if(o->p.swap_iq)
 		{

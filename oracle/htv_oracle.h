@@ -105,6 +105,11 @@ typedef struct {
 	double nicam_carrier;
 	double nicam_beta;
 	double am_mono_carrier;
+	/* FM video (modulation == ORC_MOD_FM; ref video.h:141-143). Energy dispersal is not modelled:
+	 * no mode in scope enables it and the front end has no switch for it. */
+	double fm_level;
+	double fm_deviation;
+	double fm_energy_dispersal;
 } orc_params_t;
 
 typedef struct orc_t orc_t;

@@ -25,6 +25,16 @@ CASES = [
     ("i", 16000000, 700, True, ("--offset", "2000000")),
     ("i", 16000000, 400, True, ("--swap-iq",)),
     ("pal", 16000000, 400, True, ()),
+    # FM video: the pre-emphasis table differs per sample rate
+    ("pal-fm", 20000000, 700, True, ()),
+    ("pal-fm", 20250000, 400, True, ()),
+    ("pal-fm", 14000000, 400, True, ("--noaudio",)),
+    ("pal-fm", 28000000, 300, True, ()),
+    ("pal-fm", 20000000, 700, False, ()),
+    ("ntsc-fm", 18000000, 600, True, ()),
+    ("ntsc-fm", 20250000, 400, True, ()),
+    ("secam-fm", 20250000, 400, True, ()),
+    ("pal-fm", 20000000, 400, True, ("--offset", "-3000000", "--swap-iq")),
 ]
 
 
