@@ -223,7 +223,7 @@ static int pull_audio(htv_t *s, int64_t need, void *stream)
  * where delay = 1 with a video filter and 0 without (measured on the reference, see
  * tests/test_oracle_vs_ref.py::test_passthru_alignment). A stream that ends adds whole lines
  * only (the `fread() == 0 -> return` at video.c:3530). */
-int htv_passthru_delay_lines(const htv_t *s) { return(s->tab->dp.vf_type ? 1 : 0); }
+int htv_passthru_delay_lines(const htv_t *s) { return(s->tab->dp.shift > 0 ? 1 : 0); }
 
 int htv_set_passthru(htv_t *s, htv_passthru_read_t read, void *ctx)
 {

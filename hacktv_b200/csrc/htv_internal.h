@@ -15,6 +15,7 @@ typedef struct { int16_t i, q; } htv_c16_t;
 typedef struct { int32_t i, q; } htv_c32_t;
 
 #define HTV_VF_NTAPS   51      /* ref video.c:3671,3744 */
+#define HTV_FMV_MAXTAPS 72     /* FM video pre-emphasis: 67 or 71 taps (ref video.c:2016-2099) */
 #define HTV_MAX_CTAPS  31      /* chroma Gaussian LPF taps we accept (13 @16M, 15 @20M, 11 @13.5M) */
 #define HTV_AUDIO_RATE 32000   /* ref hacktv.h:30 */
 #define HTV_NICAM_SYMBOL_RATE 364000
@@ -70,6 +71,11 @@ typedef struct {
 	int32_t secam_lpf[15], secam_notch[51];
 	double iir_a1, iir_b0, iir_b1;
 
+	/* FM video (ref video.c:2299-2335, 3452-3464, 3678-3740): the filtered composite + sound
+	 * carriers become the modulating signal of a Q31 phasor; pre-emphasis taps in application order */
+	int32_t have_fmv, fmv_level, fmv_ntaps, fmv_pad;
+	int32_t fmv_taps[HTV_FMV_MAXTAPS];
+
 	/* post mixers */
 	int32_t swap_iq, have_offset;
 	uint64_t offset_ang;           /* turns * 2^64 per sample */
@@ -89,6 +95,7 @@ struct htv_tables_t {
 	int16_t *burst_win;     int burst_width;
 
 	uint64_t *fm_ang;                              /* 65536: effective angle of each FM LUT entry, turns * 2^64 */
+	uint64_t *fmv_ang;                             /* the same for the FM video modulator's LUT */
 	int32_t afir_v[HTV_AFIR_N], afir_f[HTV_AFIR_N]; /* audio FIR taps in application order */
 	int16_t lim_shape[HTV_LIM_W];
 

@@ -69,6 +69,12 @@ struct DevTables {
 	uint8_t *nic_local;               // RS: inclusive prefix (mod 4) of the DQPSK steps inside the symbol's frame
 	uint8_t *nic_ftot;                // RF: total step of frame k (mod 4)
 	uint8_t *nic_fstart;              // RF: differential symbol state before frame k
+	// FM video
+	const uint64_t *fmv_ang;          // 65536: effective rotation of each modulator LUT entry, turns * 2^64
+	int16_t *fmv_base;                // [rows][W] modulating signal of the current sub-batch
+	unsigned long long *fmv_tot;      // [rows] phase advance over each row
+	unsigned long long *fmv_rowbase;  // [rows] phase before each row
+	unsigned long long *fmv_carry;    // phase after the last row rendered so far
 };
 
 #define LOFF 33                       // luma window index = x + LOFF (aligned 128-bit loads at x0 - 25)
@@ -137,6 +143,7 @@ struct htv_dev_t {
 	int mod_grid;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
 	int sub_lines;
+	size_t fmv_smem;
 	size_t raster_smem, mod_smem;
 	int last_mod_lines;
 };
@@ -1412,44 +1419,16 @@ __global__ void k_secam_carry(SecScratch ss, int idx, int pass_final)
 
 // Everything k_mod does for 4 consecutive samples once the composite window is in shared
 // memory. cwin[j] = composite sample x0 - 25 - CSKEW + j (16-byte aligned).
-template<int CSKEW>
-__device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
-	const int *cwin, const short *ntp, int x0, int row, int16_t *out, const int16_t *acc)
+// The sound carriers of 4 consecutive samples, added into oi/oq (ref video.c:3261-3450,
+// nicam728.c:342-411). Shared by the AM/VSB modulator and the FM-video baseband kernel.
+// PRECISE (FM video only): the carrier is evaluated in fp64 from the full 64-bit phase. An FM
+// modulator integrates its input, so a sound-carrier sample that is 1 LSB off turns everything
+// after it; the fast fp32 evaluation loses the sign of a carrier sample that lands on a zero
+// crossing (an unmodulated 6.5 MHz carrier at 20 Msps does so every 40 samples).
+template<bool PRECISE>
+__device__ __forceinline__ void sound_add(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
+	const short *ntp, int x0, int (&oi)[SPT], int (&oq)[SPT])
 {
-	const int W = dp.W;
-	int oi[SPT], oq[SPT];
-	if(dp.vf_type)
-	{
-		// c[j] = composite sample x0 - 25 + j
-		int c[(SPT + 2 * HALO + 2 + CSKEW + 3) / 4 * 4];
-		const int4 *pc = reinterpret_cast<const int4 *>(cwin);
-		#pragma unroll
-		for(int i = 0; i < (SPT + 2 * HALO + 2 + CSKEW + 3) / 4; i++)
-		{
-			const int4 a = pc[i];
-			c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
-		}
-		#pragma unroll
-		for(int k = 0; k < SPT; k++)
-		{
-			int ai = c[k + HALO + CSKEW] * dp.vf_i[HALO], aq = 0;
-			// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
-			#pragma unroll
-			for(int y = 0; y < HALO; y++)
-			{
-				ai += (c[k + y + CSKEW] + c[k + 2 * HALO - y + CSKEW]) * dp.vf_i[y];
-				aq += (c[k + y + CSKEW] - c[k + 2 * HALO - y + CSKEW]) * dp.vf_q[y];
-			}
-			oi[k] = sat16i(ai >> 15);
-			oq[k] = sat16i(aq >> 15);                               // vf_q is all zero for the real low-pass
-		}
-	}
-	else
-	{
-		#pragma unroll
-		for(int k = 0; k < SPT; k++) { oi[k] = cwin[k + HALO + CSKEW]; oq[k] = 0; }
-	}
-
 	if(dp.have_fm || dp.have_am)
 	{
 		// at most one audio-sample boundary falls inside 4 consecutive samples
@@ -1473,10 +1452,21 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 			if(dp.have_fm)
 			{
 				const unsigned long long ph = second ? phB : phA;
-				float sn, cs;
-				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
-				oi[k] += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
-				oq[k] += ((int) floorf(amp * sn) * dp.fm_level) >> 15;
+				if(PRECISE)
+				{
+					double sn, cs;
+					sincospi((double) (long long) ph * 1.0842021724855044e-19, &sn, &cs);     // 2 / 2^64
+					const double ampd = 32767.999984741211 - (double) (kk + 1) * 1.52587890625e-5;
+					oi[k] += (min((int) floor(ampd * cs), 32767) * dp.fm_level) >> 15;
+					oq[k] += (min((int) floor(ampd * sn), 32767) * dp.fm_level) >> 15;
+				}
+				else
+				{
+					float sn, cs;
+					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
+					oi[k] += ((int) floorf(amp * cs) * dp.fm_level) >> 15;
+					oq[k] += ((int) floorf(amp * sn) * dp.fm_level) >> 15;
+				}
 				phA += angA; phB += angB;
 			}
 			if(dp.have_am)
@@ -1554,6 +1544,13 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 		}
 	}
 
+}
+
+// Mixers after the modulation (ref video.c:3466-3515), the channel combiner and the store.
+__device__ __forceinline__ void post_store(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
+	int x0, int row, int (&oi)[SPT], int (&oq)[SPT], int16_t *out, const int16_t *acc)
+{
+	const int W = dp.W;
 	// every addition above is an int16 wrap-around addition in the reference; wrapping once is the same
 	if(dp.swap_iq || dp.have_offset)
 	{
@@ -1586,7 +1583,7 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 				const unsigned long long ph = la.off_phase0 + dp.offset_ang * (unsigned long long) (x + 1);
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
-				bi = (int) floorf(amp * cs); bq = (int) floorf(amp * sn);
+				bi = min((int) floorf(amp * cs), 32767); bq = min((int) floorf(amp * sn), 32767);   // pi >> 16 <= 32767
 			}
 			const int ri = (oi[k] * bi - oq[k] * bq) >> 15, rq = (oi[k] * bq + oq[k] * bi) >> 15;
 			oi[k] = wrap16i(ri); oq[k] = wrap16i(rq);
@@ -1649,6 +1646,254 @@ __device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTable
 			for(int k = 0; k < SPT; k++) if(x0 + k < W) o[k] = (int16_t) (oi[k] + (acc ? acc[lbase + x0 + k] : 0));
 		}
 	}
+}
+
+template<int CSKEW>
+__device__ __forceinline__ void mod_body(const htv_dparams_t &dp, const DevTables &dt, const LineAudio &la,
+	const int *cwin, const short *ntp, int x0, int row, int16_t *out, const int16_t *acc)
+{
+	const int W = dp.W;
+	int oi[SPT], oq[SPT];
+	if(dp.vf_type)
+	{
+		// c[j] = composite sample x0 - 25 + j
+		int c[(SPT + 2 * HALO + 2 + CSKEW + 3) / 4 * 4];
+		const int4 *pc = reinterpret_cast<const int4 *>(cwin);
+		#pragma unroll
+		for(int i = 0; i < (SPT + 2 * HALO + 2 + CSKEW + 3) / 4; i++)
+		{
+			const int4 a = pc[i];
+			c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
+		}
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			int ai = c[k + HALO + CSKEW] * dp.vf_i[HALO], aq = 0;
+			// VSB: I taps symmetric, Q taps antisymmetric (complex band-pass of a real low-pass)
+			#pragma unroll
+			for(int y = 0; y < HALO; y++)
+			{
+				ai += (c[k + y + CSKEW] + c[k + 2 * HALO - y + CSKEW]) * dp.vf_i[y];
+				aq += (c[k + y + CSKEW] - c[k + 2 * HALO - y + CSKEW]) * dp.vf_q[y];
+			}
+			oi[k] = sat16i(ai >> 15);
+			oq[k] = sat16i(aq >> 15);                               // vf_q is all zero for the real low-pass
+		}
+	}
+	else
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) { oi[k] = cwin[k + HALO + CSKEW]; oq[k] = 0; }
+	}
+
+	sound_add<false>(dp, dt, la, ntp, x0, oi, oq);
+	post_store(dp, dt, la, x0, row, oi, oq, out, acc);
+}
+
+
+// ---------------------------------------------------------------------------
+// FM video (ref _vid_fmmod_process video.c:3452-3464, _fm_modulator 2299-2335; modes pal-fm,
+// ntsc-fm, secam-fm). The reference multiplies a Q31 phasor, once per output sample, by the LUT
+// entry the sample's baseband value selects - a recurrence over the whole stream. Closed form,
+// as for the sound carriers: phase(n) = sum over samples <= n of the rotation each LUT entry
+// actually applies (dt.fmv_ang, 0.64 turns), amplitude from the renormalisation counter. Three
+// launches per sub-batch:
+//   k_fmv_base  one CTA per line: pre-emphasis FIR (optional, 67/71 taps, asymmetric) over the
+//               composite stream + sound carriers -> baseband int16 (kept in L2) and the line's
+//               total rotation;
+//   k_fmv_scan  one CTA: exclusive prefix of the line totals on top of the carried phase;
+//   k_fmv_mod   one CTA per line: per-sample prefix inside the line, sin/cos, level, then the
+//               common post stage (IQ swap, offset mixer, combiner, 128-bit stores).
+// With a pre-emphasis filter the reference's modulator also integrates the pipeline's fill line
+// (the filter output for the line before the stream); that row is computed and scanned like
+// any other and simply not stored (out_row0 = -1).
+// ---------------------------------------------------------------------------
+
+#define FOFF 40                       // baseband window index = x + FOFF (>= 35 = 71 / 2)
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *sm)
+{
+	#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if(lane == 0) sm[w] = v;
+	__syncthreads();
+	if(w == 0)
+	{
+		v = lane < (int) ((blockDim.x + 31) >> 5) ? sm[lane] : 0;
+		#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+	}
+	return(v);                                                      // valid in thread 0
+}
+
+template<int NT>
+__global__ void __launch_bounds__(384)
+k_fmv_base(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const int16_t *comp, const int16_t *sadd, int pre)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int W4 = (W + 3) & ~3;
+	const int CW = W4 + 2 * FOFF;
+	int *cw = reinterpret_cast<int *>(smem_raw);                    // index = x + FOFF
+	short *ntp = reinterpret_cast<short *>(cw + CW);
+	__shared__ LineAudio la;
+	__shared__ unsigned long long red[12];
+	const int tid = threadIdx.x;
+
+	{
+		const int4 *sa = reinterpret_cast<const int4 *>(lap + blockIdx.x);
+		int4 *da = reinterpret_cast<int4 *>(&la);
+		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
+	}
+	if(dp.have_nicam)
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	{
+		// the launch's composite stream starts one line early: row b begins at (b + 1) * W - or at
+		// b * W when row 0 is the pipeline's fill line (`pre`), whose history is zero
+		const size_t r = (size_t) blockIdx.x + 1 - pre;
+		const int16_t *cs = comp + r * W;
+		const int16_t *sa = sadd ? sadd + r * W : NULL;
+		const bool first = pre && blockIdx.x == 0;
+		for(int i = tid; i < CW; i += blockDim.x)
+		{
+			const int x = i - FOFF;
+			int v = 0;
+			if(!(first && x < 0))
+			{
+				v = __ldg(cs + x);
+				if(sa) v = wrap16i(v + __ldg(sa + x));              // SECAM subcarrier of the same stream position
+			}
+			cw[i] = v;
+		}
+	}
+	__syncthreads();
+
+	const int x0 = tid * SPT;
+	unsigned long long rot = 0;
+	if(x0 < W)
+	{
+		int oi[SPT], oq[SPT];
+		if(NT > 0)
+		{
+			// out[x] = sat16(sum_y win[x - NT/2 + y] * taps[y] >> 15), ref fir.c:304-355 as a centred FIR
+			int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+			const int *w = cw + x0 - NT / 2 + FOFF;
+			int w0 = w[0], w1 = w[1], w2 = w[2];
+			#pragma unroll
+			for(int y = 0; y < NT; y++)
+			{
+				const int w3 = w[y + 3], t = dp.fmv_taps[y];
+				a0 += w0 * t; a1 += w1 * t; a2 += w2 * t; a3 += w3 * t;
+				w0 = w1; w1 = w2; w2 = w3;
+			}
+			oi[0] = sat16i(a0 >> 15); oi[1] = sat16i(a1 >> 15); oi[2] = sat16i(a2 >> 15); oi[3] = sat16i(a3 >> 15);
+		}
+		else
+		{
+			#pragma unroll
+			for(int k = 0; k < SPT; k++) oi[k] = cw[x0 + k + FOFF];
+		}
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) oq[k] = 0;
+		sound_add<true>(dp, dt, la, ntp, x0, oi, oq);                // only the I sum modulates (ref video.c:3460)
+		int16_t *b = dt.fmv_base + (size_t) blockIdx.x * W + x0;
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			if(x0 + k < W)
+			{
+				const int v = wrap16i(oi[k]);
+				b[k] = (int16_t) v;
+				rot += __ldg(dt.fmv_ang + v + 32768);
+			}
+		}
+	}
+	rot = block_sum_u64(rot, red);
+	if(tid == 0) dt.fmv_tot[blockIdx.x] = rot;
+}
+
+__global__ void __launch_bounds__(1024) k_fmv_scan(const DevTables dt, int nrows)
+{
+	__shared__ unsigned long long part[1024];
+	const int tid = threadIdx.x;
+	const int per = (nrows + 1023) / 1024;
+	const int r0 = tid * per, r1 = min(nrows, r0 + per);
+	unsigned long long sum = 0;
+	for(int r = r0; r < r1; r++) sum += dt.fmv_tot[r];
+	part[tid] = sum;
+	__syncthreads();
+	for(int o = 1; o < 1024; o <<= 1)
+	{
+		const unsigned long long v = tid >= o ? part[tid - o] : 0;
+		__syncthreads();
+		part[tid] += v;
+		__syncthreads();
+	}
+	unsigned long long run = *dt.fmv_carry + part[tid] - sum;      // exclusive
+	for(int r = r0; r < r1; r++) { dt.fmv_rowbase[r] = run; run += dt.fmv_tot[r]; }
+	__syncthreads();
+	if(tid == 1023) *dt.fmv_carry += part[1023];
+}
+
+__global__ void __launch_bounds__(384)
+k_fmv_mod(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, int16_t *out,
+	const int16_t *acc, int acc_rows, int out_row0)
+{
+	__shared__ LineAudio la;
+	__shared__ unsigned long long wsum[12];
+	const int W = dp.W, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	{
+		const int4 *sa = reinterpret_cast<const int4 *>(lap + blockIdx.x);
+		int4 *da = reinterpret_cast<int4 *>(&la);
+		for(int i = tid; i < (int) (sizeof(LineAudio) / 16); i += blockDim.x) da[i] = __ldg(sa + i);
+	}
+	const int x0 = tid * SPT;
+	unsigned long long p[SPT];
+	unsigned long long run = 0;
+	{
+		const int16_t *b = dt.fmv_base + (size_t) blockIdx.x * W + x0;
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			if(x0 + k < W) run += __ldg(dt.fmv_ang + (int) b[k] + 32768);
+			p[k] = run;                                             // inclusive inside the thread
+		}
+	}
+	// exclusive prefix of the thread totals across the CTA
+	unsigned long long inc = run;
+	#pragma unroll
+	for(int o = 1; o < 32; o <<= 1)
+	{
+		const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+		if(lane >= o) inc += v;
+	}
+	if(lane == 31) wsum[wid] = inc;
+	__syncthreads();
+	unsigned long long before = dt.fmv_rowbase[blockIdx.x] + inc - run;
+	for(int w = 0; w < wid; w++) before += wsum[w];
+
+	const int row = (int) blockIdx.x + out_row0;
+	if(x0 >= W || row < 0) return;
+	int oi[SPT], oq[SPT];
+	int kk = la.kk0 + x0; if(kk >= 32767) kk -= 32767;
+	#pragma unroll
+	for(int k = 0; k < SPT; k++, kk++)
+	{
+		if(kk >= 32767) kk -= 32767;
+		// amplitude of the Q31 phasor kk+1 multiplications after a renormalisation (as the sound carriers)
+		const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
+		const unsigned long long ph = before + p[k];
+		float sn, cs;
+		__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);       // pi / 2^31
+		oi[k] = (min((int) floorf(amp * cs), 32767) * dp.fmv_level) >> 15;    // pi >> 16 <= 32767
+		oq[k] = (min((int) floorf(amp * sn), 32767) * dp.fmv_level) >> 15;
+	}
+	post_store(dp, dt, la, x0, row, oi, oq, out, row < acc_rows ? acc : NULL);
 }
 
 template<int MAXT, int MINB>
@@ -1859,6 +2104,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.clut = (const htv_c16_t *) dev_copy(d, t->clut, sizeof(htv_c16_t) * t->clut_len);
 	dt.burst_win = (const int16_t *) dev_copy(d, t->burst_win, sizeof(int16_t) * (t->burst_width + 1));
 	dt.fm_ang = (const uint64_t *) dev_copy(d, t->fm_ang, t->fm_ang ? sizeof(uint64_t) * 65536 : 0);
+	dt.fmv_ang = (const uint64_t *) dev_copy(d, t->fmv_ang, t->fmv_ang ? sizeof(uint64_t) * 65536 : 0);
 	dt.afir_v = (const int32_t *) dev_copy(d, t->afir_v, sizeof(t->afir_v));
 	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
 	dt.lim_shape = (const int16_t *) dev_copy(d, t->lim_shape, sizeof(t->lim_shape));
@@ -1949,7 +2195,22 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		htv_dev_destroy(d);
 		return(NULL);
 	}
-	if(!secam && (W & 3) == 0)
+	if(dp.have_fmv)
+	{
+		const size_t rows = (size_t) d->sub_lines + 4;
+		dt.fmv_base = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W + 256);
+		dt.fmv_tot = (unsigned long long *) dev_zero(d, sizeof(unsigned long long) * rows);
+		dt.fmv_rowbase = (unsigned long long *) dev_zero(d, sizeof(unsigned long long) * rows);
+		dt.fmv_carry = (unsigned long long *) dev_zero(d, sizeof(unsigned long long));
+		d->fmv_smem = sizeof(int) * (W4 + 2 * FOFF) + sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7);
+		if(!dt.fmv_ang || !dt.fmv_base || !dt.fmv_tot || !dt.fmv_rowbase || !dt.fmv_carry)
+		{
+			snprintf(err, errlen, "device allocation failed");
+			htv_dev_destroy(d);
+			return(NULL);
+		}
+	}
+	if(!secam && (W & 3) == 0 && !dp.have_fmv)
 	{
 		int nsm = 148;
 		cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
@@ -2135,6 +2396,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 {
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
+	// FM video with a pre-emphasis filter: the modulator also integrates the pipeline's fill line
+	const int fm_skip = d->dp.have_fmv && d->dp.fmv_ntaps > 0 && line0 == 0 ? 1 : 0;
 	if(nlines > d->desc_cap)
 	{
 		cudaStreamSynchronize(st);
@@ -2143,7 +2406,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		d->d_desc_r = d->d_desc_a = NULL;
 		d->desc_cap = 0;
 		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
-		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * (size_t) nlines));
+		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
@@ -2153,7 +2416,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		CK(cudaEventRecord(d->ev_in, st));
 		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 	}
-	k_line_desc_a<<<(nlines + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0, nlines);
+	k_line_desc_a<<<(nlines + fm_skip + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0 - fm_skip, nlines + fm_skip);
 	CK(cudaEventRecord(d->ev_audio, d->side));
 	d->side_armed = 0;
 	bool joined = false;
@@ -2224,7 +2487,20 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		}
 		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
-		if(d->d_comp32)
+		if(d->dp.have_fmv)
+		{
+			const int pre = fm_skip && done == 0 ? 1 : 0, rows = n + pre;
+			const LineAudio *lap = ld.a + done + fm_skip - pre;
+			const htv_dparams_t &dp = d->dp;
+			if(dp.fmv_ntaps == 67) k_fmv_base<67><<<rows, d->line_threads, d->fmv_smem, st>>>(dp, d->dt, lap, cstream, sadd, pre);
+			else if(dp.fmv_ntaps == 71) k_fmv_base<71><<<rows, d->line_threads, d->fmv_smem, st>>>(dp, d->dt, lap, cstream, sadd, pre);
+			else if(dp.fmv_ntaps == 0) k_fmv_base<0><<<rows, d->line_threads, d->fmv_smem, st>>>(dp, d->dt, lap, cstream, sadd, pre);
+			else { fprintf(stderr, "hacktv_b200: unsupported FM pre-emphasis length %d\n", dp.fmv_ntaps); return(HTV_ERROR); }
+			k_fmv_scan<<<1, 1024, 0, st>>>(d->dt, rows);
+			k_fmv_mod<<<rows, d->line_threads, 0, st>>>(dp, d->dt, lap, o, acc, acc_rows, -pre);
+			d->launches += 2;
+		}
+		else if(d->d_comp32)
 		{
 			const int grid = n < d->mod_grid ? n : d->mod_grid;
 			if(d->line_threads <= 256) k_mod_tma<256, 4><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_comp32, n, o, acc, acc_rows);

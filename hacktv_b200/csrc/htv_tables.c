@@ -16,6 +16,7 @@
 #include <string.h>
 #include <math.h>
 #include "htv_internal.h"
+#include "htv_fm_taps.h"
 
 #define IRT1090 2.0738786  /* 10-90% -> 0-100% for integrated raised-cosine edges (ref common.h:29) */
 
@@ -283,7 +284,7 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	struct htv_tables_t *t;
 	htv_config_t *c;
 	htv_dparams_t *dp;
-	double line_s, d;
+	double line_s, d, slevel;
 	int i, n;
 
 	if(!conf || sample_rate == 0) return(NULL);
@@ -292,9 +293,9 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		fprintf(stderr, "hacktv_b200: raster type %d is not on the accelerated path\n", conf->type);
 		return(NULL);
 	}
-	if(conf->modulation == HTV_FM)
+	if(conf->modulation == HTV_FM && conf->fm_energy_dispersal != 0)
 	{
-		fprintf(stderr, "hacktv_b200: FM video modulation is not on the accelerated path\n");
+		fprintf(stderr, "hacktv_b200: FM energy dispersal is not on the accelerated path\n");
 		return(NULL);
 	}
 
@@ -331,7 +332,9 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	dp->swap_iq = c->swap_iq;
 
 	/* levels, ref video.c:3855-3881 */
-	dp->vlevel = c->video_level * c->level;
+	/* slevel: sub-carrier level; 1.0 when FM modulating, else the overall level (ref video.c:3856-3860) */
+	slevel = c->modulation == HTV_FM ? 1.0 : c->level;
+	dp->vlevel = c->video_level * slevel;
 	if(c->invert_video)
 	{
 		double w = c->white_level;
@@ -496,6 +499,29 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	{
 		/* ref video.c:3653-3764 */
 		double lp[HTV_VF_NTAPS];
+		if(c->modulation == HTV_FM)
+		{
+			/* ref video.c:3678-3740: a fixed CCIR-405 pre-emphasis table per standard and rate */
+			const double *taps;
+			#define FMT(a) do { taps = a; dp->fmv_ntaps = sizeof(a) / sizeof(double); } while(0)
+			if(c->lines == 525)
+			{
+				if(sample_rate == 18000000) FMT(htv_fm_525_18_taps);
+				else FMT(htv_fm_525_2025_taps);
+			}
+			else
+			{
+				if(sample_rate == 14000000) FMT(htv_fm_625_14_taps);
+				else if(sample_rate == 20000000) FMT(htv_fm_625_20_taps);
+				else if(sample_rate == 28000000) FMT(htv_fm_625_28_taps);
+				else FMT(htv_fm_625_2025_taps);
+			}
+			#undef FMT
+			quantise(dp->fmv_taps, taps, dp->fmv_ntaps, 1);
+			dp->shift = dp->W;
+		}
+		else
+		{
 		if(c->modulation == HTV_VSB)
 		{
 			/* complex band-pass = low-pass shifted to the band centre, ref fir.c:230-255 */
@@ -538,13 +564,23 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		/* the filter's one-line pipeline delay makes the audio stages run one
 		 * line ahead of the emitted stream (ref video.c:3244,3268) */
 		dp->shift = dp->W;
+		}
+	}
+
+	if(c->modulation == HTV_FM)
+	{
+		/* ref video.c:4564-4570: carrier 0 Hz, deviation fm_deviation per unit of signal */
+		dp->have_fmv = 1;
+		dp->fmv_level = (int16_t) round(INT16_MAX * (c->fm_level * c->level));
+		t->fmv_ang = malloc(sizeof(uint64_t) * 65536);
+		build_fm_angles(t->fmv_ang, sample_rate, 0, c->fm_deviation);
 	}
 
 	/* audio subcarriers, ref video.c:4404-4558 */
 	if(c->fm_mono_level > 0 && c->fm_mono_carrier != 0)
 	{
 		dp->have_fm = 1;
-		dp->fm_level = (int16_t) round(INT16_MAX * (c->fm_mono_level * c->level));
+		dp->fm_level = (int16_t) round(INT16_MAX * (c->fm_mono_level * slevel));
 		t->fm_ang = malloc(sizeof(uint64_t) * 65536);
 		build_fm_angles(t->fm_ang, sample_rate, c->fm_mono_carrier, c->fm_mono_deviation);
 		if(c->fm_mono_preemph)
@@ -564,7 +600,7 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	if(c->am_audio_level > 0 && c->am_mono_carrier != 0)
 	{
 		dp->have_am = 1;
-		dp->am_level = (int16_t) round(INT16_MAX * (c->am_audio_level * c->level));
+		dp->am_level = (int16_t) round(INT16_MAX * (c->am_audio_level * slevel));
 		dp->am_ang = carrier_angle(sample_rate, c->am_mono_carrier);
 	}
 
@@ -585,7 +621,7 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 			double xx = (double) x / h;
 			double ham = (xx < -1 || xx > 1) ? 0 : 0.54 - 0.46 * cos((M_PI * (1.0 + xx)));
 			double r = root_rc(((double) x) / sps, c->nicam_beta, 1.0) * ham;
-			r *= M_SQRT1_2 * INT16_MAX * (c->nicam_level * c->level);
+			r *= M_SQRT1_2 * INT16_MAX * (c->nicam_level * slevel);
 			t->nicam_taps[x + h] = lround(r);
 		}
 		g = gcd64(sample_rate, HTV_NICAM_SYMBOL_RATE);
@@ -691,7 +727,7 @@ void htv_tables_free(htv_tables_t *t)
 {
 	if(!t) return;
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
-	free(t->fm_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
+	free(t->fm_ang); free(t->fmv_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
 	free(t);
 }
@@ -731,6 +767,7 @@ const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count)
 	if(!strcmp(name, "burst_win") && t->burst_win) return(view16(t, t->burst_win, t->burst_width, count));
 	if(!strcmp(name, "chroma_taps") && dp->chroma_ntaps) return(view32(t, dp->chroma_taps, dp->chroma_ntaps, count));
 	if(!strcmp(name, "vsb_itaps") && dp->vf_type) return(view32(t, dp->vf_i, HTV_VF_NTAPS, count));
+	if(!strcmp(name, "fmv_taps") && dp->fmv_ntaps) return(view32(t, dp->fmv_taps, dp->fmv_ntaps, count));
 	if(!strcmp(name, "vsb_qtaps") && dp->vf_type == 3) return(view32(t, dp->vf_q, HTV_VF_NTAPS, count));
 	if(!strcmp(name, "nicam_taps") && t->nicam_taps) return(view16(t, t->nicam_taps, t->nicam_ntaps, count));
 	if(!strcmp(name, "secam_lpf") && t->secam_bell) return(view32(t, dp->secam_lpf, 15, count));

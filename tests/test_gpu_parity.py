@@ -58,6 +58,16 @@ CASES = [
     ("i", 16000000, 700, dict(vfilter=True, swap_iq=True), 1),
     ("i", 16000000, 700, dict(vfilter=True, invert_video=True, noaudio=True), 0),
     ("i", 16000000, 700, dict(vfilter=True, level=0.7, volume=2.0), 1),
+    # FM video: closed-form phase = prefix sum over every sample. Without a
+    # sound carrier the modulating signal is exact integer work, so the phase is exact: +-1 LSB for ever.
+    ("pal-fm", 20000000, 700, dict(vfilter=True, noaudio=True), 1),
+    ("pal-fm", 20000000, 700, dict(noaudio=True), 1),
+    ("pal-fm", 20250000, 500, dict(vfilter=True, noaudio=True), 1),
+    ("pal-fm", 14000000, 500, dict(vfilter=True, noaudio=True), 1),
+    ("ntsc-fm", 18000000, 600, dict(vfilter=True, noaudio=True), 1),
+    ("ntsc-fm", 20250000, 600, dict(vfilter=True, noaudio=True), 1),      # W = 1287, 71 taps
+    ("secam-fm", 20250000, 500, dict(vfilter=True, noaudio=True), 1),
+    ("pal-fm", 20000000, 500, dict(vfilter=True, noaudio=True, deviation=8e6, level=0.5), 1),
 ]
 
 
@@ -165,3 +175,63 @@ def test_memory_source_equals_callback_source(built):
     b.open_memory_source(frames, audio, audio_block=1000)
     y = b.render_host(1400); b.close()
     assert np.array_equal(x, y)
+
+
+def test_fm_video_chunking_and_offset(built):
+    """The FM video phase is carried across calls and sub-batches; the offset mixer follows it."""
+    H = built
+    conf = H.mode_config("pal-fm", vfilter=True)
+    a = H.Encoder(conf, 20000000); a.open_test_source()
+    whole = a.render_host(1400); a.close()
+    b = H.Encoder(conf, 20000000); b.open_test_source()
+    parts = np.concatenate([b.render_host(n) for n in (1, 311, 313, 625, 150)]); b.close()
+    assert np.array_equal(whole, parts)
+    # full-scale FM video (|IQ| reaches 32768.2 through the reference's floors) overflows int16 in the offset
+    # mixer now and then, in the reference too: compare modulo the wrap
+    got, want = _pair(H, "pal-fm", 20000000, 500, vfilter=True, noaudio=True, offset=-3000000, swap_iq=True)
+    d = np.abs((got.astype(np.int32) - want.astype(np.int32) + 32768) % 65536 - 32768)
+    assert d.max() <= 3 and (d <= 1).mean() > 0.999, (d.max(), (d <= 1).mean())     # +-1 turned by the mixer, +-1 of its NCO
+    got, want = _pair(H, "pal-fm", 20000000, 500, vfilter=True, noaudio=True, offset=2500000, level=0.5)
+    d = _diff(got, want)
+    assert d.max() <= 2 and (d <= 1).mean() > 0.99, (d.max(), (d <= 1).mean())
+
+
+def test_fm_video_long_run_stays_within_one_lsb(built):
+    """> 9000 lines: several sub-batches, hundreds of renormalisation periods, no drift."""
+    got, want = _pair(built, "pal-fm", 20000000, 9500, vfilter=True, noaudio=True)
+    d = _diff(got, want)
+    assert d.max() <= 1, d.max()
+
+
+@pytest.mark.parametrize("mode,rate,nlines,kw", [
+    ("pal-fm", 20000000, 2500, dict(vfilter=True)),
+    ("pal-fm", 20000000, 700, dict()),
+    ("ntsc-fm", 18000000, 1100, dict(vfilter=True)),
+    ("secam-fm", 20250000, 700, dict(vfilter=True)),
+])
+def test_fm_video_with_sound_carrier(built, mode, rate, nlines, kw):
+    """With a sound subcarrier the modulating signal inherits the carrier's +-1 LSB (closed-form NCO against
+    the reference's Q31 recurrence), and an FM modulator INTEGRATES its input: every baseband sample that is
+    1 LSB off turns everything after it by one LUT step (2 pi * deviation / 32767 / fs = 1.5e-4 rad, 5 LSB of
+    arc at full scale), and because the 6.5 MHz carrier repeats every 40 samples at 20 Msps such samples come
+    in runs inside one 32 kHz audio sample. No parallel formulation can avoid this - the reference's own
+    truncation noise decides those samples (FM video). Parity is therefore stated as:
+    the same signal up to a slowly wandering common rotation (measured: a random walk of ~15 LUT steps =
+    2e-3 rad over 700 lines), the instantaneous frequency identical except at < 0.5 % of the samples, a third to
+    two thirds of the lines within 1 LSB once the line's mean rotation is removed. Without the sound carrier (above) the path is
+    exact to +-1 LSB for ever."""
+    got, want = _pair(built, mode, rate, nlines, **kw)
+    g = got.astype(np.float64).reshape(nlines, -1, 2); g = g[..., 0] + 1j * g[..., 1]
+    w = want.astype(np.float64).reshape(nlines, -1, 2); w = w[..., 0] + 1j * w[..., 1]
+    rot = np.angle((g * np.conj(w)).sum(axis=1))
+    res = g * np.exp(-1j * rot)[:, None] - w
+    worst = np.maximum(np.abs(res.real), np.abs(res.imag)).max(axis=1)
+    step = 2 * np.pi * 16e6 / 32767 / rate
+    print(f"{mode} {rate}: worst residual {worst.max():.2f} LSB, lines within 1.5 LSB {(worst <= 1.5).mean():.4f}, "
+          f"rotation after {nlines} lines {rot[-1] / step:.1f} LUT steps (max {np.abs(rot).max() / step:.1f})")
+    assert (worst <= 1.5).mean() > 0.25, (worst <= 1.5).mean()
+    assert worst.max() <= 150.0, worst.max()
+    assert np.abs(rot).max() < step * (60 + 0.05 * nlines), np.abs(rot).max() / step
+    df = np.angle(g[:, 1:] * np.conj(g[:, :-1])) - np.angle(w[:, 1:] * np.conj(w[:, :-1]))
+    df = (df + np.pi) % (2 * np.pi) - np.pi
+    assert (np.abs(df) > 0.6 * step).mean() < 0.005, (np.abs(df) > 0.6 * step).mean()

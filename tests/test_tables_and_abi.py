@@ -108,10 +108,10 @@ def test_product_never_links_the_oracle(built):
 
 
 def test_unsupported_configs_fail_loudly(built):
-    conf = built.mode_config("i")
-    conf.modulation = 3          # FM video: not on the accelerated path
+    conf = built.mode_config("pal-fm")
+    conf.fm_energy_dispersal = 0.0625    # FM energy dispersal: not on the accelerated path
     with pytest.raises(RuntimeError):
-        built.Tables(conf, 16000000)
+        built.Tables(conf, 20000000)
     conf = built.mode_config("i")
     conf.type = 3                # 819-line raster
     with pytest.raises(RuntimeError):
@@ -125,3 +125,15 @@ def test_encoder_needs_a_gpu_or_says_so(built):
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError):
         built.Encoder("i", 16000000)
+
+
+def test_fm_video_tables_match_the_oracle(built):
+    """FM video (ref video.c:3678-3740, 4564-4570): pre-emphasis taps per sample rate."""
+    for mode, rate, n in (("pal-fm", 20000000, 67), ("pal-fm", 20250000, 67), ("pal-fm", 14000000, 67),
+                          ("ntsc-fm", 18000000, 67), ("ntsc-fm", 20250000, 71)):   # 28 Msps: line wider than the kernels' 1536
+        conf = built.mode_config(mode, vfilter=True)
+        t = built.Tables(conf, rate)
+        o = orc.Oracle(conf, rate)
+        a, b = t.get("fmv_taps"), o.table("vsb_itaps")
+        assert a is not None and len(a) == n and np.array_equal(a, b), (mode, rate)
+        o.close()
