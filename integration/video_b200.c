@@ -6,7 +6,7 @@
  * rest of hacktv links to: vid_init, vid_next_line, vid_free, vid_info,
  * vid_get_framebuffer_length (ref video.h:512-516). hacktv.c, av*.c, rf*.c stay untouched;
  * the stock encoder in video.c is kept as the fallback for every configuration the GPU
- * path does not cover (teletext, scramblers, MAC, FM video, ...) by building it with
+ * path does not cover (teletext, scramblers, MAC, energy dispersal, ...) by building it with
  *     -Dvid_init=cpu_vid_init -Dvid_next_line=cpu_vid_next_line -Dvid_free=cpu_vid_free
  *     -Dvid_info=cpu_vid_info -Dvid_get_framebuffer_length=cpu_vid_get_framebuffer_length
  * (see oracle/Makefile target `dropin`, which does exactly that without touching a source).
@@ -41,7 +41,7 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 {
 	if(getenv("HACKTV_NO_B200")) return(0);
 	if(c->type != VID_RASTER_625 && c->type != VID_RASTER_525) return(0);
-	if(c->modulation == VID_FM) return(0);
+	if(c->modulation == VID_FM && c->fm_energy_dispersal != 0) return(0);
 	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
 	if(pixel_rate && pixel_rate != sample_rate) return(0);
 	if(c->teletext || c->wss || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
@@ -64,7 +64,7 @@ static void _translate(htv_config_t *h, const vid_config_t *c)
 	CP(gamma); CP(rw_co); CP(gw_co); CP(bw_co); CP(colour_mode); CP(volume); CP(colour_bw);
 	CP(burst_width); CP(burst_left); CP(burst_level); CP(burst_rise); CP(ev_co); CP(eu_co);
 	CP(fm_mono_carrier); CP(fm_mono_deviation); CP(fm_mono_preemph); CP(nicam_carrier); CP(nicam_beta);
-	CP(am_mono_carrier);
+	CP(am_mono_carrier); CP(fm_level); CP(fm_deviation); CP(fm_energy_dispersal);
 #undef CP
 	h->frame_rate_num = c->frame_rate.num; h->frame_rate_den = c->frame_rate.den;
 	h->colour_carrier_num = c->colour_carrier.num; h->colour_carrier_den = c->colour_carrier.den;

@@ -29,9 +29,10 @@ def _run(binary, args, nbytes):
     ("-m i -s 16000000 --filter", 4, 1),
     ("-m m -s 13500000 --filter", 4, 1),
     ("-m l -s 16000000 --filter", 4, 1),
+    ("-m pal-fm -s 20000000 --filter --noaudio", 4, 1),
 ])
 def test_same_cli_same_bytes(args, per, tol):
-    w = 858 if "13500000" in args else 1024
+    w = 858 if "13500000" in args else (1280 if "20000000" in args else 1024)
     lines = 1300 if w == 1024 else 1100
     a = _run(DROPIN, args, lines * w * per)
     b = _run(STOCK, args, lines * w * per)

@@ -9,7 +9,8 @@ import hacktv_b200 as H
 
 CONFIGS = [("cfg1 pal 16M (real)", "pal", 16000000, False), ("cfg2 i 16M --filter", "i", 16000000, True),
            ("cfg3 m 13.5M --filter", "m", 13500000, True), ("cfg4 l 16M --filter (SECAM)", "l", 16000000, True),
-           ("cfg5 i 20M --filter", "i", 20000000, True)]
+           ("cfg5 i 20M --filter", "i", 20000000, True),
+           ("next: pal-fm 20M --filter (FM video)", "pal-fm", 20000000, True)]
 for name, mode, rate, filt in CONFIGS:
     enc = H.Encoder(H.mode_config(mode, vfilter=filt), rate)
     enc.open_test_source()
