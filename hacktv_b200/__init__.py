@@ -73,6 +73,15 @@ class Frame(C.Structure):
 _READ_VIDEO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Frame))
 _READ_AUDIO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 _PASSTHRU_READ = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class VbiLine(C.Structure):
+    """htv_vbi_line_t"""
+    _fields_ = [("line", C.c_int), ("replace_from", C.c_int), ("replace_to", C.c_int), ("replace_value", C.c_int),
+                ("add", C.c_void_p)]
+
+
+_READ_VBI = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.POINTER(VbiLine)), C.POINTER(C.c_int))
 _CLOSE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
@@ -127,6 +136,7 @@ def lib() -> C.CDLL:
     L.htv_mix_add.restype = C.c_int; L.htv_mix_add.argtypes = [vp, vp, sz, vp]
     L.htv_set_passthru.restype = C.c_int; L.htv_set_passthru.argtypes = [vp, _PASSTHRU_READ, vp]
     L.htv_passthru_delay_lines.restype = C.c_int; L.htv_passthru_delay_lines.argtypes = [vp]
+    L.htv_set_vbi_source.restype = C.c_int; L.htv_set_vbi_source.argtypes = [vp, _READ_VBI, vp]
     for f in ("htv_samples_per_line", "htv_active_width", "htv_active_lines", "htv_lines_per_frame",
               "htv_sample_rate", "htv_is_complex", "htv_bytes_per_sample"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
@@ -325,6 +335,32 @@ class Encoder:
         r = self._L.htv_set_passthru(self._h, cb, None)
         if r != HTV_OK:
             raise RuntimeError("htv_set_passthru failed (it must precede the first rendered line)")
+
+    def set_vbi_lines(self, lines, every=1):
+        """htv_set_vbi_source with a fixed set of overlays: `lines` = [(line, add or None, (from, to, value))],
+        reported for every `every`-th frame (1 = all frames)."""
+        arr = (VbiLine * len(lines))()
+        for i, (line, add, rep) in enumerate(lines):
+            arr[i].line = line
+            arr[i].replace_from, arr[i].replace_to, arr[i].replace_value = rep
+            if add is not None:
+                add = np.ascontiguousarray(add, dtype=np.int16)
+                assert add.size == self.width
+                self._keep.append(add)
+                arr[i].add = add.ctypes.data
+        n = len(lines)
+
+        def read(ctx, frame, out, count):
+            if (frame - 1) % every:
+                count[0] = 0
+                return HTV_OK
+            out[0] = C.cast(arr, C.POINTER(VbiLine))
+            count[0] = n
+            return HTV_OK
+        cb = _READ_VBI(read)
+        self._keep += [cb, arr]
+        if self._L.htv_set_vbi_source(self._h, cb, None) != HTV_OK:
+            raise RuntimeError("htv_set_vbi_source failed")
 
     @property
     def passthru_delay_lines(self) -> int:

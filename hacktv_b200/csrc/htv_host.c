@@ -40,6 +40,12 @@ struct htv_t {
 	int64_t audio_have;           /* source pairs uploaded so far (absolute count) */
 	int16_t *zeros;
 
+	/* VBI overlays pulled from the source, kept until their line has been rendered */
+	htv_read_vbi_t vbi_read;
+	void *vbi_ctx;
+	struct { long long line; int from, to, value; int16_t *add; } *ov;
+	int nov, ov_cap;
+
 	/* channel combiner (ref --passthru, video.c:3517-3541, 4607-4634) */
 	htv_passthru_read_t pt_read;
 	void *pt_ctx;
@@ -63,6 +69,8 @@ struct htv_t {
 	int16_t *h_iq;                /* interleaved scratch for real modes */
 	htv_line_t line;
 };
+
+static void drop_overlays_before(htv_t *s, long long line);
 
 const char *htv_version(void) { return("hacktv_b200 0.1 (sm_100a)"); }
 
@@ -139,6 +147,8 @@ void htv_free(htv_t *s)
 		htv_dev_stream_free(s->st_compute); htv_dev_stream_free(s->st_copy);
 		htv_dev_destroy(s->dev);
 	}
+	drop_overlays_before(s, 0x7FFFFFFFFFFFFFFFLL);
+	free(s->ov);
 	htv_dev_free_pinned(s->h_frame);
 	htv_dev_free_pinned(s->pt_host);
 	free(s->pt_tmp);
@@ -275,6 +285,74 @@ static int pull_passthru(htv_t *s, int n, void *stream)
 	return(lines);
 }
 
+/* ---- VBI overlays ------------------------------------------------------------
+ * The reference's VBI stages (teletext, WSS, VITS, VITC, CC608: ref video.c:4213-4357) each add a
+ * sparse int16 waveform to a finished raster line (vbidata_render, vbidata.c:186-239; WSS first sets
+ * part of line 23 to black, wss.c:182-185). They stay host code: whoever builds the packets hands
+ * the encoder, once per frame, the lines they touch; the raster kernel applies them. */
+int htv_set_vbi_source(htv_t *s, htv_read_vbi_t read, void *ctx)
+{
+	if(!s) return(HTV_ERROR);
+	s->vbi_read = read;
+	s->vbi_ctx = ctx;
+	return(HTV_OK);
+}
+
+static void drop_overlays_before(htv_t *s, long long line)
+{
+	int i, k = 0;
+	for(i = 0; i < s->nov; i++)
+	{
+		if(s->ov[i].line < line) { free(s->ov[i].add); continue; }
+		s->ov[k++] = s->ov[i];
+	}
+	s->nov = k;
+}
+
+/* Pull frame f's overlays (f 0-based); returns 0, or 1 if they do not fit this launch sequence */
+static int pull_overlays(htv_t *s, int64_t f)
+{
+	const htv_vbi_line_t *lines = NULL;
+	int n = 0, i, j;
+	if(s->vbi_read(s->vbi_ctx, (int) (f + 1), &lines, &n) != HTV_OK || n <= 0 || !lines) return(0);
+	if(s->nov + n > htv_dev_overlay_capacity()) return(1);
+	if(s->nov + n > s->ov_cap)
+	{
+		s->ov_cap = (s->nov + n) * 2;
+		s->ov = realloc(s->ov, sizeof(*s->ov) * s->ov_cap);
+	}
+	for(i = 0; i < n; i++)
+	{
+		const long long gl = (long long) f * s->lines + (lines[i].line - 1);
+		if(lines[i].line < 1 || lines[i].line > s->lines) continue;
+		/* keep the table sorted by line (frames arrive in order; lines of a frame may not) */
+		for(j = s->nov; j > 0 && s->ov[j - 1].line > gl; j--) s->ov[j] = s->ov[j - 1];
+		s->ov[j].line = gl;
+		s->ov[j].from = lines[i].replace_from; s->ov[j].to = lines[i].replace_to; s->ov[j].value = lines[i].replace_value;
+		s->ov[j].add = NULL;
+		if(lines[i].add)
+		{
+			s->ov[j].add = malloc(sizeof(int16_t) * s->W);
+			memcpy(s->ov[j].add, lines[i].add, sizeof(int16_t) * s->W);
+		}
+		s->nov++;
+	}
+	return(0);
+}
+
+static int send_overlays(htv_t *s, long long end_line)
+{
+	long long line[2048];
+	int from[2048], to[2048], value[2048], i, n = 0;
+	const int16_t *add[2048];
+	for(i = 0; i < s->nov && s->ov[i].line < end_line && n < 2048; i++, n++)
+	{
+		line[n] = s->ov[i].line; from[n] = s->ov[i].from; to[n] = s->ov[i].to; value[n] = s->ov[i].value;
+		add[n] = s->ov[i].add;
+	}
+	return(htv_dev_set_overlays(s->dev, n, line, from, to, value, add));
+}
+
 /* One device launch sequence for lines [L0, L0 + n): at most MAX_NEW_FRAMES new pictures */
 static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream)
 {
@@ -292,6 +370,7 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	/* pictures and PCM go up on the encoder's own upload stream, ahead of the kernels queued on
 	 * `stream` for the previous chunk and beside the caller's device-to-host copies */
 	up = htv_dev_uploads_begin(s->dev);
+	drop_overlays_before(s, L0);
 
 	/* pictures: one pull per frame, at its first line (ref video.c:4873-4881) */
 	for(f = f0; f <= f1; f++)
@@ -302,6 +381,13 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 			if(nnew >= MAX_NEW_FRAMES)
 			{
 				/* every free picture slot is in use by this launch: stop at this frame boundary */
+				n = (int) (f * s->lines - L0);
+				break;
+			}
+			if(s->vbi_read && pull_overlays(s, f))
+			{
+				/* the overlay table of this launch sequence is full: stop at this frame boundary */
+				if(f == f0) return(HTV_ERROR);
 				n = (int) (f * s->lines - L0);
 				break;
 			}
@@ -339,6 +425,11 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	{
 		const int64_t m1 = (L0 + n) * (int64_t) s->W + dp->shift;
 		r = pull_audio(s, fetches_by(m1 - 1, s->tab->rate), up);
+		if(r != HTV_OK) return(r);
+	}
+	if(s->vbi_read || s->nov)
+	{
+		r = send_overlays(s, L0 + n);
 		if(r != HTV_OK) return(r);
 	}
 	r = htv_dev_uploads_end(s->dev, stream);

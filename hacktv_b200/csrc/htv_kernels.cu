@@ -69,6 +69,11 @@ struct DevTables {
 	uint8_t *nic_local;               // RS: inclusive prefix (mod 4) of the DQPSK steps inside the symbol's frame
 	uint8_t *nic_ftot;                // RF: total step of frame k (mod 4)
 	uint8_t *nic_fstart;              // RF: differential symbol state before frame k
+	// VBI overlays of the current launch sequence (sorted by global line index)
+	int ov_n;
+	const long long *ov_line;         // [ov_n] global line index
+	const int4 *ov_meta;              // [ov_n] replace_from, replace_to, replace_value, row of ov_add or -1
+	const int16_t *ov_add;            // [rows][W]
 	// FM video
 	const uint64_t *fmv_ang;          // 65536: effective rotation of each modulator LUT entry, turns * 2^64
 	int16_t *fmv_base;                // [rows][W] modulating signal of the current sub-batch
@@ -99,6 +104,7 @@ struct SecScratch {
 };
 
 #define MAPBUFS 16
+#define HTV_OV_CAP 2048                // VBI overlay lines per launch sequence
 
 struct htv_dev_t {
 	int device;
@@ -117,6 +123,11 @@ struct htv_dev_t {
 	cudaEvent_t ev_map[MAPBUFS];
 	int map_i;
 	int16_t *d_pcm;
+	// VBI overlays: pinned staging + device copies, refilled per launch sequence
+	long long *h_ov_line, *d_ov_line;
+	int4 *h_ov_meta, *d_ov_meta;
+	int16_t *h_ov_add, *d_ov_add;
+	cudaEvent_t ev_ov;
 	// carries
 	int64_t fm_jc;                    // last audio index whose fm_B entry is valid (-1 at start)
 	int64_t nic_kc;                   // first frame whose nic_fstart is valid for a restart
@@ -522,7 +533,9 @@ struct __align__(16) LineRaster {
 	int sec_prev_comp;                // ... and which component of it: 1 u, 2 v
 	int pad1;
 	long long sec_prev_row;           // pixel offset of that row
-	long long pad2;
+	// VBI overlay on this line (ref vbidata.c:186-239, wss.c:182-185): I[from, to) = value, then I += add
+	int ov_from, ov_to, ov_value, ov_add; // ov_add: row of dt.ov_add, -1 none; ov_from >= ov_to: no replace
+	int ov_any, pad2;
 };
 
 // Sound-carrier state at the start of a line
@@ -602,6 +615,17 @@ __device__ void line_raster(const htv_dparams_t &dp, const DevTables &dt, int64_
 	li.valid = L >= 0;
 	li.nent = 0;
 	li.sec_proc = 0;
+	li.ov_any = 0; li.ov_from = li.ov_to = 0; li.ov_value = 0; li.ov_add = -1;
+	if(dt.ov_n > 0 && L >= 0)
+	{
+		int lo = 0, hi = dt.ov_n - 1;
+		while(lo < hi) { const int mid = (lo + hi) >> 1; if(dt.ov_line[mid] < L) lo = mid + 1; else hi = mid; }
+		if(dt.ov_line[lo] == L)
+		{
+			const int4 m = dt.ov_meta[lo];
+			li.ov_any = 1; li.ov_from = m.x; li.ov_to = m.y; li.ov_value = m.z; li.ov_add = m.w;
+		}
+	}
 	if(dp.colour_mode == HTV_SECAM) line_secam(dp, dt, L, li);
 	if(L < 0) { li.frame = li.line = li.code = li.pal = 0; li.al = li.ar = -1; li.row_off = -1; li.clut_off = 0; return; }
 	const int64_t f0 = L / dp.lines;
@@ -957,6 +981,17 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 		}
 	}
 	if(x0 >= W) return;
+	if(li.ov_any)
+	{
+		// VBI stages run on the finished line (ref video.c:4213-4357 register them behind the raster)
+		#pragma unroll
+		for(int k = 0; k < SPT; k++)
+		{
+			const int x = x0 + k;
+			if(x >= li.ov_from && x < li.ov_to) val[k] = li.ov_value;
+			if(li.ov_add >= 0 && x < W) val[k] = wrap16i(val[k]) + dt.ov_add[(size_t) li.ov_add * W + x];
+		}
+	}
 	if(comp32)
 	{
 		// int32 stream for the TMA-fed modulator (values are int16-wrapped as the reference's buffer is)
@@ -1396,6 +1431,25 @@ k_secam_seq(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const 
 		if(!changed) break;
 		if(threadIdx.x == 0) atomicAdd(ss.flags, 1);                // the successor is stale unless we fix it now
 		in = out;
+	}
+}
+
+// SECAM: the VBI stages sit behind the SECAM stage (ref video.c:4211-4357), so an overlay line is
+// folded in once the chain has produced the line's subcarrier: composite + subcarrier -> replace /
+// add -> composite, subcarrier row cleared. One CTA per row, a handful of rows per frame do work.
+__global__ void __launch_bounds__(256) k_overlay_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int16_t *sadd)
+{
+	const LineRaster &li = lr[blockIdx.x];
+	if(!li.ov_any) return;
+	const int W = dp.W;
+	const size_t o = (size_t) blockIdx.x * W;
+	for(int x = threadIdx.x; x < W; x += blockDim.x)
+	{
+		int v = wrap16i((int) comp[o + x] + (int) sadd[o + x]);
+		if(x >= li.ov_from && x < li.ov_to) v = li.ov_value;
+		if(li.ov_add >= 0) v += dt.ov_add[(size_t) li.ov_add * W + x];
+		comp[o + x] = (int16_t) v;
+		sadd[o + x] = 0;
 	}
 }
 
@@ -2280,6 +2334,9 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
 	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32);
 	if(d->h_map) cudaFreeHost(d->h_map);
+	if(d->h_ov_line) { cudaFreeHost(d->h_ov_line); cudaFreeHost(d->h_ov_meta); cudaFreeHost(d->h_ov_add); }
+	cudaFree(d->d_ov_line); cudaFree(d->d_ov_meta); cudaFree(d->d_ov_add);
+	if(d->ev_ov) cudaEventDestroy(d->ev_ov);
 	for(int i = 0; i < MAPBUFS; i++) if(d->ev_map[i]) cudaEventDestroy(d->ev_map[i]);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
@@ -2305,6 +2362,48 @@ extern "C" int htv_dev_uploads_end(htv_dev_t *d, void *stream)
 {
 	CK(cudaEventRecord(d->ev_up, d->up));
 	CK(cudaStreamWaitEvent((cudaStream_t) stream, d->ev_up, 0));
+	return(HTV_OK);
+}
+
+extern "C" int htv_dev_overlay_capacity(void) { return(HTV_OV_CAP); }
+
+// Overlay table of the next launch sequence: n entries sorted by global line index; add rows are
+// copied out of the caller's buffers here (pinned staging), so they may change after the call.
+extern "C" int htv_dev_set_overlays(htv_dev_t *d, int n, const long long *line, const int *from, const int *to,
+	const int *value, const int16_t *const *add)
+{
+	const int W = d->dp.W;
+	if(n > HTV_OV_CAP) return(HTV_ERROR);
+	if(n > 0 && !d->h_ov_line)
+	{
+		CK(cudaMallocHost((void **) &d->h_ov_line, sizeof(long long) * HTV_OV_CAP));
+		CK(cudaMallocHost((void **) &d->h_ov_meta, sizeof(int4) * HTV_OV_CAP));
+		CK(cudaMallocHost((void **) &d->h_ov_add, sizeof(int16_t) * (size_t) HTV_OV_CAP * W));
+		CK(cudaMalloc((void **) &d->d_ov_line, sizeof(long long) * HTV_OV_CAP));
+		CK(cudaMalloc((void **) &d->d_ov_meta, sizeof(int4) * HTV_OV_CAP));
+		CK(cudaMalloc((void **) &d->d_ov_add, sizeof(int16_t) * (size_t) HTV_OV_CAP * W));
+		CK(cudaEventCreateWithFlags(&d->ev_ov, cudaEventDisableTiming));
+		d->dt.ov_line = d->d_ov_line; d->dt.ov_meta = d->d_ov_meta; d->dt.ov_add = d->d_ov_add;
+	}
+	d->dt.ov_n = n;
+	if(n == 0) return(HTV_OK);
+	CK(cudaEventSynchronize(d->ev_ov));                            // the previous table has left the staging buffers
+	int rows = 0;
+	for(int i = 0; i < n; i++)
+	{
+		d->h_ov_line[i] = line[i];
+		int row = -1;
+		if(add[i]) { row = rows++; memcpy(d->h_ov_add + (size_t) row * W, add[i], sizeof(int16_t) * W); }
+		d->h_ov_meta[i] = make_int4(from[i], to[i], value[i], row);
+	}
+	// on the upload stream: the table of the previous sequence may still be read by its kernels, but
+	// uploads_begin made this stream wait for the sequence two back only - so order behind the
+	// previous sequence explicitly
+	CK(cudaStreamWaitEvent(d->up, d->ev_chunk[(d->chunk_i + 1) & 1], 0));
+	CK(cudaMemcpyAsync(d->d_ov_line, d->h_ov_line, sizeof(long long) * n, cudaMemcpyHostToDevice, d->up));
+	CK(cudaMemcpyAsync(d->d_ov_meta, d->h_ov_meta, sizeof(int4) * n, cudaMemcpyHostToDevice, d->up));
+	if(rows) CK(cudaMemcpyAsync(d->d_ov_add, d->h_ov_add, sizeof(int16_t) * (size_t) rows * W, cudaMemcpyHostToDevice, d->up));
+	CK(cudaEventRecord(d->ev_ov, d->up));
 	return(HTV_OK);
 }
 
@@ -2476,6 +2575,11 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				return(HTV_ERROR);
 			}
 			k_secam_carry<<<1, 32, 0, st>>>(d->sec, n - 1, pass - 1);
+			if(d->dt.ov_n > 0)
+			{
+				k_overlay_secam<<<n + 3, 256, 0, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec.add);
+				d->launches++;
+			}
 			cstream = d->d_comp + d->dp.W;          // k_mod's line b sits at row b + 2
 			sadd = d->sec.add + d->dp.W;
 		}

@@ -189,6 +189,23 @@ extern void htv_av_close(htv_av_t *av);
 extern int htv_av_memory_open(htv_av_t *av, const uint32_t *frames, size_t nframes,
 	const int16_t *audio, size_t audio_pairs, size_t audio_block, int static_video);
 
+/* VBI overlays - the hook the reference's VBI stages (teletext, WSS, VITS, VITC, CC608; registered
+ * behind the raster and SECAM stages, ref video.c:4213-4357) need from the encoder: each of them adds an
+ * int16 waveform to a finished line (vbidata_render, ref vbidata.c:186-239; wss_render first sets part of
+ * line 23 to black, ref wss.c:182-185). The packet / waveform builders stay host code; once per frame, when
+ * its first line is rendered, `read` reports the lines they touch: I[replace_from, replace_to) =
+ * replace_value (skipped when from >= to), then I[x] += add[x] for the W samples of the line (int16 wrap;
+ * NULL = nothing to add). At most one entry per line; entries must stay clear of the first and last 40
+ * samples of a line (VBI data does). The arrays need only stay valid until `read` returns. */
+typedef struct {
+	int line;                     /* 1-based, as the reference counts */
+	int replace_from, replace_to;
+	int replace_value;
+	const int16_t *add;
+} htv_vbi_line_t;
+typedef int (*htv_read_vbi_t)(void *ctx, int frame /* 1-based */, const htv_vbi_line_t **lines, int *nlines);
+extern int htv_set_vbi_source(htv_t *s, htv_read_vbi_t read, void *ctx);
+
 extern htv_line_t *htv_next_line(htv_t *s);
 
 /* Batched extension. Renders the next `nlines` scan lines of the stream.

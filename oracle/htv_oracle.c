@@ -393,6 +393,8 @@ struct orc_t {
 	/* sources */
 	const uint32_t *frames; int nframes;
 	const int16_t *pcm; size_t pcm_pairs; size_t pcm_pos;
+	struct { int line, from, to, value; const int16_t *add; } vbi[64];
+	int nvbi;
 	int have_fmv; fm_t fm_video;                       /* FM video modulator (video.c:2299-2335) */
 	const int16_t *pt; size_t pt_len; size_t pt_pos;   /* passthru stream (complex samples) */
 
@@ -1053,6 +1055,22 @@ static void raster_line(orc_t *o, int64_t L)
 	}
 }
 
+/* VBI stages (ref video.c:4213-4402) are registered behind the raster AND the SECAM stage, in front
+ * of the video filter: they see - and WSS partly overwrites - the finished composite line */
+static void vbi_line(orc_t *o, int64_t L)
+{
+	const int W = o->width;
+	int line = L % o->p.lines + 1;
+	int16_t *l = ring_line(o, L);
+	int b, x;
+	for(b = 0; b < o->nvbi; b++)
+	{
+		if(o->vbi[b].line != line) continue;
+		for(x = o->vbi[b].from; x < o->vbi[b].to && x < W; x++) if(x >= 0) l[x] = (int16_t) o->vbi[b].value;
+		if(o->vbi[b].add) for(x = 0; x < W; x++) l[x] = (int16_t) (l[x] + o->vbi[b].add[x]);
+	}
+}
+
 /* ------------------------------------------------------------------------ */
 /* SECAM chroma: ref video.c:3068-3233                                      */
 /* ------------------------------------------------------------------------ */
@@ -1512,6 +1530,14 @@ void orc_close(orc_t *o)
 }
 
 void orc_set_frames(orc_t *o, const uint32_t *rgb, int nframes) { o->frames = rgb; o->nframes = nframes; }
+void orc_add_vbi_line(orc_t *o, int line, int replace_from, int replace_to, int replace_value, const int16_t *add)
+{
+	if(o->nvbi >= 64) return;
+	o->vbi[o->nvbi].line = line; o->vbi[o->nvbi].from = replace_from; o->vbi[o->nvbi].to = replace_to;
+	o->vbi[o->nvbi].value = replace_value; o->vbi[o->nvbi].add = add;
+	o->nvbi++;
+}
+
 void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex) { o->pt = iq; o->pt_len = ncomplex; o->pt_pos = 0; }
 void orc_set_audio(orc_t *o, const int16_t *pcm, size_t npairs) { o->pcm = pcm; o->pcm_pairs = npairs; o->pcm_pos = 0; }
 
@@ -1599,6 +1625,8 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 				secam_line(o, ring_line(o, L), L / o->p.lines + 1, L % o->p.lines + 1);
 			}
 		}
+
+		if(o->nvbi) vbi_line(o, t);
 
 		prev = ring_line(o, t - 1);
 		cur  = ring_line(o, t);

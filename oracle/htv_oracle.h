@@ -134,6 +134,13 @@ extern void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex);
  * rf_file.c:97-116,226-233): appends the next nlines scan lines of the emitted
  * stream to out - int16 I,Q interleaved for complex modes, I only for real
  * modes. Returns the number of samples written. */
+/* VBI overlays (ref vbidata.c:186-239 adds int16 deltas into a line after the raster stage; wss.c:182-185
+ * first overwrites part of line 23): applied to `line` (1-based) of every frame after its
+ * raster and SECAM stages, before the video filter (the order video.c:4206-4357 registers
+ * them in). `add` (W values, may be NULL) is borrowed. Overlays must stay clear of the first and
+ * last 40 samples of a line (VBI data does). */
+extern void orc_add_vbi_line(orc_t *o, int line, int replace_from, int replace_to, int replace_value, const int16_t *add);
+
 extern size_t orc_render(orc_t *o, int nlines, int16_t *out);
 
 /* Geometry (reference video.c:3844-3853 and friends) */

@@ -92,7 +92,7 @@ static void _usage(void)
 {
 	fprintf(stderr,
 		"ref_harness -m MODE -s RATE [--pixelrate N] [--filter] [--noaudio] [--nonicam]\n"
-		"            [--nocolour] [--offset HZ] [--swap-iq] [--level F] [--volume F] [--passthru FILE]\n"
+		"            [--nocolour] [--offset HZ] [--swap-iq] [--level F] [--volume F] [--passthru FILE] [--wss MODE]\n"
 		"            [--skip LINES] [--lines N] [-o FILE] [--bench] [--geometry]\n"
 		"            [--frames FILE.rgb32] [--audio FILE.s16le] [--audio-block N]\n");
 	exit(2);
@@ -103,7 +103,7 @@ int main(int argc, char **argv)
 	static hacktv_t s;
 	const vid_configs_t *vc;
 	vid_config_t conf;
-	const char *mode = "i", *out = NULL, *frames_fn = NULL, *audio_fn = NULL, *passthru_fn = NULL;
+	const char *mode = "i", *out = NULL, *frames_fn = NULL, *audio_fn = NULL, *passthru_fn = NULL, *wss_mode = NULL;
 	unsigned int rate = 16000000, pixelrate = 0;
 	int filter = 0, noaudio = 0, nonicam = 0, nocolour = 0, swap_iq = 0, bench = 0, geometry = 0;
 	long long offset = 0, skip = 0, lines = 625;
@@ -138,6 +138,7 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "--audio") && i + 1 < argc) audio_fn = argv[++i];
 		else if(!strcmp(argv[i], "--audio-block") && i + 1 < argc) audio_block = strtoul(argv[++i], NULL, 10);
 		else if(!strcmp(argv[i], "--passthru") && i + 1 < argc) passthru_fn = argv[++i];
+		else if(!strcmp(argv[i], "--wss") && i + 1 < argc) wss_mode = argv[++i];
 		else _usage();
 	}
 
@@ -165,6 +166,7 @@ int main(int argc, char **argv)
 	if(filter) conf.vfilter = 1;
 	conf.swap_iq = swap_iq;
 	conf.offset = offset;
+	conf.wss = (char *) wss_mode;                          /* hacktv.c --wss; video.c:4234-4242 */
 	conf.passthru = (char *) passthru_fn;                 /* hacktv.c --passthru; video.c:4607-4634 */
 	conf.volume = (float) volume * 256 + 0.5;
 	conf.raw_bb_white_level = INT16_MAX;

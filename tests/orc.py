@@ -29,6 +29,7 @@ def lib():
         L.orc_set_frames.restype = None; L.orc_set_frames.argtypes = [vp, vp, C.c_int]
         L.orc_set_audio.restype = None; L.orc_set_audio.argtypes = [vp, vp, C.c_size_t]
         L.orc_set_passthru.restype = None; L.orc_set_passthru.argtypes = [vp, vp, C.c_size_t]
+        L.orc_add_vbi_line.restype = None; L.orc_add_vbi_line.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.orc_render.restype = C.c_size_t; L.orc_render.argtypes = [vp, C.c_int, vp]
         for f in ("orc_width", "orc_active_width", "orc_active_lines", "orc_is_complex"):
             getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
@@ -74,6 +75,16 @@ class Oracle:
         iq = np.ascontiguousarray(iq, dtype=np.int16)
         self._L.orc_set_passthru(self._o, iq.ctypes.data, iq.shape[0])
         self._keep.append(iq)
+
+    def add_vbi_line(self, line, add=None, replace=(0, 0, 0)):
+        """A VBI overlay on `line` (1-based) of every frame: I[from:to] = value, then I += add."""
+        p = None
+        if add is not None:
+            add = np.ascontiguousarray(add, dtype=np.int16)
+            assert add.size == self.width
+            self._keep.append(add)
+            p = add.ctypes.data
+        self._L.orc_add_vbi_line(self._o, line, replace[0], replace[1], replace[2], p)
 
     def open_test_source(self):
         self.set_source(test_pattern(self.active_width, self.active_lines)[None], test_tone())

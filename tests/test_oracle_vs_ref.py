@@ -90,6 +90,40 @@ def test_passthru_alignment(built, tmp_path, mode, rate, filt, extra, ext_lines)
     assert not np.array_equal(plain, want)
 
 
+def wss_overlay(built, mode, rate, wss="16:9"):
+    """What the reference's WSS stage does to line 23 (wss.c:154-193): part of the line set to black, then the
+    bit waveform added. Recovered from the reference itself: unfiltered, no sound, no colour (the SECAM stage
+    runs after WSS and would filter it), with and without --wss."""
+    conf = built.mode_config(mode, noaudio=True)
+    t = built.Tables(conf, rate)
+    W, half = int(t.get("geometry")[0]), int(t.get("geometry")[1])
+    black = int(t.get("levels")[1])
+    t.close()
+    per = 2 if conf.output_type == 0 else 1
+    plain = orc.run_ref(mode, rate, 30, extra=("--noaudio", "--nocolour")).reshape(30, W, per)[22, :, 0].astype(np.int32)
+    with_wss = orc.run_ref(mode, rate, 30, extra=("--noaudio", "--nocolour", "--wss", wss)).reshape(30, W, per)[22, :, 0].astype(np.int32)
+    blank_to = int(round(rate * 42.5e-6))
+    base = plain.copy()
+    base[half:blank_to] = black
+    return (with_wss - base).astype(np.int16), (half, blank_to, black)
+
+
+@pytest.mark.parametrize("mode,rate,filt,extra", [("i", 16000000, True, ()), ("pal", 16000000, False, ()),
+                                                  ("l", 16000000, True, ()), ("secam", 16000000, False, ())])
+def test_vbi_overlay_is_where_the_reference_puts_wss(built, mode, rate, filt, extra):
+    """The overlay hook (after the raster, before SECAM / filter / sound) carries the reference's own WSS
+    waveform to exactly the reference's --wss output, in modes other than the one it was recovered from."""
+    add, rep = wss_overlay(built, mode, rate)
+    assert np.count_nonzero(add) > 100
+    o = orc.Oracle(_conf(built, mode, filt, extra), rate)
+    o.open_test_source()
+    o.add_vbi_line(23, add, rep)
+    got = o.render(700)
+    o.close()
+    want = orc.run_ref(mode, rate, 700, vfilter=filt, extra=tuple(extra) + ("--wss", "16:9"))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+
+
 def test_oracle_equals_reference_on_random_input(built):
     rng = np.random.default_rng(7)
     conf = built.mode_config("i", vfilter=True)
