@@ -174,6 +174,8 @@ size_t htv_get_framebuffer_length(htv_t *s)
 
 htv_av_t *htv_av(htv_t *s) { return(&s->av); }
 int htv_samples_per_line(const htv_t *s) { return(s->W); }
+int htv_half_line(const htv_t *s) { return(s->tab->dp.half_width); }
+void htv_signal_levels(const htv_t *s, int levels[4]) { htv_tables_levels(s->tab, levels); }
 int htv_active_width(const htv_t *s) { return(s->tab->dp.active_width); }
 int htv_active_lines(const htv_t *s) { return(s->tab->dp.active_lines); }
 int htv_lines_per_frame(const htv_t *s) { return(s->lines); }
@@ -309,13 +311,16 @@ static void drop_overlays_before(htv_t *s, long long line)
 	s->nov = k;
 }
 
-/* Pull frame f's overlays (f 0-based); returns 0, or 1 if they do not fit this launch sequence */
-static int pull_overlays(htv_t *s, int64_t f)
+#define MAX_VBI_LINES_PER_FRAME 64
+
+/* Pull frame f's overlays (f 0-based), after its picture - as the reference's VBI stages run after the
+ * frame was loaded (ref video.c:4873-4904, then the line processes) */
+static void pull_overlays(htv_t *s, int64_t f)
 {
 	const htv_vbi_line_t *lines = NULL;
 	int n = 0, i, j;
-	if(s->vbi_read(s->vbi_ctx, (int) (f + 1), &lines, &n) != HTV_OK || n <= 0 || !lines) return(0);
-	if(s->nov + n > htv_dev_overlay_capacity()) return(1);
+	if(s->vbi_read(s->vbi_ctx, (int) (f + 1), &lines, &n) != HTV_OK || n <= 0 || !lines) return;
+	if(n > MAX_VBI_LINES_PER_FRAME) n = MAX_VBI_LINES_PER_FRAME;
 	if(s->nov + n > s->ov_cap)
 	{
 		s->ov_cap = (s->nov + n) * 2;
@@ -337,7 +342,6 @@ static int pull_overlays(htv_t *s, int64_t f)
 		}
 		s->nov++;
 	}
-	return(0);
 }
 
 static int send_overlays(htv_t *s, long long end_line)
@@ -384,10 +388,9 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 				n = (int) (f * s->lines - L0);
 				break;
 			}
-			if(s->vbi_read && pull_overlays(s, f))
+			if(s->vbi_read && f > f0 && s->nov + MAX_VBI_LINES_PER_FRAME > htv_dev_overlay_capacity())
 			{
 				/* the overlay table of this launch sequence is full: stop at this frame boundary */
-				if(f == f0) return(HTV_ERROR);
 				n = (int) (f * s->lines - L0);
 				break;
 			}
@@ -417,6 +420,7 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 				if(s->av.read_video) s->av.read_video = NULL;
 				s->cur_slot = -1;
 			}
+			if(s->vbi_read) pull_overlays(s, f);
 		}
 		map[nmap++] = s->cur_slot;
 	}

@@ -113,6 +113,8 @@ struct htv_tables_t {
 	int32_t *scratch;                              /* htv_tables_get */
 };
 
+extern void htv_tables_levels(const struct htv_tables_t *t, int levels[4]);
+
 /* ---- device layer (htv_kernels.cu), all C linkage ---------------------- */
 
 typedef struct htv_dev_t htv_dev_t;

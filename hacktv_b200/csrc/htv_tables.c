@@ -753,6 +753,17 @@ static const int32_t *view32(struct htv_tables_t *t, const int32_t *v, int n, in
 	return(t->scratch);
 }
 
+/* vid_t.white_level, black_level, blanking_level, sync_level (ref video.c:3877-3881; the conf copy was
+ * already swapped for --invert-video) */
+void htv_tables_levels(const htv_tables_t *t, int levels[4])
+{
+	const htv_config_t *c = &t->conf;
+	levels[0] = (int16_t) round(c->white_level * t->dp.vlevel * INT16_MAX);
+	levels[1] = (int16_t) round(c->black_level * t->dp.vlevel * INT16_MAX);
+	levels[2] = t->dp.blank;
+	levels[3] = (int16_t) round(c->sync_level * t->dp.vlevel * INT16_MAX);
+}
+
 const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count)
 {
 	const htv_dparams_t *dp = &t->dp;
@@ -774,11 +785,7 @@ const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count)
 	if(!strcmp(name, "secam_notch") && t->secam_bell) return(view32(t, dp->secam_notch, 51, count));
 	if(!strcmp(name, "levels"))
 	{
-		const htv_config_t *c = &t->conf;
-		tmp[0] = (int16_t) round(c->white_level * dp->vlevel * INT16_MAX);
-		tmp[1] = (int16_t) round(c->black_level * dp->vlevel * INT16_MAX);
-		tmp[2] = dp->blank;
-		tmp[3] = (int16_t) round(c->sync_level * dp->vlevel * INT16_MAX);
+		htv_tables_levels(t, tmp);
 		return(view32(t, tmp, 4, count));
 	}
 	if(!strcmp(name, "geometry"))

@@ -245,6 +245,8 @@ extern int htv_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void
 
 /* Geometry / state accessors (fields hacktv.c reads from vid_t, ref video.h:358-420) */
 extern int htv_samples_per_line(const htv_t *s);   /* vid_t.width */
+extern int htv_half_line(const htv_t *s);          /* vid_t.half_width */
+extern void htv_signal_levels(const htv_t *s, int levels[4]);   /* vid_t.white_level, black_level, blanking_level, sync_level */
 extern int htv_active_width(const htv_t *s);
 extern int htv_active_lines(const htv_t *s);
 extern int htv_lines_per_frame(const htv_t *s);

@@ -27,7 +27,14 @@ extern size_t cpu_vid_get_framebuffer_length(vid_t *s);
 extern vid_line_t *cpu_vid_next_line(vid_t *s);
 
 #define MAX_ENCODERS 16
-static struct { vid_t *vid; htv_t *htv; vid_line_t line; uint32_t *packed; uint64_t serial; } _enc[MAX_ENCODERS];
+#define MAX_VBI 8
+static struct {
+	vid_t *vid; htv_t *htv; vid_line_t line; uint32_t *packed; uint64_t serial;
+	/* VBI stages: the reference's own code builds the waveforms, the encoder's overlay hook carries them */
+	int16_t *vbi_scratch;           /* one line, I/Q interleaved, as the stock stages expect it */
+	int16_t *vbi_add[MAX_VBI];
+	htv_vbi_line_t vbi[MAX_VBI];
+} _enc[MAX_ENCODERS];
 
 static int _find(vid_t *s)
 {
@@ -44,7 +51,7 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 	if(c->modulation == VID_FM && c->fm_energy_dispersal != 0) return(0);
 	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
 	if(pixel_rate && pixel_rate != sample_rate) return(0);
-	if(c->teletext || c->wss || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
+	if(c->teletext || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
 	   c->d11 || c->systercnr || c->acp || c->vits || c->vitc || c->cc608 || c->sis || c->eurocrypt) return(0);
 	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);
 	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
@@ -77,6 +84,7 @@ static int _read_video(void *ctx, htv_frame_t *out)
 	vid_t *s = ctx;
 	av_frame_t f;
 	if(i < 0 || av_read_video(&s->av, &f) != AV_OK || !f.framebuffer) return(HTV_ERROR);
+	s->vframe = f;                                  /* WSS auto mode reads its pixel aspect ratio (wss.c:168-180) */
 	out->width = f.width; out->height = f.height;
 	out->serial = ++_enc[i].serial;                 /* a pulled frame may have changed: always upload */
 	if(f.pixel_stride == 1 && f.line_stride == f.width) { out->framebuffer = f.framebuffer; return(HTV_OK); }
@@ -95,6 +103,49 @@ static int _read_audio(void *ctx, const int16_t **samples, size_t *npairs)
 	int r = av_read_audio(&s->av, &p, npairs);
 	*samples = p;
 	return(r == AV_OK ? HTV_OK : HTV_ERROR);
+}
+
+/* Run one of the reference's own VBI stages (vid_lineprocess_process_t, ref video.h:332) on an empty line
+ * and hand what it drew to the encoder's overlay hook. `rep_*`: the part of the line the stage overwrites
+ * before adding (only WSS does: wss.c:182-185). */
+static int _vbi_stage(int i, int slot, vid_lineprocess_process_t stage, void *arg, int frame, int line,
+	int rep_from, int rep_to, int rep_value)
+{
+	vid_t *s = _enc[i].vid;
+	vid_line_t l, *lp = &l;
+	int x, W = s->width, any = 0;
+	memset(&l, 0, sizeof(l));
+	memset(_enc[i].vbi_scratch, 0, sizeof(int16_t) * 2 * W);
+	l.output = _enc[i].vbi_scratch; l.width = W; l.frame = frame; l.line = line;
+	l.previous = l.next = &l;
+	stage(s, arg, 1, &lp);
+	if(!_enc[i].vbi_add[slot]) _enc[i].vbi_add[slot] = malloc(sizeof(int16_t) * W);
+	for(x = 0; x < W; x++)
+	{
+		int16_t v = l.output[x * 2] - (x >= rep_from && x < rep_to ? rep_value : 0);
+		_enc[i].vbi_add[slot][x] = v;
+		any |= v;
+	}
+	if(!any && rep_from >= rep_to) return(0);
+	_enc[i].vbi[slot] = (htv_vbi_line_t) { line, rep_from, rep_to, rep_value, _enc[i].vbi_add[slot] };
+	return(1);
+}
+
+/* htv_read_vbi_t: once per frame (ref: the stages run per line, video.c:4906-4921) */
+static int _read_vbi(void *ctx, int frame, const htv_vbi_line_t **lines, int *nlines)
+{
+	vid_t *s = ctx;
+	int i = _find(s), n = 0;
+	if(i < 0) return(HTV_ERROR);
+	s->frame = frame;
+	if(s->conf.wss)
+	{
+		/* WSS lives on line 23 (wss.c:160-166) and blanks [half_width, blank_width) first */
+		n += _vbi_stage(i, n, wss_render, &s->wss, frame, 23, s->half_width, s->wss.blank_width, s->black_level);
+	}
+	*lines = _enc[i].vbi;
+	*nlines = n;
+	return(HTV_OK);
 }
 
 /* --passthru: the external stream as the reference reads it (video.c:3527-3533) */
@@ -138,9 +189,22 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	s->pixel_rate = pixel_rate ? pixel_rate : sample_rate;
 	s->width = s->max_width = htv_samples_per_line(h);
 	s->active_width = htv_active_width(h);
+	{
+		int lv[4];
+		htv_signal_levels(h, lv);
+		s->white_level = lv[0]; s->black_level = lv[1]; s->blanking_level = lv[2]; s->sync_level = lv[3];
+		s->half_width = htv_half_line(h);
+	}
 	s->thread_abort = 1;                             /* no CPU stage threads to join */
 	s->passthru = pt;
 	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
+	if(conf->wss)
+	{
+		/* ref video.c:4234-4242 */
+		if(wss_init(&s->wss, s, conf->wss) != VID_OK) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
+		_enc[i].vbi_scratch = malloc(sizeof(int16_t) * 2 * s->width);
+		htv_set_vbi_source(h, _read_vbi, s);
+	}
 	htv_av(h)->ctx = s;
 	htv_av(h)->read_video = _read_video;
 	htv_av(h)->read_audio = _read_audio;
@@ -172,6 +236,9 @@ void vid_free(vid_t *s)
 	htv_av(_enc[i].htv)->close = NULL;
 	htv_free(_enc[i].htv);
 	free(_enc[i].packed);
+	if(s->conf.wss) wss_free(&s->wss);
+	free(_enc[i].vbi_scratch);
+	{ int k; for(k = 0; k < MAX_VBI; k++) free(_enc[i].vbi_add[k]); }
 	memset(&_enc[i], 0, sizeof(_enc[i]));
 	memset(s, 0, sizeof(vid_t));
 }
