@@ -52,7 +52,7 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
 	if(pixel_rate && pixel_rate != sample_rate) return(0);
 	if(c->teletext || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
-	   c->d11 || c->systercnr || c->acp || c->vits || c->vitc || c->cc608 || c->sis || c->eurocrypt) return(0);
+	   c->d11 || c->systercnr || c->acp || c->vits || c->cc608 || c->sis || c->eurocrypt) return(0);
 	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);
 	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
 	if(c->interlace || c->frame_orientation) return(0);
@@ -143,6 +143,15 @@ static int _read_vbi(void *ctx, int frame, const htv_vbi_line_t **lines, int *nl
 		/* WSS lives on line 23 (wss.c:160-166) and blanks [half_width, blank_width) first */
 		n += _vbi_stage(i, n, wss_render, &s->wss, frame, 23, s->half_width, s->wss.blank_width, s->black_level);
 	}
+	if(s->conf.vitc)
+	{
+		/* the time code sits on two lines of each field (vitc.c:122-126) */
+		int k;
+		for(k = 0; k < 4; k++)
+		{
+			n += _vbi_stage(i, n, vitc_render, &s->vitc, frame, s->vitc.lines[k >> 1] + (k & 1) * 2, 0, 0, 0);
+		}
+	}
 	*lines = _enc[i].vbi;
 	*nlines = n;
 	return(HTV_OK);
@@ -198,10 +207,11 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	s->thread_abort = 1;                             /* no CPU stage threads to join */
 	s->passthru = pt;
 	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
-	if(conf->wss)
+	if(conf->wss || conf->vitc)
 	{
-		/* ref video.c:4234-4242 */
-		if(wss_init(&s->wss, s, conf->wss) != VID_OK) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
+		/* ref video.c:4234-4242, 4305-4315: the stock stages, initialised as vid_init does */
+		if((conf->wss && wss_init(&s->wss, s, conf->wss) != VID_OK) ||
+		   (conf->vitc && vitc_init(&s->vitc, s) != VID_OK)) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
 		_enc[i].vbi_scratch = malloc(sizeof(int16_t) * 2 * s->width);
 		htv_set_vbi_source(h, _read_vbi, s);
 	}
@@ -237,6 +247,7 @@ void vid_free(vid_t *s)
 	htv_free(_enc[i].htv);
 	free(_enc[i].packed);
 	if(s->conf.wss) wss_free(&s->wss);
+	if(s->conf.vitc) vitc_free(&s->vitc);
 	free(_enc[i].vbi_scratch);
 	{ int k; for(k = 0; k < MAX_VBI; k++) free(_enc[i].vbi_add[k]); }
 	memset(&_enc[i], 0, sizeof(_enc[i]));

@@ -34,6 +34,8 @@ def _run(binary, args, nbytes):
     ("-m i -s 16000000 --filter --noaudio --wss 16:9", 4, 0),
     ("-m l -s 16000000 --filter --wss auto", 4, 1),
     ("-m pal -s 16000000 --wss 14:9-letterbox", 2, 0),
+    ("-m i -s 16000000 --filter --noaudio --vitc --wss 4:3", 4, 0),
+    ("-m m -s 13500000 --filter --vitc", 4, 1),
 ])
 def test_same_cli_same_bytes(args, per, tol):
     w = 858 if "13500000" in args else (1280 if "20000000" in args else 1024)
