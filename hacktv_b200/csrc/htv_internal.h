@@ -119,12 +119,6 @@ extern void htv_tables_levels(const struct htv_tables_t *t, int levels[4]);
 
 typedef struct htv_dev_t htv_dev_t;
 
-/* Per-launch description of a run of consecutive scan lines */
-typedef struct {
-	int64_t line0;          /* global index of the first line (0 = frame 1 line 1) */
-	int32_t nlines;
-	int32_t frame_slot0;    /* frame slot table index of the frame containing line0 */
-} htv_run_t;
 
 extern int htv_dev_count(void);
 extern htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen);

@@ -94,7 +94,6 @@ struct __align__(16) SecState {
 struct SecScratch {
 	int16_t *cb;                      // [lines][W]   low-passed baseband without the aliased-tail terms
 	int *tail;                        // [lines][SEC_TAIL] raw sums of the last outputs
-	int16_t *y;                       // [lines][W + 2] after IIR + clamp (FM input)
 	int16_t *add;                     // [lines][W]   subcarrier samples to add to the composite
 	SecState *st[2];                  // [lines] outgoing state, ping-pong between passes
 	SecState *used;                   // [lines] the incoming state the line was last computed from
@@ -131,7 +130,6 @@ struct htv_dev_t {
 	// carries
 	int64_t fm_jc;                    // last audio index whose fm_B entry is valid (-1 at start)
 	int64_t nic_kc;                   // first frame whose nic_fstart is valid for a restart
-	int have_run;
 	uint64_t launches;
 	int timing;
 	cudaEvent_t ev0, ev1;
@@ -143,7 +141,6 @@ struct htv_dev_t {
 	int side_armed;
 	int ev_pending;
 	int line_threads;
-	size_t line_smem;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
 	int desc_cap;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
@@ -2285,7 +2282,6 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		const size_t rows = (size_t) d->sub_lines + 3;
 		d->sec.cb = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W);
 		d->sec.tail = (int *) dev_zero(d, sizeof(int) * rows * SEC_TAIL);
-		d->sec.y = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * (W + 2));
 		d->sec.add = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W + 256);
 		d->sec.st[0] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
 		d->sec.st[1] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
@@ -2296,7 +2292,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		d->sec_passes = 64;
 		d->sec_smem = (size_t) (dp.burst_width + 2) * 12 + 2 * (((W + 7) & ~7) + ((W + 2 + 7) & ~7) + ((dp.burst_width + 2 + 7) & ~7)) + 64;
 		cudaFuncSetAttribute(k_secam_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
-		if(!d->sec.cb || !d->sec.y || !d->sec.add || !d->sec.flags)
+		if(!d->sec.cb || !d->sec.add || !d->sec.flags)
 		{
 			snprintf(err, errlen, "device allocation failed");
 			htv_dev_destroy(d);
