@@ -27,7 +27,7 @@ extern size_t cpu_vid_get_framebuffer_length(vid_t *s);
 extern vid_line_t *cpu_vid_next_line(vid_t *s);
 
 #define MAX_ENCODERS 16
-#define MAX_VBI 8
+#define MAX_VBI 64
 static struct {
 	vid_t *vid; htv_t *htv; vid_line_t line; uint32_t *packed; uint64_t serial;
 	/* VBI stages: the reference's own code builds the waveforms, the encoder's overlay hook carries them */
@@ -51,7 +51,7 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 	if(c->modulation == VID_FM && c->fm_energy_dispersal != 0) return(0);
 	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
 	if(pixel_rate && pixel_rate != sample_rate) return(0);
-	if(c->teletext || c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
+	if(c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
 	   c->d11 || c->systercnr || c->acp || c->vits || c->cc608 || c->sis || c->eurocrypt) return(0);
 	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);
 	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
@@ -105,52 +105,45 @@ static int _read_audio(void *ctx, const int16_t **samples, size_t *npairs)
 	return(r == AV_OK ? HTV_OK : HTV_ERROR);
 }
 
-/* Run one of the reference's own VBI stages (vid_lineprocess_process_t, ref video.h:332) on an empty line
- * and hand what it drew to the encoder's overlay hook. `rep_*`: the part of the line the stage overwrites
- * before adding (only WSS does: wss.c:182-185). */
-static int _vbi_stage(int i, int slot, vid_lineprocess_process_t stage, void *arg, int frame, int line,
-	int rep_from, int rep_to, int rep_value)
-{
-	vid_t *s = _enc[i].vid;
-	vid_line_t l, *lp = &l;
-	int x, W = s->width, any = 0;
-	memset(&l, 0, sizeof(l));
-	memset(_enc[i].vbi_scratch, 0, sizeof(int16_t) * 2 * W);
-	l.output = _enc[i].vbi_scratch; l.width = W; l.frame = frame; l.line = line;
-	l.previous = l.next = &l;
-	stage(s, arg, 1, &lp);
-	if(!_enc[i].vbi_add[slot]) _enc[i].vbi_add[slot] = malloc(sizeof(int16_t) * W);
-	for(x = 0; x < W; x++)
-	{
-		int16_t v = l.output[x * 2] - (x >= rep_from && x < rep_to ? rep_value : 0);
-		_enc[i].vbi_add[slot][x] = v;
-		any |= v;
-	}
-	if(!any && rep_from >= rep_to) return(0);
-	_enc[i].vbi[slot] = (htv_vbi_line_t) { line, rep_from, rep_to, rep_value, _enc[i].vbi_add[slot] };
-	return(1);
-}
-
-/* htv_read_vbi_t: once per frame (ref: the stages run per line, video.c:4906-4921) */
+/* htv_read_vbi_t, once per frame: run the reference's own VBI stages (vid_lineprocess_process_t, ref
+ * video.h:332), in the order vid_init registers them (ref video.c:4213-4357: ... wss ... vitc ... teletext),
+ * line by line on an empty line buffer - exactly what they see in the stock pipeline, vbialloc included -
+ * and hand what they drew to the encoder's overlay hook. Only WSS overwrites before it adds: part of line 23
+ * is set to black (wss.c:182-185), which is passed on as the overlay's replace range. */
 static int _read_vbi(void *ctx, int frame, const htv_vbi_line_t **lines, int *nlines)
 {
 	vid_t *s = ctx;
-	int i = _find(s), n = 0;
+	int i = _find(s), n = 0, line, x, dirty = 1;
+	const int W = s->width;
 	if(i < 0) return(HTV_ERROR);
 	s->frame = frame;
-	if(s->conf.wss)
+	for(line = 1; line <= s->conf.lines && n < MAX_VBI; line++)
 	{
-		/* WSS lives on line 23 (wss.c:160-166) and blanks [half_width, blank_width) first */
-		n += _vbi_stage(i, n, wss_render, &s->wss, frame, 23, s->half_width, s->wss.blank_width, s->black_level);
-	}
-	if(s->conf.vitc)
-	{
-		/* the time code sits on two lines of each field (vitc.c:122-126) */
-		int k;
-		for(k = 0; k < 4; k++)
+		vid_line_t l, *lp = &l;
+		int rep_from = 0, rep_to = 0, rep_value = 0, any = 0;
+		int16_t *add;
+		if(dirty) memset(_enc[i].vbi_scratch, 0, sizeof(int16_t) * 2 * W);
+		memset(&l, 0, sizeof(l));
+		l.output = _enc[i].vbi_scratch; l.width = W; l.frame = frame; l.line = line;
+		l.previous = l.next = &l;
+		if(s->conf.wss)
 		{
-			n += _vbi_stage(i, n, vitc_render, &s->vitc, frame, s->vitc.lines[k >> 1] + (k & 1) * 2, 0, 0, 0);
+			wss_render(s, &s->wss, 1, &lp);
+			if(line == 23) { rep_from = s->half_width; rep_to = s->wss.blank_width; rep_value = s->black_level; }
 		}
+		if(s->conf.vitc) vitc_render(s, &s->vitc, 1, &lp);
+		if(s->conf.teletext) tt_render_line(s, &s->tt, 1, &lp);
+		dirty = l.vbialloc;
+		if(!l.vbialloc) continue;
+		if(!_enc[i].vbi_add[n]) _enc[i].vbi_add[n] = malloc(sizeof(int16_t) * W);
+		add = _enc[i].vbi_add[n];
+		for(x = 0; x < W; x++)
+		{
+			add[x] = l.output[x * 2] - (x >= rep_from && x < rep_to ? rep_value : 0);
+			any |= add[x];
+		}
+		if(!any && rep_from >= rep_to) continue;
+		_enc[i].vbi[n++] = (htv_vbi_line_t) { line, rep_from, rep_to, rep_value, add };
 	}
 	*lines = _enc[i].vbi;
 	*nlines = n;
@@ -207,11 +200,12 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	s->thread_abort = 1;                             /* no CPU stage threads to join */
 	s->passthru = pt;
 	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
-	if(conf->wss || conf->vitc)
+	if(conf->wss || conf->vitc || conf->teletext)
 	{
-		/* ref video.c:4234-4242, 4305-4315: the stock stages, initialised as vid_init does */
+		/* ref video.c:4234-4242, 4305-4315, 4346-4358: the stock stages, initialised as vid_init does */
 		if((conf->wss && wss_init(&s->wss, s, conf->wss) != VID_OK) ||
-		   (conf->vitc && vitc_init(&s->vitc, s) != VID_OK)) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
+		   (conf->vitc && vitc_init(&s->vitc, s) != VID_OK) ||
+		   (conf->teletext && tt_init(&s->tt, s, conf->teletext) != VID_OK)) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
 		_enc[i].vbi_scratch = malloc(sizeof(int16_t) * 2 * s->width);
 		htv_set_vbi_source(h, _read_vbi, s);
 	}
@@ -248,6 +242,7 @@ void vid_free(vid_t *s)
 	free(_enc[i].packed);
 	if(s->conf.wss) wss_free(&s->wss);
 	if(s->conf.vitc) vitc_free(&s->vitc);
+	if(s->conf.teletext) tt_free(&s->tt);
 	free(_enc[i].vbi_scratch);
 	{ int k; for(k = 0; k < MAX_VBI; k++) free(_enc[i].vbi_add[k]); }
 	memset(&_enc[i], 0, sizeof(_enc[i]));

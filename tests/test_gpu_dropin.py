@@ -61,3 +61,20 @@ def test_readme_two_channel_pipeline():
     b = pipeline(STOCK, n)
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert d.max() <= 2, f"max |diff| {d.max()}"
+
+
+def test_teletext_vitc_wss_through_the_stock_stages(tmp_path):
+    """The reference's teletext (raw packet source: deterministic), VITC and WSS stages run inside the adapter in
+    vid_init's order, vbialloc included (teletext skips the lines VITC took); 34 VBI lines per frame ride the
+    encoder's overlay hook."""
+    rng = np.random.default_rng(1)
+    raw = tmp_path / "packets.t42"
+    rng.integers(0, 256, size=42 * 500, dtype=np.uint8).tofile(raw)
+    args = f"-m i -s 16000000 --filter --noaudio --teletext raw:{raw} --vitc --wss 16:9"
+    n = 1900 * 1024 * 4
+    a = _run(DROPIN, args, n)
+    b = _run(STOCK, args, n)
+    assert np.array_equal(a, b), f"{np.count_nonzero(a != b)} values differ"
+    plain = _run(STOCK, "-m i -s 16000000 --filter --noaudio", n)
+    changed = np.nonzero((b != plain).reshape(1900, -1).any(axis=1))[0]
+    assert len(changed) > 90                                      # 3 frames x (32 teletext - 4 + 4 VITC + 1 WSS) lines
