@@ -195,8 +195,8 @@ extern int htv_av_memory_open(htv_av_t *av, const uint32_t *frames, size_t nfram
  * line 23 to black, ref wss.c:182-185). The packet / waveform builders stay host code; once per frame, when
  * its first line is rendered, `read` reports the lines they touch: I[replace_from, replace_to) =
  * replace_value (skipped when from >= to), then I[x] += add[x] for the W samples of the line (int16 wrap;
- * NULL = nothing to add). At most one entry per line; entries must stay clear of the first and last 40
- * samples of a line (VBI data does). The arrays need only stay valid until `read` returns. */
+ * NULL = nothing to add). At most one entry per line; entries must leave the first 40 samples of a line
+ * alone (VBI data does: that is sync and back porch). The arrays need only stay valid until `read` returns. */
 typedef struct {
 	int line;                     /* 1-based, as the reference counts */
 	int replace_from, replace_to;

@@ -137,8 +137,8 @@ extern void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex);
 /* VBI overlays (ref vbidata.c:186-239 adds int16 deltas into a line after the raster stage; wss.c:182-185
  * first overwrites part of line 23): applied to `line` (1-based) of every frame after its
  * raster and SECAM stages, before the video filter (the order video.c:4206-4357 registers
- * them in). `add` (W values, may be NULL) is borrowed. Overlays must stay clear of the first and
- * last 40 samples of a line (VBI data does). */
+ * them in). `add` (W values, may be NULL) is borrowed. Overlays must leave the first 40 samples of
+ * a line alone (this restatement filters line t before line t+1 has been overlaid). */
 extern void orc_add_vbi_line(orc_t *o, int line, int replace_from, int replace_to, int replace_value, const int16_t *add);
 
 extern size_t orc_render(orc_t *o, int nlines, int16_t *out);
