@@ -22,7 +22,9 @@
 #include <string.h>
 #include <stdlib.h>
 #include "htv_internal.h"
+#include "htv_mma_fir.h"
 
+#define HTV_FIR_DEFAULT_MMA 0         // 1: the tensor-core video filter is the default where it applies
 #define HALO 25                       // (HTV_VF_NTAPS - 1) / 2
 #define RA_BITS 20
 #define RA (1 << RA_BITS)             // audio ring: pairs / processed samples / phase prefix
@@ -147,6 +149,8 @@ struct htv_dev_t {
 	int sec_passes;
 	size_t sec_smem;
 	int *d_comp32;                    // int32 composite scratch for the TMA-fed modulator (4 | W, not SECAM)
+	uint8_t *d_planes;                // high / low byte planes of the composite stream for k_mod_mma (32 | W, video filter on)
+	size_t plane_stride, modm_smem;
 	size_t modt_smem;
 	int mod_grid;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
@@ -874,7 +878,8 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 // ---------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(384, 4)
-k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int *comp32)
+k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int *comp32,
+	uint8_t *planes, size_t plane_stride)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -988,6 +993,16 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 			if(x >= li.ov_from && x < li.ov_to) val[k] = li.ov_value;
 			if(li.ov_add >= 0 && x < W) val[k] = wrap16i(val[k]) + dt.ov_add[(size_t) li.ov_add * W + x];
 		}
+	}
+	if(planes)
+	{
+		// high / low byte planes for the tensor-core video filter (k_mod_mma): v = 256 hi + lo
+		uint8_t *p = planes + (size_t) blockIdx.x * W + x0;
+		*reinterpret_cast<unsigned *>(p) = ((val[0] >> 8) & 0xFF) | (((val[1] >> 8) & 0xFF) << 8) |
+			(((val[2] >> 8) & 0xFF) << 16) | ((unsigned) (val[3] >> 8) << 24);
+		*reinterpret_cast<unsigned *>(p + plane_stride) = (val[0] & 0xFF) | ((val[1] & 0xFF) << 8) |
+			((val[2] & 0xFF) << 16) | ((unsigned) val[3] << 24);
+		return;
 	}
 	if(comp32)
 	{
@@ -2101,6 +2116,169 @@ k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 	}
 }
 
+
+// ---------------------------------------------------------------------------
+// Persistent modulator with the video filter on the tensor cores (htv_mma_fir.h): the 51-tap
+// int16 FIR is an exact int8 contraction - the composite stream arrives as a high-byte and a
+// low-byte plane (written by k_raster, fetched by the TMA), the taps as a banded Toeplitz
+// operand split the same way, and four mma.sync.m16n8k32 (s8/u8 mixes) per k-step leave three
+// int32 partial sums per output that recombine to the reference's int32 accumulator
+// (ref fir.c:564-615). Each warp owns one 16-row x 8-column tile of I and of Q, so a lane ends
+// with I and Q of the same four samples; they go through a shared-memory exchange buffer to
+// the thread that owns the four consecutive samples for the sound carriers and the store.
+// The scalar FIR this replaces was 51 half-rate IMAD + 50 IADD per sample (45 % of k_mod_tma).
+// Used whenever 32 | W, a video filter is on, and the mode is not SECAM / FM video.
+// ---------------------------------------------------------------------------
+
+#define MMA_I8(NAME, AT, BT) \
+__device__ __forceinline__ void NAME(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) \
+{ \
+	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32." AT "." BT ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+		: "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) \
+		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1)); \
+}
+MMA_I8(mma_ss, "s8", "s8")
+MMA_I8(mma_su, "s8", "u8")
+MMA_I8(mma_us, "u8", "s8")
+MMA_I8(mma_uu, "u8", "u8")
+
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const uint8_t *planes, size_t plane_stride,
+	int nlines, int16_t *out, const int16_t *acc, int acc_rows)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int MT = mf_mtiles(W);
+	const int PB = mf_plane_bytes(W), WB = mf_window_bytes(W);
+	// [buffer][plane] byte windows, the B operand, the exchange buffer, two descriptors, the NICAM pulse
+	unsigned char *pl0 = smem_raw;
+	uint4 *btab = reinterpret_cast<uint4 *>(pl0 + 4 * PB);              // [j 4][s 3][I/Q 2][lane 32]: hi b0, hi b1, lo b0, lo b1
+	unsigned *fir = reinterpret_cast<unsigned *>(btab + 4 * MF_KSTEPS * 2 * 32);
+	LineAudio *lab[2];
+	lab[0] = reinterpret_cast<LineAudio *>(fir + MT * 16 * MF_ROWW);
+	lab[1] = lab[0] + 1;
+	short *ntp = reinterpret_cast<short *>(lab[1] + 1);
+	__shared__ __align__(8) unsigned long long bar[2];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	const unsigned bytes = (unsigned) (2 * WB + sizeof(LineAudio));
+	const bool hasq = dp.vf_type == 3;
+
+	if(dp.have_nicam)
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	for(int i = tid; i < 4 * MF_KSTEPS * 2 * 32; i += blockDim.x)
+	{
+		const int l = i & 31, q = (i >> 5) & 1, js = i >> 6, s = js % MF_KSTEPS, j = js / MF_KSTEPS;
+		const int32_t *taps = q ? dp.vf_q : dp.vf_i;
+		btab[i] = make_uint4(mf_b_word(taps, j, s, l, 0), mf_b_word(taps, j, s, l, 1), mf_b_word(taps, j, s, l, 2), mf_b_word(taps, j, s, l, 3));
+	}
+	// the rows of the last m-tile past the line are multiplied too (and dropped): keep them defined
+	// (only the bytes behind the window: the TMA never writes them)
+	for(int i = tid; i < 4 * (PB - WB) / 4; i += blockDim.x)
+	{
+		const int per = (PB - WB) / 4;
+		reinterpret_cast<unsigned *>(pl0 + (i / per) * PB + WB)[i % per] = 0;
+	}
+	if(tid == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[0])));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[1])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	// the zero fill above went through the generic proxy, the TMA writes through the async proxy
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	__syncthreads();
+
+	int row = blockIdx.x;
+	if(tid == 0 && row < nlines)
+	{
+		// the launch's composite stream starts one line early: line `row` begins at (row + 1) * W
+		const uint8_t *src = planes + ((size_t) row + 1) * W - MF_LEAD;
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(bytes) : "memory");
+		tma_load(pl0, src, WB, &bar[0]);
+		tma_load(pl0 + PB, src + plane_stride, WB, &bar[0]);
+		tma_load(lab[0], lap + row, sizeof(LineAudio), &bar[0]);
+	}
+	unsigned phase[2] = { 0, 0 };
+	for(int it = 0; row < nlines; it++, row += gridDim.x)
+	{
+		const int cb = it & 1, nb = cb ^ 1;
+		const int nrow = row + gridDim.x;
+		if(tid == 0 && nrow < nlines)
+		{
+			const uint8_t *src = planes + ((size_t) nrow + 1) * W - MF_LEAD;
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(bytes) : "memory");
+			tma_load(pl0 + (2 * nb) * PB, src, WB, &bar[nb]);
+			tma_load(pl0 + (2 * nb + 1) * PB, src + plane_stride, WB, &bar[nb]);
+			tma_load(lab[nb], lap + nrow, sizeof(LineAudio), &bar[nb]);
+		}
+		mbar_wait(&bar[cb], phase[cb]);
+		phase[cb] ^= 1;
+
+		// ---- video filter: one (m-tile, n-tile) unit per warp ------------------
+		const unsigned char *ph = pl0 + (2 * cb) * PB, *plo = ph + PB;
+		for(int u = warp; u < MT * 4; u += nwarps)
+		{
+			const int mt = u >> 2, j = u & 3;
+			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
+			int qhh[4] = { 0, 0, 0, 0 }, qmid[4] = { 0, 0, 0, 0 }, qll[4] = { 0, 0, 0, 0 };
+			#pragma unroll
+			for(int s = 0; s < MF_KSTEPS; s++)
+			{
+				const int o0 = mf_a_offset(mt, s, lane, 0), o1 = mf_a_offset(mt, s, lane, 1);
+				const uint2 h0 = *reinterpret_cast<const uint2 *>(ph + o0), h1 = *reinterpret_cast<const uint2 *>(ph + o1);
+				const uint2 l0 = *reinterpret_cast<const uint2 *>(plo + o0), l1 = *reinterpret_cast<const uint2 *>(plo + o1);
+				const unsigned ah[4] = { h0.x, h1.x, h0.y, h1.y }, al[4] = { l0.x, l1.x, l0.y, l1.y };
+				const uint4 bi = btab[((j * MF_KSTEPS + s) * 2 + 0) * 32 + lane];
+				mma_ss(ihh, ah, bi.x, bi.y);
+				mma_su(imid, ah, bi.z, bi.w);
+				mma_us(imid, al, bi.x, bi.y);
+				mma_uu(ill, al, bi.z, bi.w);
+				if(hasq)
+				{
+					const uint4 bq = btab[((j * MF_KSTEPS + s) * 2 + 1) * 32 + lane];
+					mma_ss(qhh, ah, bq.x, bq.y);
+					mma_su(qmid, ah, bq.z, bq.w);
+					mma_us(qmid, al, bq.x, bq.y);
+					mma_uu(qll, al, bq.z, bq.w);
+				}
+			}
+			unsigned pk[4];
+			#pragma unroll
+			for(int ci = 0; ci < 4; ci++)
+			{
+				const int vi = sat16i(mf_combine(ihh[ci], imid[ci], ill[ci]) >> 15);
+				const int vq = sat16i(mf_combine(qhh[ci], qmid[ci], qll[ci]) >> 15);    // 0 without Q taps
+				pk[ci] = ((unsigned) vi & 0xFFFFu) | ((unsigned) vq << 16);
+			}
+			const int xa = mf_out_x(mt, j, lane, 0), xb = mf_out_x(mt, j, lane, 2);
+			if(xa < W) *reinterpret_cast<uint2 *>(fir + mf_fir_index(xa)) = make_uint2(pk[0], pk[1]);
+			if(xb < W) *reinterpret_cast<uint2 *>(fir + mf_fir_index(xb)) = make_uint2(pk[2], pk[3]);
+		}
+		__syncthreads();
+
+		// ---- sound carriers, mixers, store: four consecutive samples per thread ----
+		const int x0 = tid * SPT;
+		if(x0 < W)
+		{
+			const uint4 v = *reinterpret_cast<const uint4 *>(fir + mf_fir_index(x0));
+			int oi[SPT], oq[SPT];
+			oi[0] = (int) (short) (v.x & 0xFFFF); oq[0] = (int) v.x >> 16;
+			oi[1] = (int) (short) (v.y & 0xFFFF); oq[1] = (int) v.y >> 16;
+			oi[2] = (int) (short) (v.z & 0xFFFF); oq[2] = (int) v.z >> 16;
+			oi[3] = (int) (short) (v.w & 0xFFFF); oq[3] = (int) v.w >> 16;
+			const LineAudio &la = *lab[cb];
+			sound_add<false>(dp, dt, la, ntp, x0, oi, oq);
+			post_store(dp, dt, la, x0, row, oi, oq, out, row < acc_rows ? acc : NULL);
+		}
+		__syncthreads();                                            // planes, descriptor and exchange buffer are free again
+	}
+}
+
 // ---------------------------------------------------------------------------
 // Device layer (C linkage)
 // ---------------------------------------------------------------------------
@@ -2276,6 +2454,25 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		cudaFuncSetAttribute(k_mod_tma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
 		cudaFuncSetAttribute(k_mod_tma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
 		d->mod_grid = nsm * (d->line_threads <= 256 ? 4 : 2);
+		// the video filter on the tensor cores: HTV_FIR=mma / HTV_FIR=scalar overrides the default
+		const char *sel = getenv("HTV_FIR");
+		const bool want_mma = sel ? !strcmp(sel, "mma") : HTV_FIR_DEFAULT_MMA;
+		if(want_mma && dp.vf_type && W % MF_T == 0)
+		{
+			d->plane_stride = ((size_t) d->sub_lines + 3) * W + 256;
+			d->modm_smem = (size_t) 4 * mf_plane_bytes(W) + sizeof(uint4) * 4 * MF_KSTEPS * 2 * 32 +
+				sizeof(unsigned) * mf_mtiles(W) * 16 * MF_ROWW + 2 * sizeof(LineAudio) +
+				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
+			if(cudaMalloc((void **) &d->d_planes, 2 * d->plane_stride) != cudaSuccess)
+			{
+				snprintf(err, errlen, "device allocation failed");
+				htv_dev_destroy(d);
+				return(NULL);
+			}
+			cudaMemset(d->d_planes, 0, 2 * d->plane_stride);
+			cudaFuncSetAttribute(k_mod_mma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modm_smem);
+			cudaFuncSetAttribute(k_mod_mma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modm_smem);
+		}
 	}
 	if(secam)
 	{
@@ -2328,7 +2525,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	cudaSetDevice(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
 	if(d->h_ov_line) { cudaFreeHost(d->h_ov_line); cudaFreeHost(d->h_ov_meta); cudaFreeHost(d->h_ov_add); }
 	cudaFree(d->d_ov_line); cudaFree(d->d_ov_meta); cudaFree(d->d_ov_add);
@@ -2582,7 +2779,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else
 		{
 			// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
-			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32);
+			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride);
 			d->launches++;
 		}
 		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
@@ -2599,6 +2796,12 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_fmv_scan<<<1, 1024, 0, st>>>(d->dt, rows);
 			k_fmv_mod<<<rows, d->line_threads, 0, st>>>(dp, d->dt, lap, o, acc, acc_rows, -pre);
 			d->launches += 2;
+		}
+		else if(d->d_planes)
+		{
+			const int grid = n < d->mod_grid ? n : d->mod_grid;
+			if(d->line_threads <= 256) k_mod_mma<256, 4><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, n, o, acc, acc_rows);
+			else k_mod_mma<384, 2><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, n, o, acc, acc_rows);
 		}
 		else if(d->d_comp32)
 		{
