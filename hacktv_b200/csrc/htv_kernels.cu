@@ -39,6 +39,7 @@
 	fprintf(stderr, "hacktv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return(HTV_ERROR); } } while(0)
 
 struct DevTables {
+	const uint32_t *mma_atab;         // tap operand of the tensor-core video filter, fragment order (htv_mma_fir.h)
 	const uint16_t *codes;
 	const int16_t *pulse_values;
 	const double *glut;
@@ -2120,22 +2121,26 @@ k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 // ---------------------------------------------------------------------------
 // Persistent modulator with the video filter on the tensor cores (htv_mma_fir.h): the 51-tap
 // int16 FIR is an exact int8 contraction - the composite stream arrives as a high-byte and a
-// low-byte plane (written by k_raster, fetched by the TMA), the taps as a banded Toeplitz
-// operand split the same way, and four mma.sync.m16n8k32 (s8/u8 mixes) per k-step leave three
-// int32 partial sums per output that recombine to the reference's int32 accumulator
-// (ref fir.c:564-615). Each warp owns one 16-row x 8-column tile of I and of Q, so a lane ends
-// with I and Q of the same four samples; they go through a shared-memory exchange buffer to
-// the thread that owns the four consecutive samples for the sound carriers and the store.
+// low-byte plane (written by k_raster, fetched by the TMA) and is the B operand, loaded
+// straight from the window with one 64-bit shared-memory load per fragment; the taps are the
+// banded Toeplitz A operand, split the same way and laid out in fragment order on the host
+// (dt.mma_atab). Four mma.sync.m16n8k32 (s8/u8 mixes) per k-step leave three int32 partial
+// sums per output that recombine to the reference's int32 accumulator (ref fir.c:564-615).
+// A warp owns one tile of 128 consecutive samples, I and Q; the results go through a
+// shared-memory exchange buffer to the thread that owns four consecutive samples for the sound
+// carriers and the store. Buffering: planes x2, exchange x2, descriptors x3 - one
+// __syncthreads per line (between filter and sound phase), so a warp that is done with line i
+// starts filtering line i + 1 while the others still add the sound carriers of line i.
 // The scalar FIR this replaces was 51 half-rate IMAD + 50 IADD per sample (45 % of k_mod_tma).
-// Used whenever 32 | W, a video filter is on, and the mode is not SECAM / FM video.
+// Used whenever 128 | W, a video filter is on, and the mode is not SECAM / FM video.
 // ---------------------------------------------------------------------------
 
 #define MMA_I8(NAME, AT, BT) \
-__device__ __forceinline__ void NAME(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) \
+__device__ __forceinline__ void NAME(int (&d)[4], const uint4 &a, const uint2 &b) \
 { \
-	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32." AT "." BT ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+	asm("mma.sync.aligned.m16n8k32.row.col.s32." AT "." BT ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
 		: "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) \
-		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1)); \
+		: "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y)); \
 }
 MMA_I8(mma_ss, "s8", "s8")
 MMA_I8(mma_su, "s8", "u8")
@@ -2149,16 +2154,14 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int W = dp.W;
-	const int MT = mf_mtiles(W);
 	const int PB = mf_plane_bytes(W), WB = mf_window_bytes(W);
-	// [buffer][plane] byte windows, the B operand, the exchange buffer, two descriptors, the NICAM pulse
+	const int FW = (W / 32) * MF_ROWW;                                  // words of one exchange buffer
+	// [buffer][plane] byte windows, the tap operand, two exchange buffers, three descriptors, the NICAM pulse
 	unsigned char *pl0 = smem_raw;
-	uint4 *btab = reinterpret_cast<uint4 *>(pl0 + 4 * PB);              // [j 4][s 3][I/Q 2][lane 32]: hi b0, hi b1, lo b0, lo b1
-	unsigned *fir = reinterpret_cast<unsigned *>(btab + 4 * MF_KSTEPS * 2 * 32);
-	LineAudio *lab[2];
-	lab[0] = reinterpret_cast<LineAudio *>(fir + MT * 16 * MF_ROWW);
-	lab[1] = lab[0] + 1;
-	short *ntp = reinterpret_cast<short *>(lab[1] + 1);
+	uint4 *atab = reinterpret_cast<uint4 *>(pl0 + 4 * PB);              // [k-step][I hi, I lo, Q hi, Q lo][lane]
+	unsigned *fir0 = reinterpret_cast<unsigned *>(atab + MF_ATAB_WORDS / 4);
+	LineAudio *lab0 = reinterpret_cast<LineAudio *>(fir0 + 2 * FW);
+	short *ntp = reinterpret_cast<short *>(lab0 + 3);
 	__shared__ __align__(8) unsigned long long bar[2];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 	const unsigned bytes = (unsigned) (2 * WB + sizeof(LineAudio));
@@ -2170,14 +2173,8 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 		int4 *dst = reinterpret_cast<int4 *>(ntp);
 		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
-	for(int i = tid; i < 4 * MF_KSTEPS * 2 * 32; i += blockDim.x)
-	{
-		const int l = i & 31, q = (i >> 5) & 1, js = i >> 6, s = js % MF_KSTEPS, j = js / MF_KSTEPS;
-		const int32_t *taps = q ? dp.vf_q : dp.vf_i;
-		btab[i] = make_uint4(mf_b_word(taps, j, s, l, 0), mf_b_word(taps, j, s, l, 1), mf_b_word(taps, j, s, l, 2), mf_b_word(taps, j, s, l, 3));
-	}
-	// the rows of the last m-tile past the line are multiplied too (and dropped): keep them defined
-	// (only the bytes behind the window: the TMA never writes them)
+	for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
+	// the bytes behind the window are multiplied by zero taps only; the TMA never writes them
 	for(int i = tid; i < 4 * (PB - WB) / 4; i += blockDim.x)
 	{
 		const int per = (PB - WB) / 4;
@@ -2189,8 +2186,6 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[1])));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	// the zero fill above went through the generic proxy, the TMA writes through the async proxy
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	__syncthreads();
 
 	int row = blockIdx.x;
@@ -2201,63 +2196,63 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(bytes) : "memory");
 		tma_load(pl0, src, WB, &bar[0]);
 		tma_load(pl0 + PB, src + plane_stride, WB, &bar[0]);
-		tma_load(lab[0], lap + row, sizeof(LineAudio), &bar[0]);
+		tma_load(lab0, lap + row, sizeof(LineAudio), &bar[0]);
 	}
 	unsigned phase[2] = { 0, 0 };
+	int l3 = 0;                                                         // it % 3: descriptor buffer of this line
 	for(int it = 0; row < nlines; it++, row += gridDim.x)
 	{
 		const int cb = it & 1, nb = cb ^ 1;
+		const int n3 = l3 == 2 ? 0 : l3 + 1;
 		const int nrow = row + gridDim.x;
 		if(tid == 0 && nrow < nlines)
 		{
+			// plane buffer nb was last read by the filter phase of line it - 1 and descriptor n3 by the
+			// sound phase of line it - 2: every thread was past both when it reached the barrier of
+			// line it - 1, which this thread has left
 			const uint8_t *src = planes + ((size_t) nrow + 1) * W - MF_LEAD;
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(bytes) : "memory");
 			tma_load(pl0 + (2 * nb) * PB, src, WB, &bar[nb]);
 			tma_load(pl0 + (2 * nb + 1) * PB, src + plane_stride, WB, &bar[nb]);
-			tma_load(lab[nb], lap + nrow, sizeof(LineAudio), &bar[nb]);
+			tma_load(lab0 + n3, lap + nrow, sizeof(LineAudio), &bar[nb]);
 		}
 		mbar_wait(&bar[cb], phase[cb]);
 		phase[cb] ^= 1;
 
-		// ---- video filter: one (m-tile, n-tile) unit per warp ------------------
+		// ---- video filter: one tile of 128 samples per warp ---------------------
 		const unsigned char *ph = pl0 + (2 * cb) * PB, *plo = ph + PB;
-		for(int u = warp; u < MT * 4; u += nwarps)
+		unsigned *fir = fir0 + cb * FW;                                  // last read in the sound phase of line it - 2
+		for(int nt = warp; nt < mf_tiles(W); nt += nwarps)
 		{
-			const int mt = u >> 2, j = u & 3;
 			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
 			int qhh[4] = { 0, 0, 0, 0 }, qmid[4] = { 0, 0, 0, 0 }, qll[4] = { 0, 0, 0, 0 };
+			const int o0 = mf_b_offset(nt, 0, lane);
 			#pragma unroll
 			for(int s = 0; s < MF_KSTEPS; s++)
 			{
-				const int o0 = mf_a_offset(mt, s, lane, 0), o1 = mf_a_offset(mt, s, lane, 1);
-				const uint2 h0 = *reinterpret_cast<const uint2 *>(ph + o0), h1 = *reinterpret_cast<const uint2 *>(ph + o1);
-				const uint2 l0 = *reinterpret_cast<const uint2 *>(plo + o0), l1 = *reinterpret_cast<const uint2 *>(plo + o1);
-				const unsigned ah[4] = { h0.x, h1.x, h0.y, h1.y }, al[4] = { l0.x, l1.x, l0.y, l1.y };
-				const uint4 bi = btab[((j * MF_KSTEPS + s) * 2 + 0) * 32 + lane];
-				mma_ss(ihh, ah, bi.x, bi.y);
-				mma_su(imid, ah, bi.z, bi.w);
-				mma_us(imid, al, bi.x, bi.y);
-				mma_uu(ill, al, bi.z, bi.w);
+				const uint2 xh = *reinterpret_cast<const uint2 *>(ph + o0 + 32 * s);
+				const uint2 xl = *reinterpret_cast<const uint2 *>(plo + o0 + 32 * s);
+				const uint4 aih = atab[(s * 4 + 0) * 32 + lane], ail = atab[(s * 4 + 1) * 32 + lane];
+				mma_ss(ihh, aih, xh);
+				mma_su(imid, aih, xl);
+				mma_us(imid, ail, xh);
+				mma_uu(ill, ail, xl);
 				if(hasq)
 				{
-					const uint4 bq = btab[((j * MF_KSTEPS + s) * 2 + 1) * 32 + lane];
-					mma_ss(qhh, ah, bq.x, bq.y);
-					mma_su(qmid, ah, bq.z, bq.w);
-					mma_us(qmid, al, bq.x, bq.y);
-					mma_uu(qll, al, bq.z, bq.w);
+					const uint4 aqh = atab[(s * 4 + 2) * 32 + lane], aql = atab[(s * 4 + 3) * 32 + lane];
+					mma_ss(qhh, aqh, xh);
+					mma_su(qmid, aqh, xl);
+					mma_us(qmid, aql, xh);
+					mma_uu(qll, aql, xl);
 				}
 			}
-			unsigned pk[4];
 			#pragma unroll
 			for(int ci = 0; ci < 4; ci++)
 			{
 				const int vi = sat16i(mf_combine(ihh[ci], imid[ci], ill[ci]) >> 15);
 				const int vq = sat16i(mf_combine(qhh[ci], qmid[ci], qll[ci]) >> 15);    // 0 without Q taps
-				pk[ci] = ((unsigned) vi & 0xFFFFu) | ((unsigned) vq << 16);
+				fir[mf_fir_index(mf_out_x(nt, lane, ci))] = ((unsigned) vi & 0xFFFFu) | ((unsigned) vq << 16);
 			}
-			const int xa = mf_out_x(mt, j, lane, 0), xb = mf_out_x(mt, j, lane, 2);
-			if(xa < W) *reinterpret_cast<uint2 *>(fir + mf_fir_index(xa)) = make_uint2(pk[0], pk[1]);
-			if(xb < W) *reinterpret_cast<uint2 *>(fir + mf_fir_index(xb)) = make_uint2(pk[2], pk[3]);
 		}
 		__syncthreads();
 
@@ -2271,11 +2266,11 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 			oi[1] = (int) (short) (v.y & 0xFFFF); oq[1] = (int) v.y >> 16;
 			oi[2] = (int) (short) (v.z & 0xFFFF); oq[2] = (int) v.z >> 16;
 			oi[3] = (int) (short) (v.w & 0xFFFF); oq[3] = (int) v.w >> 16;
-			const LineAudio &la = *lab[cb];
+			const LineAudio &la = lab0[l3];
 			sound_add<false>(dp, dt, la, ntp, x0, oi, oq);
 			post_store(dp, dt, la, x0, row, oi, oq, out, row < acc_rows ? acc : NULL);
 		}
-		__syncthreads();                                            // planes, descriptor and exchange buffer are free again
+		l3 = n3;
 	}
 }
 
@@ -2457,11 +2452,14 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		// the video filter on the tensor cores: HTV_FIR=mma / HTV_FIR=scalar overrides the default
 		const char *sel = getenv("HTV_FIR");
 		const bool want_mma = sel ? !strcmp(sel, "mma") : HTV_FIR_DEFAULT_MMA;
-		if(want_mma && dp.vf_type && W % MF_T == 0)
+		if(want_mma && dp.vf_type && W % MF_TILE == 0)
 		{
+			uint32_t atab[MF_ATAB_WORDS];
+			mf_build_atab(dp.vf_i, dp.vf_q, atab);
+			d->dt.mma_atab = (const uint32_t *) dev_copy(d, atab, sizeof(atab));
 			d->plane_stride = ((size_t) d->sub_lines + 3) * W + 256;
-			d->modm_smem = (size_t) 4 * mf_plane_bytes(W) + sizeof(uint4) * 4 * MF_KSTEPS * 2 * 32 +
-				sizeof(unsigned) * mf_mtiles(W) * 16 * MF_ROWW + 2 * sizeof(LineAudio) +
+			d->modm_smem = (size_t) 4 * mf_plane_bytes(W) + sizeof(uint32_t) * MF_ATAB_WORDS +
+				sizeof(unsigned) * 2 * (W / 32) * MF_ROWW + 3 * sizeof(LineAudio) +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
 			if(cudaMalloc((void **) &d->d_planes, 2 * d->plane_stride) != cudaSuccess)
 			{

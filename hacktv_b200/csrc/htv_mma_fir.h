@@ -1,26 +1,27 @@
 /* The 51-tap video filter (ref _vid_filter_process video.c:3235-3248, fir_int16_scomplex_process
  * fir.c:564-615) as an exact int8 tensor-core contraction. Index arithmetic only, shared by the
- * CUDA kernel (k_mod_mma, htv_kernels.cu) and the host-side emulation in tests/ so the fragment
- * mapping can be checked without a GPU.
+ * CUDA kernel (k_mod_mma, htv_kernels.cu), the host code that builds the tap operand, and the
+ * host-side emulation in tests/ so the fragment mapping can be checked without a GPU.
  *
  * out[x] = sum_{y=0..50} comp[x - 25 + y] * tap[y]                       (centred FIR)
  *
- * A line is cut into rows of MF_T = 32 outputs: x = 32 r + c. With k' = c + y + MF_SHIFT
- *   A[r][k'] = comp[32 r + k' - MF_LEAD]      (overlapping windows of one contiguous stream)
- *   B[k'][c] = tap[k' - MF_SHIFT - c]         (banded Toeplitz, zero outside 0..50)
- * so out = A x B with K = 96 (3 k-steps of 32). MF_LEAD = 25 + MF_SHIFT = 32 puts byte 0 of the
- * window 32 samples before the line: every row starts on a 32-byte boundary.
+ * A line is cut into stream rows of MF_M = 16 outputs: x = 16 r + m. With k' = m + y + MF_SHIFT
+ *   A[m][k'] = tap[k' - MF_SHIFT - m]         (banded Toeplitz, zero outside 0..50, constant)
+ *   B[k'][r] = comp[16 r + k' - MF_LEAD]      (overlapping windows of one contiguous stream)
+ * so out = A x B with K = 96 (3 k-steps of 32; taps reach k' = 72). MF_LEAD = 25 + MF_SHIFT = 32
+ * puts byte 0 of the window 32 samples before the line: every row starts on a 16-byte boundary.
+ * One mma tile is 16 outputs x 8 rows = 128 consecutive samples; a warp owns one tile of a line.
  *
  * int16 x int16 products are made exact by the byte split v = 256 hi + lo (hi signed, lo
- * unsigned): x h = 65536 xh hh + 256 (xh hl + xl hh) + xl hl - three int32 accumulators fed by
+ * unsigned): h x = 65536 hh xh + 256 (hh xl + hl xh) + hl xl - three int32 accumulators fed by
  * four mma.sync.m16n8k32 (s8.s8, s8.u8, u8.s8, u8.u8); each partial sum stays below 2^23.
  *
- * Fragment use (PTX ISA, m16n8k32 integer): lane = 4 g + t. A register a0/a2 carries k-slots
- * 4t..4t+3 / 16+4t..16+4t+3 of row g, a1/a3 the same of row g + 8; B register b0/b1 carries
- * those slots of column g. The k index is a summation index, so slots may name any k' as long
- * as A and B agree: here lane t's (a0, a2) = the 8 consecutive bytes k' = 32 s + 8 t .. + 7
- * (one 64-bit shared-memory load; a warp reads 256 contiguous bytes, conflict-free) and
- * (b0, b1) the matching taps. */
+ * Fragment use (PTX ISA, m16n8k32 integer): lane = 4 g + t. B register b0 / b1 carries k-slots
+ * 4t..4t+3 / 16+4t..16+4t+3 of column g; A register a0 / a2 those slots of row g, a1 / a3 of row
+ * g + 8. The k index is a summation index, so slots may name any k' as long as A and B agree:
+ * here lane t's (b0, b1) = the 8 consecutive stream bytes k' = 32 s + 8 t .. + 7 of row g - one
+ * 64-bit shared-memory load straight into the register pair, no shuffling - and (a0 .. a3) the
+ * matching taps, prepared once on the host in fragment order (one 128-bit load per fragment). */
 #ifndef HTV_MMA_FIR_H
 #define HTV_MMA_FIR_H
 
@@ -32,50 +33,59 @@
 #define MF_HD static inline
 #endif
 
-#define MF_T       32      /* outputs per A row */
+#define MF_M       16      /* outputs per stream row */
+#define MF_TILE    128     /* samples per mma tile (16 outputs x 8 rows) */
 #define MF_NTAPS   51
 #define MF_SHIFT   7
 #define MF_LEAD    32      /* window byte 0 = composite sample -32 of the line */
 #define MF_KSTEPS  3       /* K = 96 */
-#define MF_ROWW    40      /* exchange buffer: words per row of 32 outputs (bank-conflict-free both ways) */
+#define MF_ROWW    40      /* exchange buffer: words per 32 outputs (bank-conflict-free both ways) */
+#define MF_ATAB_WORDS (MF_KSTEPS * 4 * 32 * 4)   /* tap operand: [k-step][I hi, I lo, Q hi, Q lo][lane] x 4 registers */
 
-/* rows of 32 outputs in a line, m16 tiles, bytes of one plane buffer in shared memory */
-MF_HD int mf_rows(int W) { return(W / MF_T); }
-MF_HD int mf_mtiles(int W) { return((W / MF_T + 15) / 16); }
-MF_HD int mf_plane_bytes(int W) { return(mf_mtiles(W) * 16 * MF_T + 64); }    /* >= W + 64, multiple of 16 */
-MF_HD int mf_window_bytes(int W) { return(W + 2 * MF_LEAD); }                  /* what the TMA brings per plane */
+/* tiles in a line (W must be a multiple of 128), bytes of one plane buffer in shared memory,
+ * bytes the TMA brings per plane (the tail of the buffer is read by zero taps only) */
+MF_HD int mf_tiles(int W) { return(W / MF_TILE); }
+MF_HD int mf_plane_bytes(int W) { return(W + 96); }
+MF_HD int mf_window_bytes(int W) { return(W + 2 * MF_LEAD); }
 
-/* byte offset, inside a plane window, of the 8 bytes lane (g, t) loads for m-tile mt, k-step s;
- * half = 0: row g, half = 1: row g + 8 */
-MF_HD int mf_a_offset(int mt, int s, int lane, int half)
+/* byte offset, inside a plane window, of the 8 stream bytes lane (g, t) loads for tile nt, k-step s */
+MF_HD int mf_b_offset(int nt, int s, int lane)
 {
 	const int g = lane >> 2, t = lane & 3;
-	return(MF_T * (mt * 16 + g + 8 * half) + 32 * s + 8 * t);
+	return(MF_M * (8 * nt + g) + 32 * s + 8 * t);
 }
 
-/* one 32-bit B register. taps[51] in application order (tap[y] multiplies comp[x - 25 + y]).
- * j = n-tile (columns 8 j .. 8 j + 7), s = k-step, w: bit 0 = b1 (second four k'), bit 1 = low byte plane */
-MF_HD uint32_t mf_b_word(const int32_t *taps, int j, int s, int lane, int w)
+/* one 32-bit register of the tap operand. taps[51] in application order (tap[y] multiplies
+ * comp[x - 25 + y]); s = k-step, reg = 0..3 (a0..a3), lo = low byte plane */
+MF_HD uint32_t mf_a_word(const int32_t *taps, int s, int lane, int reg, int lo)
 {
 	const int g = lane >> 2, t = lane & 3;
-	const int c = 8 * j + g;
-	const int kp0 = 32 * s + 8 * t + (w & 1) * 4;
+	const int m = g + ((reg & 1) ? 8 : 0);
+	const int kp0 = 32 * s + 8 * t + ((reg & 2) ? 4 : 0);
 	uint32_t r = 0;
 	for(int e = 0; e < 4; e++)
 	{
-		const int y = kp0 + e - MF_SHIFT - c;
+		const int y = kp0 + e - MF_SHIFT - m;
 		const int h = (y >= 0 && y < MF_NTAPS) ? taps[y] : 0;
-		const uint32_t b = (w & 2) ? ((uint32_t) h & 0xFFu) : (((uint32_t) h >> 8) & 0xFFu);
+		const uint32_t b = lo ? ((uint32_t) h & 0xFFu) : (((uint32_t) h >> 8) & 0xFFu);
 		r |= b << (8 * e);
 	}
 	return(r);
 }
 
-/* sample index of accumulator register ci (0..3) of lane (g, t) for m-tile mt, n-tile j */
-MF_HD int mf_out_x(int mt, int j, int lane, int ci)
+/* the whole tap operand in the order k_mod_mma reads it; out[MF_ATAB_WORDS] */
+MF_HD void mf_build_atab(const int32_t *itaps, const int32_t *qtaps, uint32_t *out)
+{
+	for(int s = 0; s < MF_KSTEPS; s++) for(int kind = 0; kind < 4; kind++) for(int lane = 0; lane < 32; lane++)
+		for(int reg = 0; reg < 4; reg++)
+			out[((s * 4 + kind) * 32 + lane) * 4 + reg] = mf_a_word((kind & 2) ? qtaps : itaps, s, lane, reg, kind & 1);
+}
+
+/* sample index of accumulator register ci (0..3) of lane (g, t) for tile nt */
+MF_HD int mf_out_x(int nt, int lane, int ci)
 {
 	const int g = lane >> 2, t = lane & 3;
-	return(MF_T * (mt * 16 + g + ((ci & 2) ? 8 : 0)) + 8 * j + 2 * t + (ci & 1));
+	return(MF_TILE * nt + MF_M * (2 * t + (ci & 1)) + g + ((ci & 2) ? 8 : 0));
 }
 
 /* word index of sample x in the exchange buffer */

@@ -53,7 +53,7 @@ int main(int argc, char **argv)
 	const int W = argc > 1 ? atoi(argv[1]) : 1024;
 	rng_state = argc > 2 ? (uint32_t) atoi(argv[2]) : 1;
 	const int extreme = argc > 3 ? atoi(argv[3]) : 0;
-	if(W % MF_T) { printf("W must be a multiple of %d\n", MF_T); return(2); }
+	if(W % MF_TILE) { printf("W must be a multiple of %d\n", MF_TILE); return(2); }
 
 	/* a composite stream of three lines; the middle one is filtered */
 	int16_t *comp = malloc(sizeof(int16_t) * 3 * W);
@@ -83,43 +83,41 @@ int main(int argc, char **argv)
 		pl[i] = (uint8_t) (v & 0xFF);
 	}
 
-	const int R = mf_rows(W), MT = mf_mtiles(W);
-	uint32_t *fir = calloc((size_t) MT * 16 * MF_ROWW, sizeof(uint32_t));
-	for(int u = 0; u < MT * 4; u++)
+	uint32_t atab[MF_ATAB_WORDS];
+	mf_build_atab(taps[0], taps[1], atab);
+	uint32_t *fir = calloc((size_t) (W / 32) * MF_ROWW, sizeof(uint32_t));
+	uint8_t *seen = calloc((size_t) W, 1);
+	for(int nt = 0; nt < mf_tiles(W); nt++)
 	{
-		const int mt = u >> 2, j = u & 3;
 		int32_t acc[2][3][32][4];
 		memset(acc, 0, sizeof(acc));
 		for(int s = 0; s < MF_KSTEPS; s++)
 		{
-			uint32_t ah[32][4], al[32][4], b[2][2][32][2];
+			uint32_t a[4][32][4], bh[32][2], bl[32][2];
 			for(int lane = 0; lane < 32; lane++)
 			{
-				for(int half = 0; half < 2; half++)
-				{
-					const int off = mf_a_offset(mt, s, lane, half);
-					if(off + 8 > PB) { printf("A load out of the plane buffer\n"); return(1); }
-					uint32_t w[2];
-					memcpy(w, ph + off, 8); ah[lane][half] = w[0]; ah[lane][2 + half] = w[1];
-					memcpy(w, pl + off, 8); al[lane][half] = w[0]; al[lane][2 + half] = w[1];
-				}
-				for(int q = 0; q < 2; q++) for(int w = 0; w < 4; w++)
-					b[q][w >> 1][lane][w & 1] = mf_b_word(taps[q], j, s, lane, w);
+				const int off = mf_b_offset(nt, s, lane);
+				if(off + 8 > PB) { printf("stream load out of the plane buffer\n"); return(1); }
+				memcpy(bh[lane], ph + off, 8);
+				memcpy(bl[lane], pl + off, 8);
+				for(int kind = 0; kind < 4; kind++)
+					memcpy(a[kind][lane], atab + ((s * 4 + kind) * 32 + lane) * 4, 16);
 			}
 			for(int q = 0; q < 2; q++)
 			{
-				mma_emu(acc[q][0], ah, b[q][0], 1, 1);
-				mma_emu(acc[q][1], ah, b[q][1], 1, 0);
-				mma_emu(acc[q][1], al, b[q][0], 0, 1);
-				mma_emu(acc[q][2], al, b[q][1], 0, 0);
+				mma_emu(acc[q][0], a[2 * q], bh, 1, 1);        /* taps hi x stream hi */
+				mma_emu(acc[q][1], a[2 * q], bl, 1, 0);        /* taps hi x stream lo */
+				mma_emu(acc[q][1], a[2 * q + 1], bh, 0, 1);    /* taps lo x stream hi */
+				mma_emu(acc[q][2], a[2 * q + 1], bl, 0, 0);    /* taps lo x stream lo */
 			}
 		}
 		for(int lane = 0; lane < 32; lane++) for(int ci = 0; ci < 4; ci++)
 		{
-			const int x = mf_out_x(mt, j, lane, ci);
-			if(x / MF_T >= R) continue;
+			const int x = mf_out_x(nt, lane, ci);
+			if(x < 0 || x >= W) { printf("output index %d out of the line\n", x); return(1); }
 			const int vi = mf_combine(acc[0][0][lane][ci], acc[0][1][lane][ci], acc[0][2][lane][ci]);
 			const int vq = mf_combine(acc[1][0][lane][ci], acc[1][1][lane][ci], acc[1][2][lane][ci]);
+			if(seen[x]++) { printf("sample %d written twice\n", x); return(1); }
 			fir[mf_fir_index(x)] = ((uint32_t) sat16(vi >> 15) & 0xFFFF) | ((uint32_t) sat16(vq >> 15) << 16);
 		}
 	}
@@ -134,6 +132,7 @@ int main(int argc, char **argv)
 			sq += (uint32_t) ((int32_t) line[x - 25 + y] * taps[1][y]);
 		}
 		const int ei = sat16((int32_t) si >> 15), eq = sat16((int32_t) sq >> 15);
+		if(!seen[x]) { printf("sample %d never written\n", x); return(1); }
 		const uint32_t got = fir[mf_fir_index(x)];
 		if((int16_t) (got & 0xFFFF) != ei || (int16_t) (got >> 16) != eq)
 		{

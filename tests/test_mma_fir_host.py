@@ -18,7 +18,7 @@ def emu(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("W", [1024, 1280, 864, 1536, 32])
+@pytest.mark.parametrize("W", [1024, 1280, 1152, 1536, 128])
 @pytest.mark.parametrize("extreme", [0, 1])
 def test_fragment_mapping_reproduces_the_fir(emu, W, extreme):
     for seed in (1, 2, 3):

@@ -26,9 +26,9 @@ ends = [i for i, l in enumerate(dis) if l.startswith(".text.") and i > start]
 end = ends[0] if ends else len(dis)
 seq, cur = [], None
 for l in dis[start:end]:
-    m = re.search(r'//## File ".*?", line (\d+)', l)
+    m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur = int(m.group(1)); continue
+        cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         seq.append((cur, l.strip()))
 
@@ -41,11 +41,22 @@ agg, samp = collections.Counter(), collections.Counter()
 for (ln, _), r in zip(seq, data):
     agg[ln] += int(r[ie]); samp[ln] += int(r[ss])
 tot, ts = sum(agg.values()), sum(samp.values())
-src = open(os.path.join(ROOT, "hacktv_b200", "csrc", "htv_kernels.cu")).read().split("\n")
+srcs = {}
+def text_of(ln):
+    if not ln:
+        return ""
+    f, n = ln
+    if f not in srcs:
+        try:
+            srcs[f] = open(os.path.join(ROOT, "hacktv_b200", "csrc", f)).read().split("\n")
+        except OSError:
+            srcs[f] = []
+    pre = "" if f == "htv_kernels.cu" else "[" + f + "] "
+    return pre + (srcs[f][n - 1].strip()[:100] if 0 < n <= len(srcs[f]) else "")
 print(f"# {kern}: {n} SASS instructions, {tot} warp-instructions executed, {ts} stall samples")
 for ln, c in agg.most_common(topn):
-    text = src[ln - 1].strip()[:100] if ln else ""
-    print(f"{ln:5d} {100 * c / tot:5.1f}% inst {100 * samp[ln] / max(ts, 1):5.1f}% stall | {text}")
+    text = text_of(ln)
+    print(f"{(ln[1] if ln else 0):5d} {100 * c / tot:5.1f}% inst {100 * samp[ln] / max(ts, 1):5.1f}% stall | {text}")
 
 rr = list(csv.reader(raw_csv.split("\n")))
 h, u, r0 = rr[0], rr[1], rr[2]
