@@ -39,12 +39,15 @@ MODE, RATE, FILTER = "i", 16_000_000, True
 WORKLOAD = "PAL-I (-m i) 16 Msps --filter: VSB + FM mono + NICAM-728 + colour, built-in test pattern"
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 REF_THREADS = 3          # main/raster + vfilter + audio (reference video.c:4692: 1 + nthreads)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_mod_tma launch (7 232 lines, 29.6 MB of IQ) from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_mod_raw.txt (38.48 MB read + 3.22 MB written: ncu
-# flushes L2 between replays, so the L2-resident composite scratch is re-read from HBM and most of the
-# output is still in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 41_701_120
-NCU_TRAFFIC_LINES = 7232
+# dram__bytes_read.sum + dram__bytes_write.sum of one modulator launch from the `ncu --set full` captures
+# (ncu flushes L2 between replays, so the L2-resident composite scratch is re-read from HBM and most of the
+# output is still in L2 when the kernel ends), per scan line of 1024 samples:
+#   k_mod_mma (default; profiles/r01_ncu_mod_mma_raw.txt): 8 192 lines, 21.71 MB read (two byte planes) + 0.11 MB written
+#   k_mod_tma (HTV_FIR=scalar; profiles/r01_ncu_mod_raw.txt): 7 232 lines, 38.48 MB read (int32 scratch) + 3.22 MB written
+NCU_TRAFFIC_BYTES_PER_LINE = {"mma": 21_822_208 / 8192, "scalar": 41_701_120 / 7232}
+FIR = "scalar" if os.environ.get("HTV_FIR") == "scalar" else "mma"
+KERNEL = {"mma": "k_mod_mma (video filter on the tensor cores: exact int8 byte-split mma.sync + sound carriers + IQ store)",
+          "scalar": "k_mod_tma (scalar video filter + sound carriers + IQ store)"}[FIR]
 
 
 def measured_peak_gbs():
@@ -306,11 +309,11 @@ def main():
                        "realtime_x": round(value / world / (RATE / 1e6), 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if kern_lines == NCU_TRAFFIC_LINES else None,
-                         "kernel": "k_mod (video filter + sound carriers + IQ store)", "kernel_ms": round(k_ms, 4),
+                         "traffic": int(round(NCU_TRAFFIC_BYTES_PER_LINE[FIR] * kern_lines)) if enc.width == 1024 else None,
+                         "kernel": KERNEL, "kernel_ms": round(k_ms, 4),
                          "lines_per_launch": kern_lines, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_samples * 4,
-                         "note": "4 B per complex sample written once; the kernel is integer-ALU bound (DESIGN.md), not HBM bound"},
+                         "note": "4 B per complex sample written once; the kernel is issue-slot bound (DESIGN.md section 4), not HBM bound"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

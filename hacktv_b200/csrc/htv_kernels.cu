@@ -24,7 +24,7 @@
 #include "htv_internal.h"
 #include "htv_mma_fir.h"
 
-#define HTV_FIR_DEFAULT_MMA 0         // 1: the tensor-core video filter is the default where it applies
+#define HTV_FIR_DEFAULT_MMA 1         // the tensor-core video filter is the default where it applies (HTV_FIR=scalar turns it off)
 #define HALO 25                       // (HTV_VF_NTAPS - 1) / 2
 #define RA_BITS 20
 #define RA (1 << RA_BITS)             // audio ring: pairs / processed samples / phase prefix
