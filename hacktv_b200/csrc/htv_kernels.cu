@@ -152,6 +152,7 @@ struct htv_dev_t {
 	int *d_comp32;                    // int32 composite scratch for the TMA-fed modulator (4 | W, not SECAM)
 	uint8_t *d_planes;                // high / low byte planes of the composite stream for k_mod_mma (32 | W, video filter on)
 	size_t plane_stride, modm_smem;
+	int plane_pitch;                  // 0: planes are the contiguous stream; else bytes per line row (htv_mma_fir.h)
 	size_t modt_smem;
 	int mod_grid;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
@@ -880,7 +881,7 @@ __device__ __forceinline__ void chroma_fir4(const htv_dparams_t &dp, const int *
 
 __global__ void __launch_bounds__(384, 4)
 k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int *comp32,
-	uint8_t *planes, size_t plane_stride)
+	uint8_t *planes, size_t plane_stride, int plane_pitch)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -994,6 +995,34 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 			if(x >= li.ov_from && x < li.ov_to) val[k] = li.ov_value;
 			if(li.ov_add >= 0 && x < W) val[k] = wrap16i(val[k]) + dt.ov_add[(size_t) li.ov_add * W + x];
 		}
+	}
+	if(planes && plane_pitch)
+	{
+		// pitched byte planes (htv_mma_fir.h): one self-contained row per line, the first / last
+		// MF_LEAD samples repeated in the halo of the previous / next row of this launch
+		uint8_t *rowp = planes + (size_t) blockIdx.x * plane_pitch;
+		if(x0 + SPT <= W)
+		{
+			*reinterpret_cast<unsigned *>(rowp + MF_LEAD + x0) = ((val[0] >> 8) & 0xFF) | (((val[1] >> 8) & 0xFF) << 8) |
+				(((val[2] >> 8) & 0xFF) << 16) | ((unsigned) (val[3] >> 8) << 24);
+			*reinterpret_cast<unsigned *>(rowp + plane_stride + MF_LEAD + x0) = (val[0] & 0xFF) | ((val[1] & 0xFF) << 8) |
+				((val[2] & 0xFF) << 16) | ((unsigned) val[3] << 24);
+		}
+		const bool head = x0 < MF_LEAD && blockIdx.x > 0, tail = x0 + SPT > W - MF_LEAD && blockIdx.x + 1 < gridDim.x;
+		if(head || tail || x0 + SPT > W)
+		{
+			#pragma unroll
+			for(int k = 0; k < SPT; k++)
+			{
+				const int x = x0 + k;
+				if(x >= W) break;
+				const uint8_t hi = (uint8_t) ((val[k] >> 8) & 0xFF), lo = (uint8_t) (val[k] & 0xFF);
+				if(x0 + SPT > W) { rowp[MF_LEAD + x] = hi; rowp[plane_stride + MF_LEAD + x] = lo; }
+				if(head && x < MF_LEAD) { uint8_t *q = rowp - plane_pitch + MF_LEAD + W + x; q[0] = hi; q[plane_stride] = lo; }
+				if(tail && x >= W - MF_LEAD) { uint8_t *q = rowp + plane_pitch + (x - (W - MF_LEAD)); q[0] = hi; q[plane_stride] = lo; }
+			}
+		}
+		return;
 	}
 	if(planes)
 	{
@@ -2150,12 +2179,13 @@ MMA_I8(mma_uu, "u8", "u8")
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const uint8_t *planes, size_t plane_stride,
-	int nlines, int16_t *out, const int16_t *acc, int acc_rows)
+	int pitch, int nlines, int16_t *out, const int16_t *acc, int acc_rows)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int W = dp.W;
-	const int PB = mf_plane_bytes(W), WB = mf_window_bytes(W);
-	const int FW = (W / 32) * MF_ROWW;                                  // words of one exchange buffer
+	// pitch != 0: one self-contained row per line (any W); 0: the planes are the contiguous stream (128 | W)
+	const int WB = pitch ? mf_row_bytes(W) : mf_window_bytes(W), PB = pitch ? WB : mf_plane_bytes(W);
+	const int FW = mf_tiles(W) * 4 * MF_ROWW;                           // words of one exchange buffer
 	// [buffer][plane] byte windows, the tap operand, two exchange buffers, three descriptors, the NICAM pulse
 	unsigned char *pl0 = smem_raw;
 	uint4 *atab = reinterpret_cast<uint4 *>(pl0 + 4 * PB);              // [k-step][I hi, I lo, Q hi, Q lo][lane]
@@ -2175,6 +2205,7 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 	}
 	for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
 	// the bytes behind the window are multiplied by zero taps only; the TMA never writes them
+	// (contiguous layout; a pitched row arrives whole)
 	for(int i = tid; i < 4 * (PB - WB) / 4; i += blockDim.x)
 	{
 		const int per = (PB - WB) / 4;
@@ -2192,7 +2223,7 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 	if(tid == 0 && row < nlines)
 	{
 		// the launch's composite stream starts one line early: line `row` begins at (row + 1) * W
-		const uint8_t *src = planes + ((size_t) row + 1) * W - MF_LEAD;
+		const uint8_t *src = pitch ? planes + ((size_t) row + 1) * pitch : planes + ((size_t) row + 1) * W - MF_LEAD;
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(bytes) : "memory");
 		tma_load(pl0, src, WB, &bar[0]);
 		tma_load(pl0 + PB, src + plane_stride, WB, &bar[0]);
@@ -2210,7 +2241,7 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 			// plane buffer nb was last read by the filter phase of line it - 1 and descriptor n3 by the
 			// sound phase of line it - 2: every thread was past both when it reached the barrier of
 			// line it - 1, which this thread has left
-			const uint8_t *src = planes + ((size_t) nrow + 1) * W - MF_LEAD;
+			const uint8_t *src = pitch ? planes + ((size_t) nrow + 1) * pitch : planes + ((size_t) nrow + 1) * W - MF_LEAD;
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(bytes) : "memory");
 			tma_load(pl0 + (2 * nb) * PB, src, WB, &bar[nb]);
 			tma_load(pl0 + (2 * nb + 1) * PB, src + plane_stride, WB, &bar[nb]);
@@ -2449,19 +2480,29 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		cudaFuncSetAttribute(k_mod_tma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
 		cudaFuncSetAttribute(k_mod_tma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
 		d->mod_grid = nsm * (d->line_threads <= 256 ? 4 : 2);
-		// the video filter on the tensor cores: HTV_FIR=mma / HTV_FIR=scalar overrides the default
+	}
+	if(!secam && !dp.have_fmv && dp.vf_type)
+	{
+		// the video filter on the tensor cores (k_mod_mma): the default where 128 | W (planes = the
+		// contiguous stream); HTV_FIR=mma also takes it for any other width through the pitched plane
+		// layout (htv_mma_fir.h; NTSC 858 - not yet the default), HTV_FIR=scalar turns it off
 		const char *sel = getenv("HTV_FIR");
-		const bool want_mma = sel ? !strcmp(sel, "mma") : HTV_FIR_DEFAULT_MMA;
-		if(want_mma && dp.vf_type && W % MF_TILE == 0)
+		const bool forced = sel && !strcmp(sel, "mma");
+		const bool want_mma = sel ? forced : HTV_FIR_DEFAULT_MMA;
+		if(want_mma && (W % MF_TILE == 0 || forced))
 		{
+			int nsm = 148;
+			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+			d->mod_grid = nsm * (d->line_threads <= 256 ? 4 : 2);
 			uint32_t atab[MF_ATAB_WORDS];
 			mf_build_atab(dp.vf_i, dp.vf_q, atab);
 			d->dt.mma_atab = (const uint32_t *) dev_copy(d, atab, sizeof(atab));
-			d->plane_stride = ((size_t) d->sub_lines + 3) * W + 256;
-			d->modm_smem = (size_t) 4 * mf_plane_bytes(W) + sizeof(uint32_t) * MF_ATAB_WORDS +
-				sizeof(unsigned) * 2 * (W / 32) * MF_ROWW + 3 * sizeof(LineAudio) +
+			d->plane_pitch = W % MF_TILE == 0 ? 0 : mf_pitch(W);
+			d->plane_stride = ((size_t) d->sub_lines + 3) * (d->plane_pitch ? d->plane_pitch : W) + 256;
+			d->modm_smem = (size_t) 4 * (d->plane_pitch ? mf_row_bytes(W) : mf_plane_bytes(W)) + sizeof(uint32_t) * MF_ATAB_WORDS +
+				sizeof(unsigned) * 2 * mf_tiles(W) * 4 * MF_ROWW + 3 * sizeof(LineAudio) +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
-			if(cudaMalloc((void **) &d->d_planes, 2 * d->plane_stride) != cudaSuccess)
+			if(!d->dt.mma_atab || cudaMalloc((void **) &d->d_planes, 2 * d->plane_stride) != cudaSuccess)
 			{
 				snprintf(err, errlen, "device allocation failed");
 				htv_dev_destroy(d);
@@ -2777,7 +2818,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else
 		{
 			// raster lines done-1 .. done+n (descriptor index = line - (line0 - 1))
-			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride);
+			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride, d->plane_pitch);
 			d->launches++;
 		}
 		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
@@ -2798,8 +2839,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else if(d->d_planes)
 		{
 			const int grid = n < d->mod_grid ? n : d->mod_grid;
-			if(d->line_threads <= 256) k_mod_mma<256, 4><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, n, o, acc, acc_rows);
-			else k_mod_mma<384, 2><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, n, o, acc, acc_rows);
+			if(d->line_threads <= 256) k_mod_mma<256, 4><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, d->plane_pitch, n, o, acc, acc_rows);
+			else k_mod_mma<384, 2><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, ld.a + done, d->d_planes, d->plane_stride, d->plane_pitch, n, o, acc, acc_rows);
 		}
 		else if(d->d_comp32)
 		{

@@ -42,11 +42,19 @@
 #define MF_ROWW    40      /* exchange buffer: words per 32 outputs (bank-conflict-free both ways) */
 #define MF_ATAB_WORDS (MF_KSTEPS * 4 * 32 * 4)   /* tap operand: [k-step][I hi, I lo, Q hi, Q lo][lane] x 4 registers */
 
-/* tiles in a line (W must be a multiple of 128), bytes of one plane buffer in shared memory,
- * bytes the TMA brings per plane (the tail of the buffer is read by zero taps only) */
-MF_HD int mf_tiles(int W) { return(W / MF_TILE); }
+/* Two layouts of the byte planes in device memory:
+ *  contiguous (128 | W): the planes are the composite stream itself, line after line; the window of a
+ *    line starts MF_LEAD bytes before it (16-byte aligned because 16 | W). mf_window_bytes() arrive
+ *    by TMA, the buffer is mf_plane_bytes() long and its tail is read by zero taps only.
+ *  pitched (any W): one row of `pitch` bytes per line, byte i = sample i - MF_LEAD of that line;
+ *    k_raster also writes a line's first / last MF_LEAD samples into the halo of the previous / next
+ *    row, so a row is self-contained and 16-byte aligned whatever W is (NTSC: 858). mf_row_bytes()
+ *    arrive by TMA; bytes past sample W + MF_LEAD meet zero taps only (any finite value will do). */
+MF_HD int mf_tiles(int W) { return((W + MF_TILE - 1) / MF_TILE); }
 MF_HD int mf_plane_bytes(int W) { return(W + 96); }
 MF_HD int mf_window_bytes(int W) { return(W + 2 * MF_LEAD); }
+MF_HD int mf_row_bytes(int W) { return(MF_TILE * mf_tiles(W) + 96); }
+MF_HD int mf_pitch(int W) { return(MF_TILE * mf_tiles(W) + 128); }
 
 /* byte offset, inside a plane window, of the 8 stream bytes lane (g, t) loads for tile nt, k-step s */
 MF_HD int mf_b_offset(int nt, int s, int lane)

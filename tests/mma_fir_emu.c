@@ -3,7 +3,9 @@
  * ISA fragment tables, and the result is compared with the direct 51-tap sum the reference
  * computes (ref fir.c:564-615). Built and run by tests/test_mma_fir_host.py; no GPU involved.
  *
- * usage: mma_fir_emu W seed extreme(0|1)   -> prints "OK <checked>" or the first mismatch */
+ * usage: mma_fir_emu W seed extreme(0|1) [pitched(0|1)]   -> prints "OK <checked>" or the first mismatch
+ * pitched = 1: the planes are built row by row the way k_raster's pitched branch writes them (own
+ * samples + halos into the neighbouring rows) and any W is allowed; 0: contiguous stream, 128 | W. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -53,7 +55,8 @@ int main(int argc, char **argv)
 	const int W = argc > 1 ? atoi(argv[1]) : 1024;
 	rng_state = argc > 2 ? (uint32_t) atoi(argv[2]) : 1;
 	const int extreme = argc > 3 ? atoi(argv[3]) : 0;
-	if(W % MF_TILE) { printf("W must be a multiple of %d\n", MF_TILE); return(2); }
+	const int pitched = argc > 4 ? atoi(argv[4]) : 0;
+	if(!pitched && W % MF_TILE) { printf("W must be a multiple of %d\n", MF_TILE); return(2); }
 
 	/* a composite stream of three lines; the middle one is filtered */
 	int16_t *comp = malloc(sizeof(int16_t) * 3 * W);
@@ -72,21 +75,57 @@ int main(int argc, char **argv)
 	}
 
 	/* byte planes of the window, as k_raster writes them and the TMA delivers them */
-	const int PB = mf_plane_bytes(W);
+	const int PB = pitched ? mf_row_bytes(W) : mf_plane_bytes(W);
 	uint8_t *ph = malloc(PB), *pl = malloc(PB);
-	for(int i = 0; i < PB; i++) { ph[i] = (uint8_t) rng(); pl[i] = (uint8_t) rng(); }   /* garbage past the window */
 	const int16_t *line = comp + W;
-	for(int i = 0; i < mf_window_bytes(W); i++)
+	if(!pitched)
 	{
-		const int v = line[i - MF_LEAD];
-		ph[i] = (uint8_t) ((v >> 8) & 0xFF);
-		pl[i] = (uint8_t) (v & 0xFF);
+		for(int i = 0; i < PB; i++) { ph[i] = (uint8_t) rng(); pl[i] = (uint8_t) rng(); }   /* garbage past the window */
+		for(int i = 0; i < mf_window_bytes(W); i++)
+		{
+			const int v = line[i - MF_LEAD];
+			ph[i] = (uint8_t) ((v >> 8) & 0xFF);
+			pl[i] = (uint8_t) (v & 0xFF);
+		}
+	}
+	else
+	{
+		/* three rows of `pitch` bytes; every "thread" (x0 = 0, 4, ...) of every line writes its own
+		 * samples and, at the line's edges, the neighbours' halos - k_raster's pitched branch */
+		const int pitch = mf_pitch(W), nrows = 3;
+		if(pitch < PB || pitch % 16) { printf("bad pitch\n"); return(1); }
+		uint8_t *rows_h = malloc((size_t) nrows * pitch), *rows_l = malloc((size_t) nrows * pitch);
+		uint8_t *wr = calloc((size_t) nrows * pitch, 1);
+		for(int i = 0; i < nrows * pitch; i++) { rows_h[i] = (uint8_t) rng(); rows_l[i] = (uint8_t) rng(); }   /* stale bytes */
+		for(int b = 0; b < nrows; b++) for(int x0 = 0; x0 < W; x0 += 4)
+		{
+			const int16_t *val = comp + b * W + x0;
+			uint8_t *rh = rows_h + (size_t) b * pitch, *rl = rows_l + (size_t) b * pitch, *rw = wr + (size_t) b * pitch;
+			if(x0 + 4 <= W)
+				for(int k = 0; k < 4; k++) { rh[MF_LEAD + x0 + k] = (val[k] >> 8) & 0xFF; rl[MF_LEAD + x0 + k] = val[k] & 0xFF; rw[MF_LEAD + x0 + k]++; }
+			const int head = x0 < MF_LEAD && b > 0, tail = x0 + 4 > W - MF_LEAD && b + 1 < nrows;
+			if(head || tail || x0 + 4 > W)
+				for(int k = 0; k < 4; k++)
+				{
+					const int x = x0 + k;
+					if(x >= W) break;
+					const uint8_t hi = (val[k] >> 8) & 0xFF, lo = val[k] & 0xFF;
+					if(x0 + 4 > W) { rh[MF_LEAD + x] = hi; rl[MF_LEAD + x] = lo; rw[MF_LEAD + x]++; }
+					if(head && x < MF_LEAD) { rh[-pitch + MF_LEAD + W + x] = hi; rl[-pitch + MF_LEAD + W + x] = lo; rw[-pitch + MF_LEAD + W + x]++; }
+					if(tail && x >= W - MF_LEAD) { rh[pitch + x - (W - MF_LEAD)] = hi; rl[pitch + x - (W - MF_LEAD)] = lo; rw[pitch + x - (W - MF_LEAD)]++; }
+				}
+		}
+		/* the middle row: every byte the non-zero taps can reach is written exactly once */
+		for(int i = 0; i < W + 2 * MF_LEAD; i++)
+			if(wr[pitch + i] != 1) { printf("row byte %d written %d times\n", i, wr[pitch + i]); return(1); }
+		memcpy(ph, rows_h + pitch, PB);
+		memcpy(pl, rows_l + pitch, PB);
 	}
 
 	uint32_t atab[MF_ATAB_WORDS];
 	mf_build_atab(taps[0], taps[1], atab);
-	uint32_t *fir = calloc((size_t) (W / 32) * MF_ROWW, sizeof(uint32_t));
-	uint8_t *seen = calloc((size_t) W, 1);
+	uint32_t *fir = calloc((size_t) mf_tiles(W) * 4 * MF_ROWW, sizeof(uint32_t));
+	uint8_t *seen = calloc((size_t) mf_tiles(W) * MF_TILE, 1);
 	for(int nt = 0; nt < mf_tiles(W); nt++)
 	{
 		int32_t acc[2][3][32][4];
@@ -114,7 +153,7 @@ int main(int argc, char **argv)
 		for(int lane = 0; lane < 32; lane++) for(int ci = 0; ci < 4; ci++)
 		{
 			const int x = mf_out_x(nt, lane, ci);
-			if(x < 0 || x >= W) { printf("output index %d out of the line\n", x); return(1); }
+			if(x < 0 || x >= mf_tiles(W) * MF_TILE) { printf("output index %d out of the tiles\n", x); return(1); }
 			const int vi = mf_combine(acc[0][0][lane][ci], acc[0][1][lane][ci], acc[0][2][lane][ci]);
 			const int vq = mf_combine(acc[1][0][lane][ci], acc[1][1][lane][ci], acc[1][2][lane][ci]);
 			if(seen[x]++) { printf("sample %d written twice\n", x); return(1); }

@@ -24,3 +24,13 @@ def test_fragment_mapping_reproduces_the_fir(emu, W, extreme):
     for seed in (1, 2, 3):
         out = subprocess.run([emu, str(W), str(seed), str(extreme)], capture_output=True, text=True)
         assert out.returncode == 0 and out.stdout.startswith("OK %d" % W), out.stdout
+
+
+@pytest.mark.parametrize("W", [858, 864, 1287, 1024, 1135, 129])
+def test_pitched_plane_layout_for_any_width(emu, W):
+    """Rows built the way k_raster's pitched branch writes them (own samples + halos in the neighbouring
+    rows): NTSC 858, 13.5 Msps PAL 864, the 20.25 Msps NTSC width 1287, odd widths."""
+    for seed in (1, 2):
+        for extreme in (0, 1):
+            out = subprocess.run([emu, str(W), str(seed), str(extreme), "1"], capture_output=True, text=True)
+            assert out.returncode == 0 and out.stdout.startswith("OK %d" % W), out.stdout
