@@ -106,6 +106,7 @@ struct SecScratch {
 };
 
 #define MAPBUFS 16
+#define HTV_MAX_ALLOCS 128            // device tables owned by one encoder (about 50 for SECAM-L with AM + NICAM)
 #define HTV_OV_CAP 2048                // VBI overlay lines per launch sequence
 
 struct htv_dev_t {
@@ -114,7 +115,7 @@ struct htv_dev_t {
 	DevTables dt;
 	size_t frame_pixels;
 	int max_slots;
-	void *alloc[64];
+	void *alloc[HTV_MAX_ALLOCS];
 	int nalloc;
 	uint32_t *d_frames;
 	int32_t *d_frame_map;
@@ -2312,9 +2313,9 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 static void *dev_copy(htv_dev_t *d, const void *src, size_t bytes)
 {
 	void *p = NULL;
-	if(!src || !bytes) return(NULL);
+	if(!src || !bytes || d->nalloc >= HTV_MAX_ALLOCS) return(NULL);
 	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
-	cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+	if(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(p); return(NULL); }
 	d->alloc[d->nalloc++] = p;
 	return(p);
 }
@@ -2322,8 +2323,8 @@ static void *dev_copy(htv_dev_t *d, const void *src, size_t bytes)
 static void *dev_zero(htv_dev_t *d, size_t bytes)
 {
 	void *p = NULL;
-	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
-	cudaMemset(p, 0, bytes);
+	if(d->nalloc >= HTV_MAX_ALLOCS || cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
+	if(cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return(NULL); }
 	d->alloc[d->nalloc++] = p;
 	return(p);
 }
