@@ -2484,13 +2484,14 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	}
 	if(!secam && !dp.have_fmv && dp.vf_type)
 	{
-		// the video filter on the tensor cores (k_mod_mma): the default where 128 | W (planes = the
-		// contiguous stream); HTV_FIR=mma also takes it for any other width through the pitched plane
-		// layout (htv_mma_fir.h; NTSC 858 - not yet the default), HTV_FIR=scalar turns it off
+		// the video filter on the tensor cores (k_mod_mma): the default for the line widths it has been
+		// validated at on a B200 (1024 = 16 Msps, 1280 = 20 Msps: BASELINE configs 2 and 5). HTV_FIR=mma
+		// takes it for every width - other multiples of 128 through the same contiguous planes, the rest
+		// (NTSC 858) through the pitched plane layout (htv_mma_fir.h); HTV_FIR=scalar turns it off
 		const char *sel = getenv("HTV_FIR");
 		const bool forced = sel && !strcmp(sel, "mma");
 		const bool want_mma = sel ? forced : HTV_FIR_DEFAULT_MMA;
-		if(want_mma && (W % MF_TILE == 0 || forced))
+		if(want_mma && (W == 1024 || W == 1280 || forced))
 		{
 			int nsm = 148;
 			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);

