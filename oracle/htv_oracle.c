@@ -404,6 +404,14 @@ struct orc_t {
 	int64_t next_emit;          /* next line index to emit */
 	int16_t *ring[4];           /* composite I, W + pad each */
 
+	/* --pixelrate: the raster side (everything above) runs at `rate` / `width`, the stages from the
+	 * resampler on at `srate` / `swidth` (ref video.c:3839-3853, 4361-4368). Equal without a resampler. */
+	int srate, swidth;
+	int rs_on, rs_I, rs_D, rs_ataps;
+	int16_t *rs_taps;           /* [rs_I][rs_ataps], the order fir_int16_init lays them out */
+	int16_t *rring[4];          /* resampled lines, swidth each */
+	int64_t next_resamp;
+
 	int32_t *tbl;               /* scratch for orc_table */
 };
 
@@ -945,8 +953,12 @@ static inline int16_t *ring_line(orc_t *o, int64_t L) { return(o->ring[((L % 4) 
 
 static void blank_line(orc_t *o, int16_t *l)
 {
+	/* ref video.c:2935-2939 blanks max_width samples: with a resampler that widens the line the
+	 * buffer is longer than the raster line, and the block FIRs' reads past the line end
+	 *  find the blanking level there instead of the heap */
+	const int n = o->swidth > o->width ? o->swidth : o->width;
 	int x;
-	for(x = 0; x < o->width; x++) l[x] = o->blank;
+	for(x = 0; x < n; x++) l[x] = o->blank;
 }
 
 static void raster_line(orc_t *o, int64_t L)
@@ -1159,15 +1171,15 @@ static void audio_line(orc_t *o, int16_t *iq /* interleaved, W samples */)
 {
 	int x;
 
-	for(x = 0; x < o->width; x++)
+	for(x = 0; x < o->swidth; x++)
 	{
 		int16_t add[2] = { 0, 0 };
 
 		o->interp += 32000;
-		if(o->interp >= o->rate)
+		if(o->interp >= o->srate)
 		{
 			int i;
-			o->interp -= o->rate;
+			o->interp -= o->srate;
 
 			if(o->pcm && o->pcm_pairs)
 			{
@@ -1210,14 +1222,14 @@ static void audio_line(orc_t *o, int16_t *iq /* interleaved, W samples */)
 		iq[x * 2 + 1] += add[1];
 	}
 
-	if(o->have_nicam) nicam_output(&o->nicam, iq, o->width);
+	if(o->have_nicam) nicam_output(&o->nicam, iq, o->swidth);
 }
 
 /* ref video.c:3482-3515 */
 static void offset_line(orc_t *o, int16_t *iq)
 {
 	int x;
-	for(x = 0; x < o->width; x++)
+	for(x = 0; x < o->swidth; x++)
 	{
 		int32_t ai = iq[x * 2 + 0], aq = iq[x * 2 + 1], bi, bq;
 		c32_mul(&o->off_phase, &o->off_phase, &o->off_delta);
@@ -1237,6 +1249,16 @@ size_t orc_params_size(void) { return(sizeof(orc_params_t)); }
 
 orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 {
+	return(orc_open2(params, sample_rate, 0));
+}
+
+/* vid_init with a pixel rate (ref video.c:3812, 3839): the raster is built at pixel_rate and a
+ * polyphase FIR (ref _init_vresampler video.c:3627-3651, fir_int16_resampler_init fir.c:393-428)
+ * brings it to sample_rate in front of the video filter. Only rate pairs that give every line the
+ * same number of output samples are restated (the reference lets the line width vary otherwise);
+ * FM video is not. */
+orc_t *orc_open2(const orc_params_t *params, unsigned int sample_rate, unsigned int pixel_rate)
+{
 	orc_t *o = calloc(1, sizeof(orc_t));
 	orc_params_t *p;
 	double width, d;
@@ -1245,7 +1267,8 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	if(!o) return(NULL);
 	o->p = *params;
 	p = &o->p;
-	o->rate = sample_rate;
+	o->rate = pixel_rate ? pixel_rate : sample_rate;
+	o->srate = sample_rate;
 
 	if(p->type != ORC_RASTER_625 && p->type != ORC_RASTER_525) { free(o); return(NULL); }
 	if(p->modulation == ORC_MOD_FM && p->fm_energy_dispersal != 0) { free(o); return(NULL); }
@@ -1266,6 +1289,34 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	o->active_left = round(o->rate * p->active_left);
 	o->active_width = ceil(o->rate * p->active_width);
 	if(o->active_width > o->width) o->active_width = o->width;
+	o->swidth = o->width;
+	if(o->srate != o->rate)
+	{
+		/* fir.c:393-428: r = out / in = I / D, (21 I) | 1 taps of a Kaiser low-pass at rate I, gain I;
+		 * fir.c:263-295: ataps = ceil(ntaps / I) taps per phase, phase p column c = tap[ntaps - I + p - c I] */
+		int64_t g = gcd64(o->srate, o->rate);
+		int ntaps, ph, col;
+		double *taps;
+		o->rs_I = (int) (o->srate / g);
+		o->rs_D = (int) (o->rate / g);
+		o->swidth = round((double) o->srate * width);
+		if(p->modulation == ORC_MOD_FM || ((int64_t) o->width * o->rs_I) % o->rs_D != 0 ||
+		   (int64_t) o->width * o->rs_I / o->rs_D != o->swidth) { free(o); return(NULL); }
+		ntaps = (21 * o->rs_I) | 1;
+		taps = calloc(ntaps, sizeof(double));
+		if(o->rs_I > o->rs_D) design_low_pass(taps, ntaps, o->rs_I, 0.45, o->rs_I);
+		else design_low_pass(taps, ntaps, o->rs_I, 0.45 * o->rs_I / o->rs_D, o->rs_I);
+		o->rs_ataps = (ntaps + o->rs_I - 1) / o->rs_I;
+		o->rs_taps = calloc((size_t) o->rs_I * o->rs_ataps, sizeof(int16_t));
+		for(ph = 0; ph < o->rs_I; ph++) for(col = 0; col < o->rs_ataps; col++)
+		{
+			int idx = ntaps - o->rs_I + ph - col * o->rs_I;
+			if(idx >= 0 && idx < ntaps) o->rs_taps[ph * o->rs_ataps + col] = lround(taps[idx] * 32767.0);
+		}
+		free(taps);
+		for(i = 0; i < 4; i++) o->rring[i] = calloc(o->swidth + 64, sizeof(int16_t));
+		o->rs_on = 1;
+	}
 
 	/* video.c:3855-3881 */
 	o->slevel = p->modulation == ORC_MOD_FM ? 1.0 : p->level;
@@ -1419,7 +1470,7 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 		if(p->modulation == ORC_MOD_VSB)
 		{
 			double taps[51 * 2];
-			design_complex_band_pass(taps, 51, o->rate, -p->vsb_lower_bw, p->vsb_upper_bw, 1);
+			design_complex_band_pass(taps, 51, o->srate, -p->vsb_lower_bw, p->vsb_upper_bw, 1);
 			o->vf_type = 3;
 			o->vf_ntaps = 51;
 			o->vf_itaps = quantise_taps(taps + 0, 51, 2);
@@ -1433,14 +1484,14 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 			#define FMT(t) do { taps = t; ntaps = sizeof(t) / sizeof(double); } while(0)
 			if(p->lines == 525)
 			{
-				if(o->rate == 18000000) FMT(orc_fm_525_18_taps);
+				if(o->srate == 18000000) FMT(orc_fm_525_18_taps);
 				else FMT(orc_fm_525_2025_taps);
 			}
 			else
 			{
-				if(o->rate == 14000000) FMT(orc_fm_625_14_taps);
-				else if(o->rate == 20000000) FMT(orc_fm_625_20_taps);
-				else if(o->rate == 28000000) FMT(orc_fm_625_28_taps);
+				if(o->srate == 14000000) FMT(orc_fm_625_14_taps);
+				else if(o->srate == 20000000) FMT(orc_fm_625_20_taps);
+				else if(o->srate == 28000000) FMT(orc_fm_625_28_taps);
 				else FMT(orc_fm_625_2025_taps);
 			}
 			#undef FMT
@@ -1451,7 +1502,7 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 		else
 		{
 			double taps[51];
-			design_low_pass(taps, 51, o->rate, p->video_bw, 1);
+			design_low_pass(taps, 51, o->srate, p->video_bw, 1);
 			o->vf_type = 1;
 			o->vf_ntaps = 51;
 			o->vf_itaps = quantise_taps(taps, 51, 1);
@@ -1462,7 +1513,7 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	if(p->fm_mono_level > 0 && p->fm_mono_carrier != 0)
 	{
 		o->have_fm = 1;
-		fm_init(&o->fm_mono, o->rate, p->fm_mono_carrier, p->fm_mono_deviation, p->fm_mono_level * o->slevel);
+		fm_init(&o->fm_mono, o->srate, p->fm_mono_carrier, p->fm_mono_deviation, p->fm_mono_level * o->slevel);
 		if(p->fm_mono_preemph)
 		{
 			const double *t = p->fm_mono_preemph == ORC_PREEMPH_50US ? fm_audio_50us_taps :
@@ -1474,19 +1525,19 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 	if(p->nicam_level > 0 && p->nicam_carrier != 0)
 	{
 		o->have_nicam = 1;
-		nicam_init(&o->nicam, o->rate, (unsigned int) p->nicam_carrier, p->nicam_beta, p->nicam_level * o->slevel);
+		nicam_init(&o->nicam, o->srate, (unsigned int) p->nicam_carrier, p->nicam_beta, p->nicam_level * o->slevel);
 	}
 	if(p->am_audio_level > 0 && p->am_mono_carrier != 0)
 	{
 		o->have_am = 1;
-		am_init(&o->am_mono, o->rate, p->am_mono_carrier, p->am_audio_level * o->slevel);
+		am_init(&o->am_mono, o->srate, p->am_mono_carrier, p->am_audio_level * o->slevel);
 	}
 
 	if(p->modulation == ORC_MOD_FM)
 	{
 		/* video.c:4564-4585 */
 		o->have_fmv = 1;
-		fm_init(&o->fm_video, o->rate, 0, p->fm_deviation, p->fm_level * p->level);
+		fm_init(&o->fm_video, o->srate, 0, p->fm_deviation, p->fm_level * p->level);
 	}
 
 	if(p->offset != 0)
@@ -1495,14 +1546,14 @@ orc_t *orc_open(const orc_params_t *params, unsigned int sample_rate)
 		o->off_counter = I16MAX;
 		o->off_phase.i = I16MAX;
 		o->off_phase.q = 0;
-		d = 2.0 * M_PI / o->rate * p->offset;
+		d = 2.0 * M_PI / o->srate * p->offset;
 		o->off_delta.i = lround(cos(d) * I32MAX);
 		o->off_delta.q = lround(sin(d) * I32MAX);
 	}
 
 	for(i = 0; i < 4; i++)
 	{
-		o->ring[i] = calloc(o->width + 64, sizeof(int16_t));
+		o->ring[i] = calloc((o->swidth > o->width ? o->swidth : o->width) + 64, sizeof(int16_t));
 		blank_line(o, o->ring[i]);
 	}
 
@@ -1514,7 +1565,8 @@ void orc_close(orc_t *o)
 	int i;
 	if(!o) return;
 	for(i = 0; i < 5; i++) free(o->syncs[i].value);
-	for(i = 0; i < 4; i++) free(o->ring[i]);
+	for(i = 0; i < 4; i++) { free(o->ring[i]); free(o->rring[i]); }
+	free(o->rs_taps);
 	free(o->clut); free(o->chroma); free(o->chroma_taps); free(o->burst_win);
 	free(o->fm_secam.lut); free(o->secam_lpf); free(o->secam_notch); free(o->secam_bell);
 	free(o->vf_itaps); free(o->vf_qtaps);
@@ -1541,7 +1593,8 @@ void orc_add_vbi_line(orc_t *o, int line, int replace_from, int replace_to, int 
 void orc_set_passthru(orc_t *o, const int16_t *iq, size_t ncomplex) { o->pt = iq; o->pt_len = ncomplex; o->pt_pos = 0; }
 void orc_set_audio(orc_t *o, const int16_t *pcm, size_t npairs) { o->pcm = pcm; o->pcm_pairs = npairs; o->pcm_pos = 0; }
 
-int orc_width(const orc_t *o) { return(o->width); }
+int orc_width(const orc_t *o) { return(o->swidth); }
+int orc_raster_width(const orc_t *o) { return(o->width); }
 int orc_active_width(const orc_t *o) { return(o->active_width); }
 int orc_active_lines(const orc_t *o) { return(o->p.active_lines); }
 int orc_is_complex(const orc_t *o) { return(o->complex); }
@@ -1550,9 +1603,33 @@ int orc_is_complex(const orc_t *o) { return(o->complex); }
 /* Render: the flattened vid_next_line loop                                 */
 /* ------------------------------------------------------------------------ */
 
+/* ref _vid_filter_process video.c:3235-3248 feeding fir_int16_process fir.c:304-355 with the
+ * resampler's taps, in closed form of the global output index j: the newest input consumed is
+ * i = floor(j D / I), the phase (j D) mod I, the window the rs_ataps inputs ending at i (zero
+ * before the stream). Line L of the resampled stream needs raster lines L - 1 and L final. */
+static void resample_line(orc_t *o, int64_t L)
+{
+	const int Wp = o->width, Ws = o->swidth, I = o->rs_I, D = o->rs_D, A = o->rs_ataps;
+	int16_t *dst = o->rring[((L % 4) + 4) % 4];
+	int k, c;
+	for(k = 0; k < Ws; k++)
+	{
+		const int64_t j = L * Ws + k;
+		const int64_t in = (j * D) / I;
+		const int16_t *t = o->rs_taps + ((j * D) % I) * A;
+		int32_t a = 0;
+		for(c = 0; c < A; c++)
+		{
+			const int64_t n = in - A + 1 + c;
+			if(n >= 0) a += ring_line(o, n / Wp)[n % Wp] * t[c];
+		}
+		dst[k] = sat16(a >> 15);
+	}
+}
+
 size_t orc_render(orc_t *o, int nlines, int16_t *out)
 {
-	const int W = o->width;
+	const int W = o->swidth;
 	int16_t *iq = malloc(sizeof(int16_t) * 2 * W);
 	size_t n = 0;
 	int k, x, y;
@@ -1569,13 +1646,22 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		 *   3268). */
 		if(o->p.colour_mode == ORC_COLOUR_SECAM)
 		{
-			int16_t *fill = malloc(sizeof(int16_t) * (W + 64));
+			int16_t *fill = calloc((o->swidth > o->width ? o->swidth : o->width) + 64, sizeof(int16_t));
 			for(k = 0; k < 2; k++)
 			{
 				blank_line(o, fill);
 				secam_line(o, fill, 1, 0);
 			}
 			free(fill);
+		}
+		if(o->rs_on)
+		{
+			/* the resampler is one more two-line stage: its first output line lands in a fill
+			 * buffer too (width W from then on), so everything behind it runs one line earlier
+			 * still - the sound carriers, the offset mixer and the passthru stream */
+			memset(iq, 0, sizeof(int16_t) * 2 * W);
+			audio_line(o, iq);
+			if(o->p.offset != 0) offset_line(o, iq);
 		}
 		if(o->vf_type)
 		{
@@ -1606,6 +1692,11 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 			/* ... and the passthru stage spends its first line on that buffer too */
 			if(o->pt) o->pt_pos = o->pt_len < (size_t) W ? o->pt_len : (size_t) W;
 		}
+		if(o->rs_on && o->pt)
+		{
+			size_t skip = (size_t) W * (o->vf_type ? 2 : 1);
+			o->pt_pos = o->pt_len < skip ? o->pt_len : skip;
+		}
 	}
 
 	for(k = 0; k < nlines; k++)
@@ -1613,6 +1704,34 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		int64_t t = o->next_emit;
 		int16_t *prev, *cur, *next;
 
+		if(o->rs_on)
+		{
+			/* The emitted line t is line t + 1 of the resampled stream (the stage writes into
+			 * the buffer one line back and, unlike the video filter, pads no delay), filtered
+			 * across lines t and t + 2 of it. Raster lines are final once the next one is
+			 * rastered (sync back-spill), SECAM and the VBI overlays have run on them. */
+			while(o->next_resamp <= t + 2)
+			{
+				int64_t L = o->next_resamp;
+				while(o->next_raster <= L + 1) raster_line(o, o->next_raster++);
+				if(o->p.colour_mode == ORC_COLOUR_SECAM)
+				{
+					while(o->next_secam <= L)
+					{
+						int64_t M = o->next_secam++;
+						secam_line(o, ring_line(o, M), M / o->p.lines + 1, M % o->p.lines + 1);
+					}
+				}
+				if(o->nvbi) vbi_line(o, L);
+				resample_line(o, L);
+				o->next_resamp++;
+			}
+			prev = o->rring[t % 4];
+			cur  = o->rring[(t + 1) % 4];
+			next = o->rring[(t + 2) % 4];
+		}
+		else
+		{
 		/* raster through t+1 (sync back-spill, filter look-ahead) */
 		while(o->next_raster <= t + 1) raster_line(o, o->next_raster++);
 
@@ -1631,6 +1750,7 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 		prev = ring_line(o, t - 1);
 		cur  = ring_line(o, t);
 		next = ring_line(o, t + 1);
+		}
 
 		if(o->vf_type)
 		{
@@ -1638,7 +1758,7 @@ size_t orc_render(orc_t *o, int nlines, int16_t *out)
 			 * the stream; samples before the first are zero (calloc'd window) */
 			int h = o->vf_ntaps / 2;
 			int32_t *win = malloc(sizeof(int32_t) * (W + 2 * h));
-			for(x = 0; x < h; x++) win[x] = (t == 0) ? 0 : prev[W - h + x];
+			for(x = 0; x < h; x++) win[x] = (t == 0 && !o->rs_on) ? 0 : prev[W - h + x];
 			for(x = 0; x < W; x++) win[h + x] = cur[x];
 			for(x = 0; x < h; x++) win[h + W + x] = next[x];
 			for(x = 0; x < W; x++)

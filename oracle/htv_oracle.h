@@ -119,6 +119,8 @@ extern size_t orc_params_size(void);
 /* vid_init (reference video.c:3812-4704). sample_rate == pixel_rate (the
  * resampler, video.c:3627-3651, is out of scope). Returns NULL on bad params. */
 extern orc_t *orc_open(const orc_params_t *p, unsigned int sample_rate);
+/* vid_init with pixel_rate != sample_rate: the --pixelrate resampler (ref video.c:3627-3651, 4361-4368) */
+extern orc_t *orc_open2(const orc_params_t *p, unsigned int sample_rate, unsigned int pixel_rate);
 extern void orc_close(orc_t *o);
 
 /* AV source (reference av.h:64-116 callbacks, flattened): frames are RGB32
@@ -145,6 +147,7 @@ extern size_t orc_render(orc_t *o, int nlines, int16_t *out);
 
 /* Geometry (reference video.c:3844-3853 and friends) */
 extern int orc_width(const orc_t *o);
+extern int orc_raster_width(const orc_t *o);
 extern int orc_active_width(const orc_t *o);
 extern int orc_active_lines(const orc_t *o);
 extern int orc_is_complex(const orc_t *o);

@@ -25,13 +25,14 @@ def lib():
         vp = C.c_void_p
         L.orc_params_size.restype = C.c_size_t
         L.orc_open.restype = vp; L.orc_open.argtypes = [vp, C.c_uint]
+        L.orc_open2.restype = vp; L.orc_open2.argtypes = [vp, C.c_uint, C.c_uint]
         L.orc_close.restype = None; L.orc_close.argtypes = [vp]
         L.orc_set_frames.restype = None; L.orc_set_frames.argtypes = [vp, vp, C.c_int]
         L.orc_set_audio.restype = None; L.orc_set_audio.argtypes = [vp, vp, C.c_size_t]
         L.orc_set_passthru.restype = None; L.orc_set_passthru.argtypes = [vp, vp, C.c_size_t]
         L.orc_add_vbi_line.restype = None; L.orc_add_vbi_line.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.orc_render.restype = C.c_size_t; L.orc_render.argtypes = [vp, C.c_int, vp]
-        for f in ("orc_width", "orc_active_width", "orc_active_lines", "orc_is_complex"):
+        for f in ("orc_width", "orc_raster_width", "orc_active_width", "orc_active_lines", "orc_is_complex"):
             getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [vp]
         L.orc_table.restype = C.POINTER(C.c_int32); L.orc_table.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
         L.orc_test_pattern.restype = None; L.orc_test_pattern.argtypes = [C.c_int, C.c_int, vp]
@@ -46,14 +47,15 @@ class Oracle:
     """orc_t. `conf` is a hacktv_b200.Config: htv_config_t and orc_params_t share one layout
     (checked against orc_params_size())."""
 
-    def __init__(self, conf, sample_rate):
+    def __init__(self, conf, sample_rate, pixel_rate=0):
         L = lib()
         assert C.sizeof(conf) == L.orc_params_size(), "orc_params_t / htv_config_t layouts differ"
         self._L = L
-        self._o = L.orc_open(C.byref(conf), sample_rate)
+        self._o = L.orc_open2(C.byref(conf), sample_rate, pixel_rate)
         if not self._o:
             raise RuntimeError("orc_open failed")
         self.width = L.orc_width(self._o)
+        self.raster_width = L.orc_raster_width(self._o)    # differs from width with a --pixelrate resampler
         self.active_width = L.orc_active_width(self._o)
         self.active_lines = L.orc_active_lines(self._o)
         self.complex = bool(L.orc_is_complex(self._o))
@@ -81,7 +83,7 @@ class Oracle:
         p = None
         if add is not None:
             add = np.ascontiguousarray(add, dtype=np.int16)
-            assert add.size == self.width
+            assert add.size == self.raster_width
             self._keep.append(add)
             p = add.ctypes.data
         self._L.orc_add_vbi_line(self._o, line, replace[0], replace[1], replace[2], p)

@@ -49,3 +49,20 @@ def test_after_ten_seconds_bit_exact(built, name):
     assert hashlib.sha256(b.tobytes()).hexdigest() == g["b_sha256"]
     z = np.load(os.path.join(HERE, "golden", name + ".npz"))
     assert np.array_equal(b.reshape(g["b_lines"], -1)[z["b_lines"]], z["b"])
+
+
+GOLD_PR = json.load(open(os.path.join(HERE, "golden", "golden_pixelrate.json")))
+
+
+@pytest.mark.parametrize("name", sorted(GOLD_PR))
+def test_pixelrate_resampler_bit_exact(built, name):
+    """--pixelrate: raster at the pixel rate + the reference's polyphase resampler (fixtures from
+    tests/golden/make_golden_pixelrate.py)."""
+    g = GOLD_PR[name]
+    o = orc.Oracle(built.mode_config(g["mode"], vfilter=g["filter"]), g["rate"], g["pixel_rate"])
+    o.open_test_source()
+    a = o.render(g["lines"])
+    o.close()
+    assert hashlib.sha256(a.tobytes()).hexdigest() == g["sha256"]
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    assert np.array_equal(a.reshape(g["lines"], g["values_per_line"])[z["lines"]], z["a"])

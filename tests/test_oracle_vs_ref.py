@@ -143,3 +143,87 @@ def test_unpatched_heap_differs_only_near_line_ends():
     a = orc.run_ref("i", 16000000, 700, vfilter=True).reshape(700, 1024, 2)
     b = orc.run_ref("i", 16000000, 700, vfilter=True, rawheap=True).reshape(700, 1024, 2)
     assert np.array_equal(a[:, 32:-32], b[:, 32:-32])
+
+
+# --pixelrate: raster at the pixel rate, the reference's polyphase resampler
+# (video.c:3627-3651, fir.c:393-428) to the sample rate in front of the video filter. The oracle restates the
+# rate pairs that keep the line width constant; the CUDA path does not take them yet (htv_init refuses).
+PIXELRATE_CASES = [
+    ("pal", 16000000, 13500000, 700, False, ()),                 # 864 -> 1024 samples per line, I/D = 32/27
+    ("i", 16000000, 13500000, 700, True, ()),                    # + VSB filter, FM + NICAM two lines ahead
+    ("i", 16000000, 13500000, 400, False, ()),                   # resampler alone: one line ahead
+    ("i", 16000000, 13500000, 400, True, ("--offset", "2000000")),
+    ("i", 20000000, 13500000, 400, True, ()),                    # 40/27
+    ("i", 13500000, 16000000, 400, True, ()),                    # resampling down, 27/32
+    ("i", 16000000, 14000000, 300, True, ()),                    # 8/7
+    ("m", 13500000, 9000000, 400, True, ()),                     # NTSC, 3/2
+    ("l", 16000000, 13500000, 700, True, ()),                    # SECAM: the FIRs' reads past the line end find the blanking level
+    ("l", 13500000, 16000000, 300, True, ()),
+    ("secam", 16000000, 13500000, 400, False, ()),
+    ("d", 20000000, 13500000, 300, True, ()),
+]
+
+
+@pytest.mark.parametrize("mode,rate,prate,nlines,filt,extra", PIXELRATE_CASES)
+def test_pixelrate_resampler_equals_reference(built, mode, rate, prate, nlines, filt, extra):
+    o = orc.Oracle(_conf(built, mode, filt, extra), rate, prate)
+    o.open_test_source()
+    got = o.render(nlines)
+    o.close()
+    want = orc.run_ref(mode, rate, nlines, vfilter=filt, extra=tuple(extra) + ("--pixelrate", str(prate)))
+    assert got.size == want.size
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+
+
+def test_pixelrate_later_window_and_random_input(built):
+    """A window two frames in (phase of the polyphase filter, NICAM frame counter) and random pictures + audio."""
+    conf = built.mode_config("i", vfilter=True)
+    o = orc.Oracle(conf, 16000000, 13500000)
+    o.open_test_source()
+    got = o.render(1700)[1400 * 2048:]
+    o.close()
+    want = orc.run_ref("i", 16000000, 300, skip=1400, vfilter=True, extra=("--pixelrate", "13500000"))
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(5)
+    o = orc.Oracle(conf, 16000000, 13500000)
+    frames = rng.integers(0, 1 << 24, size=(2, o.active_lines, o.active_width), dtype=np.uint32)
+    audio = rng.integers(-32768, 32767, size=(30000, 2), dtype=np.int16)
+    o.set_source(frames, audio)
+    got = o.render(900)
+    o.close()
+    want = orc.run_ref("i", 16000000, 900, vfilter=True, frames=frames, audio=audio, audio_block=4000,
+                       extra=("--pixelrate", "13500000"))
+    assert np.array_equal(got, want)
+
+
+def test_pixelrate_with_passthru_and_wss(built, tmp_path):
+    """Two fill lines in front of the stream (resampler + filter): the passthru stage spends two external
+    lines on them; the VBI stages sit in front of the resampler."""
+    rng = np.random.default_rng(3)
+    conf = built.mode_config("i", vfilter=True)
+    o = orc.Oracle(conf, 16000000, 13500000)
+    ext = rng.integers(-32768, 32767, size=(40 * o.width + 100, 2), dtype=np.int16)
+    o.open_test_source()
+    o.set_passthru(ext)
+    got = o.render(30)
+    o.close()
+    fn = tmp_path / "ext.iq"
+    ext.tofile(fn)
+    want = orc.run_ref("i", 16000000, 30, vfilter=True, extra=("--pixelrate", "13500000", "--passthru", str(fn)))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+
+    add, rep = wss_overlay(built, "pal", 13500000)               # the waveform at the pixel rate
+    o = orc.Oracle(built.mode_config("pal"), 16000000, 13500000)
+    o.open_test_source()
+    o.add_vbi_line(23, add, rep)
+    got = o.render(100)
+    o.close()
+    want = orc.run_ref("pal", 16000000, 100, extra=("--pixelrate", "13500000", "--wss", "16:9"))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} values differ"
+
+
+def test_pixelrate_pairs_the_oracle_does_not_restate(built):
+    with pytest.raises(RuntimeError):
+        orc.Oracle(built.mode_config("i", vfilter=True), 16000000, 13400000)    # line width would vary
+    with pytest.raises(RuntimeError):
+        orc.Oracle(built.mode_config("pal-fm", vfilter=True), 20000000, 13500000)
