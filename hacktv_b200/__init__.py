@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
     L.htv_last_line_kernel_ms.restype = C.c_float; L.htv_last_line_kernel_ms.argtypes = [vp]
     L.htv_last_line_kernel_lines.restype = C.c_int; L.htv_last_line_kernel_lines.argtypes = [vp]
     L.htv_tables_create.restype = vp; L.htv_tables_create.argtypes = [C.POINTER(Config), C.c_uint]
+    L.htv_tables_create2.restype = vp; L.htv_tables_create2.argtypes = [C.POINTER(Config), C.c_uint, C.c_uint]
     L.htv_tables_free.restype = None; L.htv_tables_free.argtypes = [vp]
     L.htv_tables_get.restype = C.POINTER(C.c_int32); L.htv_tables_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
     L.htv_test_pattern.restype = None; L.htv_test_pattern.argtypes = [C.c_int, C.c_int, vp]
@@ -198,9 +199,9 @@ def mode_config(mode: str, *, vfilter=False, nocolour=False, noaudio=False, noni
 class Tables:
     """Host-only table generation (no GPU needed) - htv_tables_* in the C-ABI."""
 
-    def __init__(self, conf: Config, sample_rate: int):
+    def __init__(self, conf: Config, sample_rate: int, pixel_rate: int = 0):
         self._L = lib()
-        self._t = self._L.htv_tables_create(C.byref(conf), sample_rate)
+        self._t = self._L.htv_tables_create2(C.byref(conf), sample_rate, pixel_rate)
         if not self._t:
             raise RuntimeError("htv_tables_create failed")
 

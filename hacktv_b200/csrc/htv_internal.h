@@ -110,6 +110,12 @@ struct htv_tables_t {
 
 	uint8_t *offset_start;  int offset_start_len;  /* start-up quirk, 2 bits/sample packed 1 byte/sample */
 
+	/* --pixelrate (htv_tables_create2): resampler in front of the video filter, ref fir.c:263-355, 393-428.
+	 * rs_taps[phase * rs_ataps + c] multiplies the input (newest - rs_ataps + 1 + c). */
+	int rs_I, rs_D, rs_ataps, rs_wp;               /* interpolation, decimation, taps per phase, raster line width */
+	int16_t *rs_taps;
+	int raster_only;                               /* tables of the raster side of a --pixelrate encoder: no modulator scratch */
+
 	int32_t *scratch;                              /* htv_tables_get */
 };
 

@@ -723,9 +723,62 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	return(t);
 }
 
+/* ref vid_init video.c:3839-3853 with pixel_rate != sample_rate, _init_vresampler video.c:3627-3651,
+ * fir_int16_resampler_init fir.c:393-428, fir_int16_init fir.c:263-295 */
+htv_tables_t *htv_tables_create2(const htv_config_t *conf, unsigned int sample_rate, unsigned int pixel_rate)
+{
+	htv_tables_t *t;
+	double line_s, *taps;
+	int64_t g;
+	int ntaps, ph, col;
+
+	if(pixel_rate == 0 || pixel_rate == sample_rate) return(htv_tables_create(conf, sample_rate));
+	if(!conf || sample_rate == 0) return(NULL);
+	if(conf->modulation == HTV_FM)
+	{
+		fprintf(stderr, "hacktv_b200: --pixelrate with FM video is not on the accelerated path\n");
+		return(NULL);
+	}
+	t = htv_tables_create(conf, sample_rate);
+	if(!t) return(NULL);
+	line_s = (double) t->conf.frame_rate_den / t->conf.frame_rate_num / t->conf.lines;
+	t->rs_wp = round((double) pixel_rate * line_s);
+	g = gcd64(sample_rate, pixel_rate);
+	t->rs_I = (int) (sample_rate / g);
+	t->rs_D = (int) (pixel_rate / g);
+	if(((int64_t) t->rs_wp * t->rs_I) % t->rs_D != 0 || (int64_t) t->rs_wp * t->rs_I / t->rs_D != t->dp.W)
+	{
+		/* the reference lets the line width vary from line to line then (fir_int16_process returns what
+		 * the inputs of a line yield); the batched path needs one width */
+		fprintf(stderr, "hacktv_b200: pixel rate %u -> sample rate %u does not keep the line width constant\n", pixel_rate, sample_rate);
+		htv_tables_free(t);
+		return(NULL);
+	}
+	ntaps = (21 * t->rs_I) | 1;
+	taps = calloc(ntaps, sizeof(double));
+	if(!taps) { htv_tables_free(t); return(NULL); }
+	if(t->rs_I > t->rs_D) lowpass(taps, ntaps, t->rs_I, 0.45, t->rs_I);
+	else lowpass(taps, ntaps, t->rs_I, 0.45 * t->rs_I / t->rs_D, t->rs_I);
+	t->rs_ataps = (ntaps + t->rs_I - 1) / t->rs_I;
+	t->rs_taps = calloc((size_t) t->rs_I * t->rs_ataps, sizeof(int16_t));
+	if(!t->rs_taps) { free(taps); htv_tables_free(t); return(NULL); }
+	for(ph = 0; ph < t->rs_I; ph++) for(col = 0; col < t->rs_ataps; col++)
+	{
+		/* fir.c:281-289: phase ph, column col holds tap[ntaps - I + ph - col I] */
+		const int idx = ntaps - t->rs_I + ph - col * t->rs_I;
+		if(idx >= 0 && idx < ntaps) t->rs_taps[ph * t->rs_ataps + col] = (int16_t) lround(taps[idx] * 32767.0);
+	}
+	free(taps);
+	/* one more two-line stage in front of the sound carriers, the offset mixer and the passthru
+	 * stream: they run a further line ahead (measured on the reference) */
+	t->dp.shift += t->dp.W;
+	return(t);
+}
+
 void htv_tables_free(htv_tables_t *t)
 {
 	if(!t) return;
+	free(t->rs_taps);
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
 	free(t->fm_ang); free(t->fmv_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
@@ -783,6 +836,12 @@ const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count)
 	if(!strcmp(name, "nicam_taps") && t->nicam_taps) return(view16(t, t->nicam_taps, t->nicam_ntaps, count));
 	if(!strcmp(name, "secam_lpf") && t->secam_bell) return(view32(t, dp->secam_lpf, 15, count));
 	if(!strcmp(name, "secam_notch") && t->secam_bell) return(view32(t, dp->secam_notch, 51, count));
+	if(!strcmp(name, "rs_taps") && t->rs_taps) return(view16(t, t->rs_taps, t->rs_I * t->rs_ataps, count));
+	if(!strcmp(name, "rs_geometry") && t->rs_taps)
+	{
+		tmp[0] = t->rs_I; tmp[1] = t->rs_D; tmp[2] = t->rs_ataps; tmp[3] = t->rs_wp; tmp[4] = dp->shift;
+		return(view32(t, tmp, 5, count));
+	}
 	if(!strcmp(name, "levels"))
 	{
 		htv_tables_levels(t, tmp);

@@ -267,10 +267,16 @@ extern int htv_last_line_kernel_lines(const htv_t *s);
 typedef struct htv_tables_t htv_tables_t;
 
 extern htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_rate);
+/* The sample-rate side of vid_init(sample_rate, pixel_rate != sample_rate): everything from the
+ * --pixelrate resampler on (ref _init_vresampler video.c:3627-3651, 4361-4368; fir_int16_resampler_init
+ * fir.c:393-428): the polyphase taps ("rs_taps", "rs_geometry" = I, D, taps per phase, raster width), the
+ * video filter and sound carriers at sample_rate, and the extra line of pipeline lead. NULL for rate
+ * pairs whose line width would vary and for FM video. pixel_rate 0 or == sample_rate: htv_tables_create. */
+extern htv_tables_t *htv_tables_create2(const htv_config_t *conf, unsigned int sample_rate, unsigned int pixel_rate);
 extern void htv_tables_free(htv_tables_t *t);
 /* Named int32 views for tests: "sync0".."sync4", "sync_off", "burst_win",
  * "chroma_taps", "vsb_itaps", "vsb_qtaps", "levels", "nicam_taps", "geometry",
- * "secam_lpf", "secam_notch". Returns NULL for an unknown / absent table. */
+ * "secam_lpf", "secam_notch", "rs_taps", "rs_geometry". Returns NULL for an unknown / absent table. */
 extern const int32_t *htv_tables_get(htv_tables_t *t, const char *name, int *count);
 
 /* ---- RF sink (int16 file sink only) ------------------------------------ */

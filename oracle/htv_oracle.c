@@ -1852,6 +1852,12 @@ const int32_t *orc_table(orc_t *o, const char *name, int *count)
 		for(i = 0; i < 5; i++) tmp[i] = o->syncs[i].offset;
 		return(tbl16(o, tmp, 5, count));
 	}
+	if(strcmp(name, "rs_taps") == 0 && o->rs_on) return(tbl16(o, o->rs_taps, o->rs_I * o->rs_ataps, count));
+	if(strcmp(name, "rs_geometry") == 0 && o->rs_on)
+	{
+		tmp[0] = o->rs_I; tmp[1] = o->rs_D; tmp[2] = o->rs_ataps; tmp[3] = o->width;
+		return(tbl16(o, tmp, 4, count));
+	}
 	if(strcmp(name, "burst_win") == 0 && o->burst_win) return(tbl16(o, o->burst_win, o->burst_width, count));
 	if(strcmp(name, "chroma_taps") == 0 && o->chroma_taps) return(tbl16(o, o->chroma_taps, o->chroma_ntaps, count));
 	if(strcmp(name, "vsb_itaps") == 0 && o->vf_itaps) return(tbl16(o, o->vf_itaps, o->vf_ntaps, count));

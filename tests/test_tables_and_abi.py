@@ -137,3 +137,34 @@ def test_fm_video_tables_match_the_oracle(built):
         a, b = t.get("fmv_taps"), o.table("vsb_itaps")
         assert a is not None and len(a) == n and np.array_equal(a, b), (mode, rate)
         o.close()
+
+
+@pytest.mark.parametrize("mode,rate,prate,filt", [("i", 16000000, 13500000, True), ("i", 20000000, 13500000, False),
+                                                  ("i", 13500000, 16000000, True), ("m", 13500000, 9000000, True),
+                                                  ("i", 16000000, 14000000, True), ("l", 16000000, 13500000, True)])
+def test_pixelrate_resampler_tables_equal_the_oracle(built, mode, rate, prate, filt):
+    """htv_tables_create2: the --pixelrate resampler's polyphase taps and geometry (ref fir.c:263-295,
+    393-428) against the oracle, which is pinned to the reference's --pixelrate output."""
+    import orc
+    conf = built.mode_config(mode, vfilter=filt)
+    t = built.Tables(conf, rate, prate)
+    o = orc.Oracle(conf, rate, prate)
+    assert np.array_equal(t.get("rs_taps"), o.table("rs_taps"))
+    g, og = t.get("rs_geometry"), o.table("rs_geometry")
+    assert np.array_equal(g[:4], og)
+    assert g[4] == (2 if filt else 1) * o.width          # sound carriers, offset mixer, passthru: lines of lead
+    plain = built.Tables(conf, rate)
+    for name in ("vsb_itaps", "vsb_qtaps", "nicam_taps", "levels"):
+        a, b = t.get(name), plain.get(name)
+        assert (a is None and b is None) or np.array_equal(a, b)
+    t.close(); o.close(); plain.close()
+
+
+def test_pixelrate_pairs_that_are_refused(built):
+    with pytest.raises(RuntimeError):
+        built.Tables(built.mode_config("i"), 16000000, 13400000)             # line width would vary
+    with pytest.raises(RuntimeError):
+        built.Tables(built.mode_config("pal-fm"), 20000000, 13500000)        # FM video
+    t = built.Tables(built.mode_config("i"), 16000000, 16000000)             # no resampler at all
+    assert t.get("rs_taps") is None
+    t.close()
