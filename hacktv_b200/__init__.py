@@ -224,11 +224,13 @@ class Tables:
 class Encoder:
     """htv_t: one RF channel on the current CUDA device."""
 
-    def __init__(self, mode, sample_rate: int = 16_000_000, **overrides):
+    def __init__(self, mode, sample_rate: int = 16_000_000, pixel_rate: int = 0, **overrides):
+        """pixel_rate != 0 and != sample_rate: the raster is built at pixel_rate and resampled (hacktv's
+        --pixelrate); that path has not run on a GPU yet."""
         self._L = lib()
         self.conf = mode if isinstance(mode, Config) else mode_config(mode, **overrides)
         h = C.c_void_p()
-        r = self._L.htv_init(C.byref(h), sample_rate, 0, C.byref(self.conf))
+        r = self._L.htv_init(C.byref(h), sample_rate, pixel_rate, C.byref(self.conf))
         if r != HTV_OK or not h:
             raise RuntimeError(f"htv_init failed ({r}): no CUDA device or unsupported configuration")
         self._h = h

@@ -27,6 +27,12 @@ struct htv_t {
 	int W, lines, complex, bps;
 
 	/* stream position */
+	/* --pixelrate (ref vid_init video.c:3839, _init_vresampler 3627-3651): the raster side - tables, pictures,
+	 * frame map, VBI overlays - lives in a second device context built at the pixel rate; the resampler,
+	 * video filter, sound carriers and output stay in `dev` at the sample rate. Without a resampler
+	 * rtab == tab and rdev == dev. */
+	struct htv_tables_t *rtab;
+	htv_dev_t *rdev;
 	int64_t next_line;            /* next scan line to render (0 = frame 1 line 1) */
 
 	/* video frames */
@@ -91,22 +97,41 @@ int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, con
 
 	if(!out) return(HTV_ERROR);
 	*out = NULL;
-	if(pixel_rate != 0 && pixel_rate != sample_rate)
-	{
-		fprintf(stderr, "hacktv_b200: --pixelrate resampling is not on the accelerated path\n");
-		return(HTV_ERROR);
-	}
 	s = calloc(1, sizeof(htv_t));
 	if(!s) return(HTV_OUT_OF_MEMORY);
 
-	s->tab = htv_tables_create(conf, sample_rate);
+	s->tab = htv_tables_create2(conf, sample_rate, pixel_rate);
 	if(!s->tab) { free(s); return(HTV_ERROR); }
+	s->rtab = s->tab;
+	if(s->tab->rs_taps)
+	{
+		/* the raster side at the pixel rate: same mode, no sound carriers, filter or mixers */
+		htv_config_t rc = *conf;
+		rc.vfilter = 0; rc.offset = 0; rc.swap_iq = 0;
+		rc.fm_mono_level = 0; rc.nicam_level = 0; rc.am_audio_level = 0;
+		s->rtab = htv_tables_create(&rc, pixel_rate);
+		if(!s->rtab || s->rtab->dp.W != s->tab->rs_wp)
+		{
+			htv_tables_free(s->rtab != s->tab ? s->rtab : NULL);
+			htv_tables_free(s->tab);
+			free(s);
+			return(HTV_ERROR);
+		}
+		s->rtab->raster_only = 1;
+	}
 
 	/* No GPU, no encoder: there is deliberately no CPU fallback */
 	s->dev = htv_dev_create(s->tab, MAX_FRAME_SLOTS, err, sizeof(err));
+	s->rdev = s->dev;
+	if(s->dev && s->rtab != s->tab)
+	{
+		s->rdev = htv_dev_create(s->rtab, MAX_FRAME_SLOTS, err, sizeof(err));
+		if(!s->rdev) { htv_dev_destroy(s->dev); s->dev = NULL; }
+	}
 	if(!s->dev)
 	{
 		fprintf(stderr, "hacktv_b200: cannot initialise the CUDA encoder: %s\n", err);
+		if(s->rtab != s->tab) htv_tables_free(s->rtab);
 		htv_tables_free(s->tab);
 		free(s);
 		return(HTV_ERROR);
@@ -118,8 +143,8 @@ int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, con
 	s->bps = s->complex ? 4 : 2;
 	s->cur_frame = -1;
 	s->cur_slot = -1;
-	s->av.width = s->tab->dp.active_width;
-	s->av.height = s->tab->dp.active_lines;
+	s->av.width = s->rtab->dp.active_width;
+	s->av.height = s->rtab->dp.active_lines;
 	s->zeros = htv_dev_alloc_pinned(65536 * 2 * sizeof(int16_t));    /* pinned: uploads stay asynchronous */
 	if(!s->zeros) { htv_free(s); return(HTV_OUT_OF_MEMORY); }
 	memset(s->zeros, 0, 65536 * 2 * sizeof(int16_t));
@@ -145,6 +170,7 @@ void htv_free(htv_t *s)
 		htv_dev_event_free(s->ev_rendered[0]); htv_dev_event_free(s->ev_rendered[1]);
 		htv_dev_event_free(s->ev_copied[0]); htv_dev_event_free(s->ev_copied[1]);
 		htv_dev_stream_free(s->st_compute); htv_dev_stream_free(s->st_copy);
+		if(s->rdev && s->rdev != s->dev) htv_dev_destroy(s->rdev);
 		htv_dev_destroy(s->dev);
 	}
 	drop_overlays_before(s, 0x7FFFFFFFFFFFFFFFLL);
@@ -154,6 +180,7 @@ void htv_free(htv_t *s)
 	free(s->pt_tmp);
 	free(s->h_iq);
 	htv_dev_free_pinned(s->zeros);
+	if(s->rtab != s->tab) htv_tables_free(s->rtab);
 	htv_tables_free(s->tab);
 	free(s);
 }
@@ -162,21 +189,22 @@ void htv_info(htv_t *s)
 {
 	const htv_config_t *c = &s->tab->conf;
 	fprintf(stderr, "Video: %dx%d %.2f fps (full frame %dx%d)\n",
-		s->tab->dp.active_width, c->active_lines,
-		(double) c->frame_rate_num / c->frame_rate_den, s->W, c->lines);
+		s->rtab->dp.active_width, c->active_lines,
+		(double) c->frame_rate_num / c->frame_rate_den, s->rtab->dp.W, c->lines);
+	if(s->rtab != s->tab) fprintf(stderr, "Pixel rate: %d\n", (int) s->rtab->rate);
 	fprintf(stderr, "Sample rate: %d\n", (int) s->tab->rate);
 }
 
 size_t htv_get_framebuffer_length(htv_t *s)
 {
-	return(sizeof(uint32_t) * s->tab->dp.active_width * s->tab->conf.active_lines);
+	return(sizeof(uint32_t) * s->rtab->dp.active_width * s->tab->conf.active_lines);
 }
 
 htv_av_t *htv_av(htv_t *s) { return(&s->av); }
 int htv_samples_per_line(const htv_t *s) { return(s->W); }
-int htv_half_line(const htv_t *s) { return(s->tab->dp.half_width); }
+int htv_half_line(const htv_t *s) { return(s->rtab->dp.half_width); }   /* of the raster (VBI stages draw there) */
 void htv_signal_levels(const htv_t *s, int levels[4]) { htv_tables_levels(s->tab, levels); }
-int htv_active_width(const htv_t *s) { return(s->tab->dp.active_width); }
+int htv_active_width(const htv_t *s) { return(s->rtab->dp.active_width); }
 int htv_active_lines(const htv_t *s) { return(s->tab->dp.active_lines); }
 int htv_lines_per_frame(const htv_t *s) { return(s->lines); }
 int htv_sample_rate(const htv_t *s) { return((int) s->tab->rate); }
@@ -235,7 +263,7 @@ static int pull_audio(htv_t *s, int64_t need, void *stream)
  * where delay = 1 with a video filter and 0 without (measured on the reference, see
  * tests/test_oracle_vs_ref.py::test_passthru_alignment). A stream that ends adds whole lines
  * only (the `fread() == 0 -> return` at video.c:3530). */
-int htv_passthru_delay_lines(const htv_t *s) { return(s->tab->dp.shift > 0 ? 1 : 0); }
+int htv_passthru_delay_lines(const htv_t *s) { return(s->tab->dp.shift / s->tab->dp.W); }   /* 0, 1; 2 with a resampler and a filter */
 
 int htv_set_passthru(htv_t *s, htv_passthru_read_t read, void *ctx)
 {
@@ -337,8 +365,8 @@ static void pull_overlays(htv_t *s, int64_t f)
 		s->ov[j].add = NULL;
 		if(lines[i].add)
 		{
-			s->ov[j].add = malloc(sizeof(int16_t) * s->W);
-			memcpy(s->ov[j].add, lines[i].add, sizeof(int16_t) * s->W);
+			s->ov[j].add = malloc(sizeof(int16_t) * s->rtab->dp.W);            /* a raster line (pixel rate) */
+			memcpy(s->ov[j].add, lines[i].add, sizeof(int16_t) * s->rtab->dp.W);
 		}
 		s->nov++;
 	}
@@ -354,26 +382,27 @@ static int send_overlays(htv_t *s, long long end_line)
 		line[n] = s->ov[i].line; from[n] = s->ov[i].from; to[n] = s->ov[i].to; value[n] = s->ov[i].value;
 		add[n] = s->ov[i].add;
 	}
-	return(htv_dev_set_overlays(s->dev, n, line, from, to, value, add));
+	return(htv_dev_set_overlays(s->rdev, n, line, from, to, value, add));
 }
 
 /* One device launch sequence for lines [L0, L0 + n): at most MAX_NEW_FRAMES new pictures */
 static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream)
 {
 	int n = *pn, nnew = 0;
-	const htv_dparams_t *dp = &s->tab->dp;
+	const htv_dparams_t *dp = &s->tab->dp, *rdp = &s->rtab->dp;
 	const int64_t L0 = s->next_line;
 	const int64_t f0 = L0 / s->lines, f1 = (L0 + n - 1) / s->lines;
 	int32_t map[4096];
 	int64_t f;
 	int r, nmap = 0;
-	void *up;
+	void *up, *rup;
 
 	if(f1 - f0 + 1 > 4096) return(HTV_ERROR);
 
 	/* pictures and PCM go up on the encoder's own upload stream, ahead of the kernels queued on
 	 * `stream` for the previous chunk and beside the caller's device-to-host copies */
 	up = htv_dev_uploads_begin(s->dev);
+	rup = s->rdev != s->dev ? htv_dev_uploads_begin(s->rdev) : up;
 	drop_overlays_before(s, L0);
 
 	/* pictures: one pull per frame, at its first line (ref video.c:4873-4881) */
@@ -398,17 +427,17 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 			s->cur_frame = f;
 			if(s->av.read_video && s->av.read_video(s->av.ctx, &fr) == HTV_OK && fr.framebuffer)
 			{
-				if(fr.width != dp->active_width || fr.height != dp->active_lines)
+				if(fr.width != rdp->active_width || fr.height != rdp->active_lines)
 				{
 					fprintf(stderr, "hacktv_b200: source frame is %dx%d, the raster needs %dx%d\n",
-						fr.width, fr.height, dp->active_width, dp->active_lines);
+						fr.width, fr.height, rdp->active_width, rdp->active_lines);
 					return(HTV_ERROR);
 				}
 				if(!s->have_serial || fr.serial != s->cur_serial || s->cur_slot < 0)
 				{
 					s->cur_slot = s->next_slot;
 					s->next_slot = (s->next_slot + 1) % MAX_FRAME_SLOTS;
-					r = htv_dev_upload_frame(s->dev, s->cur_slot, fr.framebuffer, up);
+					r = htv_dev_upload_frame(s->rdev, s->cur_slot, fr.framebuffer, rup);
 					if(r != HTV_OK) return(r);
 					s->cur_serial = fr.serial;
 					s->have_serial = 1;
@@ -438,8 +467,13 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	}
 	r = htv_dev_uploads_end(s->dev, stream);
 	if(r != HTV_OK) return(r);
+	if(s->rdev != s->dev)
+	{
+		r = htv_dev_uploads_end(s->rdev, stream);
+		if(r != HTV_OK) return(r);
+	}
 
-	r = htv_dev_set_frame_map(s->dev, map, nmap, f0, stream);
+	r = htv_dev_set_frame_map(s->rdev, map, nmap, f0, stream);
 	if(r != HTV_OK) return(r);
 
 	if(dp->have_fm || dp->have_am || dp->have_nicam)
@@ -461,7 +495,8 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 			if(acc_lines < 0) return(HTV_ERROR);
 			acc = s->pt_dev;
 		}
-		r = htv_dev_render_lines(s->dev, L0, n, d_out, acc, acc_lines, stream);
+		if(s->rdev != s->dev) r = htv_dev_render_lines_rs(s->dev, s->rdev, L0, n, d_out, acc, acc_lines, stream);
+		else r = htv_dev_render_lines(s->dev, L0, n, d_out, acc, acc_lines, stream);
 		if(r != HTV_OK) return(r);
 	}
 	s->next_line += n;

@@ -145,6 +145,9 @@ extern int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *str
 /* the line kernel(s): render lines [line0, line0 + nlines) to d_out (device) */
 extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out,
 	const int16_t *d_acc, int acc_lines, void *stream);
+/* --pixelrate: d = sample-rate context, r = raster context at the pixel rate (htv_kernels.cu) */
+extern int htv_dev_render_lines_rs(htv_dev_t *d, htv_dev_t *r, int64_t line0, int nlines, int16_t *d_out,
+	const int16_t *d_acc, int acc_lines, void *stream);
 extern void *htv_dev_event_new_timed(void);
 extern float htv_dev_event_elapsed(void *e0, void *e1);
 extern int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *stream);

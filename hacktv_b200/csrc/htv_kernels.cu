@@ -154,6 +154,9 @@ struct htv_dev_t {
 	uint8_t *d_planes;                // high / low byte planes of the composite stream for k_mod_mma (32 | W, video filter on)
 	size_t plane_stride, modm_smem;
 	int plane_pitch;                  // 0: planes are the contiguous stream; else bytes per line row (htv_mma_fir.h)
+	// --pixelrate: this is the sample-rate side; the raster runs in a second context at the pixel rate
+	int rs_I, rs_D, rs_ataps, rs_wp;
+	int16_t *d_rs_taps;
 	size_t modt_smem;
 	int mod_grid;
 	int16_t *d_comp;                  // composite scratch, (sub + 3) lines, reused by every sub-batch (stays in L2)
@@ -2466,7 +2469,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			return(NULL);
 		}
 	}
-	if(!secam && (W & 3) == 0 && !dp.have_fmv)
+	if(!secam && (W & 3) == 0 && !dp.have_fmv && !t->raster_only)
 	{
 		int nsm = 148;
 		cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
@@ -2482,7 +2485,18 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		cudaFuncSetAttribute(k_mod_tma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modt_smem);
 		d->mod_grid = nsm * (d->line_threads <= 256 ? 4 : 2);
 	}
-	if(!secam && !dp.have_fmv && dp.vf_type)
+	if(t->rs_taps)
+	{
+		d->rs_I = t->rs_I; d->rs_D = t->rs_D; d->rs_ataps = t->rs_ataps; d->rs_wp = t->rs_wp;
+		d->d_rs_taps = (int16_t *) dev_copy(d, t->rs_taps, sizeof(int16_t) * t->rs_I * t->rs_ataps);
+		if(!d->d_rs_taps || secam)
+		{
+			snprintf(err, errlen, secam ? "--pixelrate with SECAM is not on the accelerated path yet" : "device allocation failed");
+			htv_dev_destroy(d);
+			return(NULL);
+		}
+	}
+	if(!secam && !dp.have_fmv && dp.vf_type && !t->raster_only)
 	{
 		// the video filter on the tensor cores (k_mod_mma): the default for the line widths it has been
 		// validated at on a B200 (1024 = 16 Msps, 1280 = 20 Msps: BASELINE configs 2 and 5). HTV_FIR=mma
@@ -2858,6 +2872,142 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
 	CK(cudaEventRecord(d->ev_chunk[d->chunk_i & 1], st));
 	d->chunk_i++;
+	CK(cudaGetLastError());
+	return(HTV_OK);
+}
+
+// ---------------------------------------------------------------------------
+// --pixelrate: the raster is built at the pixel rate by a second
+// device context and the reference's polyphase resampler (ref _init_vresampler video.c:3627-3651,
+// fir_int16_resampler_init fir.c:393-428, fir_int16_process fir.c:304-355) brings it to the sample
+// rate in front of the video filter. Closed form of the output index (oracle resample_line, pinned
+// to the reference): output k of resampled line R uses the rs_ataps inputs ending at
+// R * Wp + floor(k D / I) with the taps of phase (k D) mod I (a whole line is a whole number of
+// periods because Ws D = Wp I). Row b of `comp` is raster line first - 1 + b of the launch; row b
+// of the output is resampled line first + b, which reaches back into comp rows b and b + 1.
+// Output goes wherever the modulator of this context reads: byte planes, int32 or int16 stream.
+// NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): htv_init only takes this
+// path when pixel_rate != sample_rate, tests are opt-in (HTV_TEST_UNVALIDATED=1).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(384)
+k_resample(const int16_t *comp, int Wp, int Ws, int I, int D, int A, const int16_t *taps,
+	uint8_t *planes, size_t plane_stride, int *comp32, int16_t *comp16)
+{
+	const int b = blockIdx.x;
+	const int x0 = threadIdx.x * SPT;
+	if(x0 >= Ws) return;
+	const int16_t *in = comp + (size_t) (b + 1) * Wp;                   // input 0 of resampled line first + b
+	int v[SPT];
+	#pragma unroll
+	for(int k = 0; k < SPT; k++)
+	{
+		const int x = x0 + k;
+		const int xd = x * D, pos = xd / I, ph = xd - pos * I;              // x D < 2^31 for any line width here
+		const int16_t *w = in + pos - A + 1;
+		const int16_t *t = taps + ph * A;
+		int a = 0;
+		for(int c = 0; c < A; c++) a += (int) w[c] * (int) __ldg(t + c);
+		v[k] = sat16i(a >> 15);
+	}
+	const size_t o = (size_t) b * Ws + x0;
+	if(planes)
+	{
+		*reinterpret_cast<unsigned *>(planes + o) = ((v[0] >> 8) & 0xFF) | (((v[1] >> 8) & 0xFF) << 8) |
+			(((v[2] >> 8) & 0xFF) << 16) | ((unsigned) (v[3] >> 8) << 24);
+		*reinterpret_cast<unsigned *>(planes + plane_stride + o) = (v[0] & 0xFF) | ((v[1] & 0xFF) << 8) |
+			((v[2] & 0xFF) << 16) | ((unsigned) v[3] << 24);
+	}
+	else if(comp32) *reinterpret_cast<int4 *>(comp32 + o) = make_int4(v[0], v[1], v[2], v[3]);
+	else
+	{
+		#pragma unroll
+		for(int k = 0; k < SPT; k++) if(x0 + k < Ws) comp16[o + k] = (int16_t) v[k];
+	}
+}
+
+// d: the sample-rate context (sound carriers, video filter, output); r: the raster context built
+// from tables at the pixel rate (pictures, frame map and VBI overlays are uploaded to it).
+extern "C" int htv_dev_render_lines_rs(htv_dev_t *d, htv_dev_t *r, int64_t line0, int nlines, int16_t *d_out,
+	const int16_t *d_acc, int acc_lines, void *stream)
+{
+	cudaStream_t st = (cudaStream_t) stream;
+	if(nlines <= 0) return(HTV_OK);
+	if(!d->d_rs_taps || d->plane_pitch || d->dp.have_fmv || r->dp.colour_mode == HTV_SECAM || (d->dp.W & 3)) return(HTV_ERROR);
+	if(nlines > d->desc_cap)
+	{
+		cudaStreamSynchronize(st);
+		cudaStreamSynchronize(d->side);
+		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
+		d->d_desc_r = d->d_desc_a = NULL;
+		d->desc_cap = 0;
+		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
+		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
+		d->desc_cap = nlines;
+	}
+	if(nlines + 1 > r->desc_cap)
+	{
+		cudaStreamSynchronize(st);
+		cudaFree(r->d_desc_r); cudaFree(r->d_desc_a);
+		r->d_desc_r = r->d_desc_a = NULL;
+		r->desc_cap = 0;
+		CK(cudaMalloc(&r->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 4)));
+		CK(cudaMalloc(&r->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 2)));
+		r->desc_cap = nlines + 1;
+	}
+	// raster descriptors for lines line0 - 2 .. line0 + nlines + 1 (one line more than without a resampler:
+	// the emitted line t is resampled line t + 1 and the video filter looks into t + 2)
+	LineDescs ldr = { (LineRaster *) r->d_desc_r + 1, (LineAudio *) r->d_desc_a };
+	LineDescs lda = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
+	k_line_desc_r<<<(nlines + 4 + 63) / 64, 64, 0, st>>>(r->dp, r->dt, ldr, line0, nlines + 1);
+	if(!d->side_armed)
+	{
+		CK(cudaEventRecord(d->ev_in, st));
+		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+	}
+	k_line_desc_a<<<(nlines + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, lda, line0, nlines);
+	CK(cudaEventRecord(d->ev_audio, d->side));
+	d->side_armed = 0;
+	bool joined = false;
+	d->launches += 2;
+	const int Ws = d->dp.W, Wp = r->dp.W;
+	int sub = d->sub_lines < r->sub_lines ? d->sub_lines : r->sub_lines;
+	for(int done = 0; done < nlines; done += sub)
+	{
+		const int n = nlines - done < sub ? nlines - done : sub;
+		const bool last = done + n >= nlines;
+		int16_t *o = d_out + (size_t) done * Ws * (d->dp.complex_out ? 2 : 1);
+		const int16_t *acc = d_acc && acc_lines > done ? d_acc + (size_t) done * Ws * (d->dp.complex_out ? 2 : 1) : NULL;
+		const int acc_rows = acc ? acc_lines - done : 0;
+		// raster lines line0 + done - 1 .. line0 + done + n + 1 -> rows 0 .. n + 2 of the raster context's int16 stream
+		k_raster<<<n + 3, r->line_threads, r->raster_smem, st>>>(r->dp, r->dt, ldr.r + done, r->d_comp, NULL, NULL, 0, 0);
+		// resampled lines line0 + done .. line0 + done + n + 1 -> rows 0 .. n + 1 of this context's scratch
+		k_resample<<<n + 2, d->line_threads, 0, st>>>(r->d_comp, Wp, Ws, d->rs_I, d->rs_D, d->rs_ataps, d->d_rs_taps,
+			d->d_planes, d->plane_stride, d->d_planes ? NULL : d->d_comp32, d->d_comp);
+		d->launches += 2;
+		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
+		if(d->timing && last) cudaEventRecord(d->ev0, st);
+		if(d->d_planes)
+		{
+			const int grid = n < d->mod_grid ? n : d->mod_grid;
+			if(d->line_threads <= 256) k_mod_mma<256, 4><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_planes, d->plane_stride, 0, n, o, acc, acc_rows);
+			else k_mod_mma<384, 2><<<grid, d->line_threads, d->modm_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_planes, d->plane_stride, 0, n, o, acc, acc_rows);
+		}
+		else if(d->d_comp32)
+		{
+			const int grid = n < d->mod_grid ? n : d->mod_grid;
+			if(d->line_threads <= 256) k_mod_tma<256, 4><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_comp32, n, o, acc, acc_rows);
+			else k_mod_tma<384, 2><<<grid, d->line_threads, d->modt_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_comp32, n, o, acc, acc_rows);
+		}
+		else if(d->line_threads <= 256) k_mod<256, 4><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_comp, NULL, o, acc, acc_rows);
+		else k_mod<384, 2><<<n, d->line_threads, d->mod_smem, st>>>(d->dp, d->dt, lda.a + done, d->d_comp, NULL, o, acc, acc_rows);
+		d->launches++;
+		if(last) d->last_mod_lines = n;
+	}
+	if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
+	CK(cudaEventRecord(d->ev_chunk[d->chunk_i & 1], st));
+	d->chunk_i++;
+	CK(cudaEventRecord(r->ev_chunk[r->chunk_i & 1], st));
+	r->chunk_i++;
 	CK(cudaGetLastError());
 	return(HTV_OK);
 }
