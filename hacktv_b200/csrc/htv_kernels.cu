@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include "htv_internal.h"
 #include "htv_mma_fir.h"
+#include "htv_resample.h"
 
 #define HTV_FIR_DEFAULT_MMA 1         // the tensor-core video filter is the default where it applies (HTV_FIR=scalar turns it off)
 #define HALO 25                       // (HTV_VF_NTAPS - 1) / 2
@@ -2899,16 +2900,7 @@ k_resample(const int16_t *comp, int Wp, int Ws, int I, int D, int A, const int16
 	const int16_t *in = comp + (size_t) (b + 1) * Wp;                   // input 0 of resampled line first + b
 	int v[SPT];
 	#pragma unroll
-	for(int k = 0; k < SPT; k++)
-	{
-		const int x = x0 + k;
-		const int xd = x * D, pos = xd / I, ph = xd - pos * I;              // x D < 2^31 for any line width here
-		const int16_t *w = in + pos - A + 1;
-		const int16_t *t = taps + ph * A;
-		int a = 0;
-		for(int c = 0; c < A; c++) a += (int) w[c] * (int) __ldg(t + c);
-		v[k] = sat16i(a >> 15);
-	}
+	for(int k = 0; k < SPT; k++) v[k] = rs_output(in, x0 + k, I, D, A, taps);
 	const size_t o = (size_t) b * Ws + x0;
 	if(planes)
 	{
