@@ -107,6 +107,7 @@ struct SecScratch {
 };
 
 #define MAPBUFS 16
+#define HTV_SIDE_EVENTS 32
 #define HTV_MAX_ALLOCS 128            // device tables owned by one encoder (about 50 for SECAM-L with AM + NICAM)
 #define HTV_OV_CAP 2048                // VBI overlay lines per launch sequence
 
@@ -144,6 +145,12 @@ struct htv_dev_t {
 	unsigned chunk_i;
 	cudaEvent_t ev_in, ev_audio;
 	int side_armed;
+	// HTV_SIDE=split (opt-in, not yet run on a GPU): the NICAM pre-pass on a second side stream beside the
+	// FM one, and the sound-carrier descriptors launched per sub-batch, so the first modulator launch
+	// waits for its own 8 192 descriptors instead of the whole call's
+	int side_split;
+	cudaStream_t side2;
+	cudaEvent_t ev_nic, ev_sub[HTV_SIDE_EVENTS];
 	int ev_pending;
 	int line_threads;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
@@ -2565,6 +2572,16 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
+	{
+		const char *sd = getenv("HTV_SIDE");
+		d->side_split = sd && !strcmp(sd, "split") && !dp.have_fmv;
+		if(d->side_split)
+		{
+			cudaStreamCreateWithFlags(&d->side2, cudaStreamNonBlocking);
+			cudaEventCreateWithFlags(&d->ev_nic, cudaEventDisableTiming);
+			for(int i = 0; i < HTV_SIDE_EVENTS; i++) cudaEventCreateWithFlags(&d->ev_sub[i], cudaEventDisableTiming);
+		}
+	}
 	// the table build and the memsets above ran on the default stream, which the (non-blocking)
 	// streams the encoder works on do not wait for
 	if(cudaDeviceSynchronize() != cudaSuccess)
@@ -2592,6 +2609,9 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
+	if(d->side2) cudaStreamDestroy(d->side2);
+	if(d->ev_nic) cudaEventDestroy(d->ev_nic);
+	for(int i = 0; i < HTV_SIDE_EVENTS; i++) if(d->ev_sub[i]) cudaEventDestroy(d->ev_sub[i]);
 	if(d->up) cudaStreamDestroy(d->up);
 	if(d->ev_up) cudaEventDestroy(d->ev_up);
 	if(d->ev_chunk[0]) cudaEventDestroy(d->ev_chunk[0]);
@@ -2725,6 +2745,12 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	}
 	if(dp.have_nicam)
 	{
+		if(d->side_split)
+		{
+			// independent of the FM chain: its own stream, joined into `side` below
+			CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));
+			st = d->side2;
+		}
 		const int64_t s_lo = (int64_t) (((unsigned long long) (m0 > dp.nicam_ntaps ? m0 - dp.nicam_ntaps : 0) * dp.nicam_D) / dp.nicam_F);
 		const int64_t s_hi = (int64_t) (((unsigned long long) (m1 - 1) * dp.nicam_D) / dp.nicam_F);
 		int64_t k_lo = s_lo / 364, k_hi = s_hi / 364;
@@ -2734,6 +2760,11 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
+		if(d->side_split)
+		{
+			CK(cudaEventRecord(d->ev_nic, d->side2));
+			CK(cudaStreamWaitEvent(d->side, d->ev_nic, 0));             // the descriptors (on `side`) need both chains
+		}
 	}
 	CK(cudaGetLastError());
 	return(HTV_OK);
@@ -2764,11 +2795,29 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		CK(cudaEventRecord(d->ev_in, st));
 		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 	}
+	if(d->side_split)
+	{
+		// one descriptor launch and one event per sub-batch; a call with more than HTV_SIDE_EVENTS
+		// sub-batches reuses events, which only makes the later waits conservative
+		int i = 0;
+		for(int done = 0; done < nlines; done += d->sub_lines, i++)
+		{
+			const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
+			LineDescs lds = { ld.r, ld.a + done };
+			k_line_desc_a<<<(n + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, lds, line0 + done, n);
+			CK(cudaEventRecord(d->ev_sub[i % HTV_SIDE_EVENTS], d->side));
+			d->launches++;
+		}
+		d->launches++;
+	}
+	else
+	{
 	k_line_desc_a<<<(nlines + fm_skip + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0 - fm_skip, nlines + fm_skip);
 	CK(cudaEventRecord(d->ev_audio, d->side));
+	d->launches += 2;
+	}
 	d->side_armed = 0;
 	bool joined = false;
-	d->launches += 2;
 	for(int done = 0; done < nlines; done += d->sub_lines)
 	{
 		const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
@@ -2838,7 +2887,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride, d->plane_pitch);
 			d->launches++;
 		}
-		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
+		if(d->side_split) CK(cudaStreamWaitEvent(st, d->ev_sub[(done / d->sub_lines) % HTV_SIDE_EVENTS], 0));
+		else if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
 		if(d->dp.have_fmv)
 		{

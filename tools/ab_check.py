@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""A/B check of one run-time switch on the GPU: every case is rendered with ENV=A and ENV=B, compared bit
+for bit with each other and within the oracle tolerance, then timed device-resident (64 frames per call).
+One JSON line per result into gpurun_out/ab_<ENV>.jsonl.
+
+    python tools/ab_check.py HTV_SIDE default split
+    python tools/ab_check.py HTV_FIR scalar mma --ntsc          # also the widths 128 does not divide
+
+"default" as a value means: variable unset."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import hacktv_b200 as H
+import orc
+
+ENV, A, B = sys.argv[1], sys.argv[2], sys.argv[3]
+NTSC = "--ntsc" in sys.argv
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+LOG = open(os.path.join(ROOT, "gpurun_out", f"ab_{ENV}.jsonl"), "w")
+
+
+def emit(**kw):
+    s = json.dumps(kw)
+    print(s, flush=True)
+    LOG.write(s + "\n"); LOG.flush()
+
+
+def select(v):
+    if v == "default":
+        os.environ.pop(ENV, None)
+    else:
+        os.environ[ENV] = v
+
+
+def render(v, mode, rate, nlines, **kw):
+    select(v)
+    enc = H.Encoder(H.mode_config(mode, **kw), rate)
+    enc.open_test_source()
+    got = enc.render_host(nlines)
+    enc.close()
+    return got
+
+
+CASES = [
+    ("i", 16000000, 1300, dict(vfilter=True, noaudio=True), 0),
+    ("i", 16000000, 1300, dict(vfilter=True), 1),
+    ("i", 20000000, 700, dict(vfilter=True), 1),
+    ("pal", 16000000, 700, dict(vfilter=True), 0),
+    ("pal", 16000000, 700, dict(), 0),
+    ("l", 16000000, 700, dict(vfilter=True), 1),
+    ("i", 16000000, 700, dict(vfilter=True, nonicam=True), 1),
+]
+if NTSC:
+    CASES += [("m", 13500000, 1100, dict(vfilter=True), 1), ("m", 13500000, 1100, dict(vfilter=True, noaudio=True), 0),
+              ("i", 13500000, 700, dict(vfilter=True), 1), ("i", 18000000, 700, dict(vfilter=True), 1)]
+ok_all = True
+for mode, rate, nlines, kw, tol in CASES:
+    a = render(A, mode, rate, nlines, **kw)
+    b = render(B, mode, rate, nlines, **kw)
+    o = orc.Oracle(H.mode_config(mode, **kw), rate); o.open_test_source()
+    want = o.render(nlines); o.close()
+    d_ab = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    d_o = np.abs(b.astype(np.int32) - want.astype(np.int32))
+    ok = bool(d_ab.max() == 0 and d_o.max() <= tol)
+    ok_all &= ok
+    emit(check="parity", env=ENV, a=A, b=B, mode=mode, rate=rate, nlines=nlines, kw={k: str(v) for k, v in kw.items()},
+         a_vs_b_max=int(d_ab.max()), a_vs_b_nonzero=int(np.count_nonzero(d_ab)), b_vs_oracle_max=int(d_o.max()), tol=tol, ok=ok)
+
+# chunked rendering with B: several calls, small and large
+select(B)
+conf = H.mode_config("i", vfilter=True)
+x = H.Encoder(conf, 16000000); x.open_test_source(); whole = x.render_host(20000); x.close()
+y = H.Encoder(conf, 16000000); y.open_test_source()
+parts = np.concatenate([y.render_host(n) for n in (1, 311, 9000, 625, 10063)]); y.close()
+ok = bool(np.array_equal(whole, parts)); ok_all &= ok
+emit(check="chunking", env=ENV, b=B, ok=ok)
+
+for name, mode, rate, filt in (("cfg2 i 16M --filter", "i", 16000000, True), ("cfg5 i 20M --filter", "i", 20000000, True),
+                               ("cfg3 m 13.5M --filter", "m", 13500000, True), ("cfg1 pal 16M", "pal", 16000000, False)):
+    for v in (A, B):
+        select(v)
+        enc = H.Encoder(H.mode_config(mode, vfilter=filt), rate)
+        enc.open_test_source()
+        nlines = 64 * enc.lines
+        out = torch.empty(nlines * enc.width * 2, dtype=torch.int16, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            enc.render(nlines, out.data_ptr(), st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K = 10
+        for _ in range(K):
+            enc.render(nlines, out.data_ptr(), st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        msps = nlines * enc.width / (ms / 1e3) / 1e6
+        emit(check="timing", env=ENV, value=v, config=name, ms_per_64_frames=round(ms, 4), msamples_per_s=round(msps, 1),
+             realtime_x=round(msps / (rate / 1e6), 1))
+        enc.close()
+emit(check="summary", env=ENV, ok=bool(ok_all))
+sys.exit(0 if ok_all else 1)
