@@ -20,7 +20,9 @@ with tempfile.TemporaryDirectory() as td:
     src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     raw_csv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 
-starts = [i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l]
+# several sections can match (k_raster / k_raster_secam, template instantiations): take the shortest
+# name, and pass a longer substring (e.g. k_mod_mmaILi256) to pick an instantiation
+starts = sorted((i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l), key=lambda i: len(dis[i]))
 start = starts[0]
 ends = [i for i, l in enumerate(dis) if l.startswith(".text.") and i > start]
 end = ends[0] if ends else len(dis)
