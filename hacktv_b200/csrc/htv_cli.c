@@ -32,7 +32,7 @@ static void usage(void)
 int main(int argc, char **argv)
 {
 	const char *mode = "i", *out = NULL, *input = NULL;
-	unsigned int rate = 16000000;
+	unsigned int rate = 16000000, pixelrate = 0;   /* --pixelrate: raster at this rate, resampled to -s (not yet run on a GPU) */
 	int filter = 0, nocolour = 0, noaudio = 0, nonicam = 0, swap_iq = 0, i;
 	long long offset = 0, lines = -1, n = 0;
 	double level = 1.0, volume = 1.0;
@@ -46,6 +46,7 @@ int main(int argc, char **argv)
 		const char *a = argv[i];
 		if((!strcmp(a, "-m") || !strcmp(a, "--mode")) && i + 1 < argc) mode = argv[++i];
 		else if((!strcmp(a, "-s") || !strcmp(a, "--samplerate")) && i + 1 < argc) rate = strtoul(argv[++i], NULL, 10);
+		else if(!strcmp(a, "--pixelrate") && i + 1 < argc) pixelrate = strtoul(argv[++i], NULL, 10);
 		else if((!strcmp(a, "-o") || !strcmp(a, "--output")) && i + 1 < argc) out = argv[++i];
 		else if(!strcmp(a, "--filter")) filter = 1;
 		else if(!strcmp(a, "--nocolour") || !strcmp(a, "--nocolor")) nocolour = 1;
@@ -93,7 +94,7 @@ int main(int argc, char **argv)
 	signal(SIGTERM, on_signal);
 	signal(SIGPIPE, on_signal);
 
-	if(htv_init(&vid, rate, 0, &conf) != HTV_OK)
+	if(htv_init(&vid, rate, pixelrate, &conf) != HTV_OK)
 	{
 		fprintf(stderr, "Unable to initialise video encoder.\n");
 		return(-1);
