@@ -121,6 +121,9 @@ def lib() -> C.CDLL:
     L.htv_find_mode.restype = C.POINTER(Config); L.htv_find_mode.argtypes = [C.c_char_p]
     L.htv_config_size.restype = sz
     L.htv_init.restype = C.c_int; L.htv_init.argtypes = [C.POINTER(vp), C.c_uint, C.c_uint, C.POINTER(Config)]
+    L.htv_init_on.restype = C.c_int; L.htv_init_on.argtypes = [C.POINTER(vp), C.c_int, C.c_uint, C.c_uint, C.POINTER(Config)]
+    L.htv_device_count.restype = C.c_int; L.htv_device_count.argtypes = []
+    L.htv_device.restype = C.c_int; L.htv_device.argtypes = [vp]
     L.htv_free.restype = None; L.htv_free.argtypes = [vp]
     L.htv_info.restype = None; L.htv_info.argtypes = [vp]
     L.htv_get_framebuffer_length.restype = sz; L.htv_get_framebuffer_length.argtypes = [vp]
@@ -222,18 +225,19 @@ class Tables:
 
 
 class Encoder:
-    """htv_t: one RF channel on the current CUDA device."""
+    """htv_t: one RF channel on one CUDA device (htv_init_on; device None = the current one)."""
 
-    def __init__(self, mode, sample_rate: int = 16_000_000, pixel_rate: int = 0, **overrides):
-        """pixel_rate != 0 and != sample_rate: the raster is built at pixel_rate and resampled (hacktv's
-        --pixelrate); that path has not run on a GPU yet."""
+    def __init__(self, mode, sample_rate: int = 16_000_000, pixel_rate: int = 0, device: int | None = None, **overrides):
+        """pixel_rate != 0 and != sample_rate: the raster is built at pixel_rate and resampled to
+        sample_rate in front of the video filter (hacktv's --pixelrate)."""
         self._L = lib()
         self.conf = mode if isinstance(mode, Config) else mode_config(mode, **overrides)
         h = C.c_void_p()
-        r = self._L.htv_init(C.byref(h), sample_rate, pixel_rate, C.byref(self.conf))
+        r = self._L.htv_init_on(C.byref(h), -1 if device is None else int(device), sample_rate, pixel_rate, C.byref(self.conf))
         if r != HTV_OK or not h:
             raise RuntimeError(f"htv_init failed ({r}): no CUDA device or unsupported configuration")
         self._h = h
+        self.device = self._L.htv_device(h)
         self.width = self._L.htv_samples_per_line(h)
         self.lines = self._L.htv_lines_per_frame(h)
         self.active_width = self._L.htv_active_width(h)

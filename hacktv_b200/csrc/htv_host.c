@@ -44,6 +44,8 @@ struct htv_t {
 
 	/* audio */
 	int64_t audio_have;           /* source pairs uploaded so far (absolute count) */
+	const int16_t *pend_pcm;      /* rest of a source block larger than one ring piece: uploaded before the next read */
+	size_t pend_n;
 	int16_t *zeros;
 
 	/* VBI overlays pulled from the source, kept until their line has been rendered */
@@ -92,6 +94,14 @@ size_t htv_config_size(void) { return(sizeof(htv_config_t)); }
 
 int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf)
 {
+	return(htv_init_on(out, -1, sample_rate, pixel_rate, conf));
+}
+
+int htv_device_count(void) { return(htv_dev_count()); }
+int htv_device(const htv_t *s) { return(s ? htv_dev_device(s->dev) : -1); }
+
+int htv_init_on(htv_t **out, int device, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf)
+{
 	htv_t *s;
 	char err[256];
 
@@ -121,11 +131,11 @@ int htv_init(htv_t **out, unsigned int sample_rate, unsigned int pixel_rate, con
 	}
 
 	/* No GPU, no encoder: there is deliberately no CPU fallback */
-	s->dev = htv_dev_create(s->tab, MAX_FRAME_SLOTS, err, sizeof(err));
+	s->dev = htv_dev_create(s->tab, MAX_FRAME_SLOTS, device, err, sizeof(err));
 	s->rdev = s->dev;
 	if(s->dev && s->rtab != s->tab)
 	{
-		s->rdev = htv_dev_create(s->rtab, MAX_FRAME_SLOTS, err, sizeof(err));
+		s->rdev = htv_dev_create(s->rtab, MAX_FRAME_SLOTS, htv_dev_device(s->dev), err, sizeof(err));
 		if(!s->rdev) { htv_dev_destroy(s->dev); s->dev = NULL; }
 	}
 	if(!s->dev)
@@ -222,31 +232,41 @@ static int64_t fetches_by(int64_t m, unsigned int rate)
 	return((int64_t) (((unsigned long long) (m + 1) * HTV_AUDIO_RATE) / rate));
 }
 
-/* Make source audio available on the device up to pair index `need` (exclusive) */
+/* Make source audio available on the device up to pair index `need` (exclusive). A source may hand
+ * over blocks of any size (ref video.c:3280): one larger than a quarter of the device ring goes up in
+ * ring-sized pieces, the remainder kept for the next calls - nothing is dropped. */
 static int pull_audio(htv_t *s, int64_t need, void *stream)
 {
+	const size_t piece = htv_dev_audio_ring_pairs() / 4;
 	while(s->audio_have < need)
 	{
-		const int16_t *pcm = NULL;
-		size_t n = 0;
+		const int16_t *pcm = s->pend_pcm;
+		size_t n = s->pend_n;
 		int r = HTV_OK;
 
-		if(s->av.read_audio)
+		if(!n)
 		{
-			r = s->av.read_audio(s->av.ctx, &pcm, &n);
-			if(r != HTV_OK) { s->av.read_audio = NULL; pcm = NULL; n = 0; }
+			pcm = NULL;
+			if(s->av.read_audio)
+			{
+				r = s->av.read_audio(s->av.ctx, &pcm, &n);
+				if(r != HTV_OK) { s->av.read_audio = NULL; pcm = NULL; n = 0; }
+			}
+			if(!pcm || n == 0)
+			{
+				/* no audio from the source: silence (ref video.c:3298-3303) */
+				pcm = s->zeros;
+				n = (size_t) (need - s->audio_have);
+				if(n > 65536) n = 65536;
+			}
 		}
-		if(!pcm || n == 0)
+		s->pend_pcm = NULL; s->pend_n = 0;
+		if(n > piece)
 		{
-			/* no audio from the source: silence (ref video.c:3298-3303) */
-			pcm = s->zeros;
-			n = (size_t) (need - s->audio_have);
-			if(n > 65536) n = 65536;
-		}
-		if(n > htv_dev_audio_ring_pairs() / 4)
-		{
-			/* hand it over in pieces the ring can hold */
-			n = htv_dev_audio_ring_pairs() / 4;
+			/* only what this render call needs now (at most a piece): the device ring holds about 32 s */
+			size_t take = (size_t) (need - s->audio_have);
+			if(take > piece) take = piece;
+			if(take < n) { s->pend_pcm = pcm + take * 2; s->pend_n = n - take; n = take; }
 		}
 		r = htv_dev_upload_audio(s->dev, s->audio_have, pcm, n, stream);
 		if(r != HTV_OK) return(r);
@@ -401,9 +421,14 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 
 	/* pictures and PCM go up on the encoder's own upload stream, ahead of the kernels queued on
 	 * `stream` for the previous chunk and beside the caller's device-to-host copies */
+	/* an error between uploads_begin and uploads_end still joins the upload stream(s) back in */
+#define UP_FAIL(code) do { htv_dev_uploads_end(s->dev, stream); if(s->rdev != s->dev) htv_dev_uploads_end(s->rdev, stream); return(code); } while(0)
 	up = htv_dev_uploads_begin(s->dev);
 	rup = s->rdev != s->dev ? htv_dev_uploads_begin(s->rdev) : up;
-	drop_overlays_before(s, L0);
+	/* lines L0 - 2 .. L0 - 1 are rasterised again as the left neighbours of this launch (video / pre-emphasis
+	 * filter halo, the resampler's lead, SECAM's chain start): a VBI waveform may reach the last sample of
+	 * its line (teletext's raised cosine does, ref teletext.c:1069), so their overlays are still needed */
+	drop_overlays_before(s, L0 - 2);
 
 	/* pictures: one pull per frame, at its first line (ref video.c:4873-4881) */
 	for(f = f0; f <= f1; f++)
@@ -431,14 +456,14 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 				{
 					fprintf(stderr, "hacktv_b200: source frame is %dx%d, the raster needs %dx%d\n",
 						fr.width, fr.height, rdp->active_width, rdp->active_lines);
-					return(HTV_ERROR);
+					UP_FAIL(HTV_ERROR);
 				}
 				if(!s->have_serial || fr.serial != s->cur_serial || s->cur_slot < 0)
 				{
 					s->cur_slot = s->next_slot;
 					s->next_slot = (s->next_slot + 1) % MAX_FRAME_SLOTS;
 					r = htv_dev_upload_frame(s->rdev, s->cur_slot, fr.framebuffer, rup);
-					if(r != HTV_OK) return(r);
+					if(r != HTV_OK) UP_FAIL(r);
 					s->cur_serial = fr.serial;
 					s->have_serial = 1;
 					nnew++;
@@ -458,13 +483,14 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	{
 		const int64_t m1 = (L0 + n) * (int64_t) s->W + dp->shift;
 		r = pull_audio(s, fetches_by(m1 - 1, s->tab->rate), up);
-		if(r != HTV_OK) return(r);
+		if(r != HTV_OK) UP_FAIL(r);
 	}
 	if(s->vbi_read || s->nov)
 	{
 		r = send_overlays(s, L0 + n);
-		if(r != HTV_OK) return(r);
+		if(r != HTV_OK) UP_FAIL(r);
 	}
+#undef UP_FAIL
 	r = htv_dev_uploads_end(s->dev, stream);
 	if(r != HTV_OK) return(r);
 	if(s->rdev != s->dev)
@@ -516,6 +542,12 @@ static int render_any(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, in
 {
 	int done = 0, r, cap;
 	if(!s || nlines < 0 || !d_out) return(HTV_ERROR);
+	/* the kernels write (and, for htv_render_add, read) d_out with 128-bit accesses */
+	if(((uintptr_t) d_out & 15) != 0)
+	{
+		fprintf(stderr, "hacktv_b200: the output buffer must be 16-byte aligned\n");
+		return(HTV_ERROR);
+	}
 	cap = max_chunk_lines(s);
 	if(s->pt_read && cap > PT_MAX_LINES) cap = PT_MAX_LINES;
 	while(done < nlines)
@@ -550,11 +582,22 @@ int htv_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *cuda_
  * stay short, large enough for full PCIe rate (measured on the B200 box: 4-48 MB within 10 %) */
 #define HOST_PIECE_BYTES (8u << 20)
 
+/* On an error in the middle of the pipeline both streams are drained before returning, so no
+ * asynchronous copy is still writing into the caller's buffer afterwards. */
+static int host_fail(htv_t *s, int r)
+{
+	if(s->st_copy) htv_dev_sync(s->dev, s->st_copy);
+	if(s->st_compute) htv_dev_sync(s->dev, s->st_compute);
+	return(r);
+}
+
 int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 {
-	const size_t line_bytes = (size_t) s->W * s->bps;
-	int piece = (int) (HOST_PIECE_BYTES / line_bytes), done = 0, p = 0, r, i;
+	size_t line_bytes;
+	int piece, done = 0, p = 0, r, i;
 	if(!s || nlines < 0 || !h_out) return(HTV_ERROR);
+	line_bytes = (size_t) s->W * s->bps;
+	piece = (int) (HOST_PIECE_BYTES / line_bytes);
 	if(piece < 1) piece = 1;
 	if(piece > nlines) piece = nlines > 0 ? nlines : 1;
 	if((size_t) piece * line_bytes > s->d_stage_bytes)
@@ -569,47 +612,26 @@ int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 	}
 	if(!s->st_compute)
 	{
-		s->st_compute = htv_dev_stream_new();
-		s->st_copy = htv_dev_stream_new();
-		for(i = 0; i < 2; i++) { s->ev_rendered[i] = htv_dev_event_new(); s->ev_copied[i] = htv_dev_event_new(); }
+		s->st_compute = htv_dev_stream_new(s->dev);
+		s->st_copy = htv_dev_stream_new(s->dev);
+		for(i = 0; i < 2; i++) { s->ev_rendered[i] = htv_dev_event_new(s->dev); s->ev_copied[i] = htv_dev_event_new(s->dev); }
 	}
-	void *dbg[64][4];
-	const int debug = getenv("HTV_DEBUG_PIPE") != NULL;
-	void *dbg0 = NULL;
-	if(debug) { dbg0 = htv_dev_event_new_timed(); htv_dev_event_record(dbg0, s->st_compute); }
 	for(; done < nlines; done += piece, p++)
 	{
 		const int n = nlines - done < piece ? nlines - done : piece, b = p & 1;
 		/* the staging buffer must have been copied out before it is rendered into again */
-		if(p >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(r);
-		if(debug && p < 64) { for(i = 0; i < 4; i++) dbg[p][i] = htv_dev_event_new_timed(); htv_dev_event_record(dbg[p][0], s->st_compute); }
+		if(p >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(host_fail(s, r));
 		r = htv_render(s, n, s->d_stage[b], NULL, s->st_compute);
-		if(r != HTV_OK) return(r);
-		if(debug && p < 64) htv_dev_event_record(dbg[p][1], s->st_compute);
-		if((r = htv_dev_event_record(s->ev_rendered[b], s->st_compute)) != HTV_OK) return(r);
-		if((r = htv_dev_stream_wait(s->st_copy, s->ev_rendered[b])) != HTV_OK) return(r);
-		if(debug && p < 64) htv_dev_event_record(dbg[p][2], s->st_copy);
+		if(r != HTV_OK) return(host_fail(s, r));
+		if((r = htv_dev_event_record(s->ev_rendered[b], s->st_compute)) != HTV_OK) return(host_fail(s, r));
+		if((r = htv_dev_stream_wait(s->st_copy, s->ev_rendered[b])) != HTV_OK) return(host_fail(s, r));
 		r = htv_dev_memcpy_d2h(s->dev, (char *) h_out + (size_t) done * line_bytes, s->d_stage[b], (size_t) n * line_bytes, s->st_copy);
-		if(r != HTV_OK) return(r);
-		if(debug && p < 64) htv_dev_event_record(dbg[p][3], s->st_copy);
-		if((r = htv_dev_event_record(s->ev_copied[b], s->st_copy)) != HTV_OK) return(r);
-	}
-	if(debug)
-	{
-		int q;
-		htv_dev_sync(s->dev, s->st_copy);
-		for(q = 0; q < p && q < 64; q++)
-		{
-			fprintf(stderr, "piece %d: render %.3f..%.3f ms, copy %.3f..%.3f ms\n", q,
-				htv_dev_event_elapsed(dbg0, dbg[q][0]), htv_dev_event_elapsed(dbg0, dbg[q][1]),
-				htv_dev_event_elapsed(dbg0, dbg[q][2]), htv_dev_event_elapsed(dbg0, dbg[q][3]));
-			for(i = 0; i < 4; i++) htv_dev_event_free(dbg[q][i]);
-		}
-		htv_dev_event_free(dbg0);
+		if(r != HTV_OK) return(host_fail(s, r));
+		if((r = htv_dev_event_record(s->ev_copied[b], s->st_copy)) != HTV_OK) return(host_fail(s, r));
 	}
 	if(nsamples) *nsamples = (size_t) nlines * s->W;
 	r = htv_dev_sync(s->dev, s->st_copy);
-	if(r != HTV_OK) return(r);
+	if(r != HTV_OK) return(host_fail(s, r));
 	return(htv_dev_sync(s->dev, s->st_compute));
 }
 

@@ -127,7 +127,9 @@ typedef struct htv_dev_t htv_dev_t;
 
 
 extern int htv_dev_count(void);
-extern htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen);
+/* device: CUDA ordinal, or -1 for the calling thread's current device */
+extern htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, int device, char *err, size_t errlen);
+extern int htv_dev_device(const htv_dev_t *d);
 extern void htv_dev_destroy(htv_dev_t *d);
 /* frame slot <- host RGB (active_width x active_lines), async on stream */
 extern void *htv_dev_uploads_begin(htv_dev_t *d);
@@ -148,7 +150,7 @@ extern int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t
 /* --pixelrate: d = sample-rate context, r = raster context at the pixel rate (htv_kernels.cu) */
 extern int htv_dev_render_lines_rs(htv_dev_t *d, htv_dev_t *r, int64_t line0, int nlines, int16_t *d_out,
 	const int16_t *d_acc, int acc_lines, void *stream);
-extern void *htv_dev_event_new_timed(void);
+extern void *htv_dev_event_new_timed(htv_dev_t *d);
 extern float htv_dev_event_elapsed(void *e0, void *e1);
 extern int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalues, void *stream);
 extern int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream);
@@ -163,9 +165,9 @@ extern void htv_dev_set_timing(htv_dev_t *d, int on);
 extern float htv_dev_last_line_ms(htv_dev_t *d);
 extern int htv_dev_last_line_count(const htv_dev_t *d);
 extern size_t htv_dev_audio_ring_pairs(void);
-extern void *htv_dev_stream_new(void);
+extern void *htv_dev_stream_new(htv_dev_t *d);
 extern void htv_dev_stream_free(void *s);
-extern void *htv_dev_event_new(void);
+extern void *htv_dev_event_new(htv_dev_t *d);
 extern void htv_dev_event_free(void *e);
 extern int htv_dev_event_record(void *e, void *stream);
 extern int htv_dev_stream_wait(void *stream, void *e);

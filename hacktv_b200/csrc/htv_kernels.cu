@@ -13,8 +13,9 @@
 //     direct evaluation of the <= 6 overlapping symbols per sample          ref nicam728.c:140-411
 //   - frequency-offset mixer / IQ swap                  ref video.c:3466-3515
 //
-// No tensor cores: the path has no dense contraction. The output is written once,
-// with 128-bit streaming stores; all tables are L2/L1/shared resident.
+// The one dense contraction of the path, the 51-tap video filter, runs on the tensor cores as an exact
+// int8 byte-split contraction (k_mod_mma, htv_mma_fir.h). The output is written once, with 128-bit
+// streaming stores; all tables are L2/L1/shared resident.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,6 +39,19 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { \
 	fprintf(stderr, "hacktv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return(HTV_ERROR); } } while(0)
+
+// Every entry point that touches an encoder's device state runs with that encoder's device current
+// and leaves the calling thread's current device as it found it: a host (hacktv itself, or any C
+// program) can drive one encoder per GPU from one process, one thread per encoder or all from one.
+struct DevGuard {
+	int prev;
+	bool switched;
+	explicit DevGuard(int device) : prev(-1), switched(false)
+	{
+		if(cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+	}
+	~DevGuard() { if(switched) cudaSetDevice(prev); }
+};
 
 struct DevTables {
 	const uint32_t *mma_atab;         // tap operand of the tensor-core video filter, fragment order (htv_mma_fir.h)
@@ -107,7 +121,6 @@ struct SecScratch {
 };
 
 #define MAPBUFS 16
-#define HTV_SIDE_EVENTS 32
 #define HTV_MAX_ALLOCS 128            // device tables owned by one encoder (about 50 for SECAM-L with AM + NICAM)
 #define HTV_OV_CAP 2048                // VBI overlay lines per launch sequence
 
@@ -145,12 +158,6 @@ struct htv_dev_t {
 	unsigned chunk_i;
 	cudaEvent_t ev_in, ev_audio;
 	int side_armed;
-	// HTV_SIDE=split (opt-in, not yet run on a GPU): the NICAM pre-pass on a second side stream beside the
-	// FM one, and the sound-carrier descriptors launched per sub-batch, so the first modulator launch
-	// waits for its own 8 192 descriptors instead of the whole call's
-	int side_split;
-	cudaStream_t side2;
-	cudaEvent_t ev_nic, ev_sub[HTV_SIDE_EVENTS];
 	int ev_pending;
 	int line_threads;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
@@ -2349,7 +2356,7 @@ extern "C" int htv_dev_count(void)
 
 extern "C" size_t htv_dev_audio_ring_pairs(void) { return(RA); }
 
-extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, char *err, size_t errlen)
+extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame_slots, int device, char *err, size_t errlen)
 {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -2358,9 +2365,16 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		snprintf(err, errlen, "no CUDA device available (%s)", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
 		return(NULL);
 	}
+	if(device >= n)
+	{
+		snprintf(err, errlen, "CUDA device %d requested, %d present", device, n);
+		return(NULL);
+	}
+	if(device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;    // the calling thread's current device
+	DevGuard guard(device);
 	htv_dev_t *d = (htv_dev_t *) calloc(1, sizeof(htv_dev_t));
 	if(!d) { snprintf(err, errlen, "out of memory"); return(NULL); }
-	cudaGetDevice(&d->device);
+	d->device = device;
 	d->dp = t->dp;
 	const htv_dparams_t &dp = d->dp;
 	DevTables &dt = d->dt;
@@ -2506,14 +2520,13 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	}
 	if(!secam && !dp.have_fmv && dp.vf_type && !t->raster_only)
 	{
-		// the video filter on the tensor cores (k_mod_mma): the default for the line widths it has been
-		// validated at on a B200 (1024 = 16 Msps, 1280 = 20 Msps: BASELINE configs 2 and 5). HTV_FIR=mma
-		// takes it for every width - other multiples of 128 through the same contiguous planes, the rest
-		// (NTSC 858) through the pitched plane layout (htv_mma_fir.h); HTV_FIR=scalar turns it off
+		// the video filter on the tensor cores (k_mod_mma), the default for every line width: multiples of
+		// 128 through the contiguous byte planes, the rest (NTSC 858, 864, ...) through the pitched plane
+		// layout (htv_mma_fir.h) - both validated against the scalar filter and the oracle on a B200
+		// (tests/test_gpu_zz_mma_fir.py). HTV_FIR=scalar selects the scalar kernels (A/B runs, tests)
 		const char *sel = getenv("HTV_FIR");
-		const bool forced = sel && !strcmp(sel, "mma");
-		const bool want_mma = sel ? forced : HTV_FIR_DEFAULT_MMA;
-		if(want_mma && (W == 1024 || W == 1280 || forced))
+		const bool want_mma = sel ? strcmp(sel, "scalar") != 0 : HTV_FIR_DEFAULT_MMA;
+		if(want_mma)
 		{
 			int nsm = 148;
 			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
@@ -2572,16 +2585,6 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
-	{
-		const char *sd = getenv("HTV_SIDE");
-		d->side_split = sd && !strcmp(sd, "split") && !dp.have_fmv;
-		if(d->side_split)
-		{
-			cudaStreamCreateWithFlags(&d->side2, cudaStreamNonBlocking);
-			cudaEventCreateWithFlags(&d->ev_nic, cudaEventDisableTiming);
-			for(int i = 0; i < HTV_SIDE_EVENTS; i++) cudaEventCreateWithFlags(&d->ev_sub[i], cudaEventDisableTiming);
-		}
-	}
 	// the table build and the memsets above ran on the default stream, which the (non-blocking)
 	// streams the encoder works on do not wait for
 	if(cudaDeviceSynchronize() != cudaSuccess)
@@ -2596,7 +2599,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 extern "C" void htv_dev_destroy(htv_dev_t *d)
 {
 	if(!d) return;
-	cudaSetDevice(d->device);
+	DevGuard guard(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
 	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
@@ -2609,9 +2612,6 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
-	if(d->side2) cudaStreamDestroy(d->side2);
-	if(d->ev_nic) cudaEventDestroy(d->ev_nic);
-	for(int i = 0; i < HTV_SIDE_EVENTS; i++) if(d->ev_sub[i]) cudaEventDestroy(d->ev_sub[i]);
 	if(d->up) cudaStreamDestroy(d->up);
 	if(d->ev_up) cudaEventDestroy(d->ev_up);
 	if(d->ev_chunk[0]) cudaEventDestroy(d->ev_chunk[0]);
@@ -2623,12 +2623,14 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 // chunk's kernels, then run beside chunk c-1's. The compute stream joins at htv_dev_uploads_end.
 extern "C" void *htv_dev_uploads_begin(htv_dev_t *d)
 {
+	DevGuard guard(d->device);
 	cudaStreamWaitEvent(d->up, d->ev_chunk[d->chunk_i & 1], 0);
 	return((void *) d->up);
 }
 
 extern "C" int htv_dev_uploads_end(htv_dev_t *d, void *stream)
 {
+	DevGuard guard(d->device);
 	CK(cudaEventRecord(d->ev_up, d->up));
 	CK(cudaStreamWaitEvent((cudaStream_t) stream, d->ev_up, 0));
 	return(HTV_OK);
@@ -2641,6 +2643,7 @@ extern "C" int htv_dev_overlay_capacity(void) { return(HTV_OV_CAP); }
 extern "C" int htv_dev_set_overlays(htv_dev_t *d, int n, const long long *line, const int *from, const int *to,
 	const int *value, const int16_t *const *add)
 {
+	DevGuard guard(d->device);
 	const int W = d->dp.W;
 	if(n > HTV_OV_CAP) return(HTV_ERROR);
 	if(n > 0 && !d->h_ov_line)
@@ -2678,6 +2681,7 @@ extern "C" int htv_dev_set_overlays(htv_dev_t *d, int n, const long long *line, 
 
 extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream)
 {
+	DevGuard guard(d->device);
 	if(slot < 0 || slot >= d->max_slots) return(HTV_ERROR);
 	CK(cudaMemcpyAsync(d->d_frames + (size_t) slot * d->frame_pixels, rgb, d->frame_pixels * 4,
 		cudaMemcpyHostToDevice, (cudaStream_t) stream));
@@ -2686,6 +2690,7 @@ extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb,
 
 extern "C" int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream)
 {
+	DevGuard guard(d->device);
 	if(n > d->frame_map_cap) return(HTV_ERROR);
 	const int b = d->map_i;
 	d->map_i = (b + 1) % MAPBUFS;
@@ -2701,6 +2706,7 @@ extern "C" int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame,
 
 extern "C" int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm, size_t npairs, void *stream)
 {
+	DevGuard guard(d->device);
 	while(npairs)
 	{
 		size_t at = (size_t) (j0 & (RA - 1)), n = npairs;
@@ -2713,6 +2719,7 @@ extern "C" int htv_dev_upload_audio(htv_dev_t *d, int64_t j0, const int16_t *pcm
 
 extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void *stream)
 {
+	DevGuard guard(d->device);
 	const htv_dparams_t &dp = d->dp;
 	if(m1 <= m0) return(HTV_OK);
 	// everything the caller queued so far (PCM uploads) precedes the pre-pass, which runs on the
@@ -2745,12 +2752,6 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	}
 	if(dp.have_nicam)
 	{
-		if(d->side_split)
-		{
-			// independent of the FM chain: its own stream, joined into `side` below
-			CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));
-			st = d->side2;
-		}
 		const int64_t s_lo = (int64_t) (((unsigned long long) (m0 > dp.nicam_ntaps ? m0 - dp.nicam_ntaps : 0) * dp.nicam_D) / dp.nicam_F);
 		const int64_t s_hi = (int64_t) (((unsigned long long) (m1 - 1) * dp.nicam_D) / dp.nicam_F);
 		int64_t k_lo = s_lo / 364, k_hi = s_hi / 364;
@@ -2760,11 +2761,6 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
-		if(d->side_split)
-		{
-			CK(cudaEventRecord(d->ev_nic, d->side2));
-			CK(cudaStreamWaitEvent(d->side, d->ev_nic, 0));             // the descriptors (on `side`) need both chains
-		}
 	}
 	CK(cudaGetLastError());
 	return(HTV_OK);
@@ -2773,6 +2769,7 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int16_t *d_out,
 	const int16_t *d_acc, int acc_lines, void *stream)
 {
+	DevGuard guard(d->device);
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
 	// FM video with a pre-emphasis filter: the modulator also integrates the pipeline's fill line
@@ -2795,27 +2792,9 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		CK(cudaEventRecord(d->ev_in, st));
 		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 	}
-	if(d->side_split)
-	{
-		// one descriptor launch and one event per sub-batch; a call with more than HTV_SIDE_EVENTS
-		// sub-batches reuses events, which only makes the later waits conservative
-		int i = 0;
-		for(int done = 0; done < nlines; done += d->sub_lines, i++)
-		{
-			const int n = nlines - done < d->sub_lines ? nlines - done : d->sub_lines;
-			LineDescs lds = { ld.r, ld.a + done };
-			k_line_desc_a<<<(n + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, lds, line0 + done, n);
-			CK(cudaEventRecord(d->ev_sub[i % HTV_SIDE_EVENTS], d->side));
-			d->launches++;
-		}
-		d->launches++;
-	}
-	else
-	{
 	k_line_desc_a<<<(nlines + fm_skip + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0 - fm_skip, nlines + fm_skip);
 	CK(cudaEventRecord(d->ev_audio, d->side));
 	d->launches += 2;
-	}
 	d->side_armed = 0;
 	bool joined = false;
 	for(int done = 0; done < nlines; done += d->sub_lines)
@@ -2887,8 +2866,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride, d->plane_pitch);
 			d->launches++;
 		}
-		if(d->side_split) CK(cudaStreamWaitEvent(st, d->ev_sub[(done / d->sub_lines) % HTV_SIDE_EVENTS], 0));
-		else if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
+		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
 		if(d->dp.have_fmv)
 		{
@@ -2937,8 +2915,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 // periods because Ws D = Wp I). Row b of `comp` is raster line first - 1 + b of the launch; row b
 // of the output is resampled line first + b, which reaches back into comp rows b and b + 1.
 // Output goes wherever the modulator of this context reads: byte planes, int32 or int16 stream.
-// NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): htv_init only takes this
-// path when pixel_rate != sample_rate, tests are opt-in (HTV_TEST_UNVALIDATED=1).
+// Parity: tests/test_gpu_zz_pixelrate.py against the oracle (itself pinned to the reference's --pixelrate).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(384)
 k_resample(const int16_t *comp, int Wp, int Ws, int I, int D, int A, const int16_t *taps,
@@ -2972,6 +2949,7 @@ k_resample(const int16_t *comp, int Wp, int Ws, int I, int D, int A, const int16
 extern "C" int htv_dev_render_lines_rs(htv_dev_t *d, htv_dev_t *r, int64_t line0, int nlines, int16_t *d_out,
 	const int16_t *d_acc, int acc_lines, void *stream)
 {
+	DevGuard guard(d->device);
 	cudaStream_t st = (cudaStream_t) stream;
 	if(nlines <= 0) return(HTV_OK);
 	if(!d->d_rs_taps || d->plane_pitch || d->dp.have_fmv || r->dp.colour_mode == HTV_SECAM || (d->dp.W & 3)) return(HTV_ERROR);
@@ -3080,6 +3058,12 @@ extern "C" int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalu
 	if((((uintptr_t) d_acc) | ((uintptr_t) d_in)) & 15) return(HTV_ERROR);
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
+	{
+		// run where the accumulator lives (d_in may be peer memory)
+		cudaPointerAttributes pa;
+		if(cudaPointerGetAttributes(&pa, d_acc) == cudaSuccess && pa.type == cudaMemoryTypeDevice) dev = pa.device;
+	}
+	DevGuard guard(dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	size_t blocks = (nvalues / 8 + 255) / 256;
 	if(blocks > (size_t) nsm * 8) blocks = (size_t) nsm * 8;
@@ -3091,40 +3075,46 @@ extern "C" int htv_dev_mix_add(int16_t *d_acc, const int16_t *d_in, size_t nvalu
 
 extern "C" int htv_dev_sync(htv_dev_t *d, void *stream)
 {
+	DevGuard guard(d->device);
 	CK(cudaStreamSynchronize((cudaStream_t) stream));
 	return(HTV_OK);
 }
 
 extern "C" int htv_dev_memcpy_d2h(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream)
 {
+	DevGuard guard(d->device);
 	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
 	return(HTV_OK);
 }
 
 extern "C" int htv_dev_memcpy_h2d(htv_dev_t *d, void *dst, const void *src, size_t bytes, void *stream)
 {
+	DevGuard guard(d->device);
 	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
 	return(HTV_OK);
 }
 
 // thin stream / event wrappers for the host layer's copy-compute pipeline
-extern "C" void *htv_dev_stream_new(void) { cudaStream_t s = NULL; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); return((void *) s); }
+extern "C" void *htv_dev_stream_new(htv_dev_t *d) { DevGuard guard(d->device); cudaStream_t s = NULL; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); return((void *) s); }
 extern "C" void htv_dev_stream_free(void *s) { if(s) cudaStreamDestroy((cudaStream_t) s); }
-extern "C" void *htv_dev_event_new(void) { cudaEvent_t e = NULL; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return((void *) e); }
-extern "C" void *htv_dev_event_new_timed(void) { cudaEvent_t e = NULL; cudaEventCreate(&e); return((void *) e); }
+extern "C" void *htv_dev_event_new(htv_dev_t *d) { DevGuard guard(d->device); cudaEvent_t e = NULL; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return((void *) e); }
+extern "C" void *htv_dev_event_new_timed(htv_dev_t *d) { DevGuard guard(d->device); cudaEvent_t e = NULL; cudaEventCreate(&e); return((void *) e); }
 extern "C" float htv_dev_event_elapsed(void *e0, void *e1) { float ms = -1; cudaEventSynchronize((cudaEvent_t) e1); cudaEventElapsedTime(&ms, (cudaEvent_t) e0, (cudaEvent_t) e1); return(ms); }
 extern "C" void htv_dev_event_free(void *e) { if(e) cudaEventDestroy((cudaEvent_t) e); }
 extern "C" int htv_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return(HTV_OK); }
 extern "C" int htv_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return(HTV_OK); }
 
+extern "C" int htv_dev_device(const htv_dev_t *d) { return(d->device); }
+
 extern "C" void *htv_dev_alloc(htv_dev_t *d, size_t bytes)
 {
+	DevGuard guard(d->device);
 	void *p = NULL;
 	if(cudaMalloc(&p, bytes) != cudaSuccess) return(NULL);
 	return(p);
 }
 
-extern "C" void htv_dev_free(htv_dev_t *d, void *p) { if(p) cudaFree(p); }
+extern "C" void htv_dev_free(htv_dev_t *d, void *p) { DevGuard guard(d->device); if(p) cudaFree(p); }
 
 extern "C" void *htv_dev_alloc_pinned(size_t bytes)
 {
@@ -3142,6 +3132,7 @@ extern "C" int htv_dev_last_line_count(const htv_dev_t *d) { return(d->last_mod_
 
 extern "C" float htv_dev_last_line_ms(htv_dev_t *d)
 {
+	DevGuard guard(d->device);
 	float ms = 0;
 	if(!d->ev_pending) return(0);
 	if(cudaEventSynchronize(d->ev1) != cudaSuccess) return(0);

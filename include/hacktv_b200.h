@@ -177,6 +177,16 @@ typedef struct {
 } htv_line_t;
 
 extern int htv_init(htv_t **s, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf);
+/* Device placement (one RF channel per GPU, channel c -> device c mod N). htv_init
+ * binds the encoder to the calling thread's current CUDA device; htv_init_on to CUDA device `device`
+ * (0 .. htv_device_count() - 1; -1 = current). Every later call on the encoder runs on that device
+ * whatever the calling thread's current device is, and leaves the caller's current device unchanged: a
+ * C host drives N encoders on N GPUs from one process, from one thread or one thread per encoder (an
+ * encoder itself is not re-entrant: one call at a time per htv_t). Device pointers handed to
+ * htv_render / htv_render_add must belong to the encoder's device (or be peer-accessible from it). */
+extern int htv_init_on(htv_t **s, int device, unsigned int sample_rate, unsigned int pixel_rate, const htv_config_t *conf);
+extern int htv_device_count(void);
+extern int htv_device(const htv_t *s);
 extern void htv_free(htv_t *s);
 extern void htv_info(htv_t *s);
 extern size_t htv_get_framebuffer_length(htv_t *s);
@@ -216,7 +226,8 @@ extern htv_line_t *htv_next_line(htv_t *s);
  * htv_render_host: `h_out` is HOST memory; the call uploads what the batch
  *   needs, renders, copies the result back and returns when it is there.
  * Both return HTV_OK or an error; *nsamples (may be NULL) receives the number
- * of samples produced. Output layout is what the reference's file sink writes
+ * of samples produced. `d_out` must be 16-byte aligned (the kernels store, and htv_render_add
+ * also loads, 128 bits at a time); a misaligned pointer is refused with HTV_ERROR. Output layout is what the reference's file sink writes
  * (rf_file.c:97-116, 226-233): int16 I,Q interleaved for complex modes, int16
  * I only for real modes. */
 extern int htv_render(htv_t *s, int nlines, int16_t *d_out, size_t *nsamples, void *cuda_stream);

@@ -43,6 +43,8 @@ static int _find(vid_t *s)
 	return(-1);
 }
 
+static void _translate(htv_config_t *h, const vid_config_t *c);
+
 /* Can the accelerated path render this configuration bit for bit? */
 static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigned int pixel_rate)
 {
@@ -50,7 +52,18 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 	if(c->type != VID_RASTER_625 && c->type != VID_RASTER_525) return(0);
 	if(c->modulation == VID_FM && c->fm_energy_dispersal != 0) return(0);
 	if(c->colour_mode != VID_NONE && c->colour_mode != VID_PAL && c->colour_mode != VID_NTSC && c->colour_mode != VID_SECAM) return(0);
-	if(pixel_rate && pixel_rate != sample_rate) return(0);
+	/* --pixelrate: PAL / NTSC / mono through the device resampler; SECAM and FM video with a resampler,
+	 * and rate pairs whose line width would vary, stay on the stock encoder */
+	if(pixel_rate && pixel_rate != sample_rate)
+	{
+		htv_config_t hc;
+		htv_tables_t *t;
+		if(c->colour_mode == VID_SECAM || c->modulation == VID_FM) return(0);
+		_translate(&hc, c);
+		t = htv_tables_create2(&hc, sample_rate, pixel_rate);          /* host only: NULL when out of scope */
+		if(!t) return(0);
+		htv_tables_free(t);
+	}
 	if(c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
 	   c->d11 || c->systercnr || c->acp || c->vits || c->cc608 || c->sis || c->eurocrypt) return(0);
 	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);

@@ -4,6 +4,7 @@ the stock build: same command line, same bytes (within the +-1 LSB the sound car
 Both binaries are prebuilt by `make -C oracle ref dropin` and travel to the GPU box."""
 import os
 import subprocess
+import tempfile
 
 import numpy as np
 import pytest
@@ -17,9 +18,15 @@ pytestmark = [pytest.mark.gpu,
 
 
 def _run(binary, args, nbytes):
-    cmd = f"timeout 120 {binary} {args} -o - test 2>/dev/null | head -c {nbytes}"
-    out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=180).stdout
+    """Also proves WHICH encoder ran: the adapter's vid_info prints `Encoder: hacktv_b200 ...` (integration/
+    video_b200.c), the stock video.c does not - a bug in the adapter's _accelerated() that quietly sent a
+    configuration to the renamed stock encoder would otherwise compare the reference with itself."""
+    with tempfile.NamedTemporaryFile("r", suffix=".stderr") as err:
+        cmd = f"timeout 120 {binary} {args} -o - test 2>{err.name} | head -c {nbytes}"
+        out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=180).stdout
+        log = err.read()
     assert len(out) == nbytes, f"{binary}: got {len(out)} of {nbytes} bytes"
+    assert ("Encoder: hacktv_b200" in log) == (binary == DROPIN), f"{binary} {args}: wrong encoder ran\n{log[-500:]}"
     return np.frombuffer(out, dtype=np.int16)
 
 
@@ -36,6 +43,9 @@ def _run(binary, args, nbytes):
     ("-m pal -s 16000000 --wss 14:9-letterbox", 2, 0),
     ("-m i -s 16000000 --filter --noaudio --vitc --wss 4:3", 4, 0),
     ("-m m -s 13500000 --filter --vitc", 4, 1),
+    # --pixelrate: raster at 13.5 MHz, the reference's polyphase resampler on the device, then the usual path
+    ("-m i -s 16000000 --pixelrate 13500000 --filter --noaudio", 4, 0),
+    ("-m i -s 16000000 --pixelrate 13500000 --filter", 4, 1),
 ])
 def test_same_cli_same_bytes(args, per, tol):
     w = 858 if "13500000" in args else (1280 if "20000000" in args else 1024)
@@ -50,11 +60,14 @@ def test_readme_two_channel_pipeline():
     """README:89-90: one hacktv piped into another through --passthru; both stages on the GPU path
     against both stages stock."""
     def pipeline(binary, nbytes):
-        cmd = (f"timeout 120 {binary} -s 20000000 --offset -6750000 --level 0.5 --filter -o - test 2>/dev/null | "
-               f"timeout 120 {binary} -s 20000000 --offset 1250000 --level 0.5 --passthru /dev/stdin --filter -o - test "
-               f"2>/dev/null | head -c {nbytes}")
-        out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=300).stdout
+        with tempfile.NamedTemporaryFile("r", suffix=".stderr") as err:
+            cmd = (f"timeout 120 {binary} -s 20000000 --offset -6750000 --level 0.5 --filter -o - test 2>>{err.name} | "
+                   f"timeout 120 {binary} -s 20000000 --offset 1250000 --level 0.5 --passthru /dev/stdin --filter -o - test "
+                   f"2>>{err.name} | head -c {nbytes}")
+            out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=300).stdout
+            log = err.read()
         assert len(out) == nbytes, f"{binary}: got {len(out)} of {nbytes} bytes"
+        assert log.count("Encoder: hacktv_b200") == (2 if binary == DROPIN else 0)
         return np.frombuffer(out, dtype=np.int16)
     n = 700 * 1280 * 4
     a = pipeline(DROPIN, n)

@@ -235,3 +235,30 @@ def test_fm_video_with_sound_carrier(built, mode, rate, nlines, kw):
     df = np.angle(g[:, 1:] * np.conj(g[:, :-1])) - np.angle(w[:, 1:] * np.conj(w[:, :-1]))
     df = (df + np.pi) % (2 * np.pi) - np.pi
     assert (np.abs(df) > 0.6 * step).mean() < 0.005, (np.abs(df) > 0.6 * step).mean()
+
+
+def test_audio_block_longer_than_a_ring_piece_is_not_dropped(built):
+    """a source may hand over its PCM in one block of any size (ref video.c:3280). A block longer
+    than a quarter of the device ring (262 144 pairs = 8.2 s) goes up in pieces across render calls; nothing
+    of it is lost. 9.4 s of noise in ONE block vs the same audio in 8 192-pair blocks, compared behind
+    the 8.2 s mark; the stream in between stays on the device."""
+    import torch
+    H = built
+    rng = np.random.default_rng(5)
+    audio = rng.integers(-20000, 20000, size=(300000, 2), dtype=np.int16)
+    conf = H.mode_config("i", vfilter=True)
+    outs = []
+    for block in (0, 8192):
+        enc = H.Encoder(conf, 16000000)
+        enc.set_source(None, audio, audio_block=block)
+        scratch = torch.empty(40000 * enc.width * 2, dtype=torch.int16, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            enc.render(40000, scratch.data_ptr(), st)            # 7.68 s
+        enc.render(12000, scratch.data_ptr(), st)                # .. 8.45 s: the tail of the first piece and beyond
+        torch.cuda.synchronize()
+        outs.append(scratch[: 12000 * enc.width * 2].cpu().numpy().copy())
+        outs.append(enc.render_host(3000))                       # 9.0 s .. 9.2 s: well into the second piece
+        enc.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+    assert np.count_nonzero(outs[1]) > 1000

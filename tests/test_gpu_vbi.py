@@ -76,3 +76,23 @@ def test_overlay_chunking_and_per_frame_pull(built):
     changed = np.nonzero((whole != base).reshape(2600, W2).any(axis=1))[0]
     frames = set((changed // 625).tolist())
     assert frames == {0, 2, 4}, frames                          # frames 1, 3, 5 (1-based) carry overlays
+
+
+def test_overlay_reaching_the_line_end_survives_a_call_boundary(built):
+    """a VBI waveform may run up to the last sample of its line (teletext's raised cosine does, ref
+    teletext.c:1069); with the video filter on it then reaches into the first 25 samples of the NEXT line. A
+    render call that starts right behind such a line re-rasterises it as its left neighbour and needs its
+    overlay again."""
+    H = built
+    for mode, kw in (("i", dict(vfilter=True, noaudio=True)), ("pal-fm", dict(vfilter=True, noaudio=True))):
+        rate = 16000000 if mode == "i" else 20000000
+        conf = H.mode_config(mode, **kw)
+        a = H.Encoder(conf, rate); a.open_test_source()
+        W = a.width
+        add = np.zeros(W, dtype=np.int16); add[W - 300:] = 7000    # non-zero up to sample W - 1
+        ov = [(20, add, (0, 0, 0)), (21, add, (0, 0, 0)), (333, add, (0, 0, 0))]
+        a.set_vbi_lines(ov)
+        whole = a.render_host(700); a.close()
+        b = H.Encoder(conf, rate); b.open_test_source(); b.set_vbi_lines(ov)
+        parts = np.concatenate([b.render_host(n) for n in (20, 1, 1, 311, 367)]); b.close()   # boundaries right behind lines 20, 21, 333
+        assert np.array_equal(whole, parts), f"{mode}: {np.count_nonzero(whole != parts)} values differ"

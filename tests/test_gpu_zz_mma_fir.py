@@ -1,4 +1,4 @@
-"""The tensor-core video filter (k_mod_mma, the default where 128 | W and a video filter is on)
+"""The tensor-core video filter (k_mod_mma, the default whenever a video filter is on - any line width)
 against the scalar TMA modulator it replaces (HTV_FIR=scalar) - bit for bit, the FIR is exact
 integer work either way (ref fir.c:564-615) - and against the oracle. HTV_FIR is read when an
 encoder is created, so both variants run in one process."""
@@ -10,12 +10,6 @@ import pytest
 import orc
 
 pytestmark = pytest.mark.gpu
-
-# Code paths written after round 1's GPU minutes were spent have never run on a GPU. Their tests are kept out of
-# the default run (an unvalidated kernel could also hang it) and are the first thing to run with GPU time again:
-#   HTV_TEST_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_mma_fir.py -m gpu
-unvalidated = pytest.mark.skipif(not os.environ.get("HTV_TEST_UNVALIDATED"),
-                                 reason="not yet run on a GPU; set HTV_TEST_UNVALIDATED=1")
 
 
 def _render(H, sel, mode, rate, nlines, frames=None, audio=None, **kw):
@@ -104,16 +98,14 @@ def test_chunking_is_invisible_with_the_mma_filter(built):
     assert np.array_equal(whole, parts)
 
 
-@unvalidated
 def test_other_line_widths_take_the_same_path(built):
-    """18 Msps: W = 1152 = 9 tiles on 9 warps (288 threads) - the tile/warp split is generic (HTV_FIR=mma)."""
+    """18 Msps: W = 1152 = 9 tiles on 9 warps (288 threads) - the tile/warp split is generic."""
     H = built
     a = _render(H, "scalar", "i", 18000000, 700, vfilter=True, noaudio=True)
     b = _render(H, "mma", "i", 18000000, 700, vfilter=True, noaudio=True)
     assert np.array_equal(a, b)
 
 
-@unvalidated
 @pytest.mark.parametrize("mode,rate,nlines,kw", [
     ("m", 13500000, 1100, dict(vfilter=True, noaudio=True)),        # BASELINE config 3 geometry: W = 858
     ("m", 13500000, 1100, dict(vfilter=True)),
