@@ -22,6 +22,7 @@ typedef struct { int32_t i, q; } htv_c32_t;
 #define HTV_LIM_W      21      /* limiter width, ref video.c:4447 */
 #define HTV_AFIR_N     65      /* audio FIR taps, ref video.c:2118 */
 #define HTV_J17_N      83      /* ref nicam728.h:48 */
+#define HTV_NICAM_LUT_PAD 256   /* zero entries behind the NICAM pulse table: lanes of a partial tile index past it */
 
 /* Line code bits (one uint16 per line number, ref video.c:2447-2810 restated as a table) */
 #define HTV_LC_SYNC_MASK  0x001F   /* 5-bit pulse mask fed to the sync renderer */
@@ -90,6 +91,8 @@ struct htv_tables_t {
 
 	uint16_t *codes;        int ncodes;           /* lines + 1 */
 	int16_t *pulse_values;  int npulse_values;
+	int16_t *tmpl_out, *tmpl_keep;                 /* [tmpl_rows][W] line templates: blank + sync pulses (htv_tables.c) */
+	uint8_t *tmpl_keep_any; int tmpl_rows;         /* lines + 2 */
 	double glut[256];
 	htv_c16_t *clut;        size_t clut_len;      /* clut_width + W */
 	int16_t *burst_win;     int burst_width;

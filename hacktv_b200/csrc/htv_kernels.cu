@@ -55,6 +55,9 @@ struct DevGuard {
 
 struct DevTables {
 	const uint32_t *mma_atab;         // tap operand of the tensor-core video filter, fragment order (htv_mma_fir.h)
+	const uint32_t *chroma_atab;      // tap operand of the chroma low-pass for the fused line kernel: [hi, lo][lane] x 4 registers
+	const int16_t *tmpl_out, *tmpl_keep;   // line templates: blank + sync pulses (htv_tables.c build_templates)
+	const uint8_t *tmpl_keep_any;
 	const uint16_t *codes;
 	const int16_t *pulse_values;
 	const double *glut;
@@ -161,7 +164,11 @@ struct htv_dev_t {
 	int ev_pending;
 	int line_threads;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
+	void *d_desc_r2;                  // LineR2[cap + 2] (fused line kernel)
 	int desc_cap;
+	// the fused line kernel (htv_line.cuh): PAL / NTSC / mono, AM or VSB, no resampler
+	int use_line, kl_threads, kl_ctas;
+	size_t kl_smem;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
 	size_t sec_smem;
@@ -534,6 +541,7 @@ __global__ void __launch_bounds__(1024) k_nicam_scan(const DevTables dt, int64_t
 #define MAX_ENT 6                     // sync pulse pieces that can land on one line (2 previous + 2 own + 2 next)
 #define MAX_SEGS 6                    // audio samples overlapping one scan line (+1)
 #define MAX_SYMS 48                   // NICAM symbols overlapping one scan line
+#define MAX_BLKS 48                   // 32-sample blocks of a line (W <= 1536)
 
 // What the raster needs to know about a line (also read for the two neighbours)
 struct __align__(16) LineRaster {
@@ -570,10 +578,32 @@ struct __align__(16) LineAudio {
 	int nseg, kk0, cc0, nsym;
 	int symrow[MAX_SYMS];             // pulse-table rows: I row | Q row << 16, or -1 (use the generic sum)
 	int sym[MAX_SYMS];                // per symbol: first sample relative to the line (x4, arithmetic), bit 0: I polarity +, bit 1: Q polarity +
-	int pad1[2];
+	int nic_generic, pad1;            // fused line kernel: some symbol in effect on this line has no pulse-table row
+	// per 32-sample block b (fused line kernel, htv_line.cuh): the audio segment / NICAM symbol in effect at x = 32 b
+	unsigned char fm_blk[MAX_BLKS], nic_blk[MAX_BLKS];
+	// per symbol: x = pulse-table index base, I | Q << 16 (row * sps - first sample + KL_BIAS), y = first sample
+	// relative to the line; entry nsym is a sentinel (y = INT_MAX)
+	uint2 symb[MAX_SYMS + 1];
+	int pad2[2];
 };
 
 struct LineDescs { LineRaster *r; LineAudio *a; };
+
+// What the raster half needs to know about a line (64 bytes, read through the read-only path)
+struct __align__(16) LineR2 {
+	int valid;                        // 0: before the stream
+	int tmpl;                         // row of the line templates
+	int al, ar;                       // active sample range [al, ar), -1 if none
+	int pal;                          // 0 no chroma, +1 / -1 V-switch
+	int keep;                         // the template's keep part is non-zero somewhere
+	int ov_any, ov_from;
+	unsigned int clut_off;
+	int ov_to, ov_value, ov_add;
+	long long row_off;                // pixel offset of the source row in the frame store, -1 = black
+	long long pad;
+};
+static_assert(sizeof(LineR2) == 64, "LineR2 is read as four int4");
+
 static_assert(sizeof(LineRaster) % 16 == 0 && sizeof(LineAudio) % 16 == 0, "descriptors are copied as int4");
 
 // frame / line / picture row of scan line L; L < 0 are the pipeline-fill lines the reference's
@@ -784,6 +814,37 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 		}
 		la.nsym = ns;
 	}
+	// ---- per-block tables for the fused line kernel (htv_line.cuh) --------------------------------
+	{
+		const int nblk = (W + 31) >> 5;
+		int sg = 0;
+		for(int b = 0; b < MAX_BLKS; b++)
+		{
+			while(b < nblk && la.seg_x[sg + 1] <= 32 * b) sg++;
+			la.fm_blk[b] = (unsigned char) (sg < MAX_SEGS ? sg : MAX_SEGS - 1);
+		}
+		int generic = 0, ib = 0;
+		const int ns = la.nsym;
+		for(int i = 0; i < ns; i++)
+		{
+			const int sx = la.sym[i] >> 2, row = la.symrow[i];
+			const int bI = (row & 0xFFFF) * dp.nicam_sps - sx + 2048, bQ = ((row >> 16) & 0xFFFF) * dp.nicam_sps - sx + 2048;
+			la.symb[i] = make_uint2((unsigned) (bI & 0xFFFF) | ((unsigned) (bQ & 0xFFFF) << 16), (unsigned) sx);
+		}
+		la.symb[ns] = make_uint2(0u, 0x7FFFFFFFu);
+		for(int b = 0; b < MAX_BLKS; b++)
+		{
+			while(b < nblk && ib + 1 < ns && (la.sym[ib + 1] >> 2) <= 32 * b) ib++;
+			la.nic_blk[b] = (unsigned char) ib;
+		}
+		// the table path needs a row for every symbol in effect on the line, and at most one symbol start per block
+		if(dp.have_nicam)
+		{
+			if(!dp.nicam_lut_ok || dp.nicam_sps - 1 < 32 || ns < 1 || (la.sym[0] >> 2) > 0) generic = 1;
+			for(int i = la.nic_blk[0]; i < ns; i++) if(la.symrow[i] < 0) generic = 1;
+		}
+		la.nic_generic = generic;
+	}
 }
 
 // raster descriptors: index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
@@ -792,6 +853,26 @@ __global__ void k_line_desc_r(const __grid_constant__ htv_dparams_t dp, const De
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= nlines + 3) return;
 	line_raster(dp, dt, line0 - 2 + i, ld.r[i - 1]);
+}
+
+// the same for the fused line kernel (htv_line.cuh): compact descriptors, index 0 .. nlines+1 <-> line line0-1 .. line0+nlines
+__global__ void k_line_desc_r2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineR2 *out, int64_t line0, int nlines)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= nlines + 2) return;
+	const int64_t L = line0 - 1 + i;
+	LineRaster li;
+	line_raster(dp, dt, L, li);
+	LineR2 o;
+	o.valid = li.valid;
+	o.tmpl = L < 0 ? dp.lines + 1 : (L == 0 ? dp.lines : li.line - 1);
+	o.al = li.al; o.ar = li.ar; o.pal = li.pal;
+	o.keep = dt.tmpl_keep_any[o.tmpl];
+	o.ov_any = li.ov_any; o.ov_from = li.ov_from; o.ov_to = li.ov_to; o.ov_value = li.ov_value; o.ov_add = li.ov_add;
+	o.clut_off = li.clut_off;
+	o.row_off = li.row_off;
+	o.pad = 0;
+	out[i] = o;
 }
 
 // sound-carrier descriptors for lines line0 .. line0+nlines-1 (needs the audio pre-pass results)
@@ -2324,6 +2405,8 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 	}
 }
 
+#include "htv_line.cuh"
+
 // ---------------------------------------------------------------------------
 // Device layer (C linkage)
 // ---------------------------------------------------------------------------
@@ -2381,6 +2464,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 
 	dt.codes = (const uint16_t *) dev_copy(d, t->codes, sizeof(uint16_t) * t->ncodes);
 	dt.pulse_values = (const int16_t *) dev_copy(d, t->pulse_values, sizeof(int16_t) * (t->npulse_values + 8));
+	dt.tmpl_out = (const int16_t *) dev_copy(d, t->tmpl_out, sizeof(int16_t) * (size_t) t->tmpl_rows * t->dp.W);
+	dt.tmpl_keep = (const int16_t *) dev_copy(d, t->tmpl_keep, sizeof(int16_t) * (size_t) t->tmpl_rows * t->dp.W);
+	dt.tmpl_keep_any = (const uint8_t *) dev_copy(d, t->tmpl_keep_any, t->tmpl_rows);
 	dt.glut = (const double *) dev_copy(d, t->glut, sizeof(t->glut));
 	dt.clut = (const htv_c16_t *) dev_copy(d, t->clut, sizeof(htv_c16_t) * t->clut_len);
 	dt.burst_win = (const int16_t *) dev_copy(d, t->burst_win, sizeof(int16_t) * (t->burst_width + 1));
@@ -2390,9 +2476,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
 	dt.lim_shape = (const int16_t *) dev_copy(d, t->lim_shape, sizeof(t->lim_shape));
 	dt.nicam_taps = (const int16_t *) dev_copy(d, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
-	dt.nicam_lut = (const int16_t *) dev_copy(d, t->nicam_lut, t->nicam_lut ? sizeof(int16_t) * (t->nicam_lut_len + 8) : 0);
+	dt.nicam_lut = (const int16_t *) dev_copy(d, t->nicam_lut, t->nicam_lut ? sizeof(int16_t) * (t->nicam_lut_len + HTV_NICAM_LUT_PAD) : 0);
 	dt.nicam_tpad = (const int16_t *) dev_copy(d, t->nicam_tpad, t->nicam_tpad ? sizeof(int16_t) * ((t->dp.nicam_tpad_len + 7) & ~7) : 0);
-	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, sizeof(htv_c16_t) * t->nicam_cc_len);
+	dt.nicam_cc = (const htv_c16_t *) dev_copy(d, t->nicam_cc, t->nicam_cc ? sizeof(htv_c16_t) * (t->nicam_cc_len + t->dp.W + 64) : 0);
 	dt.nicam_prn = (const uint8_t *) dev_copy(d, t->nicam_prn, sizeof(t->nicam_prn));
 	dt.offset_start = (const uint8_t *) dev_copy(d, t->offset_start, t->offset_start ? 32768 : 0);
 	dt.secam_fm_lut = (const htv_c32_t *) dev_copy(d, t->secam_fm_lut, t->secam_fm_lut ? sizeof(htv_c32_t) * 65536 : 0);
@@ -2550,6 +2636,40 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			cudaFuncSetAttribute(k_mod_mma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modm_smem);
 		}
 	}
+	{
+		// The fused line kernel (htv_line.cuh) is the default wherever it applies: PAL / NTSC / mono rasters, AM or
+		// VSB modulation (or baseband), a chroma low-pass the tensor-core form holds (11 .. 17 taps), no resampler
+		// in front of this context. HTV_PATH=split selects the separate raster + modulator kernels (A/B runs, tests).
+		const char *sel = getenv("HTV_PATH");
+		const bool split = sel && !strcmp(sel, "split");
+		const bool chroma_ok = dp.colour_mode == HTV_MONOCHROME ||
+			((dp.colour_mode == HTV_PAL || dp.colour_mode == HTV_NTSC) && dp.chroma_ntaps >= 3 && dp.chroma_ntaps <= 17);
+		const bool vf_ok = dp.vf_type == 0 || d->dt.mma_atab != NULL;
+		if(!split && !secam && !dp.have_fmv && !t->raster_only && !t->rs_taps && chroma_ok && vf_ok && dt.tmpl_out)
+		{
+			int nsm = 148;
+			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+			const int T = mf_tiles(W);
+			d->kl_threads = 32 * T;
+			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : 2);
+			if(dp.colour_mode != HTV_MONOCHROME)
+			{
+				uint32_t ctab[256];
+				for(int lo = 0; lo < 2; lo++) for(int lane = 0; lane < 32; lane++) for(int reg = 0; reg < 4; reg++)
+					ctab[(lo * 32 + lane) * 4 + reg] = kl_chroma_a_word(dp.chroma_taps, dp.chroma_ntaps, lane, reg, lo);
+				d->dt.chroma_atab = (const uint32_t *) dev_copy(d, ctab, sizeof(ctab));
+			}
+			const size_t rowb = (size_t) mf_row_bytes(W) + 16, uvb = (size_t) MF_TILE * T + 32;
+			d->kl_smem = (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
+				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
+			d->use_line = 1;
+			#define KL_ATTR(VF, HQ) do { \
+				cudaFuncSetAttribute(k_line<VF, HQ, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+			KL_ATTR(false, false); KL_ATTR(true, false); KL_ATTR(true, true);
+			#undef KL_ATTR
+		}
+	}
 	if(secam)
 	{
 		const size_t rows = (size_t) d->sub_lines + 3;
@@ -2601,7 +2721,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	DevGuard guard(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
 	if(d->h_ov_line) { cudaFreeHost(d->h_ov_line); cudaFreeHost(d->h_ov_meta); cudaFreeHost(d->h_ov_add); }
 	cudaFree(d->d_ov_line); cudaFree(d->d_ov_meta); cudaFree(d->d_ov_add);
@@ -2778,14 +2898,50 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	{
 		cudaStreamSynchronize(st);
 		cudaStreamSynchronize(d->side);
-		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a);
-		d->d_desc_r = d->d_desc_a = NULL;
+		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2);
+		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = NULL;
 		d->desc_cap = 0;
 		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
 		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
+		CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
+	if(d->use_line)
+	{
+		// one persistent launch for the whole call: every CTA walks its own run of consecutive lines
+		const htv_dparams_t &dp = d->dp;
+		LineR2 *lr2 = (LineR2 *) d->d_desc_r2;
+		k_line_desc_r2<<<(nlines + 2 + 63) / 64, 64, 0, st>>>(dp, d->dt, lr2, line0, nlines);
+		if(!d->side_armed)
+		{
+			CK(cudaEventRecord(d->ev_in, st));
+			CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+		}
+		k_line_desc_a<<<(nlines + 63) / 64, 64, 0, d->side>>>(dp, d->dt, ld, line0, nlines);
+		CK(cudaEventRecord(d->ev_audio, d->side));
+		d->side_armed = 0;
+		CK(cudaStreamWaitEvent(st, d->ev_audio, 0));
+		// runs of at least 4 lines (every run rasters two lines more than it emits)
+		int run = (nlines + d->kl_ctas - 1) / d->kl_ctas;
+		if(run < 4) run = 4;
+		const int grid = (nlines + run - 1) / run;
+		if(d->timing) cudaEventRecord(d->ev0, st);
+		#define KL_GO(VF, HQ) do { \
+			if(d->kl_threads <= 256) k_line<VF, HQ, 256, 4><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, ld.a, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
+			else k_line<VF, HQ, 384, 2><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, ld.a, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
+		if(!dp.vf_type) KL_GO(false, false);
+		else if(dp.vf_type == 3) KL_GO(true, true);
+		else KL_GO(true, false);
+		#undef KL_GO
+		d->launches += 3;
+		d->last_mod_lines = nlines;
+		if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
+		CK(cudaEventRecord(d->ev_chunk[d->chunk_i & 1], st));
+		d->chunk_i++;
+		CK(cudaGetLastError());
+		return(HTV_OK);
+	}
 	k_line_desc_r<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
 	if(!d->side_armed)
 	{

@@ -1,0 +1,459 @@
+// hacktv_b200 - the fused line kernel (included by htv_kernels.cu).
+//
+// One persistent CTA walks a run of consecutive scan lines and does, per line, everything between
+// the picture in HBM and the int16 IQ in HBM - raster, chroma, video filter, sound carriers, mixers -
+// without the composite signal ever leaving the SM:
+//
+//   R1  template (blank + sync pulses) + picture: RGB -> Y,U,V by table (ref video.c:2864-2992)
+//   R2  chroma low-pass on the tensor cores, burst, subcarrier mix (ref video.c:3011-3040, fir.c:357-375),
+//       VBI overlay; the finished composite line goes into a 3-row ring of byte planes in shared memory
+//   M   51-tap VSB / low-pass video filter on the tensor cores (ref video.c:3235-3248, fir.c:564-615),
+//       FM / AM / NICAM sound carriers (ref video.c:3261-3450, nicam728.c:342-411), IQ swap, offset
+//       mixer (ref video.c:3466-3515), channel combiner, store.
+//
+// Thread <-> sample mapping: a warp owns one tile of 128 consecutive samples and every lane keeps its four
+// samples in the layout the m16n8k32 accumulators have anyway: lane = 4g + t holds x = 128 tile + 32 t + g + 8 j,
+// j = 0..3 (htv_mma_fir.h: mf_out_x). Both filters leave their results in exactly the registers the next
+// stage needs - no exchange through shared memory, and all four samples of a lane fall into one 32-sample
+// block, which is what the per-line sound descriptors are indexed by. Loads and stores with a stride of 8
+// samples between a lane's values are still sector-exact (8 lanes x 4 bytes = one 32-byte sector).
+
+#define KL_LEAD   MF_LEAD   // composite row: byte i = sample i - 32 of the line (htv_mma_fir.h pitched row)
+#define KL_UVLEAD 8         // chroma planes: byte i = sample i - 8
+#define KL_BIAS   2048      // NICAM pulse-table index bias (LineAudio.symb)
+
+__device__ __forceinline__ int kl_row_bytes(int W) { return(mf_row_bytes(W) + 16); }
+__device__ __forceinline__ int kl_uv_bytes(int W) { return(MF_TILE * mf_tiles(W) + 32); }
+
+// tap operand of the chroma low-pass (one k-step of 32): out[x] = sum_y u[x - h + y] tap[y], stream window byte 0 =
+// sample -8: A[m][k'] = tap[k' - m - (8 - h)]. Same fragment convention as mf_a_word (htv_mma_fir.h).
+__host__ __device__ inline uint32_t kl_chroma_a_word(const int32_t *taps, int ntaps, int lane, int reg, int lo)
+{
+	const int g = lane >> 2, t = lane & 3, h = ntaps / 2;
+	const int m = g + ((reg & 1) ? 8 : 0);
+	const int kp0 = 8 * t + ((reg & 2) ? 4 : 0);
+	uint32_t r = 0;
+	for(int e = 0; e < 4; e++)
+	{
+		const int y = kp0 + e - (KL_UVLEAD - h) - m;
+		const int v = (y >= 0 && y < ntaps) ? taps[y] : 0;
+		const uint32_t b = lo ? ((uint32_t) v & 0xFFu) : (((uint32_t) v >> 8) & 0xFFu);
+		r |= b << (8 * e);
+	}
+	return(r);
+}
+
+// one complex int16 table entry through the read-only path: x = i, y = q
+__device__ __forceinline__ short2 kl_ldc16(const htv_c16_t *p) { return(__ldg(reinterpret_cast<const short2 *>(p))); }
+
+__device__ __forceinline__ int kl_fir_out(int hh, int mid, int ll)
+{
+	return(sat16i(mf_combine(hh, mid, ll) >> 15));
+}
+
+// ---- sound carriers for the four samples of a lane (strided by 8) --------------------------------------------
+// Same arithmetic as sound_add<false> (ref video.c:3261-3450, nicam728.c:342-411); what differs is how a lane
+// finds its audio segment and NICAM symbol: all four samples lie in the 32-sample block b = xb >> 5, for which
+// the line descriptor lists the segment / symbol in effect at the block's first sample, and at most one
+// boundary of either kind falls inside a block.
+__device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTables &dt, const LineAudio *la,
+	const short *ntp, int xb, int (&oi)[4], int (&oq)[4])
+{
+	const int b = xb >> 5;
+	if(dp.have_fm || dp.have_am)
+	{
+		const int sg = __ldg(la->fm_blk + b);
+		const int nb = __ldg(la->seg_x + sg + 1);
+		const int sg1 = min(sg + 1, MAX_SEGS - 1);
+		int kk = __ldg(&la->kk0) + xb;
+		if(kk >= 32767) kk -= 32767;
+		// amplitude of the reference's Q31 phasor kk + 1 multiplications after a renormalisation
+		float kf = (float) (kk + 1);
+		if(dp.have_fm)
+		{
+			const unsigned long long angA = __ldg(la->seg_ang + sg), angB = __ldg(la->seg_ang + sg1);
+			unsigned long long phA = __ldg(la->seg_phase + sg) + angA * (unsigned long long) xb;
+			unsigned long long phB = __ldg(la->seg_phase + sg1) + angB * (unsigned long long) xb;
+			const unsigned long long stA = angA << 3, stB = angB << 3;
+			float kq = kf;
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				const unsigned long long ph = xb + 8 * j >= nb ? phB : phA;
+				if(kq > 32767.0f) kq -= 32767.0f;
+				const float amp = 32767.99998f - kq * 1.52587890625e-5f;
+				float sn, cs;
+				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
+				oi[j] += (__float2int_rd(amp * cs) * dp.fm_level) >> 15;
+				oq[j] += (__float2int_rd(amp * sn) * dp.fm_level) >> 15;
+				phA += stA; phB += stB; kq += 8.0f;
+			}
+		}
+		if(dp.have_am)
+		{
+			unsigned long long phM = __ldg(&la->am_phase0) + dp.am_ang * (unsigned long long) (xb + 1);
+			const unsigned long long stM = dp.am_ang << 3;
+			const int amA = (__ldg(la->seg_am + sg) + 32768) / 2, amB = (__ldg(la->seg_am + sg1) + 32768) / 2;
+			float kq = kf;
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				if(kq > 32767.0f) kq -= 32767.0f;
+				const float amp = 32767.99998f - kq * 1.52587890625e-5f;
+				float sn, cs;
+				__sincosf((float) (int) (phM >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+				const int smp = xb + 8 * j >= nb ? amB : amA;
+				oi[j] += (((__float2int_rd(amp * cs) * smp) >> 15) * dp.am_level) >> 15;
+				oq[j] += (((__float2int_rd(amp * sn) * smp) >> 15) * dp.am_level) >> 15;
+				phM += stM; kq += 8.0f;
+			}
+		}
+	}
+
+	if(dp.have_nicam)
+	{
+		int bi[4], bq[4];
+		if(!__ldg(&la->nic_generic))
+		{
+			// pulse-shaping table (htv_tables.c): one entry per sample and channel, index = base + x
+			const int ib = __ldg(la->nic_blk + b);
+			const uint2 cur = __ldg(la->symb + ib), nxt = __ldg(la->symb + ib + 1);
+			const int nb = (int) nxt.y;
+			const int16_t *lut = dt.nicam_lut - KL_BIAS + xb;
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				const unsigned w = xb + 8 * j >= nb ? nxt.x : cur.x;
+				bi[j] = __ldg(lut + 8 * j + (w & 0xFFFFu));
+				bq[j] = __ldg(lut + 8 * j + (w >> 16));
+			}
+		}
+		else
+		{
+			// generic sum over the symbols whose pulse covers the sample (stream start, unusual rates)
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				const int x = xb + 8 * j;
+				int i3 = 0;
+				const int ns = __ldg(&la->nsym);
+				while(i3 + 1 < ns && (__ldg(la->sym + i3 + 1) >> 2) <= x) i3++;
+				bi[j] = 0; bq[j] = 0;
+				for(int cnd = 0; cnd < NIC_CAND; cnd++)
+				{
+					const int i = i3 - cnd;
+					if(i < 0) break;
+					const int sy = __ldg(la->sym + i);
+					const int d0 = x - (sy >> 2) + NIC_TPAD;                // the table is zero outside the pulse
+					if(d0 < 0) continue;
+					const int r = ntp[d0];
+					bi[j] += (sy & 1) ? r : -r;
+					bq[j] += (sy & 2) ? r : -r;
+				}
+			}
+		}
+		// carrier table extended past its period (htv_tables.c): cc0 + x never wraps
+		const htv_c16_t *ccp = dt.nicam_cc + __ldg(&la->cc0) + xb;
+		#pragma unroll
+		for(int j = 0; j < 4; j++)
+		{
+			const short2 cc = kl_ldc16(ccp + 8 * j);
+			// the overlap-add ring holds at most 7 pulses of < 2^11: it never wraps an int16
+			oi[j] += (bi[j] * cc.x - bq[j] * cc.y) >> 15;
+			oq[j] += (bi[j] * cc.y + bq[j] * cc.x) >> 15;
+		}
+	}
+}
+
+// Mixers after the modulation (ref video.c:3466-3515), channel combiner, store - post_store for the strided layout
+__device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const DevTables &dt, const LineAudio *la,
+	int xb, int row, int (&oi)[4], int (&oq)[4], int16_t *out, const int16_t *acc)
+{
+	const int W = dp.W;
+	if(dp.swap_iq)
+	{
+		#pragma unroll
+		for(int j = 0; j < 4; j++) { const int t = oi[j]; oi[j] = oq[j]; oq[j] = t; }
+	}
+	if(dp.have_offset)
+	{
+		const long long m0 = __ldg(&la->m0);
+		const unsigned long long off0 = __ldg(&la->off_phase0);
+		#pragma unroll
+		for(int j = 0; j < 4; j++)
+		{
+			const int x = xb + 8 * j;
+			const long long m = m0 + x;
+			const int vi = wrap16i(oi[j]), vq = wrap16i(oq[j]);
+			int bi, bq;
+			if(m < 32767)
+			{
+				const unsigned char st = dt.offset_start[m];
+				bi = -(st & 1); bq = -((st >> 1) & 1);
+			}
+			else
+			{
+				const int kk = (int) (m % 32767);
+				const float amp = 32767.99998f - (float) (kk + 1) * 1.52587890625e-5f;
+				const unsigned long long ph = off0 + dp.offset_ang * (unsigned long long) (x + 1);
+				float sn, cs;
+				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+				bi = min(__float2int_rd(amp * cs), 32767); bq = min(__float2int_rd(amp * sn), 32767);   // pi >> 16 <= 32767
+			}
+			oi[j] = (vi * bi - vq * bq) >> 15;
+			oq[j] = (vi * bq + vq * bi) >> 15;
+		}
+	}
+	const size_t lbase = (size_t) row * (size_t) W;
+	if(dp.complex_out)
+	{
+		unsigned *o = reinterpret_cast<unsigned *>(out) + lbase + xb;
+		const unsigned *a = acc ? reinterpret_cast<const unsigned *>(acc) + lbase + xb : NULL;
+		#pragma unroll
+		for(int j = 0; j < 4; j++)
+		{
+			if(xb + 8 * j < W)
+			{
+				unsigned v = ((unsigned) oi[j] & 0xFFFFu) | ((unsigned) oq[j] << 16);
+				if(a) v = __vadd2(v, __ldcs(a + 8 * j));
+				__stcs(o + 8 * j, v);
+			}
+		}
+	}
+	else
+	{
+		unsigned short *o = reinterpret_cast<unsigned short *>(out) + lbase + xb;
+		#pragma unroll
+		for(int j = 0; j < 4; j++)
+		{
+			if(xb + 8 * j < W) o[8 * j] = (unsigned short) (oi[j] + (acc ? acc[lbase + xb + 8 * j] : 0));
+		}
+	}
+}
+
+// VF: a video filter is on (composite ring + tensor-core FIR); HASQ: it has Q taps (VSB)
+template<bool VF, bool HASQ, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR2 *lrp, const LineAudio *lap,
+	int nlines, int run, int16_t *out, const int16_t *acc, int acc_rows)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = dp.W;
+	const int T = mf_tiles(W);
+	const int RB = kl_row_bytes(W), UB = kl_uv_bytes(W);
+	// [row 0..2][hi, lo] composite planes | [u hi, u lo, v hi, v lo] | FIR tap operand | chroma tap operand | NICAM pulse
+	unsigned char *rows = smem_raw;
+	unsigned char *uvp = rows + (VF ? 6 * RB : 0);
+	uint4 *atab = reinterpret_cast<uint4 *>(uvp + 4 * UB);                 // [k-step][I hi, I lo, Q hi, Q lo][lane]
+	uint4 *ctab = atab + (VF ? MF_ATAB_WORDS / 4 : 0);                      // [hi, lo][lane]
+	short *ntp = reinterpret_cast<short *>(ctab + 64);
+	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
+	const int g = lane >> 2, t = lane & 3;
+	const int xb = MF_TILE * nt + 32 * t + g;                               // the lane's samples: xb + 8 j
+
+	// ---- one-time set-up -------------------------------------------------------
+	if(VF) for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
+	if(dt.chroma_atab) for(int i = tid; i < 64; i += blockDim.x) ctab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.chroma_atab) + i);
+	for(int i = tid; i < ((VF ? 6 * RB : 0) + 4 * UB) / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem_raw)[i] = 0;
+	if(dp.have_nicam)
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
+		int4 *dst = reinterpret_cast<int4 *>(ntp);
+		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	__syncthreads();
+
+	const int a = blockIdx.x * run, bnd = min(a + run, nlines);
+	if(a >= nlines) return;
+	const int full_l = dp.active_left, full_r = dp.active_left + dp.active_width;
+	const bool in_full = xb + 24 >= full_l && xb < full_r;                  // the lane touches the picture area at all
+
+	// relative line q: raster lines a-1 .. bnd (descriptor lrp[q + 1]), modulate a .. bnd-1
+	for(int q = VF ? a - 1 : a; q <= (VF ? bnd : bnd - 1); q++)
+	{
+		// ---- R1: template + picture -------------------------------------------
+		const int4 *lq = reinterpret_cast<const int4 *>(lrp + q + 1);
+		const int4 l0 = __ldg(lq), l1 = __ldg(lq + 1), l2 = __ldg(lq + 2), l3 = __ldg(lq + 3);
+		const int li_tmpl = l0.y, li_al = l0.z, li_ar = l0.w;
+		const int li_pal = l1.x, li_keep = l1.y, li_ov_any = l1.z, li_ov_from = l1.w;
+		const unsigned li_clut = (unsigned) l2.x;
+		const int li_ov_to = l2.y, li_ov_value = l2.z, li_ov_add = l2.w;
+		const long long li_row = ((long long) (unsigned) l3.x) | ((long long) l3.y << 32);
+		int val[4];
+		{
+			const int16_t *tp = dt.tmpl_out + (size_t) li_tmpl * W + xb;
+			#pragma unroll
+			for(int j = 0; j < 4; j++) val[j] = xb + 8 * j < W ? (int) __ldg(tp + 8 * j) : 0;
+		}
+		int uu[4] = { 0, 0, 0, 0 }, vv[4] = { 0, 0, 0, 0 };
+		if(in_full && li_al < li_ar)
+		{
+			const uint32_t *px = dt.frames + li_row + (xb - dp.active_left);
+			const int16_t *kp = dt.tmpl_keep + (size_t) li_tmpl * W + xb;
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				const int x = xb + 8 * j;
+				if(x >= li_al && x < li_ar)
+				{
+					const unsigned rgb = li_row >= 0 ? (__ldg(px + 8 * j) & 0xFFFFFFu) : 0u;
+					const short4 e = __ldg(dt.yuv_lut + rgb);
+					val[j] = e.x; uu[j] = e.y; vv[j] = e.z;
+					if(li_keep) val[j] += __ldg(kp + 8 * j);
+				}
+			}
+		}
+		if(li_pal)
+		{
+			if(in_full)
+			{
+				// unfiltered U, V as byte planes; outside the picture the planes stay zero (the reference filters
+				// each line on its own: zero history either side, ref fir.c:357-375)
+				unsigned char *p = uvp + KL_UVLEAD + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const int x = xb + 8 * j;
+					if(x >= full_l && x < full_r)
+					{
+						p[8 * j] = (unsigned char) (uu[j] >> 8); p[UB + 8 * j] = (unsigned char) uu[j];
+						p[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); p[3 * UB + 8 * j] = (unsigned char) vv[j];
+					}
+				}
+			}
+			__syncthreads();
+			// ---- R2: chroma low-pass (tensor cores), burst, subcarrier ---------------
+			int cu[4], cv[4];
+			{
+				int uhh[4] = { 0, 0, 0, 0 }, umid[4] = { 0, 0, 0, 0 }, ull[4] = { 0, 0, 0, 0 };
+				int vhh[4] = { 0, 0, 0, 0 }, vmid[4] = { 0, 0, 0, 0 }, vll[4] = { 0, 0, 0, 0 };
+				const int o0 = MF_M * (8 * nt + g) + 8 * t;
+				const uint4 ah = ctab[lane], al4 = ctab[32 + lane];
+				const uint2 uh = *reinterpret_cast<const uint2 *>(uvp + o0), ul = *reinterpret_cast<const uint2 *>(uvp + UB + o0);
+				const uint2 vh = *reinterpret_cast<const uint2 *>(uvp + 2 * UB + o0), vl = *reinterpret_cast<const uint2 *>(uvp + 3 * UB + o0);
+				mma_ss(uhh, ah, uh); mma_su(umid, ah, ul); mma_us(umid, al4, uh); mma_uu(ull, al4, ul);
+				mma_ss(vhh, ah, vh); mma_su(vmid, ah, vl); mma_us(vmid, al4, vh); mma_uu(vll, al4, vl);
+				// accumulator register ci <-> sample j: ci = ((j & 1) << 1) | (j >> 1)
+				cu[0] = kl_fir_out(uhh[0], umid[0], ull[0]); cu[1] = kl_fir_out(uhh[2], umid[2], ull[2]);
+				cu[2] = kl_fir_out(uhh[1], umid[1], ull[1]); cu[3] = kl_fir_out(uhh[3], umid[3], ull[3]);
+				cv[0] = kl_fir_out(vhh[0], vmid[0], vll[0]); cv[1] = kl_fir_out(vhh[2], vmid[2], vll[2]);
+				cv[2] = kl_fir_out(vhh[1], vmid[1], vll[1]); cv[3] = kl_fir_out(vhh[3], vmid[3], vll[3]);
+			}
+			if(xb + 24 >= dp.burst_left && xb < dp.burst_left + dp.burst_width)
+			{
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const int x = xb + 8 * j;
+					if(x >= dp.burst_left && x < dp.burst_left + dp.burst_width)
+					{
+						const int w = dt.burst_win[x - dp.burst_left];
+						cu[j] = (dp.burst_i * w) >> 15;
+						cv[j] = (dp.burst_q * w) >> 15;
+					}
+				}
+			}
+			{
+				const htv_c16_t *cp = dt.clut + li_clut + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					if(xb + 8 * j < W)
+					{
+						const short2 c = kl_ldc16(cp + 8 * j);
+						val[j] += ((int) c.x * cv[j] * li_pal + (int) c.y * cu[j]) >> 15;
+					}
+				}
+			}
+		}
+		if(li_ov_any)
+		{
+			// VBI stages run on the finished line (ref video.c:4213-4357 register them behind the raster)
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				const int x = xb + 8 * j;
+				if(x >= li_ov_from && x < li_ov_to) val[j] = li_ov_value;
+				if(li_ov_add >= 0 && x < W) val[j] = wrap16i(val[j]) + dt.ov_add[(size_t) li_ov_add * W + x];
+			}
+		}
+
+		int oi[4], oq[4];
+		int mrow = q;                                                       // line modulated in this iteration
+		if(VF)
+		{
+			// ---- composite line -> ring row q mod 3 (+ the neighbours' halos) ----------
+			const int r3 = (q + 3) % 3;
+			unsigned char *rp = rows + (2 * r3) * RB + KL_LEAD + xb;
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
+			{
+				if(xb + 8 * j < W) { rp[8 * j] = (unsigned char) (val[j] >> 8); rp[RB + 8 * j] = (unsigned char) val[j]; }
+			}
+			if(xb < KL_LEAD)
+			{
+				// first 32 samples: right halo of the previous line's row
+				unsigned char *hp = rows + (2 * ((q + 2) % 3)) * RB + KL_LEAD + W + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					if(xb + 8 * j < KL_LEAD) { hp[8 * j] = (unsigned char) (val[j] >> 8); hp[RB + 8 * j] = (unsigned char) val[j]; }
+				}
+			}
+			if(xb + 24 >= W - KL_LEAD && xb < W)
+			{
+				// last 32 samples: left halo of the next line's row
+				unsigned char *hp = rows + (2 * ((q + 4) % 3)) * RB + xb - (W - KL_LEAD);
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const int x = xb + 8 * j;
+					if(x >= W - KL_LEAD && x < W) { hp[8 * j] = (unsigned char) (val[j] >> 8); hp[RB + 8 * j] = (unsigned char) val[j]; }
+				}
+			}
+			__syncthreads();
+			mrow = q - 1;
+			if(mrow < a) continue;
+			// ---- M: video filter of line q - 1, one tile of 128 samples per warp -------
+			const unsigned char *ph = rows + (2 * ((mrow + 3) % 3)) * RB, *plo = ph + RB;
+			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
+			int qhh[4] = { 0, 0, 0, 0 }, qmid[4] = { 0, 0, 0, 0 }, qll[4] = { 0, 0, 0, 0 };
+			const int o0 = mf_b_offset(nt, 0, lane);
+			#pragma unroll
+			for(int s = 0; s < MF_KSTEPS; s++)
+			{
+				const uint2 xh = *reinterpret_cast<const uint2 *>(ph + o0 + 32 * s);
+				const uint2 xl = *reinterpret_cast<const uint2 *>(plo + o0 + 32 * s);
+				const uint4 aih = atab[(s * 4 + 0) * 32 + lane], ail = atab[(s * 4 + 1) * 32 + lane];
+				mma_ss(ihh, aih, xh); mma_su(imid, aih, xl); mma_us(imid, ail, xh); mma_uu(ill, ail, xl);
+				if(HASQ)
+				{
+					const uint4 aqh = atab[(s * 4 + 2) * 32 + lane], aql = atab[(s * 4 + 3) * 32 + lane];
+					mma_ss(qhh, aqh, xh); mma_su(qmid, aqh, xl); mma_us(qmid, aql, xh); mma_uu(qll, aql, xl);
+				}
+			}
+			oi[0] = kl_fir_out(ihh[0], imid[0], ill[0]); oi[1] = kl_fir_out(ihh[2], imid[2], ill[2]);
+			oi[2] = kl_fir_out(ihh[1], imid[1], ill[1]); oi[3] = kl_fir_out(ihh[3], imid[3], ill[3]);
+			if(HASQ)
+			{
+				oq[0] = kl_fir_out(qhh[0], qmid[0], qll[0]); oq[1] = kl_fir_out(qhh[2], qmid[2], qll[2]);
+				oq[2] = kl_fir_out(qhh[1], qmid[1], qll[1]); oq[3] = kl_fir_out(qhh[3], qmid[3], qll[3]);
+			}
+			else { oq[0] = oq[1] = oq[2] = oq[3] = 0; }
+		}
+		else
+		{
+			if(li_pal) __syncthreads();                                     // chroma planes are rewritten by the next line
+			#pragma unroll
+			for(int j = 0; j < 4; j++) { oi[j] = wrap16i(val[j]); oq[j] = 0; }
+		}
+
+		// ---- sound carriers, mixers, store ---------------------------------------
+		if(xb < W)
+		{
+			const LineAudio *la = lap + mrow;
+			kl_sound(dp, dt, la, ntp, xb, oi, oq);
+			kl_post_store(dp, dt, la, xb, mrow, oi, oq, out, mrow < acc_rows ? acc : NULL);
+		}
+	}
+}

@@ -243,6 +243,56 @@ static int build_pulse(int16_t *dst, int32_t *off, double offset, double width, 
 	return(len);
 }
 
+/* ---- line templates (fused line kernel) ---------------------------------- *
+ * Everything of a raster line that does not depend on the picture: the blanking level plus every
+ * sync-pulse piece that lands on the line - its own pulses, the previous line's overrun and the next
+ * line's leading edge (ref vbidata.c:186-239, video.c:2447-2810 + 2920-2960: the raster adds the pulses
+ * of line n into line n's buffer and, where they run past either end, into the neighbours').
+ *   tmpl_out[row][x]   what the line holds where no picture is drawn
+ *   tmpl_keep[row][x]  the part that is also added INSIDE the picture (the picture overwrites the line's
+ *                      own and the previous line's pieces; only the next line's edge comes later)
+ * row = line - 1 for lines 1 .. lines; row `lines` = line 1 of the very first frame (nothing before it);
+ * row lines + 1 = before the stream (zeros). int16 wrap-around sums, as the reference's line buffer. */
+static void build_templates(struct htv_tables_t *t)
+{
+	const htv_dparams_t *dp = &t->dp;
+	const int W = dp->W, nl = dp->lines, rows = nl + 2;
+	int r, s, b, d;
+	t->tmpl_rows = rows;
+	t->tmpl_out = calloc((size_t) rows * W, sizeof(int16_t));
+	t->tmpl_keep = calloc((size_t) rows * W, sizeof(int16_t));
+	t->tmpl_keep_any = calloc(rows, 1);
+	for(r = 0; r <= nl; r++)
+	{
+		const int line0 = r == nl ? 0 : r;                 /* 0-based line within the frame */
+		int16_t *o = t->tmpl_out + (size_t) r * W, *k = t->tmpl_keep + (size_t) r * W;
+		int x;
+		for(x = 0; x < W; x++) o[x] = (int16_t) dp->blank;
+		for(s = -1; s <= 1; s++)
+		{
+			int mask;
+			if(r == nl && s < 0) continue;                   /* the stream starts here */
+			mask = t->codes[((line0 + s + nl) % nl) + 1] & HTV_LC_SYNC_MASK;
+			for(b = 0; b < 5; b++)
+			{
+				const int base = dp->pulse_off[b] + s * W;
+				if(!(mask & (1 << b))) continue;
+				for(d = 0; d < dp->pulse_len[b]; d++)
+				{
+					x = base + d;
+					if(x < 0 || x >= W) continue;
+					o[x] = (int16_t) (o[x] + t->pulse_values[dp->pulse_pos[b] + d]);
+					if(s == 1)
+					{
+						k[x] = (int16_t) (k[x] + t->pulse_values[dp->pulse_pos[b] + d]);
+						if(k[x]) t->tmpl_keep_any[r] = 1;
+					}
+				}
+			}
+		}
+	}
+}
+
 /* ---- the build --------------------------------------------------------- */
 
 static double dclamp(double v, double lo, double hi) { return(v < lo ? lo : (v > hi ? hi : v)); }
@@ -386,6 +436,7 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 	}
 
 	build_codes(t);
+	build_templates(t);
 
 	if(c->colour_mode == HTV_PAL || c->colour_mode == HTV_NTSC)
 	{
@@ -652,7 +703,7 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 				const int major = minor_is_short ? sps_i : sps_i - 1, minor = minor_is_short ? sps_i - 1 : sps_i;
 				int gi, pat, phi, j;
 				t->nicam_lut_len = 6 * 64 * sps_i;
-				t->nicam_lut = calloc(t->nicam_lut_len + 8, sizeof(int16_t));
+				t->nicam_lut = calloc(t->nicam_lut_len + HTV_NICAM_LUT_PAD, sizeof(int16_t));
 				for(gi = 0; gi < 6; gi++) for(pat = 0; pat < 64; pat++) for(phi = 0; phi < sps_i; phi++)
 				{
 					int off = 0, v = 0;
@@ -670,13 +721,15 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		memcpy(t->nicam_tpad + 8, t->nicam_taps, sizeof(int16_t) * t->nicam_ntaps);
 		g = gcd64(sample_rate, freq);
 		t->nicam_cc_len = dp->nicam_cc_len = sample_rate / g;
-		t->nicam_cc = malloc(sizeof(htv_c16_t) * t->nicam_cc_len);
+		/* W + 64 entries past the period, so a line can index it from (m0 mod period) without wrapping */
+		t->nicam_cc = malloc(sizeof(htv_c16_t) * (t->nicam_cc_len + dp->W + 64));
 		d = 2.0 * M_PI / t->nicam_cc_len * (freq / g);
 		for(x = 0; x < t->nicam_cc_len; x++)
 		{
 			t->nicam_cc[x].i = round(cos(d * x) * 1.0 * INT16_MAX);
 			t->nicam_cc[x].q = round(sin(d * x) * 1.0 * INT16_MAX);
 		}
+		for(x = t->nicam_cc_len; x < t->nicam_cc_len + dp->W + 64; x++) t->nicam_cc[x] = t->nicam_cc[x - t->nicam_cc_len];
 		{
 			/* PRN whitening sequence, ref nicam728.c:96-125 */
 			int poly = 0x1FF, b;
@@ -780,6 +833,7 @@ void htv_tables_free(htv_tables_t *t)
 	if(!t) return;
 	free(t->rs_taps);
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
+	free(t->tmpl_out); free(t->tmpl_keep); free(t->tmpl_keep_any);
 	free(t->fm_ang); free(t->fmv_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
 	free(t);
