@@ -156,6 +156,8 @@ struct htv_dev_t {
 	int timing;
 	cudaEvent_t ev0, ev1;
 	cudaStream_t side;                // audio-rate pre-pass + sound descriptors run here, beside the raster
+	cudaStream_t side2;               // the NICAM half of the pre-pass (independent of the FM chain until the descriptors)
+	cudaEvent_t ev_nic;
 	cudaStream_t up;                  // picture / PCM uploads: ahead of the previous chunk's kernels
 	cudaEvent_t ev_up, ev_chunk[2];
 	unsigned chunk_i;
@@ -164,10 +166,10 @@ struct htv_dev_t {
 	int ev_pending;
 	int line_threads;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
-	void *d_desc_r2;                  // LineR2[cap + 2] (fused line kernel)
+	void *d_desc_r2, *d_desc_a2;      // LineR2[cap + 2], LineA2[cap] (fused line kernel)
 	int desc_cap;
 	// the fused line kernel (htv_line.cuh): PAL / NTSC / mono, AM or VSB, no resampler
-	int use_line, kl_threads, kl_ctas;
+	int use_line, kl_threads, kl_ctas, kl_csat;
 	size_t kl_smem;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
@@ -578,13 +580,25 @@ struct __align__(16) LineAudio {
 	int nseg, kk0, cc0, nsym;
 	int symrow[MAX_SYMS];             // pulse-table rows: I row | Q row << 16, or -1 (use the generic sum)
 	int sym[MAX_SYMS];                // per symbol: first sample relative to the line (x4, arithmetic), bit 0: I polarity +, bit 1: Q polarity +
-	int nic_generic, pad1;            // fused line kernel: some symbol in effect on this line has no pulse-table row
-	// per 32-sample block b (fused line kernel, htv_line.cuh): the audio segment / NICAM symbol in effect at x = 32 b
+	int pad1[2];
+};
+
+// Sound-carrier state of a line for the fused line kernel (htv_line.cuh), built by k_line_desc_a2 (one warp per line)
+struct __align__(16) LineA2 {
+	unsigned long long seg_phase[MAX_SEGS], seg_ang[MAX_SEGS];   // FM phase at the line's sample 0 / per sample, per audio segment
+	unsigned long long am_phase0, off_phase0;
+	long long m0;                     // audio-clock index of the line's first sample
+	int kk0, cc0;
+	int seg_x[MAX_SEGS + 2];          // first sample (relative to the line) of each audio segment, INT_MAX behind the last
+	int seg_am[MAX_SEGS];
+	int nsym, nic_generic;            // nic_generic: some symbol in effect on this line has no pulse-table row
+	// per 32-sample block b: the audio segment / NICAM symbol in effect at x = 32 b
 	unsigned char fm_blk[MAX_BLKS], nic_blk[MAX_BLKS];
-	// per symbol: x = pulse-table index base, I | Q << 16 (row * sps - first sample + KL_BIAS), y = first sample
+	// per symbol: x = pulse-table index bases, I | Q << 16 (row * sps - first sample + KL_BIAS), y = first sample
 	// relative to the line; entry nsym is a sentinel (y = INT_MAX)
 	uint2 symb[MAX_SYMS + 1];
-	int pad2[2];
+	unsigned char symc[MAX_SYMS];     // bit 0: I polarity +, bit 1: Q polarity +
+	int pad[2];
 };
 
 struct LineDescs { LineRaster *r; LineAudio *a; };
@@ -604,7 +618,7 @@ struct __align__(16) LineR2 {
 };
 static_assert(sizeof(LineR2) == 64, "LineR2 is read as four int4");
 
-static_assert(sizeof(LineRaster) % 16 == 0 && sizeof(LineAudio) % 16 == 0, "descriptors are copied as int4");
+static_assert(sizeof(LineRaster) % 16 == 0 && sizeof(LineAudio) % 16 == 0 && sizeof(LineA2) % 16 == 0, "descriptors are copied as int4");
 
 // frame / line / picture row of scan line L; L < 0 are the pipeline-fill lines the reference's
 // SECAM stage sees before line 1 (frame 1, line 0: an all-black active line, ref video.c:4665-4667)
@@ -814,37 +828,199 @@ __device__ void line_audio(const htv_dparams_t &dp, const DevTables &dt, int64_t
 		}
 		la.nsym = ns;
 	}
-	// ---- per-block tables for the fused line kernel (htv_line.cuh) --------------------------------
+}
+
+// ---------------------------------------------------------------------------
+// Sound descriptors for the fused line kernel: ONE WARP per scan line. The same closed forms as
+// line_audio() (one thread per line, a serial walk over ~30 symbols), spread over the lanes: lane = audio
+// segment, lane = NICAM symbol, lane = 32-sample block. 64-bit divisions by run-time constants go
+// through fp64 (exact below 2^52, with the exact division behind it).
+// ---------------------------------------------------------------------------
+
+// floor(n / d) and the remainder for n < 2^63, 0 < d < 2^31
+__device__ __forceinline__ unsigned long long kd_div(unsigned long long n, unsigned d, double inv, unsigned &rem)
+{
+	if(n >> 52) { const unsigned long long q = n / d; rem = (unsigned) (n - q * d); return(q); }
+	long long q = __double2ll_rd(__dmul_rn((double) (long long) n, inv));
+	long long r = (long long) n - q * (long long) d;
+	if(r < 0) { q--; r += d; }
+	else if(r >= (long long) d) { q++; r -= d; }
+	rem = (unsigned) r;
+	return((unsigned long long) q);
+}
+
+#define KD_WARPS 4
+__global__ void __launch_bounds__(32 * KD_WARPS)
+k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineA2 *out, int64_t line0, int nlines)
+{
+	__shared__ int s_blk[KD_WARPS][MAX_BLKS];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int li = blockIdx.x * KD_WARPS + wid;
+	if(li >= nlines) return;
+	LineA2 &la = out[li];
+	const int W = dp.W;
+	const long long m0 = (line0 + li) * (long long) W + dp.shift;
+	unsigned rem;
+
+	if(lane == 0)
 	{
-		const int nblk = (W + 31) >> 5;
-		int sg = 0;
-		for(int b = 0; b < MAX_BLKS; b++)
-		{
-			while(b < nblk && la.seg_x[sg + 1] <= 32 * b) sg++;
-			la.fm_blk[b] = (unsigned char) (sg < MAX_SEGS ? sg : MAX_SEGS - 1);
-		}
-		int generic = 0, ib = 0;
-		const int ns = la.nsym;
-		for(int i = 0; i < ns; i++)
-		{
-			const int sx = la.sym[i] >> 2, row = la.symrow[i];
-			const int bI = (row & 0xFFFF) * dp.nicam_sps - sx + 2048, bQ = ((row >> 16) & 0xFFFF) * dp.nicam_sps - sx + 2048;
-			la.symb[i] = make_uint2((unsigned) (bI & 0xFFFF) | ((unsigned) (bQ & 0xFFFF) << 16), (unsigned) sx);
-		}
-		la.symb[ns] = make_uint2(0u, 0x7FFFFFFFu);
-		for(int b = 0; b < MAX_BLKS; b++)
-		{
-			while(b < nblk && ib + 1 < ns && (la.sym[ib + 1] >> 2) <= 32 * b) ib++;
-			la.nic_blk[b] = (unsigned char) ib;
-		}
-		// the table path needs a row for every symbol in effect on the line, and at most one symbol start per block
-		if(dp.have_nicam)
-		{
-			if(!dp.nicam_lut_ok || dp.nicam_sps - 1 < 32 || ns < 1 || (la.sym[0] >> 2) > 0) generic = 1;
-			for(int i = la.nic_blk[0]; i < ns; i++) if(la.symrow[i] < 0) generic = 1;
-		}
-		la.nic_generic = generic;
+		la.m0 = m0;
+		kd_div((unsigned long long) m0, 32767u, 1.0 / 32767.0, rem); la.kk0 = (int) rem;
+		rem = 0;
+		if(dp.have_nicam) kd_div((unsigned long long) m0, (unsigned) dp.nicam_cc_len, 1.0 / (double) dp.nicam_cc_len, rem);
+		la.cc0 = (int) rem;
+		la.am_phase0 = dp.am_ang * (unsigned long long) m0;
+		la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
 	}
+
+	// ---- audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1) -------------
+	int myx = 0x7FFFFFFF;                                               // lane k: seg_x[k]
+	if(dp.have_fm || dp.have_am)
+	{
+		const double inv_ar = 1.0 / (double) HTV_AUDIO_RATE;
+		const long long jf = (long long) kd_div((unsigned long long) (m0 + 1) * HTV_AUDIO_RATE, (unsigned) dp.rate, 1.0 / (double) dp.rate, rem) - 1;
+		if(lane < MAX_SEGS)
+		{
+			const long long j = jf + lane;
+			// seg_start(j) = j < 0 ? 0 : ceil((j + 1) rate / 32000) - 1
+			long long st = 0;
+			if(j >= 0) st = (long long) kd_div((unsigned long long) (j + 1) * (unsigned long long) dp.rate + HTV_AUDIO_RATE - 1, HTV_AUDIO_RATE, inv_ar, rem) - 1;
+			if(st < m0 + W)
+			{
+				myx = (int) max(0ll, st - m0);
+				unsigned long long ang = 0, ph = 0;
+				if(dp.have_fm)
+				{
+					ang = dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
+					// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
+					ph = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
+				}
+				la.seg_ang[lane] = ang; la.seg_phase[lane] = ph;
+				la.seg_am[lane] = dp.have_am ? pcm_mono(dt, j, dp.volume) : 0;
+			}
+			else { la.seg_ang[lane] = 0; la.seg_phase[lane] = 0; la.seg_am[lane] = 0; }
+		}
+	}
+	if(lane < MAX_SEGS + 2) la.seg_x[lane] = lane < MAX_SEGS ? myx : 0x7FFFFFFF;
+	{
+		// segment in effect at x = 32 b: (segments starting at or before it) - 1
+		int sx[MAX_SEGS];
+		#pragma unroll
+		for(int k = 0; k < MAX_SEGS; k++) sx[k] = __shfl_sync(0xFFFFFFFFu, myx, k);
+		for(int b = lane; b < MAX_BLKS; b += 32)
+		{
+			int sg = -1;
+			#pragma unroll
+			for(int k = 0; k < MAX_SEGS; k++) sg += sx[k] <= 32 * b;
+			la.fm_blk[b] = (unsigned char) max(0, min(sg, MAX_SEGS - 1));
+		}
+	}
+
+	// ---- NICAM symbols (ref nicam728.c:342-411) ---------------------------------------------------------
+	int ns = 0, generic = 0;
+	if(dp.have_nicam)
+	{
+		const unsigned F = (unsigned) dp.nicam_F, D = (unsigned) dp.nicam_D;
+		const double inv_f = 1.0 / (double) F;
+		// symbols whose pulse can still reach this line: ntaps samples back
+		const long long sfirst = (long long) kd_div((unsigned long long) max(0ll, m0 - dp.nicam_ntaps) * D, F, inv_f, rem);
+		const long long slast = (long long) kd_div((unsigned long long) (m0 + W - 1) * D, F, inv_f, rem);
+		ns = (int) min((long long) MAX_SYMS, slast - sfirst + 1);
+		const int lead = (int) min(5ll, sfirst);
+		const long long s0 = sfirst - lead;
+		// pos(s0 + i) = ceil((s0 + i) F / D) = q0 + ceil((r0 + i F) / D)
+		unsigned r0, ks0;
+		const long long q0 = (long long) kd_div((unsigned long long) s0 * F, D, 1.0 / (double) D, r0);
+		const long long k0 = (long long) kd_div((unsigned long long) s0, 364u, 1.0 / 364.0, ks0);
+		const int minor_adv = dp.nicam_minor_short ? dp.nicam_sps - 1 : dp.nicam_sps;
+		const int dq = (int) (q0 - m0);                                 // |q0 - m0| < ntaps + W + a few symbols
+		unsigned long long MI = 0, MQ = 0, MG = 0;
+		int posr[2], code[2];
+		#pragma unroll
+		for(int r = 0; r < 2; r++)
+		{
+			const int i = lane + 32 * r;
+			const bool valid = i < lead + ns;
+			const int p = (int) ((r0 + (unsigned) i * F + D - 1) / D);
+			const int pm = i > 0 ? (int) ((r0 + (unsigned) (i - 1) * F + D - 1) / D) : 0;
+			const bool minor = valid && i > 0 && p - pm == minor_adv;    // the window's first symbol: unknown, never used
+			int ks = (int) ks0 + i;
+			long long k = k0;
+			if(ks >= 364) { ks -= 364; k++; }
+			int cd = 0;
+			if(valid)
+			{
+				const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[(s0 + i) & (RS - 1)]) & 3;
+				// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
+				cd = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
+			}
+			posr[r] = p; code[r] = cd;
+			MI |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, valid && (cd & 1)) << (32 * r);
+			MQ |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, valid && (cd & 2)) << (32 * r);
+			MG |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, minor) << (32 * r);
+		}
+		for(int b = lane; b < MAX_BLKS; b += 32) s_blk[wid][b] = 0;
+		__syncwarp();
+		// listed symbol o <-> window index i = o + lead: handled by the lane that holds i
+		#pragma unroll
+		for(int r = 0; r < 2; r++)
+		{
+			const int i = lane + 32 * r, o = i - lead;
+			if(o >= 0 && o < ns)
+			{
+				// bit j of a pattern = the j-th latest symbol (0 = this one): window bits i-5 .. i, reversed
+				const unsigned wi = i >= 5 ? (unsigned) (MI >> (i - 5)) & 63u : (unsigned) (MI << (5 - i)) & 63u;
+				const unsigned wq = i >= 5 ? (unsigned) (MQ >> (i - 5)) & 63u : (unsigned) (MQ << (5 - i)) & 63u;
+				const unsigned wg = i >= 4 ? (unsigned) (MG >> (i - 4)) & 31u : (unsigned) (MG << (4 - i)) & 31u;
+				const int patI = (int) (__brev(wi) >> 26), patQ = (int) (__brev(wq) >> 26), gaps = (int) (__brev(wg) >> 27);
+				const int sx = dq + posr[r];
+				int bI = 0xFFFF, bQ = 0xFFFF;
+				const bool row_ok = dp.nicam_lut_ok && s0 + i >= 5 && __popc(gaps) <= 1;
+				if(row_ok)
+				{
+					const int gg = gaps ? 1 + (__ffs(gaps) - 1) : 0;       // which gap (1 = newest) has the rarer spacing
+					bI = (gg * 64 + patI) * dp.nicam_sps - sx + 2048;
+					bQ = (gg * 64 + patQ) * dp.nicam_sps - sx + 2048;
+				}
+				la.symb[o] = make_uint2((unsigned) (bI & 0xFFFF) | ((unsigned) (bQ & 0xFFFF) << 16), (unsigned) sx);
+				la.symc[o] = (unsigned char) code[r];
+				// the symbol comes into effect at the first block that starts at or behind it
+				const int bo = sx <= 0 ? 0 : (sx + 31) >> 5;
+				if(bo < MAX_BLKS) atomicMax(&s_blk[wid][bo], o);
+			}
+		}
+		if(lane == 0) la.symb[ns] = make_uint2(0u, 0x7FFFFFFFu);
+		__syncwarp();
+		// running maximum over the blocks: blocks without a symbol start keep the previous symbol
+		int carry = 0;
+		for(int b0 = 0; b0 < MAX_BLKS; b0 += 32)
+		{
+			const int b = b0 + lane;
+			int v = b < MAX_BLKS ? s_blk[wid][b] : 0;
+			#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, v, o); if(lane >= o) v = max(v, u); }
+			v = max(v, carry);
+			if(b < MAX_BLKS) la.nic_blk[b] = (unsigned char) v;
+			carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+		}
+		// the table path needs a row for every symbol in effect on the line and at most one symbol start per block
+		generic = !dp.nicam_lut_ok || dp.nicam_sps - 1 < 32 || ns < 1;
+	}
+	// ... checked in a second pass: the symbols in effect are those from nic_blk[0] on
+	if(dp.have_nicam)
+	{
+		__syncwarp();
+		const int ib0 = la.nic_blk[0];
+		int bad = 0;
+		for(int o = lane; o < ns; o += 32)
+		{
+			const uint2 e = la.symb[o];
+			if(o >= ib0 && (e.x & 0xFFFFu) == 0xFFFFu) bad = 1;
+			if(o == 0 && (int) e.y > 0) bad = 1;
+		}
+		generic |= __any_sync(0xFFFFFFFFu, bad);
+	}
+	if(lane == 0) { la.nsym = ns; la.nic_generic = generic; }
 }
 
 // raster descriptors: index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
@@ -2663,11 +2839,19 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			d->kl_smem = (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
 			d->use_line = 1;
-			#define KL_ATTR(VF, HQ) do { \
-				cudaFuncSetAttribute(k_line<VF, HQ, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
-				cudaFuncSetAttribute(k_line<VF, HQ, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+			{
+				// the chroma low-pass cannot leave the int16 range when the sum of |taps| is at most 32768 (Gaussian taps: always)
+				long long sum = 0;
+				for(int i = 0; i < dp.chroma_ntaps; i++) sum += dp.chroma_taps[i] < 0 ? -dp.chroma_taps[i] : dp.chroma_taps[i];
+				d->kl_csat = sum > 32768;
+			}
+			#define KL_ATTR2(VF, HQ, FU, CS) do { \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+			#define KL_ATTR(VF, HQ) do { KL_ATTR2(VF, HQ, true, false); KL_ATTR2(VF, HQ, false, false); KL_ATTR2(VF, HQ, false, true); } while(0)
 			KL_ATTR(false, false); KL_ATTR(true, false); KL_ATTR(true, true);
 			#undef KL_ATTR
+			#undef KL_ATTR2
 		}
 	}
 	if(secam)
@@ -2699,6 +2883,8 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreate(&d->ev0);
 	cudaEventCreate(&d->ev1);
 	cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&d->side2, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&d->ev_nic, cudaEventDisableTiming);
 	cudaStreamCreateWithFlags(&d->up, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags(&d->ev_up, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_chunk[0], cudaEventDisableTiming);
@@ -2721,7 +2907,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	DevGuard guard(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
 	if(d->h_ov_line) { cudaFreeHost(d->h_ov_line); cudaFreeHost(d->h_ov_meta); cudaFreeHost(d->h_ov_add); }
 	cudaFree(d->d_ov_line); cudaFree(d->d_ov_meta); cudaFree(d->d_ov_add);
@@ -2732,6 +2918,8 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
+	if(d->side2) cudaStreamDestroy(d->side2);
+	if(d->ev_nic) cudaEventDestroy(d->ev_nic);
 	if(d->up) cudaStreamDestroy(d->up);
 	if(d->ev_up) cudaEventDestroy(d->ev_up);
 	if(d->ev_chunk[0]) cudaEventDestroy(d->ev_chunk[0]);
@@ -2872,6 +3060,9 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	}
 	if(dp.have_nicam)
 	{
+		// its own stream beside the FM chain; `side` (where the descriptors follow) joins below
+		CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));
+		st = d->side2;
 		const int64_t s_lo = (int64_t) (((unsigned long long) (m0 > dp.nicam_ntaps ? m0 - dp.nicam_ntaps : 0) * dp.nicam_D) / dp.nicam_F);
 		const int64_t s_hi = (int64_t) (((unsigned long long) (m1 - 1) * dp.nicam_D) / dp.nicam_F);
 		int64_t k_lo = s_lo / 364, k_hi = s_hi / 364;
@@ -2881,6 +3072,8 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
+		CK(cudaEventRecord(d->ev_nic, d->side2));
+		CK(cudaStreamWaitEvent(d->side, d->ev_nic, 0));
 	}
 	CK(cudaGetLastError());
 	return(HTV_OK);
@@ -2898,12 +3091,19 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	{
 		cudaStreamSynchronize(st);
 		cudaStreamSynchronize(d->side);
-		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2);
-		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = NULL;
+		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2);
+		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = NULL;
 		d->desc_cap = 0;
-		CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
-		CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
-		CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
+		if(d->use_line)
+		{
+			CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
+			CK(cudaMalloc(&d->d_desc_a2, sizeof(LineA2) * ((size_t) nlines + 1)));
+		}
+		else
+		{
+			CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
+			CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
+		}
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
@@ -2918,7 +3118,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			CK(cudaEventRecord(d->ev_in, st));
 			CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 		}
-		k_line_desc_a<<<(nlines + 63) / 64, 64, 0, d->side>>>(dp, d->dt, ld, line0, nlines);
+		LineA2 *la2 = (LineA2 *) d->d_desc_a2;
+		k_line_desc_a2<<<(nlines + KD_WARPS - 1) / KD_WARPS, 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
 		CK(cudaEventRecord(d->ev_audio, d->side));
 		d->side_armed = 0;
 		CK(cudaStreamWaitEvent(st, d->ev_audio, 0));
@@ -2927,13 +3128,17 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		if(run < 4) run = 4;
 		const int grid = (nlines + run - 1) / run;
 		if(d->timing) cudaEventRecord(d->ev0, st);
-		#define KL_GO(VF, HQ) do { \
-			if(d->kl_threads <= 256) k_line<VF, HQ, 256, 4><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, ld.a, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
-			else k_line<VF, HQ, 384, 2><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, ld.a, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
+		#define KL_GO2(VF, HQ, FU, CS) do { \
+			if(d->kl_threads <= 256) k_line<VF, HQ, FU, CS, 256, 4><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
+			else k_line<VF, HQ, FU, CS, 384, 2><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
+		// the common case (128 | W, a chroma filter that cannot overflow) gets its own instantiation; everything else the general one
+		#define KL_GO(VF, HQ) do { if(dp.W % MF_TILE == 0 && !d->kl_csat) KL_GO2(VF, HQ, true, false); \
+			else if(!d->kl_csat) KL_GO2(VF, HQ, false, false); else KL_GO2(VF, HQ, false, true); } while(0)
 		if(!dp.vf_type) KL_GO(false, false);
 		else if(dp.vf_type == 3) KL_GO(true, true);
 		else KL_GO(true, false);
 		#undef KL_GO
+		#undef KL_GO2
 		d->launches += 3;
 		d->last_mod_lines = nlines;
 		if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }

@@ -46,9 +46,22 @@ __host__ __device__ inline uint32_t kl_chroma_a_word(const int32_t *taps, int nt
 // one complex int16 table entry through the read-only path: x = i, y = q
 __device__ __forceinline__ short2 kl_ldc16(const htv_c16_t *p) { return(__ldg(reinterpret_cast<const short2 *>(p))); }
 
-__device__ __forceinline__ int kl_fir_out(int hh, int mid, int ll)
+// the three partial sums of a byte-split contraction back to the reference's int32 accumulator (mf_combine:
+// 65536 hh + 256 mid + ll with wrap-around), as two shift-adds, then >> 15
+__device__ __forceinline__ int kl_acc15(int hh, int mid, int ll)
 {
-	return(sat16i(mf_combine(hh, mid, ll) >> 15));
+	const unsigned t = (unsigned) mid + ((unsigned) hh << 8);
+	return((int) ((unsigned) ll + (t << 8)) >> 15);
+}
+__device__ __forceinline__ int kl_fir_out(int hh, int mid, int ll) { return(sat16i(kl_acc15(hh, mid, ll))); }
+
+// next-line data into L1 while this line is computed: the kernel is otherwise bound by the latency of
+// first-touch loads (descriptors, template, picture row, subcarrier table all change every line)
+// A real load whose result is only "used" at the end of the iteration: unlike prefetch.global.L1 (measured: no
+// effect on the L1 hit rate of the ld.global.nc path here) it is guaranteed to allocate the line in L1.
+__device__ __forceinline__ void kl_prefetch(const void *p, unsigned &sink)
+{
+	sink ^= __ldg(reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3));
 }
 
 // ---- sound carriers for the four samples of a lane (strided by 8) --------------------------------------------
@@ -56,7 +69,7 @@ __device__ __forceinline__ int kl_fir_out(int hh, int mid, int ll)
 // finds its audio segment and NICAM symbol: all four samples lie in the 32-sample block b = xb >> 5, for which
 // the line descriptor lists the segment / symbol in effect at the block's first sample, and at most one
 // boundary of either kind falls inside a block.
-__device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTables &dt, const LineAudio *la,
+__device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTables &dt, const LineA2 *la,
 	const short *ntp, int xb, int (&oi)[4], int (&oq)[4])
 {
 	const int b = xb >> 5;
@@ -137,14 +150,14 @@ __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTable
 				const int x = xb + 8 * j;
 				int i3 = 0;
 				const int ns = __ldg(&la->nsym);
-				while(i3 + 1 < ns && (__ldg(la->sym + i3 + 1) >> 2) <= x) i3++;
+				while(i3 + 1 < ns && (int) __ldg(&la->symb[i3 + 1].y) <= x) i3++;
 				bi[j] = 0; bq[j] = 0;
 				for(int cnd = 0; cnd < NIC_CAND; cnd++)
 				{
 					const int i = i3 - cnd;
 					if(i < 0) break;
-					const int sy = __ldg(la->sym + i);
-					const int d0 = x - (sy >> 2) + NIC_TPAD;                // the table is zero outside the pulse
+					const int sy = __ldg(la->symc + i);
+					const int d0 = x - (int) __ldg(&la->symb[i].y) + NIC_TPAD;  // the table is zero outside the pulse
 					if(d0 < 0) continue;
 					const int r = ntp[d0];
 					bi[j] += (sy & 1) ? r : -r;
@@ -166,7 +179,8 @@ __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTable
 }
 
 // Mixers after the modulation (ref video.c:3466-3515), channel combiner, store - post_store for the strided layout
-__device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const DevTables &dt, const LineAudio *la,
+template<bool FULL>
+__device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const DevTables &dt, const LineA2 *la,
 	int xb, int row, int (&oi)[4], int (&oq)[4], int16_t *out, const int16_t *acc)
 {
 	const int W = dp.W;
@@ -212,7 +226,7 @@ __device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const Dev
 		#pragma unroll
 		for(int j = 0; j < 4; j++)
 		{
-			if(xb + 8 * j < W)
+			if(FULL || xb + 8 * j < W)
 			{
 				unsigned v = ((unsigned) oi[j] & 0xFFFFu) | ((unsigned) oq[j] << 16);
 				if(a) v = __vadd2(v, __ldcs(a + 8 * j));
@@ -226,15 +240,16 @@ __device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const Dev
 		#pragma unroll
 		for(int j = 0; j < 4; j++)
 		{
-			if(xb + 8 * j < W) o[8 * j] = (unsigned short) (oi[j] + (acc ? acc[lbase + xb + 8 * j] : 0));
+			if(FULL || xb + 8 * j < W) o[8 * j] = (unsigned short) (oi[j] + (acc ? acc[lbase + xb + 8 * j] : 0));
 		}
 	}
 }
 
-// VF: a video filter is on (composite ring + tensor-core FIR); HASQ: it has Q taps (VSB)
-template<bool VF, bool HASQ, int MAXT, int MINB>
+// VF: a video filter is on (composite ring + tensor-core FIR); HASQ: it has Q taps (VSB); FULL: 128 | W (no
+// partial tile: the x < W tests fold away); CSAT: the chroma low-pass can leave the int16 range (sum of |taps| > 32768)
+template<bool VF, bool HASQ, bool FULL, bool CSAT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR2 *lrp, const LineAudio *lap,
+k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR2 *lrp, const LineA2 *lap,
 	int nlines, int run, int16_t *out, const int16_t *acc, int acc_rows)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,6 +265,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
 	const int xb = MF_TILE * nt + 32 * t + g;                               // the lane's samples: xb + 8 j
+	(void) T;
 
 	// ---- one-time set-up -------------------------------------------------------
 	if(VF) for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
@@ -267,10 +283,48 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	if(a >= nlines) return;
 	const int full_l = dp.active_left, full_r = dp.active_left + dp.active_width;
 	const bool in_full = xb + 24 >= full_l && xb < full_r;                  // the lane touches the picture area at all
+	const bool all_full = xb >= full_l && xb + 24 < full_r;                 // ... with all four samples
+	const bool in_burst = xb + 24 >= dp.burst_left && xb < dp.burst_left + dp.burst_width;
+	unsigned char *const uv0 = uvp + KL_UVLEAD + xb;                        // the lane's bytes in the four chroma planes
+	const unsigned char *const uvb = uvp + MF_M * (8 * nt + g) + 8 * t;     // ... and its chroma B fragment
+	const int fo0 = mf_b_offset(nt, 0, lane);
 
 	// relative line q: raster lines a-1 .. bnd (descriptor lrp[q + 1]), modulate a .. bnd-1
-	for(int q = VF ? a - 1 : a; q <= (VF ? bnd : bnd - 1); q++)
+	const int q0 = VF ? a - 1 : a, q1 = VF ? bnd : bnd - 1;
+	int r3 = (q0 + 3) % 3;                                                  // ring row of line q
+	unsigned sink = 0;
+	for(int q = q0; q <= q1; q++, r3 = r3 == 2 ? 0 : r3 + 1)
 	{
+		asm volatile("" :: "r"(sink));                                      // last iteration's prefetch loads end here
+		// ---- next line's first-touch data -> L1 (one 128-byte line per lane) -------------
+		if(nt == 0)
+		{
+			if(lane == 0 && q + 2 <= nlines) kl_prefetch(lrp + q + 3, sink);
+			const int ml = VF ? q : q + 1;                                  // the line the next iteration modulates
+			if(lane >= 1 && lane <= (int) (sizeof(LineA2) + 127) / 128 + 1 && ml < nlines)
+				kl_prefetch(reinterpret_cast<const char *>(lap + ml) + 128 * (lane - 1), sink);
+		}
+		else if(nt <= 3 && q + 1 <= q1)
+		{
+			const int4 *ln = reinterpret_cast<const int4 *>(lrp + q + 2);
+			if(nt == 1)
+			{
+				const int tm = __ldg(reinterpret_cast<const int *>(ln) + 1);
+				if(128 * lane < 2 * W) kl_prefetch(reinterpret_cast<const char *>(dt.tmpl_out + (size_t) tm * W) + 128 * lane, sink);
+			}
+			else if(nt == 2)
+			{
+				const int4 n3 = __ldg(ln + 3);
+				const long long ro = ((long long) (unsigned) n3.x) | ((long long) n3.y << 32);
+				if(ro >= 0 && 128 * lane < 4 * dp.active_width) kl_prefetch(reinterpret_cast<const char *>(dt.frames + ro) + 128 * lane, sink);
+			}
+			else if(dt.clut)
+			{
+				const unsigned co = (unsigned) __ldg(reinterpret_cast<const int *>(ln) + 8);
+				for(int i = lane; 128 * i < 4 * W; i += 32) kl_prefetch(reinterpret_cast<const char *>(dt.clut + co) + 128 * i, sink);
+			}
+		}
+
 		// ---- R1: template + picture -------------------------------------------
 		const int4 *lq = reinterpret_cast<const int4 *>(lrp + q + 1);
 		const int4 l0 = __ldg(lq), l1 = __ldg(lq + 1), l2 = __ldg(lq + 2), l3 = __ldg(lq + 3);
@@ -283,41 +337,66 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		{
 			const int16_t *tp = dt.tmpl_out + (size_t) li_tmpl * W + xb;
 			#pragma unroll
-			for(int j = 0; j < 4; j++) val[j] = xb + 8 * j < W ? (int) __ldg(tp + 8 * j) : 0;
+			for(int j = 0; j < 4; j++) val[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(tp + 8 * j) : 0;
 		}
 		int uu[4] = { 0, 0, 0, 0 }, vv[4] = { 0, 0, 0, 0 };
 		if(in_full && li_al < li_ar)
 		{
-			const uint32_t *px = dt.frames + li_row + (xb - dp.active_left);
-			const int16_t *kp = dt.tmpl_keep + (size_t) li_tmpl * W + xb;
-			#pragma unroll
-			for(int j = 0; j < 4; j++)
+			const uint32_t *px = dt.frames + (li_row >= 0 ? li_row : 0) + (xb - dp.active_left);
+			if(xb >= li_al && xb + 24 < li_ar && !li_keep)
 			{
-				const int x = xb + 8 * j;
-				if(x >= li_al && x < li_ar)
+				// all four samples in the picture: loads back to back, no per-sample tests
+				unsigned rgb[4];
+				#pragma unroll
+				for(int j = 0; j < 4; j++) rgb[j] = __ldg(px + 8 * j) & 0xFFFFFFu;
+				if(li_row < 0) rgb[0] = rgb[1] = rgb[2] = rgb[3] = 0u;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
 				{
-					const unsigned rgb = li_row >= 0 ? (__ldg(px + 8 * j) & 0xFFFFFFu) : 0u;
-					const short4 e = __ldg(dt.yuv_lut + rgb);
+					const short4 e = __ldg(dt.yuv_lut + rgb[j]);
 					val[j] = e.x; uu[j] = e.y; vv[j] = e.z;
-					if(li_keep) val[j] += __ldg(kp + 8 * j);
+				}
+			}
+			else
+			{
+				const int16_t *kp = dt.tmpl_keep + (size_t) li_tmpl * W + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const int x = xb + 8 * j;
+					if(x >= li_al && x < li_ar)
+					{
+						const unsigned rgb = li_row >= 0 ? (__ldg(px + 8 * j) & 0xFFFFFFu) : 0u;
+						const short4 e = __ldg(dt.yuv_lut + rgb);
+						val[j] = e.x; uu[j] = e.y; vv[j] = e.z;
+						if(li_keep) val[j] += __ldg(kp + 8 * j);
+					}
 				}
 			}
 		}
 		if(li_pal)
 		{
-			if(in_full)
+			// unfiltered U, V as byte planes; outside the picture the planes stay zero (the reference filters
+			// each line on its own: zero history either side, ref fir.c:357-375)
+			if(all_full)
 			{
-				// unfiltered U, V as byte planes; outside the picture the planes stay zero (the reference filters
-				// each line on its own: zero history either side, ref fir.c:357-375)
-				unsigned char *p = uvp + KL_UVLEAD + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					uv0[8 * j] = (unsigned char) (uu[j] >> 8); uv0[UB + 8 * j] = (unsigned char) uu[j];
+					uv0[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); uv0[3 * UB + 8 * j] = (unsigned char) vv[j];
+				}
+			}
+			else if(in_full)
+			{
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
 					const int x = xb + 8 * j;
 					if(x >= full_l && x < full_r)
 					{
-						p[8 * j] = (unsigned char) (uu[j] >> 8); p[UB + 8 * j] = (unsigned char) uu[j];
-						p[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); p[3 * UB + 8 * j] = (unsigned char) vv[j];
+						uv0[8 * j] = (unsigned char) (uu[j] >> 8); uv0[UB + 8 * j] = (unsigned char) uu[j];
+						uv0[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); uv0[3 * UB + 8 * j] = (unsigned char) vv[j];
 					}
 				}
 			}
@@ -327,19 +406,22 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			{
 				int uhh[4] = { 0, 0, 0, 0 }, umid[4] = { 0, 0, 0, 0 }, ull[4] = { 0, 0, 0, 0 };
 				int vhh[4] = { 0, 0, 0, 0 }, vmid[4] = { 0, 0, 0, 0 }, vll[4] = { 0, 0, 0, 0 };
-				const int o0 = MF_M * (8 * nt + g) + 8 * t;
 				const uint4 ah = ctab[lane], al4 = ctab[32 + lane];
-				const uint2 uh = *reinterpret_cast<const uint2 *>(uvp + o0), ul = *reinterpret_cast<const uint2 *>(uvp + UB + o0);
-				const uint2 vh = *reinterpret_cast<const uint2 *>(uvp + 2 * UB + o0), vl = *reinterpret_cast<const uint2 *>(uvp + 3 * UB + o0);
+				const uint2 uh = *reinterpret_cast<const uint2 *>(uvb), ul = *reinterpret_cast<const uint2 *>(uvb + UB);
+				const uint2 vh = *reinterpret_cast<const uint2 *>(uvb + 2 * UB), vl = *reinterpret_cast<const uint2 *>(uvb + 3 * UB);
 				mma_ss(uhh, ah, uh); mma_su(umid, ah, ul); mma_us(umid, al4, uh); mma_uu(ull, al4, ul);
 				mma_ss(vhh, ah, vh); mma_su(vmid, ah, vl); mma_us(vmid, al4, vh); mma_uu(vll, al4, vl);
 				// accumulator register ci <-> sample j: ci = ((j & 1) << 1) | (j >> 1)
-				cu[0] = kl_fir_out(uhh[0], umid[0], ull[0]); cu[1] = kl_fir_out(uhh[2], umid[2], ull[2]);
-				cu[2] = kl_fir_out(uhh[1], umid[1], ull[1]); cu[3] = kl_fir_out(uhh[3], umid[3], ull[3]);
-				cv[0] = kl_fir_out(vhh[0], vmid[0], vll[0]); cv[1] = kl_fir_out(vhh[2], vmid[2], vll[2]);
-				cv[2] = kl_fir_out(vhh[1], vmid[1], vll[1]); cv[3] = kl_fir_out(vhh[3], vmid[3], vll[3]);
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const int ci = ((j & 1) << 1) | (j >> 1);
+					cu[j] = kl_acc15(uhh[ci], umid[ci], ull[ci]);
+					cv[j] = kl_acc15(vhh[ci], vmid[ci], vll[ci]);
+					if(CSAT) { cu[j] = sat16i(cu[j]); cv[j] = sat16i(cv[j]); }
+				}
 			}
-			if(xb + 24 >= dp.burst_left && xb < dp.burst_left + dp.burst_width)
+			if(in_burst)
 			{
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
@@ -358,7 +440,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					if(xb + 8 * j < W)
+					if(FULL || xb + 8 * j < W)
 					{
 						const short2 c = kl_ldc16(cp + 8 * j);
 						val[j] += ((int) c.x * cv[j] * li_pal + (int) c.y * cu[j]) >> 15;
@@ -383,17 +465,17 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		if(VF)
 		{
 			// ---- composite line -> ring row q mod 3 (+ the neighbours' halos) ----------
-			const int r3 = (q + 3) % 3;
+			const int rprev = r3 == 0 ? 2 : r3 - 1, rnext = r3 == 2 ? 0 : r3 + 1;
 			unsigned char *rp = rows + (2 * r3) * RB + KL_LEAD + xb;
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
 			{
-				if(xb + 8 * j < W) { rp[8 * j] = (unsigned char) (val[j] >> 8); rp[RB + 8 * j] = (unsigned char) val[j]; }
+				if(FULL || xb + 8 * j < W) { rp[8 * j] = (unsigned char) (val[j] >> 8); rp[RB + 8 * j] = (unsigned char) val[j]; }
 			}
 			if(xb < KL_LEAD)
 			{
 				// first 32 samples: right halo of the previous line's row
-				unsigned char *hp = rows + (2 * ((q + 2) % 3)) * RB + KL_LEAD + W + xb;
+				unsigned char *hp = rows + (2 * rprev) * RB + KL_LEAD + W + xb;
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
@@ -403,7 +485,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			if(xb + 24 >= W - KL_LEAD && xb < W)
 			{
 				// last 32 samples: left halo of the next line's row
-				unsigned char *hp = rows + (2 * ((q + 4) % 3)) * RB + xb - (W - KL_LEAD);
+				unsigned char *hp = rows + (2 * rnext) * RB + xb - (W - KL_LEAD);
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
@@ -415,15 +497,14 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			mrow = q - 1;
 			if(mrow < a) continue;
 			// ---- M: video filter of line q - 1, one tile of 128 samples per warp -------
-			const unsigned char *ph = rows + (2 * ((mrow + 3) % 3)) * RB, *plo = ph + RB;
+			const unsigned char *ph = rows + (2 * rprev) * RB + fo0, *plo = ph + RB;
 			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
 			int qhh[4] = { 0, 0, 0, 0 }, qmid[4] = { 0, 0, 0, 0 }, qll[4] = { 0, 0, 0, 0 };
-			const int o0 = mf_b_offset(nt, 0, lane);
 			#pragma unroll
 			for(int s = 0; s < MF_KSTEPS; s++)
 			{
-				const uint2 xh = *reinterpret_cast<const uint2 *>(ph + o0 + 32 * s);
-				const uint2 xl = *reinterpret_cast<const uint2 *>(plo + o0 + 32 * s);
+				const uint2 xh = *reinterpret_cast<const uint2 *>(ph + 32 * s);
+				const uint2 xl = *reinterpret_cast<const uint2 *>(plo + 32 * s);
 				const uint4 aih = atab[(s * 4 + 0) * 32 + lane], ail = atab[(s * 4 + 1) * 32 + lane];
 				mma_ss(ihh, aih, xh); mma_su(imid, aih, xl); mma_us(imid, ail, xh); mma_uu(ill, ail, xl);
 				if(HASQ)
@@ -432,14 +513,13 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 					mma_ss(qhh, aqh, xh); mma_su(qmid, aqh, xl); mma_us(qmid, aql, xh); mma_uu(qll, aql, xl);
 				}
 			}
-			oi[0] = kl_fir_out(ihh[0], imid[0], ill[0]); oi[1] = kl_fir_out(ihh[2], imid[2], ill[2]);
-			oi[2] = kl_fir_out(ihh[1], imid[1], ill[1]); oi[3] = kl_fir_out(ihh[3], imid[3], ill[3]);
-			if(HASQ)
+			#pragma unroll
+			for(int j = 0; j < 4; j++)
 			{
-				oq[0] = kl_fir_out(qhh[0], qmid[0], qll[0]); oq[1] = kl_fir_out(qhh[2], qmid[2], qll[2]);
-				oq[2] = kl_fir_out(qhh[1], qmid[1], qll[1]); oq[3] = kl_fir_out(qhh[3], qmid[3], qll[3]);
+				const int ci = ((j & 1) << 1) | (j >> 1);
+				oi[j] = kl_fir_out(ihh[ci], imid[ci], ill[ci]);
+				oq[j] = HASQ ? kl_fir_out(qhh[ci], qmid[ci], qll[ci]) : 0;
 			}
-			else { oq[0] = oq[1] = oq[2] = oq[3] = 0; }
 		}
 		else
 		{
@@ -449,11 +529,11 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		}
 
 		// ---- sound carriers, mixers, store ---------------------------------------
-		if(xb < W)
+		if(FULL || xb < W)
 		{
-			const LineAudio *la = lap + mrow;
+			const LineA2 *la = lap + mrow;
 			kl_sound(dp, dt, la, ntp, xb, oi, oq);
-			kl_post_store(dp, dt, la, xb, mrow, oi, oq, out, mrow < acc_rows ? acc : NULL);
+			kl_post_store<FULL>(dp, dt, la, xb, mrow, oi, oq, out, mrow < acc_rows ? acc : NULL);
 		}
 	}
 }

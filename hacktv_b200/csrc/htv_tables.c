@@ -285,7 +285,8 @@ static void build_templates(struct htv_tables_t *t)
 					if(s == 1)
 					{
 						k[x] = (int16_t) (k[x] + t->pulse_values[dp->pulse_pos[b] + d]);
-						if(k[x]) t->tmpl_keep_any[r] = 1;
+						/* only where a picture can be drawn: the hsync edge of the next line sits in the front porch */
+						if(k[x] && x >= dp->active_left && x < dp->active_left + dp->active_width) t->tmpl_keep_any[r] = 1;
 					}
 				}
 			}
