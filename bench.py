@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A *step* is one pass of the hot path over one batch: FRAMES video frames (default 64 =
-40 000 scan lines = 40.96 M complex samples = 164 MB of int16 IQ, larger than the 126 MB
-L2) of BASELINE config 2: PAL System I, 16 Msps, --filter (VSB) + FM mono + NICAM-728 +
+A *step* is one pass of the hot path over one batch: FRAMES video frames (default 1024 =
+640 000 scan lines = 655 M complex samples, rendered in 16 calls of 64 frames = 164 MB of
+int16 IQ each - larger than the 126 MB L2 - into the same device buffer; 20 steps keep the
+GPU busy for > 100 ms, so the 1 kHz clock sampler sees the timed region) of BASELINE config 2: PAL System I, 16 Msps, --filter (VSB) + FM mono + NICAM-728 +
 colour, built-in test pattern and tone. With N GPUs each rank renders its own independent
 RF channel on its own GPU (weak scaling, no collective on the data path); `value` is
 the sum over channels divided by the slowest rank's device time.
 
 Keys beyond the base contract:
-  roofline      HBM-write roofline of the dominant kernel (k_mod_tma): algorithmic bytes
-                (4 B per complex sample) / CUDA-event duration of that kernel, vs the
-                measured copy bandwidth in MEASURED_PEAKS.json.
+  roofline      HBM-write roofline of the dominant kernel (k_line, the fused line kernel):
+                algorithmic bytes (4 B per complex sample) / CUDA-event duration of that
+                kernel, vs the measured copy bandwidth in MEASURED_PEAKS.json; step_frac is
+                the same for the whole step, issue the kernel's issue-slot figures from ncu.
+  extra         device-resident lines for the other BASELINE configs (1, 3, 4, 5) and, at
+                N = 1, the drop-in path: hacktv's own CLI on the adapter vs the stock CLI.
   e2e           the same metric through htv_render_host() with HOST buffers: every
                 step uploads its pictures (a live source: one upload per frame) and sound,
                 renders, and copies the IQ back to pinned host memory.
@@ -37,17 +41,18 @@ sys.path.insert(0, ROOT)
 
 MODE, RATE, FILTER = "i", 16_000_000, True
 WORKLOAD = "PAL-I (-m i) 16 Msps --filter: VSB + FM mono + NICAM-728 + colour, built-in test pattern"
+WORKLOADS = {   # --workload: the metric is quoted on cfg2; cfg5 is BASELINE config 5's per-channel load (20 Msps)
+    "cfg2": ("i", 16_000_000, True, WORKLOAD),
+    "cfg5": ("i", 20_000_000, True, "PAL-I (-m i) 20 Msps --filter: VSB + FM mono + NICAM-728 + colour, built-in test pattern (BASELINE config 5, per channel)"),
+}
+CHUNK_FRAMES = 64        # frames per htv_render call: 164 MB of IQ at 16 Msps, larger than the L2
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 REF_THREADS = 3          # main/raster + vfilter + audio (reference video.c:4692: 1 + nthreads)
-# dram__bytes_read.sum + dram__bytes_write.sum of one modulator launch from the `ncu --set full` captures
-# (ncu flushes L2 between replays, so the L2-resident composite scratch is re-read from HBM and most of the
-# output is still in L2 when the kernel ends), per scan line of 1024 samples:
-#   k_mod_mma (default; profiles/r01_ncu_mod_mma_raw.txt): 8 192 lines, 21.71 MB read (two byte planes) + 0.11 MB written
-#   k_mod_tma (HTV_FIR=scalar; profiles/r01_ncu_mod_raw.txt): 7 232 lines, 38.48 MB read (int32 scratch) + 3.22 MB written
-NCU_TRAFFIC_BYTES_PER_LINE = {"mma": 21_822_208 / 8192, "scalar": 41_701_120 / 7232}
-FIR = "scalar" if os.environ.get("HTV_FIR") == "scalar" else "mma"
-KERNEL = {"mma": "k_mod_mma (video filter on the tensor cores: exact int8 byte-split mma.sync + sound carriers + IQ store)",
-          "scalar": "k_mod_tma (scalar video filter + sound carriers + IQ store)"}[FIR]
+# From the ncu --set full capture of the shipped k_line (profiles/r02_summary.md), per scan line of 1024 samples:
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 40 000 lines, and the issue-slot figures.
+NCU = {"file": "profiles/r02_ncu_k_line_raw.txt", "lines": 40000, "dram_read": 47_686_656, "dram_write": 112_344_064,
+       "warp_instructions": 238_153_871, "issue_active_pct": 59.1}
+KERNEL = "k_line (fused line kernel: raster + chroma and video filters on the tensor cores + sound carriers + IQ store)"
 
 
 def measured_peak_gbs():
@@ -125,12 +130,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "source": "nvml" if nv else "nvidia-smi"}
 
 
-def run_reference_instances(ninst, frames, timeout=900):
+def cpu_budget():
+    """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) // int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def run_reference_instances(ninst, frames, timeout=900, mode=MODE, rate=RATE, filt=FILTER):
     """ninst concurrent reference encoders, each timing `frames` frames after a 2-frame
     warm-up; returns (aggregate Msamples/s, per-instance list, wall seconds)."""
     lines = frames * 625
-    cmd = ["timeout", str(timeout), REF_HARNESS, "-m", MODE, "-s", str(RATE), "--skip", "1250", "--lines", str(lines), "--bench"]
-    if FILTER:
+    cmd = ["timeout", str(timeout), REF_HARNESS, "-m", mode, "-s", str(rate), "--skip", "1250", "--lines", str(lines), "--bench"]
+    if filt:
         cmd.append("--filter")
     t0 = time.time()
     procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(ninst)]
@@ -149,31 +167,143 @@ def run_reference_instances(ninst, frames, timeout=900):
 def bench_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    mode, rate, filt, workload = WORKLOADS[args.workload]
+    cores = cpu_budget()
     if not os.path.exists(REF_HARNESS):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness was not built (no reference tree at build time)"}))
         return
+    # one reference encoder = main + video-filter + audio thread and cannot use more: as many encoders as fit the
+    # threads this process may use (affinity mask and cgroup quota, not the machine's core count)
     ninst = max(1, cores // REF_THREADS)
     frames = args.ref_frames
+    single, _, _ = run_reference_instances(1, max(25, frames // 2), mode=mode, rate=rate, filt=filt)
     for _ in range(args.warmup):
-        run_reference_instances(ninst, max(2, frames // 4))
-    vals, t = [], 0.0
+        run_reference_instances(ninst, max(2, frames // 4), mode=mode, rate=rate, filt=filt)
+    vals, t, pers = [], 0.0, []
     for _ in range(args.steps):
-        agg, per, wall = run_reference_instances(ninst, frames)
+        agg, per, wall = run_reference_instances(ninst, frames, mode=mode, rate=rate, filt=filt)
         vals.append(agg)
+        pers += per
         t += wall
     v = sum(vals) / len(vals)
-    sample = f"{ninst} concurrent reference encoders x {frames} frames ({frames * 625 * 1024 / 1e6:.1f} Msamples each) per step, vid_next_line loop, no sink I/O"
+    pers.sort()
+    sample = f"{ninst} concurrent reference encoders x {frames} frames ({frames * 625 * (rate // 15625) / 1e6:.1f} Msamples each) per step, vid_next_line loop, no sink I/O"
     print(json.dumps({
         "impl": "reference", "metric": "IQ Msamples/s", "value": round(v, 3), "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1000 * t / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16 (int32/int64 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": f"{ninst} processes x {REF_THREADS} threads on {cores} host cores"},
-        "cpu_baseline": {"value": round(v, 3), "unit": "Msamples/s", "cores": ninst * REF_THREADS, "kind": "reference", "sample": sample},
+        "config": {"workload": workload, "parallelism": f"{ninst} processes x {REF_THREADS} threads on {cores} usable host threads ({os.cpu_count()} in the machine)"},
+        "cpu_baseline": {"value": round(v, 3), "unit": "Msamples/s", "cores": ninst * REF_THREADS, "kind": "reference", "sample": sample,
+                         "per_instance_msamples_per_s": {"min": round(pers[0], 2), "median": round(pers[len(pers) // 2], 2), "max": round(pers[-1], 2)},
+                         "single_encoder_alone_msamples_per_s": round(single, 2)},
         "e2e": {"value": round(v, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank to the host cores next to its GPU (NVML's CPU affinity of the device) BEFORE any pinned
+    memory is allocated: with 8 ranks on a two-socket box the staging buffers and the copy threads of GPUs 4-7
+    otherwise land on the far socket (round 1: e2e scaling 0.76 at N = 8)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def device_resident(H, torch, mode, rate, filt, frames, steps, warmup, stream, clock_index=None, **kw):
+    """K steps of `frames` frames each, rendered in calls of CHUNK_FRAMES into one device buffer; CUDA events."""
+    enc = H.Encoder(H.mode_config(mode, vfilter=filt, **kw), rate)
+    enc.open_test_source()
+    chunk = min(frames, CHUNK_FRAMES) * enc.lines
+    calls = max(1, frames // min(frames, CHUNK_FRAMES))
+    nsamp = chunk * enc.width
+    out = torch.empty(nsamp * (2 if enc.complex else 1), dtype=torch.int16, device="cuda")
+    enc.set_kernel_timing(True)
+    for _ in range(warmup):
+        enc.render(chunk, out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    l0 = enc.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    return enc, out, chunk, calls, nsamp, l0, ev0, ev1
+
+
+def quick_config(H, torch, stream, name, mode, rate, filt, frames=CHUNK_FRAMES, iters=10):
+    """One device-resident line for a BASELINE config that is not the metric's workload (for `extra`)."""
+    enc = H.Encoder(H.mode_config(mode, vfilter=filt), rate)
+    enc.open_test_source()
+    n = frames * enc.lines
+    out = torch.empty(n * enc.width * (2 if enc.complex else 1), dtype=torch.int16, device="cuda")
+    for _ in range(3):
+        enc.render(n, out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        enc.render(n, out.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    msps = n * enc.width / (ms / 1e3) / 1e6
+    enc.close()
+    return {"config": name, "frames_per_step": frames, "ms_per_step": round(ms, 4), "msamples_per_s": round(msps, 1),
+            "realtime_x": round(msps / (rate / 1e6), 1)}
+
+
+def dropin_throughput(seconds=4.0):
+    """The path a hacktv user runs: hacktv's own CLI (-o file sink) on the adapter (integration/video_b200.c:
+    vid_next_line over the prefetching frame pipeline + rf_write) against the stock binary, same command line."""
+    dropin = os.path.join(ROOT, "oracle", "_ref", "hacktv_b200_dropin")
+    stock = os.path.join(ROOT, "oracle", "_ref", "hacktv_ref")
+    if not (os.path.exists(dropin) and os.path.exists(stock)):
+        return None
+    args = ["-m", "i", "-s", "16000000", "--filter"]
+    out = {"command": "-m i -s 16000000 --filter -o <sink> test"}
+
+    def piped(binary, nsamples):
+        """-o - into a pipe that is read and dropped: time for nsamples complex samples"""
+        t0 = time.time()
+        cmd = f"HACKTV_B200_PREFETCH=1 timeout 120 {binary} {' '.join(args)} -o - test 2>/dev/null | head -c {nsamples * 4} | wc -c"
+        r = subprocess.run(["bash", "-c", cmd], capture_output=True, text=True)
+        dt = time.time() - t0
+        got = int((r.stdout.strip() or "0").split()[-1])
+        return round(got / 4 / dt / 1e6, 1) if got else None
+
+    # the stock encoder: ~60 Msamples/s, 2 s of signal through a pipe costs nothing extra
+    out["stock"] = {"msamples_per_s_pipe": piped(stock, 32_000_000)}
+    # the adapter: the same pipe (what `hacktv -o - | consumer` delivers: bounded by the 64 KB pipe), and the file
+    # sink proper (-o /dev/null), timed inside the adapter (HACKTV_STATS: lines / seconds between the first
+    # vid_next_line and vid_free)
+    out["b200"] = {"msamples_per_s_pipe": piped(dropin, 256_000_000)}
+    p = subprocess.Popen(["timeout", "-s", "INT", str(seconds), dropin] + args + ["-o", "/dev/null", "test"],
+                         stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=dict(os.environ, HACKTV_STATS="1", HACKTV_B200_PREFETCH="1"))
+    err = p.communicate()[1]
+    for ln in err.splitlines():
+        if ln.startswith("{") and "lines" in ln:
+            st = json.loads(ln)
+            out["b200"]["msamples_per_s_file_sink"] = round(st["lines"] * 1024 / st["seconds"] / 1e6, 1)
+            out["b200"]["seconds"] = round(st["seconds"], 2)
+    if out["stock"]["msamples_per_s_pipe"]:
+        best = out["b200"].get("msamples_per_s_file_sink") or out["b200"]["msamples_per_s_pipe"]
+        if best:
+            out["speedup_vs_stock_cli"] = round(best / out["stock"]["msamples_per_s_pipe"], 1)
+    return out
 
 
 def main():
@@ -182,10 +312,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=64, help="video frames per step")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=1024, help="video frames per step (rendered in calls of 64 frames)")
+    ap.add_argument("--e2e-frames", type=int, default=64, help="video frames per end-to-end step")
     ap.add_argument("--ref-frames", type=int, default=100, help="frames per reference instance per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +337,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -214,28 +348,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    conf = H.mode_config(MODE, vfilter=FILTER)
-    enc = H.Encoder(conf, RATE)            # one RF channel per rank / GPU
-    enc.open_test_source()
-    nlines = args.frames * enc.lines
-    nsamp = nlines * enc.width
-    out = torch.empty(nsamp * 2, dtype=torch.int16, device="cuda")
+    mode, rate, filt, workload = WORKLOADS[args.workload]
+    conf = H.mode_config(mode, vfilter=filt)
     stream = torch.cuda.current_stream().cuda_stream
-    enc.set_kernel_timing(True)
 
     # ---- device-resident throughput ("value") ---------------------------------
-    for _ in range(args.warmup):
-        enc.render(nlines, out.data_ptr(), stream)
+    enc, out, chunk, calls, nsamp, l0, ev0, ev1 = device_resident(H, torch, mode, rate, filt, args.frames, args.steps, args.warmup, stream)
+    nlines = chunk * calls
     barrier()
-    l0 = enc.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
     with ClockSampler(local) as clk:
         time.sleep(0.005)
         clk.t0 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
-            enc.render(nlines, out.data_ptr(), stream)
+            for _ in range(calls):
+                enc.render(chunk, out.data_ptr(), stream)
         ev1.record()
         barrier()
         clk.t1 = time.perf_counter()
@@ -243,19 +370,23 @@ def main():
     launches = enc.kernel_launches - l0
     clocks = clk.summary()
     # per-launch duration of the dominant kernel, CUDA events on its own stream (untimed extra steps)
+    kern_ms = []
     for _ in range(3):
-        enc.render(nlines, out.data_ptr(), stream)
+        enc.render(chunk, out.data_ptr(), stream)
         torch.cuda.synchronize()
         kern_ms.append(enc.last_line_kernel_ms())
     kern_lines = enc.last_line_kernel_lines()
     checksum = int(out[:4096].to(torch.int32).sum().item())
+    width = enc.width
+    enc.close()
+    del out
 
     # ---- end to end through the C-ABI with host buffers ("e2e") -----------------
     e2e = None
     if not args.no_e2e:
-        e2e_frames = args.frames
-        e2e_lines = e2e_frames * enc.lines
-        enc2 = H.Encoder(conf, RATE)
+        e2e_frames = args.e2e_frames
+        enc2 = H.Encoder(conf, rate)
+        e2e_lines = e2e_frames * enc2.lines
         pic = torch.from_numpy(H.test_pattern(enc2.active_width, enc2.active_lines).astype(np.int32)).pin_memory()
         tone = torch.from_numpy(H.test_tone()).pin_memory()
         # a live source: a new picture serial every frame -> one H2D upload per frame
@@ -273,11 +404,13 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_samples = e2e_lines * enc2.width
-        h2d = e2e_frames * enc2.active_width * enc2.active_lines * 4 + int(e2e_samples / RATE * 32000) * 4
+        h2d = e2e_frames * enc2.active_width * enc2.active_lines * 4 + int(e2e_samples / rate * 32000) * 4
         e2e = {"value": round(world * e2e_samples * args.steps / tt.item() / 1e6, 2), "unit": "Msamples/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_samples * 4,
-               "frames_per_step": e2e_frames, "checksum": int(host[:4096].to(torch.int32).sum().item()),
-               "api": "htv_av_memory_open + htv_render_host (C-ABI), pinned host buffers, one picture upload per frame"}
+               "frames_per_step": e2e_frames, "ms_per_step": round(1000 * tt.item() / args.steps, 3),
+               "checksum": int(host[:4096].to(torch.int32).sum().item()),
+               "api": "htv_av_memory_open + htv_render_host (C-ABI), pinned host buffers, one picture upload per frame",
+               "numa_bound_cpus": numa_cpus}
         enc2.close()
 
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -286,42 +419,58 @@ def main():
     ms_max = t.item()
 
     if rank == 0:
-        value = world * nsamp * args.steps / (ms_max / 1e3) / 1e6
+        step_samples = nlines * width
+        value = world * step_samples * args.steps / (ms_max / 1e3) / 1e6
         peak, peak_src = measured_peak_gbs()
         k_ms = sorted(kern_ms)[len(kern_ms) // 2]
-        k_samples = kern_lines * enc.width
+        k_samples = kern_lines * width
         achieved = k_samples * 4 / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
+        step_gbs = step_samples * 4 * args.steps / (ms_max / 1e3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_HARNESS):
-            v, per, wall = run_reference_instances(1, 150)
+            v, per, wall = run_reference_instances(1, 150, mode=mode, rate=rate, filt=filt)
             cpu = {"value": round(v, 3), "unit": "Msamples/s", "cores": REF_THREADS, "kind": "reference",
-                   "sample": "1 reference encoder (main + vfilter + audio threads), 150 frames = 96 Msamples after a 2-frame warm-up, "
+                   "sample": "1 reference encoder (main + vfilter + audio threads), 150 frames after a 2-frame warm-up, "
                              "vid_next_line loop, no sink I/O (oracle/_ref/ref_harness)",
-                   "host_cores": os.cpu_count()}
+                   "host_cores": os.cpu_count(), "usable_host_threads": cpu_budget()}
+        extra = None
+        if world == 1 and not args.no_extra:
+            extra = {"configs": [
+                quick_config(H, torch, stream, "cfg1: -m pal -s 16000000 (baseband, real int16)", "pal", 16_000_000, False),
+                quick_config(H, torch, stream, "cfg3: -m m -s 13500000 --filter", "m", 13_500_000, True),
+                quick_config(H, torch, stream, "cfg4: -m l -s 16000000 --filter (SECAM)", "l", 16_000_000, True, frames=26, iters=5),
+                quick_config(H, torch, stream, "cfg5 (one channel): -m i -s 20000000 --filter", "i", 20_000_000, True)],
+                "dropin_cli": dropin_throughput()}
+        per_line = 1.0 / NCU["lines"]
         print(json.dumps({
             "metric": "IQ Msamples/s", "value": round(value, 2), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16 (int32 accumulate; RGB->YUV table built in fp64 at init)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": args.frames, "lines_per_step": nlines,
-                       "samples_per_step_per_gpu": nsamp, "parallelism": f"{world} independent RF channel(s), one per GPU, no collectives",
-                       "l2": f"each step writes {nsamp * 4 / 1e6:.0f} MB of IQ per GPU (> 126 MB L2); tables are L2-resident by design",
-                       "realtime_x": round(value / world / (RATE / 1e6), 1)},
+            "config": {"workload": workload, "frames_per_step": calls * min(args.frames, CHUNK_FRAMES), "lines_per_step": nlines,
+                       "calls_per_step": calls, "frames_per_call": min(args.frames, CHUNK_FRAMES),
+                       "samples_per_step_per_gpu": step_samples, "parallelism": f"{world} independent RF channel(s), one per GPU, no collectives",
+                       "l2": f"every call writes {nsamp * 4 / 1e6:.0f} MB of IQ per GPU (> 126 MB L2); tables are L2-resident by design",
+                       "ms_per_64_frames": round(ms_max / args.steps / calls, 4),
+                       "realtime_x": round(value / world / (rate / 1e6), 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": int(round(NCU_TRAFFIC_BYTES_PER_LINE[FIR] * kern_lines)) if enc.width == 1024 else None,
+                         "traffic": int(round((NCU["dram_read"] + NCU["dram_write"]) * per_line * kern_lines)) if width == 1024 else None,
                          "kernel": KERNEL, "kernel_ms": round(k_ms, 4),
                          "lines_per_launch": kern_lines, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_samples * 4,
+                         "step_achieved": round(step_gbs / world, 1), "step_frac": round(step_gbs / world / peak, 4),
+                         "issue": {"slots_per_sample": round(NCU["warp_instructions"] * 32 / (NCU["lines"] * 1024), 1),
+                                   "issue_active_pct": NCU["issue_active_pct"], "source": NCU["file"]},
                          "note": "4 B per complex sample written once; the kernel is issue-slot bound (DESIGN.md section 4), not HBM bound"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "checksum": checksum,
+            "extra": extra,
         }))
 
-    enc.close()
     if world > 1:
         dist.destroy_process_group()
 

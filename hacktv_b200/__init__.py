@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
     L.htv_av_memory_open.restype = C.c_int
     L.htv_av_memory_open.argtypes = [C.POINTER(AV), vp, sz, vp, sz, sz, C.c_int]
     L.htv_next_line.restype = C.POINTER(Line); L.htv_next_line.argtypes = [vp]
+    L.htv_set_prefetch.restype = C.c_int; L.htv_set_prefetch.argtypes = [vp, C.c_int]
     L.htv_render.restype = C.c_int; L.htv_render.argtypes = [vp, C.c_int, vp, C.POINTER(sz), vp]
     L.htv_render_host.restype = C.c_int; L.htv_render_host.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
     L.htv_render_add.restype = C.c_int; L.htv_render_add.argtypes = [vp, C.c_int, vp, C.POINTER(sz), vp]
@@ -388,6 +389,11 @@ class Encoder:
         r = self._L.htv_render_host(self._h, nlines, C.c_void_p(host_ptr), None)
         if r != HTV_OK:
             raise RuntimeError(f"htv_render_host failed ({r})")
+
+    def set_prefetch(self, on: bool = True):
+        """htv_set_prefetch: htv_next_line renders the following frame while the current one is consumed."""
+        if self._L.htv_set_prefetch(self._h, int(on)) != HTV_OK:
+            raise RuntimeError("htv_set_prefetch failed")
 
     def next_line(self):
         p = self._L.htv_next_line(self._h)

@@ -109,6 +109,7 @@ int main(int argc, char **argv)
 
 	if(htv_av_test_open(htv_av(vid)) == HTV_OK)
 	{
+		htv_set_prefetch(vid, 1);                          /* the test source never ends */
 		while(!_abort && (lines < 0 || n < lines))
 		{
 			htv_line_t *line = htv_next_line(vid);

@@ -69,11 +69,18 @@ struct htv_t {
 	void *st_compute, *st_copy;
 	void *ev_rendered[2], *ev_copied[2];
 
-	/* htv_next_line view */
-	int16_t *h_frame;             /* pinned, one frame of output */
+	unsigned piece_i;             /* pieces queued so far (staging buffer = piece_i & 1) */
+
+	/* htv_next_line view: two pinned frames - while the caller walks one, the next is rendered and copied */
+	int16_t *h_frame[2];          /* pinned, one frame of output each */
+	int h_cur;                    /* the frame being handed out */
 	int h_lines;                  /* lines held */
 	int h_pos;                    /* next line to hand out */
 	int64_t h_first_line;
+	int prefetch;                 /* htv_set_prefetch */
+	int pf_pending, pf_lines;     /* a frame is in flight into h_frame[h_cur ^ 1] */
+	int64_t pf_first_line;
+	void *ev_frame[2];
 	int16_t *h_iq;                /* interleaved scratch for real modes */
 	htv_line_t line;
 };
@@ -185,7 +192,8 @@ void htv_free(htv_t *s)
 	}
 	drop_overlays_before(s, 0x7FFFFFFFFFFFFFFFLL);
 	free(s->ov);
-	htv_dev_free_pinned(s->h_frame);
+	htv_dev_free_pinned(s->h_frame[0]);
+	htv_dev_free_pinned(s->h_frame[1]);
 	htv_dev_free_pinned(s->pt_host);
 	free(s->pt_tmp);
 	free(s->h_iq);
@@ -591,17 +599,17 @@ static int host_fail(htv_t *s, int r)
 	return(r);
 }
 
-int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
+/* Queue the rendering of the next nlines and their copy into host memory (8 MB pieces, rendering of one piece
+ * overlapping the copy of the previous one); returns without waiting. */
+static int host_enqueue(htv_t *s, int nlines, int16_t *h_out)
 {
-	size_t line_bytes;
-	int piece, done = 0, p = 0, r, i;
-	if(!s || nlines < 0 || !h_out) return(HTV_ERROR);
-	line_bytes = (size_t) s->W * s->bps;
-	piece = (int) (HOST_PIECE_BYTES / line_bytes);
+	const size_t line_bytes = (size_t) s->W * s->bps;
+	int piece = (int) (HOST_PIECE_BYTES / line_bytes), done = 0, r, i;
 	if(piece < 1) piece = 1;
 	if(piece > nlines) piece = nlines > 0 ? nlines : 1;
 	if((size_t) piece * line_bytes > s->d_stage_bytes)
 	{
+		if(s->st_copy) { htv_dev_sync(s->dev, s->st_copy); htv_dev_sync(s->dev, s->st_compute); }
 		for(i = 0; i < 2; i++)
 		{
 			htv_dev_free(s->dev, s->d_stage[i]);
@@ -609,18 +617,23 @@ int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 			if(!s->d_stage[i]) { s->d_stage_bytes = 0; return(HTV_OUT_OF_MEMORY); }
 		}
 		s->d_stage_bytes = (size_t) piece * line_bytes;
+		s->piece_i = 0;
 	}
 	if(!s->st_compute)
 	{
 		s->st_compute = htv_dev_stream_new(s->dev);
 		s->st_copy = htv_dev_stream_new(s->dev);
-		for(i = 0; i < 2; i++) { s->ev_rendered[i] = htv_dev_event_new(s->dev); s->ev_copied[i] = htv_dev_event_new(s->dev); }
+		for(i = 0; i < 2; i++)
+		{
+			s->ev_rendered[i] = htv_dev_event_new(s->dev); s->ev_copied[i] = htv_dev_event_new(s->dev);
+			s->ev_frame[i] = htv_dev_event_new(s->dev);
+		}
 	}
-	for(; done < nlines; done += piece, p++)
+	for(; done < nlines; done += piece, s->piece_i++)
 	{
-		const int n = nlines - done < piece ? nlines - done : piece, b = p & 1;
+		const int n = nlines - done < piece ? nlines - done : piece, b = s->piece_i & 1;
 		/* the staging buffer must have been copied out before it is rendered into again */
-		if(p >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(host_fail(s, r));
+		if(s->piece_i >= 2 && (r = htv_dev_stream_wait(s->st_compute, s->ev_copied[b])) != HTV_OK) return(host_fail(s, r));
 		r = htv_render(s, n, s->d_stage[b], NULL, s->st_compute);
 		if(r != HTV_OK) return(host_fail(s, r));
 		if((r = htv_dev_event_record(s->ev_rendered[b], s->st_compute)) != HTV_OK) return(host_fail(s, r));
@@ -629,10 +642,42 @@ int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
 		if(r != HTV_OK) return(host_fail(s, r));
 		if((r = htv_dev_event_record(s->ev_copied[b], s->st_copy)) != HTV_OK) return(host_fail(s, r));
 	}
+	return(HTV_OK);
+}
+
+int htv_render_host(htv_t *s, int nlines, int16_t *h_out, size_t *nsamples)
+{
+	int r;
+	if(!s || nlines < 0 || !h_out) return(HTV_ERROR);
+	/* a frame prefetched for htv_next_line is part of the stream: mixing the two pull styles would reorder it */
+	if(s->pf_pending) return(HTV_ERROR);
+	r = host_enqueue(s, nlines, h_out);
+	if(r != HTV_OK) return(r);
 	if(nsamples) *nsamples = (size_t) nlines * s->W;
 	r = htv_dev_sync(s->dev, s->st_copy);
 	if(r != HTV_OK) return(host_fail(s, r));
 	return(htv_dev_sync(s->dev, s->st_compute));
+}
+
+int htv_set_prefetch(htv_t *s, int on)
+{
+	if(!s) return(HTV_ERROR);
+	s->prefetch = on != 0;
+	return(HTV_OK);
+}
+
+/* Start rendering the next frame's worth of lines into h_frame[buf]; htv_next_line collects it later */
+static int frame_enqueue(htv_t *s, int buf, int n)
+{
+	int r;
+	s->pf_first_line = s->next_line;
+	r = host_enqueue(s, n, s->h_frame[buf]);
+	if(r != HTV_OK) return(r);
+	r = htv_dev_event_record(s->ev_frame[buf], s->st_copy);
+	if(r != HTV_OK) return(host_fail(s, r));
+	s->pf_lines = n;
+	s->pf_pending = 1;
+	return(HTV_OK);
 }
 
 htv_line_t *htv_next_line(htv_t *s)
@@ -640,22 +685,38 @@ htv_line_t *htv_next_line(htv_t *s)
 	if(!s) return(NULL);
 	if(s->h_pos >= s->h_lines)
 	{
-		/* refill: the rest of the current frame (a whole frame in steady state) */
-		int n = s->lines - (int) (s->next_line % s->lines);
-		if(!s->h_frame)
+		if(!s->h_frame[0])
 		{
-			s->h_frame = htv_dev_alloc_pinned((size_t) s->lines * s->W * s->bps);
+			s->h_frame[0] = htv_dev_alloc_pinned((size_t) s->lines * s->W * s->bps);
+			s->h_frame[1] = htv_dev_alloc_pinned((size_t) s->lines * s->W * s->bps);
 			s->h_iq = malloc(sizeof(int16_t) * 2 * s->W);
-			if(!s->h_frame || !s->h_iq) return(NULL);
+			if(!s->h_frame[0] || !s->h_frame[1] || !s->h_iq) return(NULL);
 		}
-		s->h_first_line = s->next_line;
-		if(htv_render_host(s, n, s->h_frame, NULL) != HTV_OK) return(NULL);
-		s->h_lines = n;
+		if(s->pf_pending)
+		{
+			/* the frame rendered while the caller consumed the previous one */
+			if(htv_dev_event_wait(s->ev_frame[s->h_cur ^ 1]) != HTV_OK) return(NULL);
+			s->h_cur ^= 1;
+			s->h_first_line = s->pf_first_line;
+			s->h_lines = s->pf_lines;
+			s->pf_pending = 0;
+		}
+		else
+		{
+			/* refill: the rest of the current frame (a whole frame in steady state) */
+			const int n = s->lines - (int) (s->next_line % s->lines);
+			s->h_first_line = s->next_line;
+			if(htv_render_host(s, n, s->h_frame[s->h_cur], NULL) != HTV_OK) return(NULL);
+			s->h_lines = n;
+		}
 		s->h_pos = 0;
+		/* htv_set_prefetch: the next frame starts its way through the GPU and the copy engine now; it pulls its
+		 * picture and sound from the source one frame earlier than the reference would */
+		if(s->prefetch && frame_enqueue(s, s->h_cur ^ 1, s->lines - (int) (s->next_line % s->lines)) != HTV_OK) return(NULL);
 	}
 	{
 		const int64_t L = s->h_first_line + s->h_pos;
-		int16_t *src = s->h_frame + (size_t) s->h_pos * s->W * (s->complex ? 2 : 1);
+		int16_t *src = s->h_frame[s->h_cur] + (size_t) s->h_pos * s->W * (s->complex ? 2 : 1);
 		if(s->complex) s->line.output = src;
 		else
 		{

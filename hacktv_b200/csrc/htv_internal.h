@@ -98,6 +98,7 @@ struct htv_tables_t {
 	int16_t *burst_win;     int burst_width;
 
 	uint64_t *fm_ang;                              /* 65536: effective angle of each FM LUT entry, turns * 2^64 */
+	float *fm_rot8;                                /* 65536 x (cos, sin) of 8 steps of fm_ang */
 	uint64_t *fmv_ang;                             /* the same for the FM video modulator's LUT */
 	int32_t afir_v[HTV_AFIR_N], afir_f[HTV_AFIR_N]; /* audio FIR taps in application order */
 	int16_t lim_shape[HTV_LIM_W];
@@ -173,6 +174,7 @@ extern void htv_dev_stream_free(void *s);
 extern void *htv_dev_event_new(htv_dev_t *d);
 extern void htv_dev_event_free(void *e);
 extern int htv_dev_event_record(void *e, void *stream);
+extern int htv_dev_event_wait(void *e);          /* host waits for the event */
 extern int htv_dev_stream_wait(void *stream, void *e);
 
 #ifdef __cplusplus

@@ -65,6 +65,7 @@ struct DevTables {
 	const htv_c16_t *clut;
 	const int16_t *burst_win;
 	const uint64_t *fm_ang;
+	const float2 *fm_rot8;            // (cos, sin) of 8 steps of fm_ang (fused line kernel)
 	const int32_t *afir_v, *afir_f;
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
@@ -234,19 +235,28 @@ __device__ __forceinline__ int pcm_mono(const DevTables &dt, int64_t j, int volu
 // Audio-rate pre-pass, FM path (ref video.c:3319-3327, fir.c:655-694, 818-870)
 // ---------------------------------------------------------------------------
 
-// var/fix inputs of the soft limiter for audio index u: two 65-tap int FIRs of the mono mix
-__global__ void k_fm_fir(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t u0, int64_t u1)
+// var/fix inputs of the soft limiter for audio index u: two 65-tap int FIRs of the mono mix. A CTA of 128
+// consecutive audio indices stages the 192 mono samples it needs and both tap sets in shared memory.
+__global__ void __launch_bounds__(128) k_fm_fir(const __grid_constant__ htv_dparams_t dp, const DevTables dt, int64_t u0, int64_t u1)
 {
-	int64_t u = u0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ int sx[128 + HTV_AFIR_N - 1];
+	__shared__ int sv[HTV_AFIR_N], sf[HTV_AFIR_N];
+	const int tid = threadIdx.x;
+	const int64_t ub = u0 + (int64_t) blockIdx.x * 128;
+	for(int i = tid; i < 128 + HTV_AFIR_N - 1; i += 128) sx[i] = pcm_mono(dt, ub - (HTV_AFIR_N - 1) + i, dp.volume);   // 0 before the stream
+	if(tid < HTV_AFIR_N) { sv[tid] = dt.afir_v[tid]; sf[tid] = dt.afir_f[tid]; }
+	__syncthreads();
+	const int64_t u = ub + tid;
 	if(u > u1) return;
 	long long av = 0, af = 0;
 	if(u >= 0)
 	{
+		#pragma unroll 13
 		for(int y = 0; y < HTV_AFIR_N; y++)
 		{
-			long long x = pcm_mono(dt, u - (HTV_AFIR_N - 1) + y, dp.volume);
-			av += x * dt.afir_v[y];
-			af += x * dt.afir_f[y];
+			const long long x = sx[tid + y];
+			av += x * sv[y];
+			af += x * sf[y];
 		}
 		av >>= 15; af >>= 15;
 		av = av < INT32_MIN ? INT32_MIN : (av > INT32_MAX ? INT32_MAX : av);
@@ -407,19 +417,24 @@ __global__ void __launch_bounds__(64) k_nicam_frames(const __grid_constant__ htv
 	if(x < 23) bits[x] = 0;
 	__syncthreads();
 
-	// J.17 pre-emphasis over the sequence of encoded blocks; history spans 3 earlier frames
+	// J.17 pre-emphasis over the sequence of encoded blocks; history spans 3 earlier frames: the 32 + 82 samples
+	// per channel this frame's filter sees are staged once (index t + 82, t relative to the frame's block)
+	__shared__ short spcm[2][32 + HTV_J17_N - 1];
+	for(int i = x; i < 2 * (32 + HTV_J17_N - 1); i += 64)
+	{
+		const int ch = i & 1;
+		int t = (i >> 1) - (HTV_J17_N - 1);
+		const int f = t < 0 ? (31 - t) >> 5 : 0;                        // how many frames back
+		t += f << 5;
+		const int64_t b = blk[f];
+		spcm[ch][i >> 1] = (short) (b < 0 ? 0 : pcm_vol(dt, b * 32 + t, ch, dp.volume));
+	}
+	__syncthreads();
 	int acc = 0;
 	{
-		const int ch = x & 1, n = x >> 1;
-		for(int xi = 0; xi < HTV_J17_N; xi++)
-		{
-			int t = n - (HTV_J17_N - 1) + xi;          // sample index relative to this frame's block
-			const int f = t < 0 ? (31 - t) >> 5 : 0;    // how many frames back
-			t += f << 5;
-			int64_t b = blk[f];
-			int v = b < 0 ? 0 : pcm_vol(dt, b * 32 + t, ch, dp.volume);
-			acc += v * c_j17[xi];
-		}
+		const short *sp = spcm[x & 1] + (x >> 1);
+		#pragma unroll
+		for(int xi = 0; xi < HTV_J17_N; xi++) acc += (int) sp[xi] * c_j17[xi];
 	}
 	int d = (short) (acc >> 15);
 
@@ -598,6 +613,7 @@ struct __align__(16) LineA2 {
 	// relative to the line; entry nsym is a sentinel (y = INT_MAX)
 	uint2 symb[MAX_SYMS + 1];
 	unsigned char symc[MAX_SYMS];     // bit 0: I polarity +, bit 1: Q polarity +
+	float2 seg_rot[MAX_SEGS];         // (cos, sin) of 8 FM angle steps of the segment
 	int pad[2];
 };
 
@@ -849,150 +865,199 @@ __device__ __forceinline__ unsigned long long kd_div(unsigned long long n, unsig
 	return((unsigned long long) q);
 }
 
+// A warp takes KD_LINES consecutive lines. Phase A, lane = line: everything that is one value per line or per audio
+// segment (the 64-bit divisions live here, once per line instead of once per lane). Phase B, for each of the
+// lines in turn, lane = NICAM symbol: positions, DQPSK state, the 6-symbol polarity patterns and spacing
+// codes through warp votes, then lane = 32-sample block for the "symbol in effect" table.
 #define KD_WARPS 4
+#define KD_LINES 8
 __global__ void __launch_bounds__(32 * KD_WARPS)
 k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineA2 *out, int64_t line0, int nlines)
 {
 	__shared__ int s_blk[KD_WARPS][MAX_BLKS];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const int li = blockIdx.x * KD_WARPS + wid;
-	if(li >= nlines) return;
-	LineA2 &la = out[li];
+	const int lbase = (blockIdx.x * KD_WARPS + wid) * KD_LINES;
+	if(lbase >= nlines) return;
 	const int W = dp.W;
-	const long long m0 = (line0 + li) * (long long) W + dp.shift;
+	const int li = lbase + lane;
+	const bool mine = lane < KD_LINES && li < nlines;
+	const long long m0 = (line0 + (mine ? li : lbase)) * (long long) W + dp.shift;
+	LineA2 &la = out[mine ? li : lbase];
 	unsigned rem;
 
-	if(lane == 0)
+	// ---- phase A: lane = line ------------------------------------------------------------------------
+	// NICAM scalars of the lane's line, handed to phase B by shuffles
+	int a_ns = 0, a_dq = 0, a_ks0 = 0, a_generic = 0;
+	int a_bk[MAX_SEGS - 1];
+	unsigned a_r0 = 0;
+	long long a_s0 = 0, a_k0 = 0;
 	{
-		la.m0 = m0;
-		kd_div((unsigned long long) m0, 32767u, 1.0 / 32767.0, rem); la.kk0 = (int) rem;
-		rem = 0;
-		if(dp.have_nicam) kd_div((unsigned long long) m0, (unsigned) dp.nicam_cc_len, 1.0 / (double) dp.nicam_cc_len, rem);
-		la.cc0 = (int) rem;
-		la.am_phase0 = dp.am_ang * (unsigned long long) m0;
-		la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
-	}
-
-	// ---- audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1) -------------
-	int myx = 0x7FFFFFFF;                                               // lane k: seg_x[k]
-	if(dp.have_fm || dp.have_am)
-	{
-		const double inv_ar = 1.0 / (double) HTV_AUDIO_RATE;
-		const long long jf = (long long) kd_div((unsigned long long) (m0 + 1) * HTV_AUDIO_RATE, (unsigned) dp.rate, 1.0 / (double) dp.rate, rem) - 1;
-		if(lane < MAX_SEGS)
-		{
-			const long long j = jf + lane;
-			// seg_start(j) = j < 0 ? 0 : ceil((j + 1) rate / 32000) - 1
-			long long st = 0;
-			if(j >= 0) st = (long long) kd_div((unsigned long long) (j + 1) * (unsigned long long) dp.rate + HTV_AUDIO_RATE - 1, HTV_AUDIO_RATE, inv_ar, rem) - 1;
-			if(st < m0 + W)
-			{
-				myx = (int) max(0ll, st - m0);
-				unsigned long long ang = 0, ph = 0;
-				if(dp.have_fm)
-				{
-					ang = dt.fm_ang[(int) dt.fm_p[(j + 1) & (RA - 1)] + 32768];
-					// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
-					ph = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
-				}
-				la.seg_ang[lane] = ang; la.seg_phase[lane] = ph;
-				la.seg_am[lane] = dp.have_am ? pcm_mono(dt, j, dp.volume) : 0;
-			}
-			else { la.seg_ang[lane] = 0; la.seg_phase[lane] = 0; la.seg_am[lane] = 0; }
-		}
-	}
-	if(lane < MAX_SEGS + 2) la.seg_x[lane] = lane < MAX_SEGS ? myx : 0x7FFFFFFF;
-	{
-		// segment in effect at x = 32 b: (segments starting at or before it) - 1
-		int sx[MAX_SEGS];
+		int kk0, cc0 = 0;
+		kd_div((unsigned long long) m0, 32767u, 1.0 / 32767.0, rem); kk0 = (int) rem;
+		if(dp.have_nicam) { kd_div((unsigned long long) m0, (unsigned) dp.nicam_cc_len, 1.0 / (double) dp.nicam_cc_len, rem); cc0 = (int) rem; }
+		int segx[MAX_SEGS + 2];
 		#pragma unroll
-		for(int k = 0; k < MAX_SEGS; k++) sx[k] = __shfl_sync(0xFFFFFFFFu, myx, k);
-		for(int b = lane; b < MAX_BLKS; b += 32)
+		for(int k = 0; k < MAX_SEGS + 2; k++) segx[k] = 0x7FFFFFFF;
+		if(mine)
 		{
-			int sg = -1;
+			la.m0 = m0; la.kk0 = kk0; la.cc0 = cc0;
+			la.am_phase0 = dp.am_ang * (unsigned long long) m0;
+			la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
+		}
+		// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
+		if(dp.have_fm || dp.have_am)
+		{
+			const double inv_ar = 1.0 / (double) HTV_AUDIO_RATE;
+			const long long jf = (long long) kd_div((unsigned long long) (m0 + 1) * HTV_AUDIO_RATE, (unsigned) dp.rate, 1.0 / (double) dp.rate, rem) - 1;
 			#pragma unroll
-			for(int k = 0; k < MAX_SEGS; k++) sg += sx[k] <= 32 * b;
-			la.fm_blk[b] = (unsigned char) max(0, min(sg, MAX_SEGS - 1));
+			for(int k = 0; k < MAX_SEGS; k++)
+			{
+				const long long j = jf + k;
+				// seg_start(j) = j < 0 ? 0 : ceil((j + 1) rate / 32000) - 1
+				long long st = 0;
+				if(j >= 0) st = (long long) kd_div((unsigned long long) (j + 1) * (unsigned long long) dp.rate + HTV_AUDIO_RATE - 1, HTV_AUDIO_RATE, inv_ar, rem) - 1;
+				unsigned long long ang = 0, ph = 0;
+				float2 rot = make_float2(1.0f, 0.0f);
+				int am = 0;
+				if(st < m0 + W && (k == 0 || segx[k - 1] != 0x7FFFFFFF))
+				{
+					segx[k] = (int) max(0ll, st - m0);
+					if(dp.have_fm)
+					{
+						const int pi = (int) dt.fm_p[(j + 1) & (RA - 1)] + 32768;
+						ang = dt.fm_ang[pi];
+						rot = dt.fm_rot8[pi];
+						// phase at relative sample x = B(j) + (m0 + x - st + 1) * ang
+						ph = dt.fm_B[(j + 1) & (RA - 1)] + ang * (unsigned long long) (m0 - st + 1);
+					}
+					if(dp.have_am) am = pcm_mono(dt, j, dp.volume);
+				}
+				if(mine) { la.seg_ang[k] = ang; la.seg_phase[k] = ph; la.seg_rot[k] = rot; la.seg_am[k] = am; }
+			}
+		}
+		if(mine)
+		{
+			#pragma unroll
+			for(int k = 0; k < MAX_SEGS + 2; k++) la.seg_x[k] = segx[k];
+		}
+		// first block (32 samples) in which segment k >= 1 is in effect at the block start; phase B builds fm_blk
+		#pragma unroll
+		for(int k = 1; k < MAX_SEGS; k++) a_bk[k - 1] = segx[k] == 0x7FFFFFFF ? 0x7FFF : (segx[k] + 31) >> 5;
+		if(dp.have_nicam)
+		{
+			const unsigned F = (unsigned) dp.nicam_F, D = (unsigned) dp.nicam_D;
+			const double inv_f = 1.0 / (double) F;
+			// the symbols a sample of this line can see: from 6 before the one in effect at the line's first sample (the pulse
+			// spans less than 6 symbol periods, and a pulse-table row needs the 5 predecessors) to the last one starting
+			// on the line - at most 32 at any rate (a line is 23.3 symbol periods): one lane each
+			const long long seff = (long long) kd_div((unsigned long long) m0 * D, F, inv_f, rem);
+			const long long slast = (long long) kd_div((unsigned long long) (m0 + W - 1) * D, F, inv_f, rem);
+			a_s0 = max(0ll, seff - 6);
+			a_ns = (int) min(32ll, slast - a_s0 + 1);
+			// pos(s0 + i) = ceil((s0 + i) F / D) = q0 + ceil((r0 + i F) / D)
+			const long long q0 = (long long) kd_div((unsigned long long) a_s0 * F, D, 1.0 / (double) D, a_r0);
+			unsigned ks0;
+			a_k0 = (long long) kd_div((unsigned long long) a_s0, 364u, 1.0 / 364.0, ks0);
+			a_ks0 = (int) ks0;
+			a_dq = (int) (q0 - m0);                                     // |q0 - m0| < ntaps + W + a few symbols
+			a_generic = !dp.nicam_lut_ok || dp.nicam_sps - 1 < 32 || a_ns < 1 || slast - a_s0 + 1 > 32;
 		}
 	}
-
-	// ---- NICAM symbols (ref nicam728.c:342-411) ---------------------------------------------------------
-	int ns = 0, generic = 0;
-	if(dp.have_nicam)
+	// ---- phase B: per line, lane = NICAM symbol (ref nicam728.c:342-411), then lane = block / table word ---------
+	const unsigned F = (unsigned) dp.nicam_F, D = (unsigned) dp.nicam_D;
+	const float inv_d = 1.0f / (float) D;
+	const int minor_adv = dp.nicam_minor_short ? dp.nicam_sps - 1 : dp.nicam_sps;
+	const int nl = min(KD_LINES, nlines - lbase);
+	for(int l = 0; l < nl; l++)
 	{
-		const unsigned F = (unsigned) dp.nicam_F, D = (unsigned) dp.nicam_D;
-		const double inv_f = 1.0 / (double) F;
-		// symbols whose pulse can still reach this line: ntaps samples back
-		const long long sfirst = (long long) kd_div((unsigned long long) max(0ll, m0 - dp.nicam_ntaps) * D, F, inv_f, rem);
-		const long long slast = (long long) kd_div((unsigned long long) (m0 + W - 1) * D, F, inv_f, rem);
-		ns = (int) min((long long) MAX_SYMS, slast - sfirst + 1);
-		const int lead = (int) min(5ll, sfirst);
-		const long long s0 = sfirst - lead;
-		// pos(s0 + i) = ceil((s0 + i) F / D) = q0 + ceil((r0 + i F) / D)
-		unsigned r0, ks0;
-		const long long q0 = (long long) kd_div((unsigned long long) s0 * F, D, 1.0 / (double) D, r0);
-		const long long k0 = (long long) kd_div((unsigned long long) s0, 364u, 1.0 / 364.0, ks0);
-		const int minor_adv = dp.nicam_minor_short ? dp.nicam_sps - 1 : dp.nicam_sps;
-		const int dq = (int) (q0 - m0);                                 // |q0 - m0| < ntaps + W + a few symbols
-		unsigned long long MI = 0, MQ = 0, MG = 0;
-		int posr[2], code[2];
-		#pragma unroll
-		for(int r = 0; r < 2; r++)
+		LineA2 &lb = out[lbase + l];
+		if(dp.have_fm || dp.have_am)
 		{
-			const int i = lane + 32 * r;
-			const bool valid = i < lead + ns;
-			const int p = (int) ((r0 + (unsigned) i * F + D - 1) / D);
-			const int pm = i > 0 ? (int) ((r0 + (unsigned) (i - 1) * F + D - 1) / D) : 0;
-			const bool minor = valid && i > 0 && p - pm == minor_adv;    // the window's first symbol: unknown, never used
-			int ks = (int) ks0 + i;
-			long long k = k0;
-			if(ks >= 364) { ks -= 364; k++; }
-			int cd = 0;
-			if(valid)
+			// segment in effect at x = 32 b = number of segments k >= 1 whose first block is <= b; lane = word of four blocks
+			int bk[MAX_SEGS - 1];
+			#pragma unroll
+			for(int k = 0; k < MAX_SEGS - 1; k++) bk[k] = __shfl_sync(0xFFFFFFFFu, a_bk[k], l);
+			if(lane < MAX_BLKS / 4)
 			{
-				const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[(s0 + i) & (RS - 1)]) & 3;
-				// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
-				cd = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
+				unsigned w = 0;
+				#pragma unroll
+				for(int e = 0; e < 4; e++)
+				{
+					int sg = 0;
+					#pragma unroll
+					for(int k = 0; k < MAX_SEGS - 1; k++) sg += bk[k] <= 4 * lane + e;
+					w |= (unsigned) sg << (8 * e);
+				}
+				reinterpret_cast<unsigned *>(lb.fm_blk)[lane] = w;
 			}
-			posr[r] = p; code[r] = cd;
-			MI |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, valid && (cd & 1)) << (32 * r);
-			MQ |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, valid && (cd & 2)) << (32 * r);
-			MG |= (unsigned long long) __ballot_sync(0xFFFFFFFFu, minor) << (32 * r);
 		}
+		else if(lane < MAX_BLKS / 4) reinterpret_cast<unsigned *>(lb.fm_blk)[lane] = 0;
+		if(!dp.have_nicam)
+		{
+			if(lane == 0) { lb.nsym = 0; lb.nic_generic = 0; lb.symb[0] = make_uint2(0u, 0x7FFFFFFFu); }
+			continue;
+		}
+		const int ns = __shfl_sync(0xFFFFFFFFu, a_ns, l);
+		const int dq = __shfl_sync(0xFFFFFFFFu, a_dq, l), ks0 = __shfl_sync(0xFFFFFFFFu, a_ks0, l);
+		const unsigned r0 = __shfl_sync(0xFFFFFFFFu, a_r0, l);
+		const long long s0 = __shfl_sync(0xFFFFFFFFu, a_s0, l), k0 = __shfl_sync(0xFFFFFFFFu, a_k0, l);
+		int generic = __shfl_sync(0xFFFFFFFFu, a_generic, l);
+		const int i = lane;                                             // window index = listed symbol index
+		const bool valid = i < ns;
+		// pos(s0 + i) - q0 = ceil((r0 + i F) / D): below 2^19, so one float multiply and a correction divide exactly
+		const unsigned num = r0 + (unsigned) i * F + D - 1;
+		unsigned p = (unsigned) __float2int_rz((float) num * inv_d);
+		{
+			const int rr = (int) num - (int) (p * D);
+			if(rr < 0) p--; else if(rr >= (int) D) p++;
+		}
+		const unsigned pprev = __shfl_up_sync(0xFFFFFFFFu, p, 1);
+		const bool minor = valid && i > 0 && (int) (p - pprev) == minor_adv;   // the window's first symbol: unknown, never used
+		int ks = ks0 + i;
+		long long k = k0;
+		if(ks >= 364) { ks -= 364; k++; }
+		int cd = 0;
+		if(valid)
+		{
+			const int sy = (dt.nic_fstart[k & (RF - 1)] + dt.nic_local[(s0 + i) & (RS - 1)]) & 3;
+			// ref nicam728.c:47,386-391: _syms = {0,1,3,2}; bit0 -> I polarity, bit1 -> Q polarity
+			cd = sy == 2 ? 3 : (sy == 3 ? 2 : sy);
+		}
+		const unsigned MI = __ballot_sync(0xFFFFFFFFu, valid && (cd & 1)), MQ = __ballot_sync(0xFFFFFFFFu, valid && (cd & 2));
+		const unsigned MG = __ballot_sync(0xFFFFFFFFu, minor);
 		for(int b = lane; b < MAX_BLKS; b += 32) s_blk[wid][b] = 0;
 		__syncwarp();
-		// listed symbol o <-> window index i = o + lead: handled by the lane that holds i
-		#pragma unroll
-		for(int r = 0; r < 2; r++)
+		int bad = 0, norow = 0;
+		if(valid)
 		{
-			const int i = lane + 32 * r, o = i - lead;
-			if(o >= 0 && o < ns)
+			// bit j of a pattern = the j-th latest symbol (0 = this one): window bits i-5 .. i, reversed
+			const unsigned wi = i >= 5 ? (MI >> (i - 5)) & 63u : (MI << (5 - i)) & 63u;
+			const unsigned wq = i >= 5 ? (MQ >> (i - 5)) & 63u : (MQ << (5 - i)) & 63u;
+			const unsigned wg = i >= 4 ? (MG >> (i - 4)) & 31u : (MG << (4 - i)) & 31u;
+			const int patI = (int) (__brev(wi) >> 26), patQ = (int) (__brev(wq) >> 26), gaps = (int) (__brev(wg) >> 27);
+			const int sx = dq + (int) p;
+			int bI = 0xFFFF, bQ = 0xFFFF;
+			// a row needs the 5 predecessors inside the window (and, as in line_audio, a stream that is 5 symbols old)
+			const bool row_ok = dp.nicam_lut_ok && i >= 5 && s0 + i >= 5 && __popc(gaps) <= 1;
+			if(row_ok)
 			{
-				// bit j of a pattern = the j-th latest symbol (0 = this one): window bits i-5 .. i, reversed
-				const unsigned wi = i >= 5 ? (unsigned) (MI >> (i - 5)) & 63u : (unsigned) (MI << (5 - i)) & 63u;
-				const unsigned wq = i >= 5 ? (unsigned) (MQ >> (i - 5)) & 63u : (unsigned) (MQ << (5 - i)) & 63u;
-				const unsigned wg = i >= 4 ? (unsigned) (MG >> (i - 4)) & 31u : (unsigned) (MG << (4 - i)) & 31u;
-				const int patI = (int) (__brev(wi) >> 26), patQ = (int) (__brev(wq) >> 26), gaps = (int) (__brev(wg) >> 27);
-				const int sx = dq + posr[r];
-				int bI = 0xFFFF, bQ = 0xFFFF;
-				const bool row_ok = dp.nicam_lut_ok && s0 + i >= 5 && __popc(gaps) <= 1;
-				if(row_ok)
-				{
-					const int gg = gaps ? 1 + (__ffs(gaps) - 1) : 0;       // which gap (1 = newest) has the rarer spacing
-					bI = (gg * 64 + patI) * dp.nicam_sps - sx + 2048;
-					bQ = (gg * 64 + patQ) * dp.nicam_sps - sx + 2048;
-				}
-				la.symb[o] = make_uint2((unsigned) (bI & 0xFFFF) | ((unsigned) (bQ & 0xFFFF) << 16), (unsigned) sx);
-				la.symc[o] = (unsigned char) code[r];
-				// the symbol comes into effect at the first block that starts at or behind it
-				const int bo = sx <= 0 ? 0 : (sx + 31) >> 5;
-				if(bo < MAX_BLKS) atomicMax(&s_blk[wid][bo], o);
+				const int gg = gaps ? __ffs(gaps) : 0;                      // which gap (1 = newest) has the rarer spacing
+				bI = (gg * 64 + patI) * dp.nicam_sps - sx + 2048;
+				bQ = (gg * 64 + patQ) * dp.nicam_sps - sx + 2048;
 			}
+			lb.symb[i] = make_uint2((unsigned) (bI & 0xFFFF) | ((unsigned) (bQ & 0xFFFF) << 16), (unsigned) sx);
+			lb.symc[i] = (unsigned char) cd;
+			// the symbol comes into effect at the first block that starts at or behind it
+			const int bo = sx <= 0 ? 0 : (sx + 31) >> 5;
+			if(bo < MAX_BLKS) atomicMax(&s_blk[wid][bo], i);
+			if(i == 0 && sx > 0) bad = 1;
+			norow = !row_ok;
 		}
-		if(lane == 0) la.symb[ns] = make_uint2(0u, 0x7FFFFFFFu);
+		if(lane == 0) lb.symb[ns] = make_uint2(0u, 0x7FFFFFFFu);
 		__syncwarp();
-		// running maximum over the blocks: blocks without a symbol start keep the previous symbol
-		int carry = 0;
+		// running maximum over the blocks: blocks without a symbol start keep the previous symbol; block 0 gets the
+		// LAST symbol starting at or before x = 0, the one in effect there
+		int carry = 0, ib0 = 0;
 		for(int b0 = 0; b0 < MAX_BLKS; b0 += 32)
 		{
 			const int b = b0 + lane;
@@ -1000,27 +1065,16 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 			#pragma unroll
 			for(int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, v, o); if(lane >= o) v = max(v, u); }
 			v = max(v, carry);
-			if(b < MAX_BLKS) la.nic_blk[b] = (unsigned char) v;
+			if(b < MAX_BLKS) lb.nic_blk[b] = (unsigned char) v;
+			if(b0 == 0) ib0 = __shfl_sync(0xFFFFFFFFu, v, 0);
 			carry = __shfl_sync(0xFFFFFFFFu, v, 31);
 		}
-		// the table path needs a row for every symbol in effect on the line and at most one symbol start per block
-		generic = !dp.nicam_lut_ok || dp.nicam_sps - 1 < 32 || ns < 1;
-	}
-	// ... checked in a second pass: the symbols in effect are those from nic_blk[0] on
-	if(dp.have_nicam)
-	{
-		__syncwarp();
-		const int ib0 = la.nic_blk[0];
-		int bad = 0;
-		for(int o = lane; o < ns; o += 32)
-		{
-			const uint2 e = la.symb[o];
-			if(o >= ib0 && (e.x & 0xFFFFu) == 0xFFFFu) bad = 1;
-			if(o == 0 && (int) e.y > 0) bad = 1;
-		}
+		// the table path needs a row for every symbol in effect on the line: those from nic_blk[0] on
+		if(norow && i >= ib0) bad = 1;
 		generic |= __any_sync(0xFFFFFFFFu, bad);
+		if(lane == 0) { lb.nsym = ns; lb.nic_generic = generic; }
+		__syncwarp();
 	}
-	if(lane == 0) { la.nsym = ns; la.nic_generic = generic; }
 }
 
 // raster descriptors: index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
@@ -2647,6 +2701,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	dt.clut = (const htv_c16_t *) dev_copy(d, t->clut, sizeof(htv_c16_t) * t->clut_len);
 	dt.burst_win = (const int16_t *) dev_copy(d, t->burst_win, sizeof(int16_t) * (t->burst_width + 1));
 	dt.fm_ang = (const uint64_t *) dev_copy(d, t->fm_ang, t->fm_ang ? sizeof(uint64_t) * 65536 : 0);
+	dt.fm_rot8 = (const float2 *) dev_copy(d, t->fm_rot8, t->fm_rot8 ? sizeof(float) * 2 * 65536 : 0);
 	dt.fmv_ang = (const uint64_t *) dev_copy(d, t->fmv_ang, t->fmv_ang ? sizeof(uint64_t) * 65536 : 0);
 	dt.afir_v = (const int32_t *) dev_copy(d, t->afir_v, sizeof(t->afir_v));
 	dt.afir_f = (const int32_t *) dev_copy(d, t->afir_f, sizeof(t->afir_f));
@@ -2836,7 +2891,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 				d->dt.chroma_atab = (const uint32_t *) dev_copy(d, ctab, sizeof(ctab));
 			}
 			const size_t rowb = (size_t) mf_row_bytes(W) + 16, uvb = (size_t) MF_TILE * T + 32;
-			d->kl_smem = (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
+			d->kl_smem = 2 * sizeof(LineA2) + 2 * sizeof(LineR2) + (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
 			d->use_line = 1;
 			{
@@ -3046,7 +3101,7 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 			if(dp.have_lim)
 			{
 				const int64_t u0 = jA - 2 * HTV_LIM_W, n = jB - u0 + 1;
-				k_fm_fir<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(dp, d->dt, u0, jB);
+				k_fm_fir<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(dp, d->dt, u0, jB);   // 128 = the kernel's tile
 				d->launches++;
 			}
 			const int64_t n = jB - jA + 1;
@@ -3119,7 +3174,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 		}
 		LineA2 *la2 = (LineA2 *) d->d_desc_a2;
-		k_line_desc_a2<<<(nlines + KD_WARPS - 1) / KD_WARPS, 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
+		k_line_desc_a2<<<(nlines + KD_LINES * KD_WARPS - 1) / (KD_LINES * KD_WARPS), 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
 		CK(cudaEventRecord(d->ev_audio, d->side));
 		d->side_armed = 0;
 		CK(cudaStreamWaitEvent(st, d->ev_audio, 0));
@@ -3463,6 +3518,7 @@ extern "C" void *htv_dev_event_new_timed(htv_dev_t *d) { DevGuard guard(d->devic
 extern "C" float htv_dev_event_elapsed(void *e0, void *e1) { float ms = -1; cudaEventSynchronize((cudaEvent_t) e1); cudaEventElapsedTime(&ms, (cudaEvent_t) e0, (cudaEvent_t) e1); return(ms); }
 extern "C" void htv_dev_event_free(void *e) { if(e) cudaEventDestroy((cudaEvent_t) e); }
 extern "C" int htv_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return(HTV_OK); }
+extern "C" int htv_dev_event_wait(void *e) { CK(cudaEventSynchronize((cudaEvent_t) e)); return(HTV_OK); }
 extern "C" int htv_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return(HTV_OK); }
 
 extern "C" int htv_dev_device(const htv_dev_t *d) { return(d->device); }

@@ -55,58 +55,74 @@ __device__ __forceinline__ int kl_acc15(int hh, int mid, int ll)
 }
 __device__ __forceinline__ int kl_fir_out(int hh, int mid, int ll) { return(sat16i(kl_acc15(hh, mid, ll))); }
 
-// next-line data into L1 while this line is computed: the kernel is otherwise bound by the latency of
-// first-touch loads (descriptors, template, picture row, subcarrier table all change every line)
-// A real load whose result is only "used" at the end of the iteration: unlike prefetch.global.L1 (measured: no
-// effect on the L1 hit rate of the ld.global.nc path here) it is guaranteed to allocate the line in L1.
-__device__ __forceinline__ void kl_prefetch(const void *p, unsigned &sink)
-{
-	sink ^= __ldg(reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3));
-}
-
 // ---- sound carriers for the four samples of a lane (strided by 8) --------------------------------------------
 // Same arithmetic as sound_add<false> (ref video.c:3261-3450, nicam728.c:342-411); what differs is how a lane
 // finds its audio segment and NICAM symbol: all four samples lie in the 32-sample block b = xb >> 5, for which
-// the line descriptor lists the segment / symbol in effect at the block's first sample, and at most one
-// boundary of either kind falls inside a block.
+// the line descriptor (in shared memory) lists the segment / symbol in effect at the block's first sample, and
+// at most one boundary of either kind falls inside a block.
+// FM carrier: one sin/cos for the lane's first sample, the other three by rotating with the segment's
+// (cos, sin) of 8 angle steps - unless an audio-segment boundary or a renormalisation of the reference's
+// phasor (every 32 767 samples) falls between the lane's samples; then every sample gets its own.
 __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTables &dt, const LineA2 *la,
 	const short *ntp, int xb, int (&oi)[4], int (&oq)[4])
 {
 	const int b = xb >> 5;
 	if(dp.have_fm || dp.have_am)
 	{
-		const int sg = __ldg(la->fm_blk + b);
-		const int nb = __ldg(la->seg_x + sg + 1);
+		const int sg = la->fm_blk[b];
+		const int nb = la->seg_x[sg + 1];
 		const int sg1 = min(sg + 1, MAX_SEGS - 1);
-		int kk = __ldg(&la->kk0) + xb;
+		int kk = la->kk0 + xb;
 		if(kk >= 32767) kk -= 32767;
 		// amplitude of the reference's Q31 phasor kk + 1 multiplications after a renormalisation
-		float kf = (float) (kk + 1);
+		const float kf = (float) (kk + 1);
+		const bool mixed = (nb > xb && nb <= xb + 24) || kk + 25 > 32767;
 		if(dp.have_fm)
 		{
-			const unsigned long long angA = __ldg(la->seg_ang + sg), angB = __ldg(la->seg_ang + sg1);
-			unsigned long long phA = __ldg(la->seg_phase + sg) + angA * (unsigned long long) xb;
-			unsigned long long phB = __ldg(la->seg_phase + sg1) + angB * (unsigned long long) xb;
-			const unsigned long long stA = angA << 3, stB = angB << 3;
-			float kq = kf;
-			#pragma unroll
-			for(int j = 0; j < 4; j++)
+			if(!mixed)
 			{
-				const unsigned long long ph = xb + 8 * j >= nb ? phB : phA;
-				if(kq > 32767.0f) kq -= 32767.0f;
-				const float amp = 32767.99998f - kq * 1.52587890625e-5f;
+				const int s0 = xb >= nb ? sg1 : sg;
+				const unsigned long long ph = la->seg_phase[s0] + la->seg_ang[s0] * (unsigned long long) xb;
+				const float2 rot = la->seg_rot[s0];
 				float sn, cs;
 				__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);   // pi / 2^31
-				oi[j] += (__float2int_rd(amp * cs) * dp.fm_level) >> 15;
-				oq[j] += (__float2int_rd(amp * sn) * dp.fm_level) >> 15;
-				phA += stA; phB += stB; kq += 8.0f;
+				float amp = 32767.99998f - kf * 1.52587890625e-5f;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					oi[j] += (__float2int_rd(amp * cs) * dp.fm_level) >> 15;
+					oq[j] += (__float2int_rd(amp * sn) * dp.fm_level) >> 15;
+					const float c2 = __fmaf_rn(cs, rot.x, -(sn * rot.y)), s2 = __fmaf_rn(sn, rot.x, cs * rot.y);
+					cs = c2; sn = s2;
+					amp -= 8.0f * 1.52587890625e-5f;
+				}
+			}
+			else
+			{
+				const unsigned long long angA = la->seg_ang[sg], angB = la->seg_ang[sg1];
+				unsigned long long phA = la->seg_phase[sg] + angA * (unsigned long long) xb;
+				unsigned long long phB = la->seg_phase[sg1] + angB * (unsigned long long) xb;
+				const unsigned long long stA = angA << 3, stB = angB << 3;
+				float kq = kf;
+				#pragma unroll
+				for(int j = 0; j < 4; j++)
+				{
+					const unsigned long long ph = xb + 8 * j >= nb ? phB : phA;
+					if(kq > 32767.0f) kq -= 32767.0f;
+					const float amp = 32767.99998f - kq * 1.52587890625e-5f;
+					float sn, cs;
+					__sincosf((float) (int) (ph >> 32) * 1.4629180792671596e-9f, &sn, &cs);
+					oi[j] += (__float2int_rd(amp * cs) * dp.fm_level) >> 15;
+					oq[j] += (__float2int_rd(amp * sn) * dp.fm_level) >> 15;
+					phA += stA; phB += stB; kq += 8.0f;
+				}
 			}
 		}
 		if(dp.have_am)
 		{
-			unsigned long long phM = __ldg(&la->am_phase0) + dp.am_ang * (unsigned long long) (xb + 1);
+			unsigned long long phM = la->am_phase0 + dp.am_ang * (unsigned long long) (xb + 1);
 			const unsigned long long stM = dp.am_ang << 3;
-			const int amA = (__ldg(la->seg_am + sg) + 32768) / 2, amB = (__ldg(la->seg_am + sg1) + 32768) / 2;
+			const int amA = (la->seg_am[sg] + 32768) / 2, amB = (la->seg_am[sg1] + 32768) / 2;
 			float kq = kf;
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
@@ -126,11 +142,11 @@ __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTable
 	if(dp.have_nicam)
 	{
 		int bi[4], bq[4];
-		if(!__ldg(&la->nic_generic))
+		if(!la->nic_generic)
 		{
 			// pulse-shaping table (htv_tables.c): one entry per sample and channel, index = base + x
-			const int ib = __ldg(la->nic_blk + b);
-			const uint2 cur = __ldg(la->symb + ib), nxt = __ldg(la->symb + ib + 1);
+			const int ib = la->nic_blk[b];
+			const uint2 cur = la->symb[ib], nxt = la->symb[ib + 1];
 			const int nb = (int) nxt.y;
 			const int16_t *lut = dt.nicam_lut - KL_BIAS + xb;
 			#pragma unroll
@@ -149,15 +165,15 @@ __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTable
 			{
 				const int x = xb + 8 * j;
 				int i3 = 0;
-				const int ns = __ldg(&la->nsym);
-				while(i3 + 1 < ns && (int) __ldg(&la->symb[i3 + 1].y) <= x) i3++;
+				const int ns = la->nsym;
+				while(i3 + 1 < ns && (int) la->symb[i3 + 1].y <= x) i3++;
 				bi[j] = 0; bq[j] = 0;
 				for(int cnd = 0; cnd < NIC_CAND; cnd++)
 				{
 					const int i = i3 - cnd;
 					if(i < 0) break;
-					const int sy = __ldg(la->symc + i);
-					const int d0 = x - (int) __ldg(&la->symb[i].y) + NIC_TPAD;  // the table is zero outside the pulse
+					const int sy = la->symc[i];
+					const int d0 = x - (int) la->symb[i].y + NIC_TPAD;      // the table is zero outside the pulse
 					if(d0 < 0) continue;
 					const int r = ntp[d0];
 					bi[j] += (sy & 1) ? r : -r;
@@ -166,7 +182,7 @@ __device__ __forceinline__ void kl_sound(const htv_dparams_t &dp, const DevTable
 			}
 		}
 		// carrier table extended past its period (htv_tables.c): cc0 + x never wraps
-		const htv_c16_t *ccp = dt.nicam_cc + __ldg(&la->cc0) + xb;
+		const htv_c16_t *ccp = dt.nicam_cc + la->cc0 + xb;
 		#pragma unroll
 		for(int j = 0; j < 4; j++)
 		{
@@ -191,8 +207,8 @@ __device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const Dev
 	}
 	if(dp.have_offset)
 	{
-		const long long m0 = __ldg(&la->m0);
-		const unsigned long long off0 = __ldg(&la->off_phase0);
+		const long long m0 = la->m0;
+		const unsigned long long off0 = la->off_phase0;
 		#pragma unroll
 		for(int j = 0; j < 4; j++)
 		{
@@ -245,8 +261,23 @@ __device__ __forceinline__ void kl_post_store(const htv_dparams_t &dp, const Dev
 	}
 }
 
+// cp.async: 16 bytes global -> shared without passing through registers
+__device__ __forceinline__ void kl_cp16(void *dst_smem, const void *src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void kl_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // VF: a video filter is on (composite ring + tensor-core FIR); HASQ: it has Q taps (VSB); FULL: 128 | W (no
 // partial tile: the x < W tests fold away); CSAT: the chroma low-pass can leave the int16 range (sum of |taps| > 32768)
+//
+// Per iteration q (one scan line) a CTA runs
+//   R1b(q)  picture values by table from the pixels fetched earlier, U / V byte planes        | __syncthreads (colour lines)
+//   R2(q)   chroma low-pass (mma), burst, subcarrier, VBI overlay, composite row q mod 3       | __syncthreads
+//   R1a(q+1) template + pixel loads of the NEXT line are issued here ...
+//   M(q-1)  ... and arrive while line q - 1 (whose right-hand halo R2(q) has just written) is filtered (mma),
+//           gets its sound carriers and is stored.
+// The line descriptors (LineR2 of q + 1, LineA2 of q - 1) come in by cp.async at the top of the iteration.
 template<bool VF, bool HASQ, bool FULL, bool CSAT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR2 *lrp, const LineA2 *lap,
@@ -254,10 +285,11 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
-	const int T = mf_tiles(W);
 	const int RB = kl_row_bytes(W), UB = kl_uv_bytes(W);
-	// [row 0..2][hi, lo] composite planes | [u hi, u lo, v hi, v lo] | FIR tap operand | chroma tap operand | NICAM pulse
-	unsigned char *rows = smem_raw;
+	// descriptors x2 | [row 0..2][hi, lo] composite planes | [u hi, u lo, v hi, v lo] | FIR taps | chroma taps | NICAM pulse
+	LineA2 *sla = reinterpret_cast<LineA2 *>(smem_raw);
+	LineR2 *slr = reinterpret_cast<LineR2 *>(sla + 2);
+	unsigned char *rows = reinterpret_cast<unsigned char *>(slr + 2);
 	unsigned char *uvp = rows + (VF ? 6 * RB : 0);
 	uint4 *atab = reinterpret_cast<uint4 *>(uvp + 4 * UB);                 // [k-step][I hi, I lo, Q hi, Q lo][lane]
 	uint4 *ctab = atab + (VF ? MF_ATAB_WORDS / 4 : 0);                      // [hi, lo][lane]
@@ -265,22 +297,25 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
 	const int xb = MF_TILE * nt + 32 * t + g;                               // the lane's samples: xb + 8 j
-	(void) T;
+
+	const int a = blockIdx.x * run, bnd = min(a + run, nlines);
+	if(a >= nlines) return;
+	// relative line q: raster lines a-1 .. bnd (descriptor lrp[q + 1]), modulate a .. bnd-1
+	const int q0 = VF ? a - 1 : a, q1 = VF ? bnd : bnd - 1;
 
 	// ---- one-time set-up -------------------------------------------------------
 	if(VF) for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
 	if(dt.chroma_atab) for(int i = tid; i < 64; i += blockDim.x) ctab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.chroma_atab) + i);
-	for(int i = tid; i < ((VF ? 6 * RB : 0) + 4 * UB) / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem_raw)[i] = 0;
+	for(int i = tid; i < ((VF ? 6 * RB : 0) + 4 * UB) / 4; i += blockDim.x) reinterpret_cast<unsigned *>(rows)[i] = 0;
 	if(dp.have_nicam)
 	{
 		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
 		int4 *dst = reinterpret_cast<int4 *>(ntp);
 		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
+	if(tid < 4) reinterpret_cast<int4 *>(slr + (q0 & 1))[tid] = __ldg(reinterpret_cast<const int4 *>(lrp + q0 + 1) + tid);
 	__syncthreads();
 
-	const int a = blockIdx.x * run, bnd = min(a + run, nlines);
-	if(a >= nlines) return;
 	const int full_l = dp.active_left, full_r = dp.active_left + dp.active_width;
 	const bool in_full = xb + 24 >= full_l && xb < full_r;                  // the lane touches the picture area at all
 	const bool all_full = xb >= full_l && xb + 24 < full_r;                 // ... with all four samples
@@ -288,94 +323,78 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	unsigned char *const uv0 = uvp + KL_UVLEAD + xb;                        // the lane's bytes in the four chroma planes
 	const unsigned char *const uvb = uvp + MF_M * (8 * nt + g) + 8 * t;     // ... and its chroma B fragment
 	const int fo0 = mf_b_offset(nt, 0, lane);
+	constexpr int NA16 = (int) (sizeof(LineA2) / 16);
 
-	// relative line q: raster lines a-1 .. bnd (descriptor lrp[q + 1]), modulate a .. bnd-1
-	const int q0 = VF ? a - 1 : a, q1 = VF ? bnd : bnd - 1;
+	// loads of line q issued one phase early: template (int16 x 4) and pixels (RGBx x 4)
+	int tm[4];
+	unsigned px[4];
+	#define KL_R1A(QQ) do { \
+		const LineR2 &ln = slr[(QQ) & 1]; \
+		const int16_t *tp_ = dt.tmpl_out + (size_t) ln.tmpl * W + xb; \
+		_Pragma("unroll") for(int j = 0; j < 4; j++) tm[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(tp_ + 8 * j) : 0; \
+		if(in_full && ln.al < ln.ar && ln.row_off >= 0) \
+		{ \
+			const uint32_t *pp_ = dt.frames + ln.row_off + (xb - dp.active_left); \
+			_Pragma("unroll") for(int j = 0; j < 4; j++) \
+			{ \
+				const int x_ = xb + 8 * j; \
+				px[j] = (x_ >= ln.al && x_ < ln.ar) ? __ldg(pp_ + 8 * j) : 0u; \
+			} \
+		} \
+		else { px[0] = px[1] = px[2] = px[3] = 0u; } \
+	} while(0)
+	KL_R1A(q0);
+
 	int r3 = (q0 + 3) % 3;                                                  // ring row of line q
-	unsigned sink = 0;
 	for(int q = q0; q <= q1; q++, r3 = r3 == 2 ? 0 : r3 + 1)
 	{
-		asm volatile("" :: "r"(sink));                                      // last iteration's prefetch loads end here
-		// ---- next line's first-touch data -> L1 (one 128-byte line per lane) -------------
-		if(nt == 0)
-		{
-			if(lane == 0 && q + 2 <= nlines) kl_prefetch(lrp + q + 3, sink);
-			const int ml = VF ? q : q + 1;                                  // the line the next iteration modulates
-			if(lane >= 1 && lane <= (int) (sizeof(LineA2) + 127) / 128 + 1 && ml < nlines)
-				kl_prefetch(reinterpret_cast<const char *>(lap + ml) + 128 * (lane - 1), sink);
-		}
-		else if(nt <= 3 && q + 1 <= q1)
-		{
-			const int4 *ln = reinterpret_cast<const int4 *>(lrp + q + 2);
-			if(nt == 1)
-			{
-				const int tm = __ldg(reinterpret_cast<const int *>(ln) + 1);
-				if(128 * lane < 2 * W) kl_prefetch(reinterpret_cast<const char *>(dt.tmpl_out + (size_t) tm * W) + 128 * lane, sink);
-			}
-			else if(nt == 2)
-			{
-				const int4 n3 = __ldg(ln + 3);
-				const long long ro = ((long long) (unsigned) n3.x) | ((long long) n3.y << 32);
-				if(ro >= 0 && 128 * lane < 4 * dp.active_width) kl_prefetch(reinterpret_cast<const char *>(dt.frames + ro) + 128 * lane, sink);
-			}
-			else if(dt.clut)
-			{
-				const unsigned co = (unsigned) __ldg(reinterpret_cast<const int *>(ln) + 8);
-				for(int i = lane; 128 * i < 4 * W; i += 32) kl_prefetch(reinterpret_cast<const char *>(dt.clut + co) + 128 * i, sink);
-			}
-		}
+		const int mrow = VF ? q - 1 : q;                                    // the line modulated in this iteration
+		// ---- descriptors of the next raster line and of the line modulated below -> shared memory -----
+		if(tid < 4) { if(q + 1 <= q1) kl_cp16(reinterpret_cast<int4 *>(slr + ((q + 1) & 1)) + tid, reinterpret_cast<const int4 *>(lrp + q + 2) + tid); }
+		else if(tid < 4 + NA16) { if(mrow >= a) kl_cp16(reinterpret_cast<int4 *>(sla + (mrow & 1)) + (tid - 4), reinterpret_cast<const int4 *>(lap + mrow) + (tid - 4)); }
 
-		// ---- R1: template + picture -------------------------------------------
-		const int4 *lq = reinterpret_cast<const int4 *>(lrp + q + 1);
-		const int4 l0 = __ldg(lq), l1 = __ldg(lq + 1), l2 = __ldg(lq + 2), l3 = __ldg(lq + 3);
-		const int li_tmpl = l0.y, li_al = l0.z, li_ar = l0.w;
-		const int li_pal = l1.x, li_keep = l1.y, li_ov_any = l1.z, li_ov_from = l1.w;
-		const unsigned li_clut = (unsigned) l2.x;
-		const int li_ov_to = l2.y, li_ov_value = l2.z, li_ov_add = l2.w;
-		const long long li_row = ((long long) (unsigned) l3.x) | ((long long) l3.y << 32);
-		int val[4];
-		{
-			const int16_t *tp = dt.tmpl_out + (size_t) li_tmpl * W + xb;
-			#pragma unroll
-			for(int j = 0; j < 4; j++) val[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(tp + 8 * j) : 0;
-		}
+		// ---- R1b: picture values of line q ---------------------------------------
+		const LineR2 &li = slr[q & 1];
+		const int li_al = li.al, li_ar = li.ar, li_pal = li.pal;
+		int val[4] = { tm[0], tm[1], tm[2], tm[3] };
 		int uu[4] = { 0, 0, 0, 0 }, vv[4] = { 0, 0, 0, 0 };
 		if(in_full && li_al < li_ar)
 		{
-			const uint32_t *px = dt.frames + (li_row >= 0 ? li_row : 0) + (xb - dp.active_left);
-			if(xb >= li_al && xb + 24 < li_ar && !li_keep)
+			if(xb >= li_al && xb + 24 < li_ar && !li.keep)
 			{
-				// all four samples in the picture: loads back to back, no per-sample tests
-				unsigned rgb[4];
-				#pragma unroll
-				for(int j = 0; j < 4; j++) rgb[j] = __ldg(px + 8 * j) & 0xFFFFFFu;
-				if(li_row < 0) rgb[0] = rgb[1] = rgb[2] = rgb[3] = 0u;
+				// all four samples in the picture
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					const short4 e = __ldg(dt.yuv_lut + rgb[j]);
+					const short4 e = __ldg(dt.yuv_lut + (px[j] & 0xFFFFFFu));
 					val[j] = e.x; uu[j] = e.y; vv[j] = e.z;
 				}
 			}
 			else
 			{
-				const int16_t *kp = dt.tmpl_keep + (size_t) li_tmpl * W + xb;
+				const int16_t *kp = dt.tmpl_keep + (size_t) li.tmpl * W + xb;
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
 					const int x = xb + 8 * j;
 					if(x >= li_al && x < li_ar)
 					{
-						const unsigned rgb = li_row >= 0 ? (__ldg(px + 8 * j) & 0xFFFFFFu) : 0u;
-						const short4 e = __ldg(dt.yuv_lut + rgb);
+						const short4 e = __ldg(dt.yuv_lut + (px[j] & 0xFFFFFFu));
 						val[j] = e.x; uu[j] = e.y; vv[j] = e.z;
-						if(li_keep) val[j] += __ldg(kp + 8 * j);
+						if(li.keep) val[j] += __ldg(kp + 8 * j);
 					}
 				}
 			}
 		}
 		if(li_pal)
 		{
+			// subcarrier table entries of this line: in flight across the barrier and the chroma filter
+			short2 cl[4];
+			{
+				const htv_c16_t *cp = dt.clut + li.clut_off + xb;
+				#pragma unroll
+				for(int j = 0; j < 4; j++) cl[j] = (FULL || xb + 8 * j < W) ? kl_ldc16(cp + 8 * j) : make_short2(0, 0);
+			}
 			// unfiltered U, V as byte planes; outside the picture the planes stay zero (the reference filters
 			// each line on its own: zero history either side, ref fir.c:357-375)
 			if(all_full)
@@ -435,37 +454,25 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 					}
 				}
 			}
-			{
-				const htv_c16_t *cp = dt.clut + li_clut + xb;
-				#pragma unroll
-				for(int j = 0; j < 4; j++)
-				{
-					if(FULL || xb + 8 * j < W)
-					{
-						const short2 c = kl_ldc16(cp + 8 * j);
-						val[j] += ((int) c.x * cv[j] * li_pal + (int) c.y * cu[j]) >> 15;
-					}
-				}
-			}
+			#pragma unroll
+			for(int j = 0; j < 4; j++) val[j] += ((int) cl[j].x * cv[j] * li_pal + (int) cl[j].y * cu[j]) >> 15;
 		}
-		if(li_ov_any)
+		if(li.ov_any)
 		{
 			// VBI stages run on the finished line (ref video.c:4213-4357 register them behind the raster)
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
 			{
 				const int x = xb + 8 * j;
-				if(x >= li_ov_from && x < li_ov_to) val[j] = li_ov_value;
-				if(li_ov_add >= 0 && x < W) val[j] = wrap16i(val[j]) + dt.ov_add[(size_t) li_ov_add * W + x];
+				if(x >= li.ov_from && x < li.ov_to) val[j] = li.ov_value;
+				if(li.ov_add >= 0 && x < W) val[j] = wrap16i(val[j]) + dt.ov_add[(size_t) li.ov_add * W + x];
 			}
 		}
 
-		int oi[4], oq[4];
-		int mrow = q;                                                       // line modulated in this iteration
+		const int rprev = r3 == 0 ? 2 : r3 - 1, rnext = r3 == 2 ? 0 : r3 + 1;
 		if(VF)
 		{
 			// ---- composite line -> ring row q mod 3 (+ the neighbours' halos) ----------
-			const int rprev = r3 == 0 ? 2 : r3 - 1, rnext = r3 == 2 ? 0 : r3 + 1;
 			unsigned char *rp = rows + (2 * r3) * RB + KL_LEAD + xb;
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
@@ -493,9 +500,17 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 					if(x >= W - KL_LEAD && x < W) { hp[8 * j] = (unsigned char) (val[j] >> 8); hp[RB + 8 * j] = (unsigned char) val[j]; }
 				}
 			}
-			__syncthreads();
-			mrow = q - 1;
-			if(mrow < a) continue;
+		}
+		if(tid < 4 + NA16) kl_cp_wait();
+		__syncthreads();                                                    // rows of line q, descriptors of q + 1 and of mrow
+
+		// ---- R1a: the next line's template and pixels start their way here -------------
+		if(q + 1 <= q1) KL_R1A(q + 1);
+		if(mrow < a) continue;
+
+		int oi[4], oq[4];
+		if(VF)
+		{
 			// ---- M: video filter of line q - 1, one tile of 128 samples per warp -------
 			const unsigned char *ph = rows + (2 * rprev) * RB + fo0, *plo = ph + RB;
 			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
@@ -523,7 +538,6 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		}
 		else
 		{
-			if(li_pal) __syncthreads();                                     // chroma planes are rewritten by the next line
 			#pragma unroll
 			for(int j = 0; j < 4; j++) { oi[j] = wrap16i(val[j]); oq[j] = 0; }
 		}
@@ -531,9 +545,10 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		// ---- sound carriers, mixers, store ---------------------------------------
 		if(FULL || xb < W)
 		{
-			const LineA2 *la = lap + mrow;
+			const LineA2 *la = sla + (mrow & 1);
 			kl_sound(dp, dt, la, ntp, xb, oi, oq);
 			kl_post_store<FULL>(dp, dt, la, xb, mrow, oi, oq, out, mrow < acc_rows ? acc : NULL);
 		}
 	}
+	#undef KL_R1A
 }

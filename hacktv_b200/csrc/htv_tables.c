@@ -635,6 +635,17 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		dp->fm_level = (int16_t) round(INT16_MAX * (c->fm_mono_level * slevel));
 		t->fm_ang = malloc(sizeof(uint64_t) * 65536);
 		build_fm_angles(t->fm_ang, sample_rate, c->fm_mono_carrier, c->fm_mono_deviation);
+		{
+			/* (cos, sin) of 8 of those steps: the fused line kernel derives a lane's samples 8 apart from the first by rotation */
+			int r;
+			t->fm_rot8 = malloc(sizeof(float) * 2 * 65536);
+			for(r = 0; r < 65536; r++)
+			{
+				long double a = (long double) (int64_t) (t->fm_ang[r] << 3) * 0x1p-64L * 2.0L * 3.14159265358979323846264338327950288L;
+				t->fm_rot8[2 * r] = (float) cosl(a);
+				t->fm_rot8[2 * r + 1] = (float) sinl(a);
+			}
+		}
 		if(c->fm_mono_preemph)
 		{
 			const double *v = c->fm_mono_preemph == HTV_50US ? audio_50us :
@@ -835,7 +846,7 @@ void htv_tables_free(htv_tables_t *t)
 	free(t->rs_taps);
 	free(t->codes); free(t->pulse_values); free(t->clut); free(t->burst_win);
 	free(t->tmpl_out); free(t->tmpl_keep); free(t->tmpl_keep_any);
-	free(t->fm_ang); free(t->fmv_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
+	free(t->fm_ang); free(t->fm_rot8); free(t->fmv_ang); free(t->nicam_taps); free(t->nicam_tpad); free(t->nicam_lut); free(t->nicam_cc);
 	free(t->secam_fm_lut); free(t->secam_bell); free(t->offset_start); free(t->scratch);
 	free(t);
 }

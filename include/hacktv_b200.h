@@ -217,6 +217,12 @@ typedef int (*htv_read_vbi_t)(void *ctx, int frame /* 1-based */, const htv_vbi_
 extern int htv_set_vbi_source(htv_t *s, htv_read_vbi_t read, void *ctx);
 
 extern htv_line_t *htv_next_line(htv_t *s);
+/* htv_next_line hands out lines of a frame held in pinned host memory. With prefetch on, the following frame
+ * is rendered and copied while the caller consumes the current one (two pinned frames), so a
+ * vid_next_line + rf_write loop is bounded by the consumer, not by a GPU round trip per frame. The price:
+ * the AV source is pulled one frame earlier than the reference would pull it - fine for sources that do not
+ * end (test pattern, live capture), wrong by one frame at the end of a file. Off by default. */
+extern int htv_set_prefetch(htv_t *s, int on);
 
 /* Batched extension. Renders the next `nlines` scan lines of the stream.
  * htv_render: `d_out` is DEVICE memory (at least htv_samples_per_line(s) *

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "video.h"
 #include "hacktv_b200.h"
 
@@ -30,6 +31,8 @@ extern vid_line_t *cpu_vid_next_line(vid_t *s);
 #define MAX_VBI 64
 static struct {
 	vid_t *vid; htv_t *htv; vid_line_t line; uint32_t *packed; uint64_t serial;
+	/* HACKTV_STATS=1: lines handed out and the wall time they took, printed by vid_free (bench.py drop-in figure) */
+	long long stat_lines; struct timespec stat_t0;
 	/* VBI stages: the reference's own code builds the waveforms, the encoder's overlay hook carries them */
 	int16_t *vbi_scratch;           /* one line, I/Q interleaved, as the stock stages expect it */
 	int16_t *vbi_add[MAX_VBI];
@@ -234,6 +237,17 @@ vid_line_t *vid_next_line(vid_t *s)
 	htv_line_t *l;
 	if(i < 0) return(cpu_vid_next_line(s));
 	if(av_eof(&s->av)) return(NULL);
+	if(_enc[i].stat_lines++ == 0)
+	{
+		clock_gettime(CLOCK_MONOTONIC, &_enc[i].stat_t0);
+		/* HACKTV_B200_PREFETCH=1: let the encoder run one frame ahead of the consumer (htv_set_prefetch). It pulls the AV
+		 * source one frame early, so it is for sources that do not end - the test pattern, live capture; at the end
+		 * of a file av_eof() (ref av.c:84-87) would fire one frame too soon. */
+		{
+			const char *pf = getenv("HACKTV_B200_PREFETCH");
+			if(pf && pf[0] == '1') htv_set_prefetch(_enc[i].htv, 1);
+		}
+	}
 	l = htv_next_line(_enc[i].htv);
 	if(!l) return(NULL);
 	memset(&_enc[i].line, 0, sizeof(vid_line_t));
@@ -248,6 +262,13 @@ void vid_free(vid_t *s)
 {
 	int i = _find(s);
 	if(i < 0) { cpu_vid_free(s); return; }
+	if(getenv("HACKTV_STATS") && _enc[i].stat_lines > 0)
+	{
+		struct timespec t1;
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		fprintf(stderr, "{\"encoder\": \"hacktv_b200\", \"lines\": %lld, \"seconds\": %.6f}\n", _enc[i].stat_lines,
+			(double) (t1.tv_sec - _enc[i].stat_t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - _enc[i].stat_t0.tv_nsec));
+	}
 	av_close(&s->av);
 	if(s->passthru) fclose(s->passthru);             /* ref video.c:4743-4746 */
 	htv_av(_enc[i].htv)->close = NULL;

@@ -19,24 +19,30 @@ sys.path.insert(0, os.path.dirname(HERE))
 import orc  # noqa: E402
 
 CONFIGS = {
-    "cfg2_i_16M_filter": ("i", 16000000, True, 625),
-    "cfg3_m_13M5_filter": ("m", 13500000, True, 525),
-    "cfg4_l_16M_filter": ("l", 16000000, True, 625),
+    "cfg2_i_16M_filter": ("i", 16000000, True, 625, ()),
+    "cfg3_m_13M5_filter": ("m", 13500000, True, 525, ()),
+    "cfg4_l_16M_filter": ("l", 16000000, True, 625, ()),
+    # config 3 without its sound carrier: everything left is integer work, so the GPU must match bit for bit at any
+    # distance into the stream (the FM carrier of config 3 sits at exactly fs / 3, see tests/test_gpu_long_stream.py)
+    "cfg3_m_13M5_filter_noaudio": ("m", 13500000, True, 525, ("--noaudio",)),
 }
 KEEP = [0, 1, 2, 3, 5, 22, 23, 24, 100, 200, 262, 263, 264, 285, 300, 310, 311, 312, 313, 314, 335, 336, 400, 500, 600, 622, 623, 624]
 
 
 def main():
     assert orc.have_ref(), "build the reference first: make -C oracle ref"
-    index = {}
-    for name, (mode, rate, filt, lpf) in CONFIGS.items():
+    index = json.load(open(os.path.join(HERE, "golden_long.json"))) if os.path.exists(os.path.join(HERE, "golden_long.json")) else {}
+    only = sys.argv[1:]
+    for name, (mode, rate, filt, lpf, extra) in CONFIGS.items():
+        if only and name not in only:
+            continue
         fps = 25.0 if lpf == 625 else 30000 / 1001
         keep = [l for l in KEEP if l < lpf]
-        entry = {"mode": mode, "rate": rate, "filter": filt, "lines_per_frame": lpf, "keep": keep, "windows": {}}
+        entry = {"mode": mode, "rate": rate, "filter": filt, "noaudio": "--noaudio" in extra, "lines_per_frame": lpf, "keep": keep, "windows": {}}
         arrays = {}
         for tag, seconds in (("b", 10.0), ("c", 34.0)):
             skip = int(np.ceil(seconds * fps)) * lpf
-            x = orc.run_ref(mode, rate, lpf, skip=skip, vfilter=filt, timeout=900)
+            x = orc.run_ref(mode, rate, lpf, skip=skip, vfilter=filt, extra=extra, timeout=900)
             x = x.reshape(lpf, -1)
             arrays[tag] = x[keep]
             entry["windows"][tag] = {"skip": skip, "values_per_line": int(x.shape[1])}

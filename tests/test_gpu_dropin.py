@@ -17,12 +17,12 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(STOCK)), reason="drop-in demo not built")]
 
 
-def _run(binary, args, nbytes):
+def _run(binary, args, nbytes, env=""):
     """Also proves WHICH encoder ran: the adapter's vid_info prints `Encoder: hacktv_b200 ...` (integration/
     video_b200.c), the stock video.c does not - a bug in the adapter's _accelerated() that quietly sent a
     configuration to the renamed stock encoder would otherwise compare the reference with itself."""
     with tempfile.NamedTemporaryFile("r", suffix=".stderr") as err:
-        cmd = f"timeout 120 {binary} {args} -o - test 2>{err.name} | head -c {nbytes}"
+        cmd = f"{env}timeout 120 {binary} {args} -o - test 2>{err.name} | head -c {nbytes}"
         out = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=180).stdout
         log = err.read()
     assert len(out) == nbytes, f"{binary}: got {len(out)} of {nbytes} bytes"
@@ -46,11 +46,16 @@ def _run(binary, args, nbytes):
     # --pixelrate: raster at 13.5 MHz, the reference's polyphase resampler on the device, then the usual path
     ("-m i -s 16000000 --pixelrate 13500000 --filter --noaudio", 4, 0),
     ("-m i -s 16000000 --pixelrate 13500000 --filter", 4, 1),
+    # HACKTV_B200_PREFETCH=1: the adapter's vid_next_line runs one frame ahead of the consumer
+    ("PREFETCH -m i -s 16000000 --filter", 4, 1),
 ])
 def test_same_cli_same_bytes(args, per, tol):
-    w = 858 if "13500000" in args else (1280 if "20000000" in args else 1024)
+    env = ""
+    if args.startswith("PREFETCH "):
+        args, env = args[len("PREFETCH "):], "HACKTV_B200_PREFETCH=1 "
+    w = 858 if "-s 13500000" in args else (1280 if "20000000" in args else 1024)
     lines = 1300 if w == 1024 else 1100
-    a = _run(DROPIN, args, lines * w * per)
+    a = _run(DROPIN, args, lines * w * per, env)
     b = _run(STOCK, args, lines * w * per)
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert d.max() <= tol, f"max |diff| {d.max()}"

@@ -262,3 +262,21 @@ def test_audio_block_longer_than_a_ring_piece_is_not_dropped(built):
         enc.close()
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
     assert np.count_nonzero(outs[1]) > 1000
+
+
+def test_next_line_prefetch_is_invisible(built):
+    """htv_set_prefetch: the frame after the one being handed out is rendered in the background (two pinned
+    frames); the lines that come out are the same, frame and line numbers included."""
+    H = built
+    conf = H.mode_config("i", vfilter=True)
+    outs = []
+    for pf in (False, True):
+        enc = H.Encoder(conf, 16000000); enc.open_test_source()
+        enc.render_host(100)                                     # start in the middle of a frame
+        enc.set_prefetch(pf)
+        got = [enc.next_line() for _ in range(1500)]
+        enc.close()
+        outs.append(got)
+    for (a, fa, la), (b, fb, lb) in zip(*outs):
+        assert fa == fb and la == lb and np.array_equal(a, b)
+    assert outs[0][0][2] == 101 and outs[0][525][1:] == (2, 1)

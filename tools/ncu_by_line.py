@@ -17,8 +17,10 @@ with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "hacktv_b200", "libhacktv_b200.so")], cwd=td, capture_output=True)
     cubin = [f for f in os.listdir(td) if "sm_100a" in f][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cubin)], capture_output=True, text=True).stdout.split("\n")
-    src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    raw_csv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a report with several kernels: NCU_KERNEL=<base name> selects one (ncu --kernel-name)
+    sel = ["--kernel-name", os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+    src_csv = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
+    raw_csv = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 
 # several sections can match (k_raster / k_raster_secam, template instantiations): take the shortest
 # name, and pass a longer substring (e.g. k_mod_mmaILi256) to pick an instantiation
