@@ -113,6 +113,12 @@ struct __align__(16) SecState {
 	double ix, iy;                    // iir_int16_t state (ref fir.c:721-735)
 };
 
+struct __align__(16) SecChk {
+	int pi, pq;                       // FM phasor before sample W - 8 (valid: the FM loop came through there)
+	int valid, pad;
+	double ixm, iym;                  // IIR state before sample W - 8
+};
+
 struct SecScratch {
 	int16_t *cb;                      // [lines][W]   low-passed baseband without the aliased-tail terms
 	int *tail;                        // [lines][SEC_TAIL] raw sums of the last outputs
@@ -122,6 +128,10 @@ struct SecScratch {
 	SecState *carry;                  // state before the first line of the chain
 	int *flags;                       // [0] outgoing states changed in the last pass, [2] lines recomputed
 	int *claim;                       // [lines] last pass that rendered the line
+	// line-parallel chain (k_sec_iir / k_sec_fm): one thread per line
+	int16_t *y;                       // [lines][W + 8] FM input: pre-emphasised, clamped baseband; [W], [W + 1] = the aliased words
+	int *chg;                         // [lines] first sample of y that changed in this pass (>= W + 2: none)
+	struct SecChk *chk;               // [lines] checkpoint before sample W - 8: FM phasor and IIR state
 };
 
 #define MAPBUFS 16
@@ -1806,6 +1816,339 @@ k_secam_seq(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const 
 	}
 }
 
+
+// ---------------------------------------------------------------------------
+// SECAM chain, line-parallel (round 2). The sample-serial parts of a line - the fp64 pre-emphasis IIR and the
+// Q31 FM recurrence (ref video.c:3068-3233, fir.c:721-735) - are run by ONE THREAD PER LINE, all lines of the
+// launch at once, from the state their predecessor produced in the previous pass (pass 0: a guess); passes repeat
+// until no line's input differs bitwise from its predecessor's output, i.e. until the sequential result is
+// reached. What makes this cheap: the IIR forgets its start within ~250 samples (a1 = -0.905), so a changed
+// predecessor state usually leaves the rounded FM input untouched, or touches only the last 7 samples (the two
+// aliased words A, B); k_sec_iir reports the first sample that changed and k_sec_fm re-runs the phasor from there -
+// from the line start, or from the checkpoint kept 8 samples before the line end.
+//   k_sec_iir  tail of the low-pass (A, B), IIR over the line -> y row, first changed sample, outgoing IIR state
+//   k_sec_fm   FM recurrence from the first changed sample -> subcarrier row, outgoing A, B
+// Rows are read and written 8 samples (16 bytes) at a time: a warp's 32 lanes walk 32 different rows.
+// ---------------------------------------------------------------------------
+
+// state handed to row c: the outgoing state of the nearest row before it that carries a subcarrier (rows without
+// one pass the state on, the two field-start lines clear A and B: ref video.c:3149-3160), or the launch's carry
+__device__ __forceinline__ SecState sec_incoming(const LineRaster *lr, const SecScratch &ss, int c, const SecState *prev_out, int &from)
+{
+	bool clr = false;
+	int p = c - 1;
+	for(; p >= 0; p--)
+	{
+		if(lr[p].sec_proc) break;
+		if(lr[p].sec_clear) clr = true;
+	}
+	from = p;
+	SecState s = p >= 0 ? prev_out[p] : *ss.carry;
+	if(clr) { s.A = 0; s.B = 0; }
+	return(s);
+}
+
+__device__ __forceinline__ double sec_iir_step(const htv_dparams_t &dp, double xin, double &ix, double &iy)
+{
+	iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
+	ix = xin;
+	return(fmin(fmax(iy, -32768.0), 32767.0));
+}
+
+__global__ void __launch_bounds__(64)
+k_sec_iir(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n) return;
+	const int W = dp.W, WY = W + 8;
+	const LineRaster &li = lr[c];
+	const SecState *prev = ss.st[(pass + 1) & 1];
+	SecState *cur = ss.st[pass & 1];
+	ss.chg[c] = 0x7FFFFFFF;
+	int from;
+	SecState in;
+	if(pass == 0)
+	{
+		// guess: A = B = 0 and the IIR state the previous subcarrier line leaves when started from rest half a line
+		// before its end (its own start state has decayed by 0.905^512 there)
+		in = sec_incoming(lr, ss, c, prev, from);
+		if(from >= 0)
+		{
+			in.A = in.B = 0; in.pad0 = in.pad1 = 0;
+			double ix = 0.0, iy = 0.0;
+			const int16_t *cbp = ss.cb + (size_t) from * W;
+			for(int x = W - 512 < 0 ? 0 : W - 512; x < W; x++) sec_iir_step(dp, (double) cbp[x], ix, iy);
+			in.ix = ix; in.iy = iy;
+		}
+	}
+	else in = sec_incoming(lr, ss, c, prev, from);
+	if(li.sec_clear) { in.A = 0; in.B = 0; }
+	if(!li.sec_proc) { cur[c] = in; return; }
+	if(pass > 0 && sec_same(in, ss.used[c])) { cur[c] = prev[c]; return; }
+	ss.used[c] = in;
+	atomicAdd(ss.flags + 2, 1);
+
+	const int16_t *cb = ss.cb + (size_t) c * W;
+	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
+	int16_t *y = ss.y + (size_t) c * WY;
+	double ix = in.ix, iy = in.iy;
+	int first = 0x7FFFFFFF;
+	const bool cmp = pass > 0;
+	const int Wv = (W & 7) == 0 ? W - 8 : 0;                             // vector part: whole groups of 8 before the tail
+	// the next group's loads are in flight while this group's 8 dependent steps run
+	int4 v = Wv > 0 ? *reinterpret_cast<const int4 *>(cb) : make_int4(0, 0, 0, 0);
+	int4 old = (cmp && Wv > 0) ? *reinterpret_cast<const int4 *>(y) : make_int4(0, 0, 0, 0);
+	for(int x = 0; x < Wv; x += 8)
+	{
+		const int4 vn = x + 8 < Wv ? *reinterpret_cast<const int4 *>(cb + x + 8) : make_int4(0, 0, 0, 0);
+		const int4 oldn = (cmp && x + 8 < Wv) ? *reinterpret_cast<const int4 *>(y + x + 8) : make_int4(0, 0, 0, 0);
+		const int w[4] = { v.x, v.y, v.z, v.w };
+		int o[4];
+		#pragma unroll
+		for(int k = 0; k < 4; k++)
+		{
+			const int a = round_away(sec_iir_step(dp, (double) (short) (w[k] & 0xFFFF), ix, iy));
+			const int b = round_away(sec_iir_step(dp, (double) (w[k] >> 16), ix, iy));
+			o[k] = (a & 0xFFFF) | (b << 16);
+		}
+		if(cmp && first == 0x7FFFFFFF && (old.x != o[0] || old.y != o[1] || old.z != o[2] || old.w != o[3]))
+		{
+			const int oo[4] = { old.x, old.y, old.z, old.w };
+			for(int k = 3; k >= 0; k--) if(oo[k] != o[k]) first = x + 2 * k + (((oo[k] ^ o[k]) & 0xFFFF) ? 0 : 1);
+		}
+		*reinterpret_cast<int4 *>(y + x) = make_int4(o[0], o[1], o[2], o[3]);
+		v = vn; old = oldn;
+	}
+	if(Wv > 0) { ss.chk[c].ixm = ix; ss.chk[c].iym = iy; }
+	for(int x = Wv; x < W; x++)
+	{
+		int v = cb[x];
+		if(x >= W - 7)
+		{
+			// finish the low-pass: taps reaching chrominance_buffer[W] and [W + 1]
+			int acc = tail[x - (W - 7)];
+			const int kA = W - x + 7, kB = W + 1 - x + 7;
+			if(kA <= 14) acc += in.A * dp.secam_lpf[kA];
+			if(kB <= 14) acc += in.B * dp.secam_lpf[kB];
+			v = sat16i(acc >> 15);
+		}
+		const short o = (short) round_away(sec_iir_step(dp, (double) v, ix, iy));
+		if(cmp && first == 0x7FFFFFFF && y[x] != o) first = x;
+		y[x] = o;
+	}
+	if(cmp && first == 0x7FFFFFFF && (y[W] != (short) in.A || y[W + 1] != (short) in.B)) first = W;
+	y[W] = (short) in.A; y[W + 1] = (short) in.B;
+	SecState out = in;
+	out.ix = ix; out.iy = iy;
+	// a line whose FM loop overruns the line end (sr > W) produces new A, B: those of the previous pass stand until
+	// k_sec_fm has looked at the line (it re-runs when the FM input changed); other lines pass A, B on
+	if(cmp && li.sec_sr > W) out.A = prev[c].A;
+	if(cmp && li.sec_sr > W + 1) out.B = prev[c].B;
+	cur[c] = out;
+	ss.chg[c] = cmp ? first : 0;
+}
+
+__global__ void __launch_bounds__(64)
+k_sec_fm(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n) return;
+	const int W = dp.W, WY = W + 8;
+	const LineRaster &li = lr[c];
+	if(!li.sec_proc) return;
+	const int first = ss.chg[c];
+	SecState *cur = ss.st[pass & 1];
+	const SecState *prev = ss.st[(pass + 1) & 1];
+	const int sl = dp.burst_left, sr = li.sec_sr;
+	if(first >= sr)
+	{
+		// the FM input is what it was: the subcarrier stands; the IIR state (or passed-on A, B) may have moved
+		if(pass > 0 && !sec_same(cur[c], prev[c])) atomicAdd(ss.flags, 1);
+		return;
+	}
+	const int16_t *y = ss.y + (size_t) c * WY;
+	int16_t *add = ss.add + (size_t) c * W;
+	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+	// restart point: the line's phasor reset, or the checkpoint before sample W - 8
+	const int ck = W - 8;
+	int x0 = sl, pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+	const SecChk k4 = ss.chk[c];
+	if(pass > 0 && first >= ck && k4.valid && ck > sl && ck < sr) { x0 = ck; pi = k4.pi; pq = k4.pq; }
+	SecState out = cur[c];
+	const bool wr = li.valid != 0;                                      // fill lines are never emitted
+	int have_ck = 0, ckpi = 0, ckpq = 0;
+	// group of 8 samples: FM input, then its LUT entries (phasor step, bell-filter gain); the next group's are fetched
+	// while this group's 8 dependent phasor steps run
+	htv_c32_t m[8], mn[8];
+	htv_c16_t g[8], gn[8];
+	#define SEC_FETCH(XB, M, G) do { \
+		short ys_[8]; \
+		if(((W & 7) == 0) && (XB) + 8 <= WY) \
+		{ \
+			const int4 v_ = *reinterpret_cast<const int4 *>(y + (XB)); \
+			ys_[0] = (short) (v_.x & 0xFFFF); ys_[1] = (short) (v_.x >> 16); ys_[2] = (short) (v_.y & 0xFFFF); ys_[3] = (short) (v_.y >> 16); \
+			ys_[4] = (short) (v_.z & 0xFFFF); ys_[5] = (short) (v_.z >> 16); ys_[6] = (short) (v_.w & 0xFFFF); ys_[7] = (short) (v_.w >> 16); \
+		} \
+		else { _Pragma("unroll") for(int k = 0; k < 8; k++) ys_[k] = (XB) + k < WY ? y[(XB) + k] : (short) 0; } \
+		_Pragma("unroll") for(int k = 0; k < 8; k++) \
+		{ \
+			int sv_ = ys_[k]; \
+			sv_ = sv_ < dmin ? dmin : (sv_ > dmax ? dmax : sv_); \
+			M[k] = dt.secam_fm_lut[sv_ + 32768]; \
+			G[k] = dt.secam_bell[(unsigned short) sv_]; \
+		} } while(0)
+	int xb = x0 & ~7;
+	SEC_FETCH(xb, m, g);
+	for(; xb < sr; xb += 8)
+	{
+		if(xb + 8 < sr) SEC_FETCH(xb + 8, mn, gn);
+		short ov[8];
+		#pragma unroll
+		for(int k = 0; k < 8; k++)
+		{
+			const int x = xb + k;
+			ov[k] = 0;
+			if(x == ck && x >= x0) { ckpi = pi; ckpq = pq; have_ck = 1; }
+			if(x >= x0 && x < sr)
+			{
+				const long long ni = (long long) pi * m[k].i - (long long) pq * m[k].q;
+				const long long nq = (long long) pi * m[k].q + (long long) pq * m[k].i;
+				pi = (int) (ni >> 31); pq = (int) (nq >> 31);
+				const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g[k].i) >> 15)
+				                     - (((((pq >> 16) * dp.secam_level) >> 15) * g[k].q) >> 15));
+				if(x < W) ov[k] = (short) ((o * dt.burst_win[x - sl]) >> 15);
+				else if(x == W) out.A = o;
+				else if(x == W + 1) out.B = o;
+			}
+		}
+		if(wr)
+		{
+			if(((W & 7) == 0) && xb >= x0 && xb + 8 <= sr && xb + 8 <= W)
+			{
+				*reinterpret_cast<int4 *>(add + xb) = make_int4((ov[0] & 0xFFFF) | (ov[1] << 16), (ov[2] & 0xFFFF) | (ov[3] << 16),
+					(ov[4] & 0xFFFF) | (ov[5] << 16), (ov[6] & 0xFFFF) | (ov[7] << 16));
+			}
+			else
+			{
+				#pragma unroll
+				for(int k = 0; k < 8; k++) { const int x = xb + k; if(x >= x0 && x < sr && x < W) add[x] = ov[k]; }
+			}
+		}
+		#pragma unroll
+		for(int k = 0; k < 8; k++) { m[k] = mn[k]; g[k] = gn[k]; }
+	}
+	#undef SEC_FETCH
+	if(have_ck) { ss.chk[c].pi = ckpi; ss.chk[c].pq = ckpq; ss.chk[c].valid = 1; }
+	else if(x0 == sl) ss.chk[c].valid = 0;
+	cur[c] = out;
+	if(pass == 0 || !sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
+}
+
+// Predictor between pass 0 and pass 1. Pass 0 ran every line with A = B = 0; the true values ripple down the lines
+// (line L's A, B enter the last 7 low-pass outputs of line L + 1, hence its last FM inputs, hence its own A, B) and
+// the error shrinks only ~3x per line - about nine more full passes. But that coupling lives entirely in the last 8
+// samples of a line: given the checkpoints pass 0 left (IIR state and FM phasor before sample W - 8), a line's
+// outgoing state follows from the incoming A, B in 8 IIR + 10 FM steps. Every thread walks that short chain down
+// SEC_PRED lines to its own, so pass 1 starts from states that are right to 3^-SEC_PRED. It only proposes states:
+// the passes after it compute every line in full and compare bit for bit, as before.
+#define SEC_PRED 10
+__device__ __forceinline__ void sec_tail_step(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li, const SecScratch &ss,
+	int r, int &A, int &B, double &ixe, double &iye)
+{
+	const int W = dp.W;
+	const SecChk ck = ss.chk[r];
+	const int16_t *cb = ss.cb + (size_t) r * W;
+	const int *tail = ss.tail + (size_t) r * SEC_TAIL;
+	double ix = ck.ixm, iy = ck.iym;
+	short ys[10];
+	#pragma unroll
+	for(int k = 0; k < 8; k++)
+	{
+		const int x = W - 8 + k;
+		int v = cb[x];
+		if(k >= 1)
+		{
+			int acc = tail[k - 1];
+			const int kA = W - x + 7, kB = W + 1 - x + 7;
+			if(kA <= 14) acc += A * dp.secam_lpf[kA];
+			if(kB <= 14) acc += B * dp.secam_lpf[kB];
+			v = sat16i(acc >> 15);
+		}
+		ys[k] = (short) round_away(sec_iir_step(dp, (double) v, ix, iy));
+	}
+	ys[8] = (short) A; ys[9] = (short) B;
+	ixe = ix; iye = iy;
+	const int sr = li.sec_sr;
+	if(!ck.valid || sr <= W) return;                                    // the FM loop stops short of the line end: A, B pass through
+	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+	int pi = ck.pi, pq = ck.pq;
+	#pragma unroll
+	for(int k = 0; k < 10; k++)
+	{
+		const int x = W - 8 + k;
+		if(x >= sr) break;
+		int sv = ys[k];
+		sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
+		const htv_c32_t m = dt.secam_fm_lut[sv + 32768];
+		const htv_c16_t g = dt.secam_bell[(unsigned short) sv];
+		const long long ni = (long long) pi * m.i - (long long) pq * m.q;
+		const long long nq = (long long) pi * m.q + (long long) pq * m.i;
+		pi = (int) (ni >> 31); pq = (int) (nq >> 31);
+		const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
+		                     - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
+		if(x == W) A = o;
+		else if(x == W + 1) B = o;
+	}
+}
+
+__global__ void __launch_bounds__(64)
+k_sec_predict(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n) return;
+	const SecState *src = ss.st[0];
+	SecState *dst = ss.st[1];
+	if(!lr[c].sec_proc) { dst[c] = src[c]; return; }
+	// the subcarrier rows r[0] = c, r[1], ... above it, and whether A, B are cleared on the way into each
+	int rows[SEC_PRED + 1], clr[SEC_PRED + 1], nr = 0, p = c;
+	bool cl = false;
+	while(nr <= SEC_PRED && p >= 0)
+	{
+		if(lr[p].sec_proc) { rows[nr] = p; clr[nr] = 0; if(nr > 0) clr[nr - 1] = cl; cl = false; nr++; }
+		if(lr[p].sec_clear) cl = true;                                   // a clearing row: cleared on entry, also for itself
+		p--;
+	}
+	// state entering the oldest row of the walk: pass 0's (approximate) output of the row before it, or the launch's carry
+	int A, B;
+	{
+		int q = rows[nr - 1] - 1;
+		bool c2 = lr[rows[nr - 1]].sec_clear != 0;
+		for(; q >= 0; q--) { if(lr[q].sec_proc) break; if(lr[q].sec_clear) c2 = true; }
+		const SecState s0 = q >= 0 ? src[q] : *ss.carry;
+		A = c2 ? 0 : s0.A; B = c2 ? 0 : s0.B;
+	}
+	double ixe = 0.0, iye = 0.0;
+	for(int i = nr - 1; i >= 0; i--)
+	{
+		if(i < nr - 1 && (clr[i] || lr[rows[i]].sec_clear)) { A = 0; B = 0; }
+		sec_tail_step(dp, dt, lr[rows[i]], ss, rows[i], A, B, ixe, iye);
+	}
+	SecState out = src[c];
+	out.A = A; out.B = B; out.ix = ixe; out.iy = iye;
+	dst[c] = out;
+}
+
+// carry for the next launch: the state after chain row `idx` of the final pass (rows without a subcarrier pass it on)
+__global__ void k_sec_carry(const LineRaster *lr, SecScratch ss, int idx, int pass_final)
+{
+	if(threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		int from;
+		SecState s = sec_incoming(lr, ss, idx + 1, ss.st[pass_final & 1], from);
+		*ss.carry = s;
+	}
+}
+
 // SECAM: the VBI stages sit behind the SECAM stage (ref video.c:4211-4357), so an overlay line is
 // folded in once the chain has produced the line's subcarrier: composite + subcarrier -> replace /
 // add -> composite, subcarrier row cleared. One CTA per row, a handful of rows per frame do work.
@@ -2921,10 +3264,13 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		d->sec.carry = (SecState *) dev_zero(d, sizeof(SecState));
 		d->sec.flags = (int *) dev_zero(d, sizeof(int) * 4);
 		d->sec.claim = (int *) dev_zero(d, sizeof(int) * rows);
+		d->sec.y = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * (W + 8) + 256);
+		d->sec.chg = (int *) dev_zero(d, sizeof(int) * rows);
+		d->sec.chk = (SecChk *) dev_zero(d, sizeof(SecChk) * rows);
 		d->sec_passes = 64;
 		d->sec_smem = (size_t) (dp.burst_width + 2) * 12 + 2 * (((W + 7) & ~7) + ((W + 2 + 7) & ~7) + ((dp.burst_width + 2 + 7) & ~7)) + 64;
 		cudaFuncSetAttribute(k_secam_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
-		if(!d->sec.cb || !d->sec.add || !d->sec.flags)
+		if(!d->sec.cb || !d->sec.add || !d->sec.flags || !d->sec.y || !d->sec.chg || !d->sec.chk)
 		{
 			snprintf(err, errlen, "device allocation failed");
 			htv_dev_destroy(d);
@@ -3235,30 +3581,46 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			cudaEvent_t dbg0 = NULL, dbg1 = NULL;
 			const bool dbg = getenv("HTV_DEBUG") != NULL;
 			if(dbg) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, st); }
-			cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
-			k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 31) / 32, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
-			d->launches += 2;
-			if(dbg)
+			const bool old_chain = getenv("HTV_SECAM") && !strcmp(getenv("HTV_SECAM"), "runs");   // round 1's warp-per-line chain (A/B)
+			int pass = 0, changed = 1;
+			if(old_chain)
 			{
-				float ms = 0;
-				cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1); cudaEventElapsedTime(&ms, dbg0, dbg1);
-				fprintf(stderr, "secam raster+pass0 for %d lines: %.3f ms\n", nch, ms);
+				cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
+				k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 31) / 32, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+				d->launches += 2;
+				pass = 1;
 			}
-			int pass = 1, changed = 1;
 			for(; pass <= d->sec_passes && changed; pass++)
 			{
 				int fl[4];
 				cudaMemsetAsync(d->sec.flags, 0, sizeof(int) * 4, st);
-				cudaMemcpyAsync(d->sec.st[pass & 1], d->sec.st[(pass + 1) & 1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
-				k_secam_seq<<<nch, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
-				d->launches++;
+				if(old_chain)
+				{
+					cudaMemcpyAsync(d->sec.st[pass & 1], d->sec.st[(pass + 1) & 1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
+					k_secam_seq<<<nch, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+					d->launches++;
+				}
+				else
+				{
+					// one thread per line: IIR (reports the first FM input sample that changed), then the FM recurrence from there
+					k_sec_iir<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+					k_sec_fm<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+					d->launches += 2;
+				}
+				if(!old_chain && pass == 0 && (d->dp.W & 7) == 0 && !getenv("HTV_SECAM_NOPRED"))
+				{
+					// propose the states pass 1 starts from (see k_sec_predict); st[0] takes them over
+					k_sec_predict<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+					cudaMemcpyAsync(d->sec.st[0], d->sec.st[1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
+					d->launches++;
+				}
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
 				changed = fl[0];
 				if(dbg)
 				{
 					float ms = 0;
-					cudaEventRecord(dbg0, st); cudaEventSynchronize(dbg0); cudaEventElapsedTime(&ms, dbg1, dbg0);
+					cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1); cudaEventElapsedTime(&ms, dbg0, dbg1);
 					fprintf(stderr, "secam pass %d: recomputed %d, output changed %d, cumulative %.3f ms\n", pass, fl[2], fl[0], ms);
 				}
 			}
@@ -3267,7 +3629,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				fprintf(stderr, "hacktv_b200: SECAM cross-line state did not converge in %d passes\n", d->sec_passes);
 				return(HTV_ERROR);
 			}
-			k_secam_carry<<<1, 32, 0, st>>>(d->sec, n - 1, pass - 1);
+			if(old_chain) k_secam_carry<<<1, 32, 0, st>>>(d->sec, n - 1, pass - 1);
+			else k_sec_carry<<<1, 32, 0, st>>>(lr, d->sec, n - 1, pass - 1);
 			if(d->dt.ov_n > 0)
 			{
 				k_overlay_secam<<<n + 3, 256, 0, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec.add);
