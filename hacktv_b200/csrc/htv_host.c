@@ -422,7 +422,9 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 	const int64_t f0 = L0 / s->lines, f1 = (L0 + n - 1) / s->lines;
 	int32_t map[4096];
 	int64_t f;
-	int r, nmap = 0;
+	int r, nmap = 0, run_n = 0, run_slot = 0;
+	const uint32_t *run_src = NULL;
+	const size_t fpix = (size_t) rdp->active_width * rdp->active_lines;
 	void *up, *rup;
 
 	if(f1 - f0 + 1 > 4096) return(HTV_ERROR);
@@ -470,8 +472,15 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 				{
 					s->cur_slot = s->next_slot;
 					s->next_slot = (s->next_slot + 1) % MAX_FRAME_SLOTS;
-					r = htv_dev_upload_frame(s->rdev, s->cur_slot, fr.framebuffer, rup);
-					if(r != HTV_OK) UP_FAIL(r);
+					/* pictures that follow each other in the caller's memory (a capture ring, htv_av_memory_open's array)
+					 * and land in consecutive slots go up as ONE copy: 2 MB copies beside the 8 MB copies coming back
+					 * keep neither PCIe direction full (measured: 4.4 ms for what full duplex moves in 3.1 ms) */
+					if(run_n > 0 && fr.framebuffer == run_src + (size_t) run_n * fpix && s->cur_slot == run_slot + run_n) run_n++;
+					else
+					{
+						if(run_n > 0 && (r = htv_dev_upload_frames(s->rdev, run_slot, run_n, run_src, rup)) != HTV_OK) UP_FAIL(r);
+						run_src = fr.framebuffer; run_slot = s->cur_slot; run_n = 1;
+					}
 					s->cur_serial = fr.serial;
 					s->have_serial = 1;
 					nnew++;
@@ -486,6 +495,7 @@ static int render_chunk(htv_t *s, int *pn, int16_t *d_out, int add, void *stream
 		}
 		map[nmap++] = s->cur_slot;
 	}
+	if(run_n > 0 && (r = htv_dev_upload_frames(s->rdev, run_slot, run_n, run_src, rup)) != HTV_OK) UP_FAIL(r);
 	/* sound: everything the audio clock reaches inside this run */
 	if(dp->have_fm || dp->have_am || dp->have_nicam)
 	{

@@ -142,6 +142,7 @@ extern int htv_dev_overlay_capacity(void);
 extern int htv_dev_set_overlays(htv_dev_t *d, int n, const long long *line, const int *from, const int *to,
 	const int *value, const int16_t *const *add);
 extern int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb, void *stream);
+extern int htv_dev_upload_frames(htv_dev_t *d, int slot, int count, const uint32_t *rgb, void *stream);
 /* slot_of_frame[i] = slot holding frame (first_frame + i) for this launch */
 extern int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame, int n, int64_t first_frame, void *stream);
 /* raw audio ring <- host PCM pairs for absolute indices [j0, j0 + n) */

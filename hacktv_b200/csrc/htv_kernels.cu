@@ -1506,18 +1506,43 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 		const int a0 = dp.active_left, a1 = dp.active_left + dp.active_width;
 		if(x0 + SPT - 1 >= a0 && x0 < a1)
 		{
-			#pragma unroll
-			for(int k = 0; k < SPT; k++)
+			if(dp.secam_pad)
 			{
-				const int x = x0 + k;
-				if(x < a0 || x >= a1) continue;
-				int acc = 0;
-				for(int t = 0; t < 51; t++)
+				// symmetric taps (checked on the host): the window of 4 outputs in registers, taps folded pairwise
+				int c[56];
+				const int4 *pc = reinterpret_cast<const int4 *>(line + x0 - 25 + LOFF);
+				#pragma unroll
+				for(int i = 0; i < 14; i++)
 				{
-					const int j = x - 25 + t;
-					acc += (j >= a0 ? line[j + LOFF] : 0) * dp.secam_notch[t];
+					const int4 a = pc[i];
+					c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
 				}
-				outv[k] = sat16i(acc >> 15);
+				#pragma unroll
+				for(int i = 0; i < 56; i++) if(x0 - 25 + i < a0) c[i] = 0;
+				#pragma unroll
+				for(int k = 0; k < SPT; k++)
+				{
+					int acc = c[k + 25] * dp.secam_notch[25];
+					#pragma unroll
+					for(int y = 0; y < 25; y++) acc += (c[k + y] + c[k + 50 - y]) * dp.secam_notch[y];
+					if(x0 + k >= a0 && x0 + k < a1) outv[k] = sat16i(acc >> 15);
+				}
+			}
+			else
+			{
+				#pragma unroll
+				for(int k = 0; k < SPT; k++)
+				{
+					const int x = x0 + k;
+					if(x < a0 || x >= a1) continue;
+					int acc = 0;
+					for(int t = 0; t < 51; t++)
+					{
+						const int j = x - 25 + t;
+						acc += (j >= a0 ? line[j + LOFF] : 0) * dp.secam_notch[t];
+					}
+					outv[k] = sat16i(acc >> 15);
+				}
 			}
 		}
 		// 15-tap low-pass of the colour-difference baseband; the two aliased words past the
@@ -3393,6 +3418,16 @@ extern "C" int htv_dev_upload_frame(htv_dev_t *d, int slot, const uint32_t *rgb,
 	DevGuard guard(d->device);
 	if(slot < 0 || slot >= d->max_slots) return(HTV_ERROR);
 	CK(cudaMemcpyAsync(d->d_frames + (size_t) slot * d->frame_pixels, rgb, d->frame_pixels * 4,
+		cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	return(HTV_OK);
+}
+
+// `count` pictures, contiguous in host memory, into `count` consecutive slots: one copy
+extern "C" int htv_dev_upload_frames(htv_dev_t *d, int slot, int count, const uint32_t *rgb, void *stream)
+{
+	DevGuard guard(d->device);
+	if(slot < 0 || count < 1 || slot + count > d->max_slots) return(HTV_ERROR);
+	CK(cudaMemcpyAsync(d->d_frames + (size_t) slot * d->frame_pixels, rgb, d->frame_pixels * 4 * (size_t) count,
 		cudaMemcpyHostToDevice, (cudaStream_t) stream));
 	return(HTV_OK);
 }

@@ -541,6 +541,9 @@ htv_tables_t *htv_tables_create(const htv_config_t *conf, unsigned int sample_ra
 		a = a / 1.0;
 		for(i = 0; i < 51; i++) taps[i] /= a;
 		quantise(dp->secam_notch, taps, 51, 1);
+		/* secam_pad: the notch taps are symmetric after quantisation (the raster kernel folds them pairwise) */
+		dp->secam_pad = 1;
+		for(i = 0; i < 25; i++) if(dp->secam_notch[i] != dp->secam_notch[50 - i]) dp->secam_pad = 0;
 		dp->secam_dmin[0] = lround((SECAM_CB_FREQ - SECAM_FM_FREQ - 350e3) / SECAM_FM_DEV * INT16_MAX);
 		dp->secam_dmax[0] = lround((SECAM_CB_FREQ - SECAM_FM_FREQ + 506e3) / SECAM_FM_DEV * INT16_MAX);
 		dp->secam_dmin[1] = lround((SECAM_CR_FREQ - SECAM_FM_FREQ - 506e3) / SECAM_FM_DEV * INT16_MAX);
