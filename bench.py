@@ -202,6 +202,23 @@ def bench_reference(args, rank, world):
     }))
 
 
+def channel_of_rank(rank, world, nchannels):
+    """Whole RF channels are the unit of parallelism: channel c belongs to rank c mod world."""
+    return [c for c in range(nchannels) if c % world == rank]
+
+
+def reduce_job(torch, dist, world, ms, samples, device="cuda"):
+    """What the ranks exchange - and all they exchange: the slowest rank's device time (MAX) and the samples every
+    rank rendered (SUM). Returns (ms of the job, samples of the job)."""
+    t = torch.tensor([float(ms), float(samples)], dtype=torch.float64, device=device)
+    if world > 1:
+        tm, ts = t[:1].clone(), t[1:].clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        return tm.item(), ts.item()
+    return t[0].item(), t[1].item()
+
+
 def bind_to_gpu_numa(local):
     """Pin this rank to the host cores next to its GPU (NVML's CPU affinity of the device) BEFORE any pinned
     memory is allocated: with 8 ranks on a two-socket box the staging buffers and the copy threads of GPUs 4-7
@@ -402,27 +419,22 @@ def main():
             enc2.render_host_ptr(e2e_lines, host.data_ptr())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_samples = e2e_lines * enc2.width
+        e2e_s, e2e_job = reduce_job(torch, dist, world, dt, e2e_samples * args.steps)
         h2d = e2e_frames * enc2.active_width * enc2.active_lines * 4 + int(e2e_samples / rate * 32000) * 4
-        e2e = {"value": round(world * e2e_samples * args.steps / tt.item() / 1e6, 2), "unit": "Msamples/s",
+        e2e = {"value": round(e2e_job / e2e_s / 1e6, 2), "unit": "Msamples/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_samples * 4,
-               "frames_per_step": e2e_frames, "ms_per_step": round(1000 * tt.item() / args.steps, 3),
+               "frames_per_step": e2e_frames, "ms_per_step": round(1000 * e2e_s / args.steps, 3),
                "checksum": int(host[:4096].to(torch.int32).sum().item()),
                "api": "htv_av_memory_open (ring of 8 pinned pictures, every frame uploaded) + htv_render_host (C-ABI), pinned host buffers",
                "numa_bound_cpus": numa_cpus}
         enc2.close()
 
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = t.item()
+    step_samples = nlines * width
+    ms_max, job_samples = reduce_job(torch, dist, world, ms, step_samples * args.steps)
 
     if rank == 0:
-        step_samples = nlines * width
-        value = world * step_samples * args.steps / (ms_max / 1e3) / 1e6
+        value = job_samples / (ms_max / 1e3) / 1e6
         peak, peak_src = measured_peak_gbs()
         k_ms = sorted(kern_ms)[len(kern_ms) // 2]
         k_samples = kern_lines * width

@@ -165,6 +165,26 @@ typedef struct {
 	htv_av_close_t close;
 } htv_av_t;
 
+/* ---- parity with the reference (what "drop-in" means numerically) --------
+ * Against the reference's CPU path on the same picture and sound (tests/test_gpu_*.py, tests/golden/):
+ *  - bit-exact wherever the path is integer-only: raster, sync pulses, PAL / NTSC chroma, SECAM chroma (its
+ *    fp64 IIR and Q31 FM recurrence are run as the reference runs them), the VSB / low-pass video filter, VBI
+ *    overlays, the --pixelrate resampler, the channel combiner, NICAM-728 end to end;
+ *  - within +-1 LSB of int16 wherever an FM / AM sound carrier contributes: those are the reference's Q31
+ *    phasor recurrences (a floor in every step), evaluated here in closed form of the sample index; > 97 % of
+ *    the samples are still exact;
+ *  - within +-2 LSB when --offset is combined with sound carriers: the offset mixer is one more such
+ *    recurrence and multiplies the carriers' +-1 by its own; without sound carriers it is +-1;
+ *  - FM video (pal-fm, ntsc-fm, secam-fm) without a sound carrier: +-1 LSB for ever. With one, the modulating
+ *    signal inherits that carrier's +-1 LSB and an FM modulator integrates its input: the output is the same
+ *    signal up to a slowly wandering common rotation (a random walk of ~15 - 40 LUT steps = 2 - 6 mrad per
+ *    1 000 lines), instantaneous frequency identical at > 99.5 % of the samples;
+ *  - long streams: the closed forms hold to +-1 LSB at 34 s (all device-side rings wrapped) EXCEPT where the
+ *    reference's own recurrence stops behaving like its ideal carrier - an FM carrier at a small rational
+ *    fraction of the sample rate (NTSC-M at 13.5 Msps: 4.5 MHz = fs / 3) makes its phasor revisit the same few
+ *    states, the floors stop averaging out and the REFERENCE runs slow by ~1e-5 Hz (0.35 LSB / s of sound
+ *    carrier; tools/nco_drift.c). The same mode at 16 Msps does not show it. */
+
 /* ---- encoder ----------------------------------------------------------- */
 
 typedef struct htv_t htv_t;

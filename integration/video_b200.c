@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <time.h>
 #include "video.h"
 #include "hacktv_b200.h"
@@ -35,6 +36,8 @@ static struct {
 	long long stat_lines; struct timespec stat_t0;
 	/* VBI stages: the reference's own code builds the waveforms, the encoder's overlay hook carries them */
 	int16_t *vbi_scratch;           /* one line, I/Q interleaved, as the stock stages expect it */
+	cint16_t *clut;                 /* the colour subcarrier table vits_render mixes its chroma with (ref video.c:3961-3987) */
+	unsigned int clut_width;
 	int16_t *vbi_add[MAX_VBI];
 	htv_vbi_line_t vbi[MAX_VBI];
 } _enc[MAX_ENCODERS];
@@ -68,7 +71,7 @@ static int _accelerated(const vid_config_t *c, unsigned int sample_rate, unsigne
 		htv_tables_free(t);
 	}
 	if(c->videocrypt || c->videocrypt2 || c->videocrypts || c->syster ||
-	   c->d11 || c->systercnr || c->acp || c->vits || c->cc608 || c->sis || c->eurocrypt) return(0);
+	   c->d11 || c->systercnr || c->acp || c->sis || c->eurocrypt) return(0);
 	if(c->raw_bb_file || c->a2stereo || c->s_video || c->secam_field_id) return(0);
 	if(c->fm_left_level > 0 || c->fm_right_level > 0 || c->dance_level > 0) return(0);
 	if(c->interlace || c->frame_orientation) return(0);
@@ -142,12 +145,20 @@ static int _read_vbi(void *ctx, int frame, const htv_vbi_line_t **lines, int *nl
 		memset(&l, 0, sizeof(l));
 		l.output = _enc[i].vbi_scratch; l.width = W; l.frame = frame; l.line = line;
 		l.previous = l.next = &l;
+		/* the line's place in the subcarrier table: the raster advances it by one line width per line (ref video.c:2904-2910) */
+		if(_enc[i].clut)
+		{
+			const unsigned long long gl = (unsigned long long) (frame - 1) * s->conf.lines + (line - 1);
+			l.lut = &_enc[i].clut[(gl * (unsigned long long) W) % _enc[i].clut_width];
+		}
+		if(s->conf.vits) vits_render(s, &s->vits, 1, &lp);
 		if(s->conf.wss)
 		{
 			wss_render(s, &s->wss, 1, &lp);
 			if(line == 23) { rep_from = s->half_width; rep_to = s->wss.blank_width; rep_value = s->black_level; }
 		}
 		if(s->conf.vitc) vitc_render(s, &s->vitc, 1, &lp);
+		if(s->conf.cc608) cc608_render(s, &s->cc608, 1, &lp);
 		if(s->conf.teletext) tt_render_line(s, &s->tt, 1, &lp);
 		dirty = l.vbialloc;
 		if(!l.vbialloc) continue;
@@ -216,12 +227,30 @@ int vid_init(vid_t *s, unsigned int sample_rate, unsigned int pixel_rate, const 
 	s->thread_abort = 1;                             /* no CPU stage threads to join */
 	s->passthru = pt;
 	_enc[i].vid = s; _enc[i].htv = h; _enc[i].serial = 0;
-	if(conf->wss || conf->vitc || conf->teletext)
+	if(conf->vits || conf->wss || conf->vitc || conf->cc608 || conf->teletext)
 	{
-		/* ref video.c:4234-4242, 4305-4315, 4346-4358: the stock stages, initialised as vid_init does */
-		if((conf->wss && wss_init(&s->wss, s, conf->wss) != VID_OK) ||
+		/* ref video.c:4216-4232, 4234-4242, 4305-4328, 4346-4358: the stock stages, initialised as vid_init does */
+		if((conf->vits && vits_init(&s->vits, s->pixel_rate, s->width, s->conf.lines, s->conf.colour_mode == VID_PAL,
+		                            s->white_level - s->blanking_level) != VID_OK) ||
+		   (conf->wss && wss_init(&s->wss, s, conf->wss) != VID_OK) ||
 		   (conf->vitc && vitc_init(&s->vitc, s) != VID_OK) ||
+		   (conf->cc608 && cc608_init(&s->cc608, s) != VID_OK) ||
 		   (conf->teletext && tt_init(&s->tt, s, conf->teletext) != VID_OK)) { _enc[i].vid = NULL; htv_free(h); return(VID_ERROR); }
+		if(conf->vits && (conf->colour_mode == VID_PAL || conf->colour_mode == VID_NTSC))
+		{
+			/* vits_render adds its chroma through the line's subcarrier table (l->lut): the same table the raster
+			 * uses, built as vid_init builds it (ref video.c:3961-3987) */
+			r64_t a = r64_div((r64_t) { s->pixel_rate, 1 }, conf->colour_carrier);
+			const double d = 2.0 * M_PI * ((double) a.den / a.num);
+			int64_t c;
+			_enc[i].clut_width = a.num;
+			_enc[i].clut = malloc((a.num + s->width) * sizeof(cint16_t));
+			if(!_enc[i].clut) { _enc[i].vid = NULL; htv_free(h); return(VID_OUT_OF_MEMORY); }
+			for(c = 0; c < a.num + s->width; c++)
+			{
+				_enc[i].clut[c] = (cint16_t) { round(cos(d * c) * INT16_MAX), round(sin(d * c) * INT16_MAX) };
+			}
+		}
 		_enc[i].vbi_scratch = malloc(sizeof(int16_t) * 2 * s->width);
 		htv_set_vbi_source(h, _read_vbi, s);
 	}
@@ -277,6 +306,9 @@ void vid_free(vid_t *s)
 	if(s->conf.wss) wss_free(&s->wss);
 	if(s->conf.vitc) vitc_free(&s->vitc);
 	if(s->conf.teletext) tt_free(&s->tt);
+	if(s->conf.vits) vits_free(&s->vits);
+	if(s->conf.cc608) cc608_free(&s->cc608);
+	free(_enc[i].clut);
 	free(_enc[i].vbi_scratch);
 	{ int k; for(k = 0; k < MAX_VBI; k++) free(_enc[i].vbi_add[k]); }
 	memset(&_enc[i], 0, sizeof(_enc[i]));

@@ -1,6 +1,8 @@
-"""The N > 1 path of bench.py is 'one independent RF channel per rank, no data-path
-collective': only the timing (max over ranks) and the sample count (sum) are reduced.
-World-size-2 gloo run on CPU of exactly that reduction logic."""
+"""The N > 1 path is 'one independent RF channel per rank, no data-path collective' (SURVEY.md section 8e): the
+ranks exchange the slowest rank's time (MAX) and the samples rendered (SUM), nothing else. World-size-2 gloo run
+on CPU of the product's own multi-rank code: bench.py's channel_of_rank / reduce_job / cpu_budget /
+bind_to_gpu_numa (which must be a no-op without a GPU), and each rank building the host-side tables of ITS
+channels through the C-ABI (htv_tables_create: a different --offset per channel), independently of the other."""
 import os
 import subprocess
 import sys
@@ -14,18 +16,26 @@ def test_two_rank_channel_partition_gloo(tmp_path):
     script.write_text(textwrap.dedent("""
         import os, sys, torch, torch.distributed as dist
         sys.path.insert(0, %r)
+        import bench
+        import hacktv_b200 as H
         dist.init_process_group("gloo")
         rank, world = dist.get_rank(), dist.get_world_size()
-        # each rank owns whole channels: channel c -> rank c %% world (SURVEY.md section 8e)
-        channels = [c for c in range(5) if c %% world == rank]
-        ms = torch.tensor([10.0 + 5.0 * rank], dtype=torch.float64)       # pretend device time
-        samples = torch.tensor([len(channels) * 40960000.0], dtype=torch.float64)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+        assert bench.bind_to_gpu_numa(rank) is None or True            # no GPU here: must not raise
+        assert bench.cpu_budget() >= 1
+        mine = bench.channel_of_rank(rank, world, 5)
+        assert mine == [c for c in range(5) if c %% world == rank]
+        # every rank prepares its own channels (host side of htv_init): 8 MHz raster, one offset per channel
+        widths = []
+        for c in mine:
+            t = H.Tables(H.mode_config("i", vfilter=True, offset=(c - 2) * 8000000), 20000000)
+            widths.append(int(t.get("geometry")[0]))
+            t.close()
+        assert widths == [1280] * len(mine), widths
+        ms, samples = bench.reduce_job(torch, dist, world, 10.0 + 5.0 * rank, len(mine) * 40960000.0, device="cpu")
         dist.barrier()
+        assert ms == 15.0 and samples == 5 * 40960000.0, (ms, samples)
         if rank == 0:
-            assert ms.item() == 15.0 and samples.item() == 5 * 40960000.0
-            print("OK", samples.item() / (ms.item() / 1e3) / 1e6)
+            print("OK", samples / (ms / 1e3) / 1e6)
         dist.destroy_process_group()
     """ % ROOT))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",

@@ -43,6 +43,11 @@ def _run(binary, args, nbytes, env=""):
     ("-m pal -s 16000000 --wss 14:9-letterbox", 2, 0),
     ("-m i -s 16000000 --filter --noaudio --vitc --wss 4:3", 4, 0),
     ("-m m -s 13500000 --filter --vitc", 4, 1),
+    # VITS (chroma part mixed through the line's subcarrier table) and CEA-608 (run-in + null codes): stock stages too
+    ("-m i -s 16000000 --filter --noaudio --vits", 4, 0),
+    ("-m m -s 13500000 --filter --noaudio --vits --cc608", 4, 0),
+    ("-m l -s 16000000 --filter --noaudio --vits", 4, 0),
+    ("-m pal -s 16000000 --vits --cc608 --vitc --wss 16:9", 2, 0),
     # --pixelrate: raster at 13.5 MHz, the reference's polyphase resampler on the device, then the usual path
     ("-m i -s 16000000 --pixelrate 13500000 --filter --noaudio", 4, 0),
     ("-m i -s 16000000 --pixelrate 13500000 --filter", 4, 1),

@@ -229,9 +229,11 @@ def test_fm_video_with_sound_carrier(built, mode, rate, nlines, kw):
     step = 2 * np.pi * 16e6 / 32767 / rate
     print(f"{mode} {rate}: worst residual {worst.max():.2f} LSB, lines within 1.5 LSB {(worst <= 1.5).mean():.4f}, "
           f"rotation after {nlines} lines {rot[-1] / step:.1f} LUT steps (max {np.abs(rot).max() / step:.1f})")
-    assert (worst <= 1.5).mean() > 0.25, (worst <= 1.5).mean()
-    assert worst.max() <= 150.0, worst.max()
-    assert np.abs(rot).max() < step * (60 + 0.05 * nlines), np.abs(rot).max() / step
+    # measured on a B200 (round 2): worst residual 25 - 60 LSB, 0.35 - 0.61 of the lines within 1.5 LSB, the common
+    # rotation peaking at 19 - 42 LUT steps over 700 - 2 500 lines
+    assert (worst <= 1.5).mean() > 0.30, (worst <= 1.5).mean()
+    assert worst.max() <= 90.0, worst.max()
+    assert np.abs(rot).max() < step * (55 + 0.01 * nlines), np.abs(rot).max() / step
     df = np.angle(g[:, 1:] * np.conj(g[:, :-1])) - np.angle(w[:, 1:] * np.conj(w[:, :-1]))
     df = (df + np.pi) % (2 * np.pi) - np.pi
     assert (np.abs(df) > 0.6 * step).mean() < 0.005, (np.abs(df) > 0.6 * step).mean()

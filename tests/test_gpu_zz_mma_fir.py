@@ -33,6 +33,18 @@ def _render(H, sel, mode, rate, nlines, frames=None, audio=None, **kw):
     return got
 
 
+def _same(a, b, tol):
+    """The filter is exact integer work either way: without sound carriers the two selections agree bit for bit.
+    HTV_FIR=scalar also selects the split raster / modulator kernels, whose FM carrier takes one sin/cos per
+    sample where the fused line kernel rotates (htv_line.cuh): with a carrier the two may round differently on a
+    few samples per thousand, never by more than the carrier's own +-1 LSB."""
+    if tol == 0:
+        assert np.array_equal(a, b), f"{np.count_nonzero(a != b)} samples differ between the two filters"
+    else:
+        d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 0.01, (d.max(), (d != 0).mean())
+
+
 CASES = [
     ("i", 16000000, 1300, dict(vfilter=True, noaudio=True), 0),      # VSB, W = 1024: 8 tiles, 8 warps
     ("i", 16000000, 1300, dict(vfilter=True), 1),                    # BASELINE config 2
@@ -49,7 +61,7 @@ def test_mma_filter_equals_scalar_filter_and_oracle(built, mode, rate, nlines, k
     H = built
     scalar = _render(H, "scalar", mode, rate, nlines, **kw)
     mma = _render(H, "mma", mode, rate, nlines, **kw)
-    assert np.array_equal(scalar, mma), f"{np.count_nonzero(scalar != mma)} samples differ between the two filters"
+    _same(scalar, mma, tol)
     o = orc.Oracle(H.mode_config(mode, **kw), rate); o.open_test_source()
     want = o.render(nlines); o.close()
     d = np.abs(mma.astype(np.int32) - want.astype(np.int32))
@@ -80,7 +92,10 @@ def test_random_pictures_full_range_through_the_byte_split(built):
     audio = rng.integers(-32768, 32767, size=(40000, 2), dtype=np.int16)
     a = _render(H, "scalar", "i", 16000000, 1900, frames=frames, audio=audio, vfilter=True)
     b = _render(H, "mma", "i", 16000000, 1900, frames=frames, audio=audio, vfilter=True)
-    assert np.array_equal(a, b)
+    _same(a, b, 1)
+    a = _render(H, "scalar", "i", 16000000, 700, frames=frames, audio=audio, vfilter=True, noaudio=True)
+    b = _render(H, "mma", "i", 16000000, 700, frames=frames, audio=audio, vfilter=True, noaudio=True)
+    _same(a, b, 0)
 
 
 def test_chunking_is_invisible_with_the_mma_filter(built):
@@ -115,4 +130,4 @@ def test_pitched_layout_any_width(built, mode, rate, nlines, kw):
     H = built
     a = _render(H, "scalar", mode, rate, nlines, **kw)
     b = _render(H, "mma", mode, rate, nlines, **kw)
-    assert np.array_equal(a, b)
+    _same(a, b, 0 if kw.get("noaudio") else 1)
