@@ -439,7 +439,7 @@ def main():
         k_ms = sorted(kern_ms)[len(kern_ms) // 2]
         k_samples = kern_lines * width
         achieved = k_samples * 4 / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
-        step_gbs = step_samples * 4 * args.steps / (ms_max / 1e3) / 1e9
+        step_gbs = step_samples * 4 * args.steps / (ms_max / 1e3) / 1e9      # per GPU: every rank writes its own IQ
         cpu = None
         if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_HARNESS):
             v, per, wall = run_reference_instances(1, 150, mode=mode, rate=rate, filt=filt)
@@ -473,7 +473,7 @@ def main():
                          "kernel": KERNEL, "kernel_ms": round(k_ms, 4),
                          "lines_per_launch": kern_lines, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_samples * 4,
-                         "step_achieved": round(step_gbs / world, 1), "step_frac": round(step_gbs / world / peak, 4),
+                         "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                          "issue": {"slots_per_sample": round(NCU["warp_instructions"] * 32 / (NCU["lines"] * 1024), 1),
                                    "issue_active_pct": NCU["issue_active_pct"], "source": NCU["file"]},
                          "note": "4 B per complex sample written once; the kernel is issue-slot bound (DESIGN.md section 4), not HBM bound"},
