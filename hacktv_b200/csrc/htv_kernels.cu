@@ -881,6 +881,9 @@ __device__ __forceinline__ unsigned long long kd_div(unsigned long long n, unsig
 // codes through warp votes, then lane = 32-sample block for the "symbol in effect" table.
 #define KD_WARPS 4
 #define KD_LINES 8
+// PART 1: audio segments, FM / AM / offset phases (needs the FM chain of the pre-pass); PART 2: NICAM symbols (needs the
+// NICAM chain). The two halves write disjoint fields and run on the two side streams, each right behind its chain.
+template<int PART>
 __global__ void __launch_bounds__(32 * KD_WARPS)
 k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineA2 *out, int64_t line0, int nlines)
 {
@@ -902,20 +905,28 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 	unsigned a_r0 = 0;
 	long long a_s0 = 0, a_k0 = 0;
 	{
-		int kk0, cc0 = 0;
-		kd_div((unsigned long long) m0, 32767u, 1.0 / 32767.0, rem); kk0 = (int) rem;
-		if(dp.have_nicam) { kd_div((unsigned long long) m0, (unsigned) dp.nicam_cc_len, 1.0 / (double) dp.nicam_cc_len, rem); cc0 = (int) rem; }
 		int segx[MAX_SEGS + 2];
 		#pragma unroll
 		for(int k = 0; k < MAX_SEGS + 2; k++) segx[k] = 0x7FFFFFFF;
-		if(mine)
+		if(PART == 1)
 		{
-			la.m0 = m0; la.kk0 = kk0; la.cc0 = cc0;
-			la.am_phase0 = dp.am_ang * (unsigned long long) m0;
-			la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
+			int kk0;
+			kd_div((unsigned long long) m0, 32767u, 1.0 / 32767.0, rem); kk0 = (int) rem;
+			if(mine)
+			{
+				la.m0 = m0; la.kk0 = kk0;
+				la.am_phase0 = dp.am_ang * (unsigned long long) m0;
+				la.off_phase0 = dp.offset_phase0 + dp.offset_ang * (unsigned long long) (m0 - 32767);
+			}
 		}
+		else if(dp.have_nicam)
+		{
+			kd_div((unsigned long long) m0, (unsigned) dp.nicam_cc_len, 1.0 / (double) dp.nicam_cc_len, rem);
+			if(mine) la.cc0 = (int) rem;
+		}
+		else if(mine) la.cc0 = 0;
 		// audio segments: audio index j is in effect from seg_start(j) up to seg_start(j + 1)
-		if(dp.have_fm || dp.have_am)
+		if(PART == 1 && (dp.have_fm || dp.have_am))
 		{
 			const double inv_ar = 1.0 / (double) HTV_AUDIO_RATE;
 			const long long jf = (long long) kd_div((unsigned long long) (m0 + 1) * HTV_AUDIO_RATE, (unsigned) dp.rate, 1.0 / (double) dp.rate, rem) - 1;
@@ -945,7 +956,7 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 				if(mine) { la.seg_ang[k] = ang; la.seg_phase[k] = ph; la.seg_rot[k] = rot; la.seg_am[k] = am; }
 			}
 		}
-		if(mine)
+		if(PART == 1 && mine)
 		{
 			#pragma unroll
 			for(int k = 0; k < MAX_SEGS + 2; k++) la.seg_x[k] = segx[k];
@@ -953,7 +964,7 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 		// first block (32 samples) in which segment k >= 1 is in effect at the block start; phase B builds fm_blk
 		#pragma unroll
 		for(int k = 1; k < MAX_SEGS; k++) a_bk[k - 1] = segx[k] == 0x7FFFFFFF ? 0x7FFF : (segx[k] + 31) >> 5;
-		if(dp.have_nicam)
+		if(PART == 2 && dp.have_nicam)
 		{
 			const unsigned F = (unsigned) dp.nicam_F, D = (unsigned) dp.nicam_D;
 			const double inv_f = 1.0 / (double) F;
@@ -981,6 +992,8 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 	for(int l = 0; l < nl; l++)
 	{
 		LineA2 &lb = out[lbase + l];
+		if(PART == 1)
+		{
 		if(dp.have_fm || dp.have_am)
 		{
 			// segment in effect at x = 32 b = number of segments k >= 1 whose first block is <= b; lane = word of four blocks
@@ -1002,6 +1015,8 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 			}
 		}
 		else if(lane < MAX_BLKS / 4) reinterpret_cast<unsigned *>(lb.fm_blk)[lane] = 0;
+		continue;
+		}
 		if(!dp.have_nicam)
 		{
 			if(lane == 0) { lb.nsym = 0; lb.nic_generic = 0; lb.symb[0] = make_uint2(0u, 0x7FFFFFFFu); }
@@ -3250,7 +3265,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
 			const int T = mf_tiles(W);
 			d->kl_threads = 32 * T;
-			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : 2);
+			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : (d->kl_threads <= 320 ? 3 : 2));
 			if(dp.colour_mode != HTV_MONOCHROME)
 			{
 				uint32_t ctab[256];
@@ -3270,6 +3285,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			}
 			#define KL_ATTR2(VF, HQ, FU, CS) do { \
 				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
 				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
 			#define KL_ATTR(VF, HQ) do { KL_ATTR2(VF, HQ, true, false); KL_ATTR2(VF, HQ, false, false); KL_ATTR2(VF, HQ, false, true); } while(0)
 			KL_ATTR(false, false); KL_ATTR(true, false); KL_ATTR(true, true);
@@ -3508,8 +3524,12 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
-		CK(cudaEventRecord(d->ev_nic, d->side2));
-		CK(cudaStreamWaitEvent(d->side, d->ev_nic, 0));
+		if(!d->use_line)
+		{
+			// the split kernels' descriptor kernel (on `side`) reads both chains
+			CK(cudaEventRecord(d->ev_nic, d->side2));
+			CK(cudaStreamWaitEvent(d->side, d->ev_nic, 0));
+		}
 	}
 	CK(cudaGetLastError());
 	return(HTV_OK);
@@ -3555,10 +3575,16 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 		}
 		LineA2 *la2 = (LineA2 *) d->d_desc_a2;
-		k_line_desc_a2<<<(nlines + KD_LINES * KD_WARPS - 1) / (KD_LINES * KD_WARPS), 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
+		// the two halves of the sound descriptors, each on the side stream of the pre-pass chain it depends on
+		const int dgrid = (nlines + KD_LINES * KD_WARPS - 1) / (KD_LINES * KD_WARPS);
+		CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));                  // ev_in: this call's place in the caller's stream (pre-pass or above)
+		k_line_desc_a2<1><<<dgrid, 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
+		k_line_desc_a2<2><<<dgrid, 32 * KD_WARPS, 0, d->side2>>>(dp, d->dt, la2, line0, nlines);
 		CK(cudaEventRecord(d->ev_audio, d->side));
+		CK(cudaEventRecord(d->ev_nic, d->side2));
 		d->side_armed = 0;
 		CK(cudaStreamWaitEvent(st, d->ev_audio, 0));
+		CK(cudaStreamWaitEvent(st, d->ev_nic, 0));
 		// runs of at least 4 lines (every run rasters two lines more than it emits)
 		int run = (nlines + d->kl_ctas - 1) / d->kl_ctas;
 		if(run < 4) run = 4;
@@ -3566,6 +3592,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		if(d->timing) cudaEventRecord(d->ev0, st);
 		#define KL_GO2(VF, HQ, FU, CS) do { \
 			if(d->kl_threads <= 256) k_line<VF, HQ, FU, CS, 256, 4><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
+			else if(d->kl_threads <= 320) k_line<VF, HQ, FU, CS, 320, 3><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
 			else k_line<VF, HQ, FU, CS, 384, 2><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
 		// the common case (128 | W, a chroma filter that cannot overflow) gets its own instantiation; everything else the general one
 		#define KL_GO(VF, HQ) do { if(dp.W % MF_TILE == 0 && !d->kl_csat) KL_GO2(VF, HQ, true, false); \
@@ -3575,7 +3602,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else KL_GO(true, false);
 		#undef KL_GO
 		#undef KL_GO2
-		d->launches += 3;
+		d->launches += 4;
 		d->last_mod_lines = nlines;
 		if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
 		CK(cudaEventRecord(d->ev_chunk[d->chunk_i & 1], st));
