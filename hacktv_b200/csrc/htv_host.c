@@ -614,7 +614,13 @@ static int host_fail(htv_t *s, int r)
 static int host_enqueue(htv_t *s, int nlines, int16_t *h_out)
 {
 	const size_t line_bytes = (size_t) s->W * s->bps;
-	int piece = (int) (HOST_PIECE_BYTES / line_bytes), done = 0, r, i;
+	size_t piece_bytes = HOST_PIECE_BYTES;
+	int piece, done = 0, r, i;
+	{
+		const char *e = getenv("HTV_HOST_PIECE_MB");                    /* experiment knob (tools/e2e_probe.py) */
+		if(e && atoi(e) > 0) piece_bytes = (size_t) atoi(e) << 20;
+	}
+	piece = (int) (piece_bytes / line_bytes);
 	if(piece < 1) piece = 1;
 	if(piece > nlines) piece = nlines > 0 ? nlines : 1;
 	if((size_t) piece * line_bytes > s->d_stage_bytes)

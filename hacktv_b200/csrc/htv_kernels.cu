@@ -3274,7 +3274,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 				d->dt.chroma_atab = (const uint32_t *) dev_copy(d, ctab, sizeof(ctab));
 			}
 			const size_t rowb = (size_t) mf_row_bytes(W) + 16, uvb = (size_t) MF_TILE * T + 32;
-			d->kl_smem = 2 * sizeof(LineA2) + 3 * sizeof(LineR2) + (dp.vf_type ? 8 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 8 * uvb + 1024 +
+			d->kl_smem = 2 * sizeof(LineA2) + 2 * sizeof(LineR2) + (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
 			d->use_line = 1;
 			{

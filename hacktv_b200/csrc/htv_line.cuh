@@ -286,12 +286,12 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
 	const int RB = kl_row_bytes(W), UB = kl_uv_bytes(W);
-	// LineA2 x2, LineR2 x3 | [row 0..3][hi, lo] composite planes | 2 x [u hi, u lo, v hi, v lo] | FIR taps | chroma taps | NICAM pulse
+	// descriptors x2 | [row 0..2][hi, lo] composite planes | [u hi, u lo, v hi, v lo] | FIR taps | chroma taps | NICAM pulse
 	LineA2 *sla = reinterpret_cast<LineA2 *>(smem_raw);
 	LineR2 *slr = reinterpret_cast<LineR2 *>(sla + 2);
-	unsigned char *rows = reinterpret_cast<unsigned char *>(slr + 3);
-	unsigned char *uvp = rows + (VF ? 8 * RB : 0);
-	uint4 *atab = reinterpret_cast<uint4 *>(uvp + 8 * UB);                 // [k-step][I hi, I lo, Q hi, Q lo][lane]
+	unsigned char *rows = reinterpret_cast<unsigned char *>(slr + 2);
+	unsigned char *uvp = rows + (VF ? 6 * RB : 0);
+	uint4 *atab = reinterpret_cast<uint4 *>(uvp + 4 * UB);                 // [k-step][I hi, I lo, Q hi, Q lo][lane]
 	uint4 *ctab = atab + (VF ? MF_ATAB_WORDS / 4 : 0);                      // [hi, lo][lane]
 	short *ntp = reinterpret_cast<short *>(ctab + 64);
 	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
@@ -301,20 +301,19 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	const int a = blockIdx.x * run, bnd = min(a + run, nlines);
 	if(a >= nlines) return;
 	// relative line q: raster lines a-1 .. bnd (descriptor lrp[q + 1]), modulate a .. bnd-1
-	// iteration q rasters line q (a-1 .. bnd with a filter: one more either side) and modulates line q - 2 (q without)
-	const int q0 = VF ? a - 1 : a, qr = VF ? bnd : bnd - 1, q1 = VF ? bnd + 1 : bnd - 1;
+	const int q0 = VF ? a - 1 : a, q1 = VF ? bnd : bnd - 1;
 
 	// ---- one-time set-up -------------------------------------------------------
 	if(VF) for(int i = tid; i < MF_ATAB_WORDS / 4; i += blockDim.x) atab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.mma_atab) + i);
 	if(dt.chroma_atab) for(int i = tid; i < 64; i += blockDim.x) ctab[i] = __ldg(reinterpret_cast<const uint4 *>(dt.chroma_atab) + i);
-	for(int i = tid; i < ((VF ? 8 * RB : 0) + 8 * UB) / 4; i += blockDim.x) reinterpret_cast<unsigned *>(rows)[i] = 0;
+	for(int i = tid; i < ((VF ? 6 * RB : 0) + 4 * UB) / 4; i += blockDim.x) reinterpret_cast<unsigned *>(rows)[i] = 0;
 	if(dp.have_nicam)
 	{
 		const int4 *src = reinterpret_cast<const int4 *>(dt.nicam_tpad);
 		int4 *dst = reinterpret_cast<int4 *>(ntp);
 		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
-	if(tid < 4) reinterpret_cast<int4 *>(slr + (q0 + 3) % 3)[tid] = __ldg(reinterpret_cast<const int4 *>(lrp + q0 + 1) + tid);
+	if(tid < 4) reinterpret_cast<int4 *>(slr + (q0 & 1))[tid] = __ldg(reinterpret_cast<const int4 *>(lrp + q0 + 1) + tid);
 	__syncthreads();
 
 	const int full_l = dp.active_left, full_r = dp.active_left + dp.active_width;
@@ -330,7 +329,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	int tm[4];
 	unsigned px[4];
 	#define KL_R1A(QQ) do { \
-		const LineR2 &ln = slr[((QQ) + 3) % 3]; \
+		const LineR2 &ln = slr[(QQ) & 1]; \
 		const int16_t *tp_ = dt.tmpl_out + (size_t) ln.tmpl * W + xb; \
 		_Pragma("unroll") for(int j = 0; j < 4; j++) tm[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(tp_ + 8 * j) : 0; \
 		if(in_full && ln.al < ln.ar && ln.row_off >= 0) \
@@ -346,27 +345,18 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	} while(0)
 	KL_R1A(q0);
 
-	for(int q = q0; q <= q1; q++)
+	int r3 = (q0 + 3) % 3;                                                  // ring row of line q
+	for(int q = q0; q <= q1; q++, r3 = r3 == 2 ? 0 : r3 + 1)
 	{
-		const int mrow = VF ? q - 2 : q;                                    // the line modulated in this iteration
-		const bool raster = q <= qr;
-		const int uq = (q & 1) ? 4 * UB : 0;                                // chroma planes of line q
-		// ---- descriptors of the next raster line and of the line modulated below -> shared memory (a third LineR2
-		// slot: stragglers of the previous iteration may still read theirs, there is one barrier per line) -----
-		if(tid < 4) { if(q + 1 <= qr) kl_cp16(reinterpret_cast<int4 *>(slr + (q + 4) % 3) + tid, reinterpret_cast<const int4 *>(lrp + q + 2) + tid); }
-		else if(tid < 4 + NA16) { if(mrow >= a && mrow < bnd) kl_cp16(reinterpret_cast<int4 *>(sla + (mrow & 1)) + (tid - 4), reinterpret_cast<const int4 *>(lap + mrow) + (tid - 4)); }
+		const int mrow = VF ? q - 1 : q;                                    // the line modulated in this iteration
+		// ---- descriptors of the next raster line and of the line modulated below -> shared memory -----
+		if(tid < 4) { if(q + 1 <= q1) kl_cp16(reinterpret_cast<int4 *>(slr + ((q + 1) & 1)) + tid, reinterpret_cast<const int4 *>(lrp + q + 2) + tid); }
+		else if(tid < 4 + NA16) { if(mrow >= a) kl_cp16(reinterpret_cast<int4 *>(sla + (mrow & 1)) + (tid - 4), reinterpret_cast<const int4 *>(lap + mrow) + (tid - 4)); }
 
-		int val[4] = { 0, 0, 0, 0 };
-		short2 cl[4];
-		int li_pal = 0;
-		const LineR2 &li = slr[(q + 3) % 3];
-		if(raster)
-		{
 		// ---- R1b: picture values of line q ---------------------------------------
-		const int li_al = li.al, li_ar = li.ar;
-		li_pal = li.pal;
-		#pragma unroll
-		for(int j = 0; j < 4; j++) val[j] = tm[j];
+		const LineR2 &li = slr[q & 1];
+		const int li_al = li.al, li_ar = li.ar, li_pal = li.pal;
+		int val[4] = { tm[0], tm[1], tm[2], tm[3] };
 		int uu[4] = { 0, 0, 0, 0 }, vv[4] = { 0, 0, 0, 0 };
 		if(in_full && li_al < li_ar)
 		{
@@ -399,6 +389,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		if(li_pal)
 		{
 			// subcarrier table entries of this line: in flight across the barrier and the chroma filter
+			short2 cl[4];
 			{
 				const htv_c16_t *cp = dt.clut + li.clut_off + xb;
 				#pragma unroll
@@ -406,14 +397,13 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			}
 			// unfiltered U, V as byte planes; outside the picture the planes stay zero (the reference filters
 			// each line on its own: zero history either side, ref fir.c:357-375)
-			unsigned char *const up = uv0 + uq;
 			if(all_full)
 			{
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					up[8 * j] = (unsigned char) (uu[j] >> 8); up[UB + 8 * j] = (unsigned char) uu[j];
-					up[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); up[3 * UB + 8 * j] = (unsigned char) vv[j];
+					uv0[8 * j] = (unsigned char) (uu[j] >> 8); uv0[UB + 8 * j] = (unsigned char) uu[j];
+					uv0[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); uv0[3 * UB + 8 * j] = (unsigned char) vv[j];
 				}
 			}
 			else if(in_full)
@@ -424,28 +414,20 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 					const int x = xb + 8 * j;
 					if(x >= full_l && x < full_r)
 					{
-						up[8 * j] = (unsigned char) (uu[j] >> 8); up[UB + 8 * j] = (unsigned char) uu[j];
-						up[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); up[3 * UB + 8 * j] = (unsigned char) vv[j];
+						uv0[8 * j] = (unsigned char) (uu[j] >> 8); uv0[UB + 8 * j] = (unsigned char) uu[j];
+						uv0[2 * UB + 8 * j] = (unsigned char) (vv[j] >> 8); uv0[3 * UB + 8 * j] = (unsigned char) vv[j];
 					}
 				}
 			}
-		}
-		}
-		// the one barrier of the line: chroma planes of line q, composite rows up to q - 1 (written after the previous
-		// barrier), descriptors of q + 1 and of the line modulated below
-		if(tid < 4 + NA16) kl_cp_wait();
-		__syncthreads();
-		if(raster && li_pal)
-		{
+			__syncthreads();
 			// ---- R2: chroma low-pass (tensor cores), burst, subcarrier ---------------
 			int cu[4], cv[4];
 			{
 				int uhh[4] = { 0, 0, 0, 0 }, umid[4] = { 0, 0, 0, 0 }, ull[4] = { 0, 0, 0, 0 };
 				int vhh[4] = { 0, 0, 0, 0 }, vmid[4] = { 0, 0, 0, 0 }, vll[4] = { 0, 0, 0, 0 };
 				const uint4 ah = ctab[lane], al4 = ctab[32 + lane];
-				const unsigned char *const ub = uvb + uq;
-				const uint2 uh = *reinterpret_cast<const uint2 *>(ub), ul = *reinterpret_cast<const uint2 *>(ub + UB);
-				const uint2 vh = *reinterpret_cast<const uint2 *>(ub + 2 * UB), vl = *reinterpret_cast<const uint2 *>(ub + 3 * UB);
+				const uint2 uh = *reinterpret_cast<const uint2 *>(uvb), ul = *reinterpret_cast<const uint2 *>(uvb + UB);
+				const uint2 vh = *reinterpret_cast<const uint2 *>(uvb + 2 * UB), vl = *reinterpret_cast<const uint2 *>(uvb + 3 * UB);
 				mma_ss(uhh, ah, uh); mma_su(umid, ah, ul); mma_us(umid, al4, uh); mma_uu(ull, al4, ul);
 				mma_ss(vhh, ah, vh); mma_su(vmid, ah, vl); mma_us(vmid, al4, vh); mma_uu(vll, al4, vl);
 				// accumulator register ci <-> sample j: ci = ((j & 1) << 1) | (j >> 1)
@@ -475,7 +457,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			#pragma unroll
 			for(int j = 0; j < 4; j++) val[j] += ((int) cl[j].x * cv[j] * li_pal + (int) cl[j].y * cu[j]) >> 15;
 		}
-		if(raster && li.ov_any)
+		if(li.ov_any)
 		{
 			// VBI stages run on the finished line (ref video.c:4213-4357 register them behind the raster)
 			#pragma unroll
@@ -487,10 +469,10 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			}
 		}
 
-		const int r3 = (q + 4) & 3, rprev = (q + 3) & 3, rnext = (q + 5) & 3;
-		if(VF && raster)
+		const int rprev = r3 == 0 ? 2 : r3 - 1, rnext = r3 == 2 ? 0 : r3 + 1;
+		if(VF)
 		{
-			// ---- composite line -> ring row q mod 4 (+ the neighbours' halos) ----------
+			// ---- composite line -> ring row q mod 3 (+ the neighbours' halos) ----------
 			unsigned char *rp = rows + (2 * r3) * RB + KL_LEAD + xb;
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
@@ -519,16 +501,18 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 				}
 			}
 		}
+		if(tid < 4 + NA16) kl_cp_wait();
+		__syncthreads();                                                    // rows of line q, descriptors of q + 1 and of mrow
+
 		// ---- R1a: the next line's template and pixels start their way here -------------
-		if(q + 1 <= qr) KL_R1A(q + 1);
-		if(mrow < a || mrow >= bnd) continue;
+		if(q + 1 <= q1) KL_R1A(q + 1);
+		if(mrow < a) continue;
 
 		int oi[4], oq[4];
 		if(VF)
 		{
-			// ---- M: video filter of line q - 2 (its right-hand halo was written behind the previous barrier), one tile
-			// of 128 samples per warp -------
-			const unsigned char *ph = rows + (2 * ((q + 2) & 3)) * RB + fo0, *plo = ph + RB;
+			// ---- M: video filter of line q - 1, one tile of 128 samples per warp -------
+			const unsigned char *ph = rows + (2 * rprev) * RB + fo0, *plo = ph + RB;
 			int ihh[4] = { 0, 0, 0, 0 }, imid[4] = { 0, 0, 0, 0 }, ill[4] = { 0, 0, 0, 0 };
 			int qhh[4] = { 0, 0, 0, 0 }, qmid[4] = { 0, 0, 0, 0 }, qll[4] = { 0, 0, 0, 0 };
 			#pragma unroll

@@ -14,7 +14,3 @@ timeout 200 $NCU --set full --import-source on -k "regex:^k_sec_iir$|^k_sec_fm$|
 echo "== whole step with the caches left alone between kernels (--cache-control none): live DRAM / L2 traffic of every kernel"
 timeout 200 $NCU --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum -c 40 --csv \
 	--log-file gpurun_out/r02_step_traffic_cache_control_none.csv python tools/run_one.py i 16000000 1 64 > /dev/null 2>&1
-echo "== bench line (not under a profiler)"
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_b200.json 2> gpurun_out/r02_bench.err
-tail -c 600 gpurun_out/r02_bench_b200.json; tail -3 gpurun_out/r02_bench.err
-ls -la gpurun_out | grep r02_
