@@ -114,24 +114,25 @@ struct __align__(16) SecState {
 };
 
 struct __align__(16) SecChk {
-	int pi, pq;                       // FM phasor before sample W - 8 (valid: the FM loop came through there)
+	int pi, pq;                       // FM phasor before sample ck (valid: the FM loop came through there)
 	int valid, pad;
-	double ixm, iym;                  // IIR state before sample W - 8
+	double ixm, iym;                  // IIR state before sample ck
 };
 
 struct SecScratch {
-	int16_t *cb;                      // [lines][W]   low-passed baseband without the aliased-tail terms
-	int *tail;                        // [lines][SEC_TAIL] raw sums of the last outputs
-	int16_t *add;                     // [lines][W]   subcarrier samples to add to the composite
-	SecState *st[2];                  // [lines] outgoing state, ping-pong between passes
-	SecState *used;                   // [lines] the incoming state the line was last computed from
+	int16_t *cbT;                     // [groups][rows][8] low-passed baseband without the aliased-tail terms
+	int *tail;                        // [rows][SEC_TAIL]  raw sums of the last outputs
+	SecState *st[2];                  // [rows] outgoing state, ping-pong between passes
+	SecState *used;                   // [rows] the incoming state the line was last computed from ...
+	SecState *outc;                   // [rows] ... and the outgoing state that computation gave
 	SecState *carry;                  // state before the first line of the chain
-	int *flags;                       // [0] outgoing states changed in the last pass, [2] lines recomputed
-	int *claim;                       // [lines] last pass that rendered the line
-	// line-parallel chain (k_sec_iir / k_sec_fm): one thread per line
-	int16_t *y;                       // [lines][W + 8] FM input: pre-emphasised, clamped baseband; [W], [W + 1] = the aliased words
-	int *chg;                         // [lines] first sample of y that changed in this pass (>= W + 2: none)
-	struct SecChk *chk;               // [lines] checkpoint before sample W - 8: FM phasor and IIR state
+	int *flags;                       // [0] outgoing states changed in the last pass, [2] lines recomputed, [3] work list length
+	int16_t *yT;                      // [groups][rows][8] FM input: pre-emphasised, rounded, clamped baseband
+	int *phT;                         // [groups][rows][8] phasor after each sample's step: (pi >> 16) & 0xFFFF | (pq >> 16) << 16
+	double *iyc;                      // [W / 64 + 1][rows] IIR state iy before sample 64 k
+	struct SecChk *chk;               // [rows] checkpoint before sample ck
+	int *list;                        // [rows] lines whose FM recurrence must be re-run in full
+	int rows;                         // row pitch of the transposed arrays
 };
 
 #define MAPBUFS 16
@@ -181,10 +182,10 @@ struct htv_dev_t {
 	int desc_cap;
 	// the fused line kernel (htv_line.cuh): PAL / NTSC / mono, AM or VSB, no resampler
 	int use_line, kl_threads, kl_ctas, kl_csat;
+	int sec_line;                     // SECAM: the modulator is the fused line kernel in its SRC form (composite rows from d_comp)
 	size_t kl_smem;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
-	size_t sec_smem;
 	int *d_comp32;                    // int32 composite scratch for the TMA-fed modulator (4 | W, not SECAM)
 	uint8_t *d_planes;                // high / low byte planes of the composite stream for k_mod_mma (32 | W, video filter on)
 	size_t plane_stride, modm_smem;
@@ -1427,12 +1428,6 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 //                   which is the sequential result bit for bit.
 // ---------------------------------------------------------------------------
 
-__device__ __forceinline__ bool sec_same(const SecState &a, const SecState &b)
-{
-	return(a.A == b.A && a.B == b.B && __double_as_longlong(a.ix) == __double_as_longlong(b.ix) &&
-	       __double_as_longlong(a.iy) == __double_as_longlong(b.iy));
-}
-
 __global__ void __launch_bounds__(384, 3)
 k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, SecScratch ss)
 {
@@ -1561,638 +1556,39 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 			}
 		}
 		// 15-tap low-pass of the colour-difference baseband; the two aliased words past the
-		// end of the line are added by k_secam_seq, so the last 7 outputs are kept as raw sums
+		// end of the line are added by the chain (sec_tail), so the last 7 outputs are kept as raw sums;
+		// cbT is the chain's transposed layout ([group of 8][row][8])
 		const size_t row = (size_t) blockIdx.x;
+		int cbo[SPT];
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
 			const int x = x0 + k;
+			cbo[k] = 0;
 			if(x >= W) break;
 			int acc = 0;
 			#pragma unroll
 			for(int t = 0; t < 15; t++) acc += cbin[x - 7 + t + 8] * dp.secam_lpf[t];
-			ss.cb[row * W + x] = (int16_t) sat16i(acc >> 15);
+			cbo[k] = sat16i(acc >> 15);
 			if(x >= W - 7) ss.tail[row * SEC_TAIL + (x - (W - 7))] = acc;
 		}
+		// 4 samples = half a group of the transposed layout
+		if(x0 < W) *reinterpret_cast<int2 *>(ss.cbT + ((((size_t) (x0 >> 3) * ss.rows + row) << 3) + (x0 & 7))) =
+			make_int2((cbo[0] & 0xFFFF) | (cbo[1] << 16), (cbo[2] & 0xFFFF) | (cbo[3] << 16));
 	}
 	const size_t o = (size_t) blockIdx.x * W + x0;
 	#pragma unroll
 	for(int k = 0; k < SPT; k++)
 	{
-		if(x0 + k < W) { comp[o + k] = (int16_t) outv[k]; ss.add[o + k] = 0; }
+		if(x0 + k < W) comp[o + k] = (int16_t) outv[k];
 	}
 }
 
-// The sample-serial part of one line, run by ONE WARP: lane 0 walks the two recurrences, all
-// lanes do the memory work around it (coalesced row load, table gathers, row store) through
-// shared memory. Incoming state -> outgoing state; when `commit` is set the subcarrier samples
-// are written to the line's row of ss.add.
-struct SecSmem {
-	short *cbS;                       // [W]     low-passed baseband
-	short *yS;                        // [W + 2] FM input (after IIR + clamp), then the two aliased words
-	htv_c32_t *mS;                    // [n]     FM phasor steps for the modulated range
-	htv_c16_t *gS;                    // [n]     bell-filter gains
-	short *oS;                        // [n]     modulator output
-};
-
-__device__ __forceinline__ SecState secam_line_warp(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
-	const SecScratch &ss, int c, const SecState &in, bool commit, const SecSmem &sm)
-{
-	const int W = dp.W, lane = threadIdx.x & 31;
-	SecState out = in;
-	if(li.sec_clear) { out.A = 0; out.B = 0; }
-	if(!li.sec_proc) return(out);
-
-	const int A = out.A, B = out.B;
-	const int16_t *cb = ss.cb + (size_t) c * W;
-	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
-	for(int x = lane; x < W; x += 32)
-	{
-		int v = cb[x];
-		if(x >= W - 7)
-		{
-			// finish the low-pass: taps reaching chrominance_buffer[W] and [W + 1]
-			int acc = tail[x - (W - 7)];
-			const int kA = W - x + 7, kB = W + 1 - x + 7;
-			if(kA <= 14) acc += A * dp.secam_lpf[kA];
-			if(kB <= 14) acc += B * dp.secam_lpf[kB];
-			v = sat16i(acc >> 15);
-		}
-		sm.cbS[x] = (short) v;
-	}
-	__syncwarp();
-	// pre-emphasis IIR in double, separately rounded operations (ref fir.c:721-735)
-	double ix = out.ix, iy = out.iy;
-	if(lane == 0)
-	{
-		#pragma unroll 4
-		for(int x = 0; x < W; x++)
-		{
-			const double xin = (double) sm.cbS[x];
-			iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
-			ix = xin;
-			const double cl = iy < -32768.0 ? -32768.0 : (iy > 32767.0 ? 32767.0 : iy);
-			sm.yS[x] = (short) round_away(cl);
-		}
-		sm.yS[W] = (short) A; sm.yS[W + 1] = (short) B;
-	}
-	ix = __shfl_sync(0xFFFFFFFFu, ix, 0); iy = __shfl_sync(0xFFFFFFFFu, iy, 0);
-	out.ix = ix; out.iy = iy;
-	__syncwarp();
-
-	// FM modulator: Q31 phasor reset every line, exact recurrence (ref video.c:2278-2297, 3211-3228)
-	const int sl = dp.burst_left, sr = li.sec_sr, n = sr - sl;
-	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	for(int i = lane; i < n; i += 32)
-	{
-		int s = sm.yS[sl + i];
-		s = s < dmin ? dmin : (s > dmax ? dmax : s);
-		sm.mS[i] = dt.secam_fm_lut[s + 32768];
-		sm.gS[i] = dt.secam_bell[(unsigned short) s];
-	}
-	__syncwarp();
-	if(lane == 0)
-	{
-		int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
-		#pragma unroll 4
-		for(int i = 0; i < n; i++)
-		{
-			const htv_c32_t m = sm.mS[i];
-			const htv_c16_t g = sm.gS[i];
-			const long long ni = (long long) pi * m.i - (long long) pq * m.q;
-			const long long nq = (long long) pi * m.q + (long long) pq * m.i;
-			pi = (int) (ni >> 31); pq = (int) (nq >> 31);
-			sm.oS[i] = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
-			                  - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
-		}
-	}
-	__syncwarp();
-	if(sr > W) out.A = sm.oS[W - sl];
-	if(sr > W + 1) out.B = sm.oS[W + 1 - sl];
-	if(commit && li.valid)                                          // fill lines are never emitted
-	{
-		int16_t *add = ss.add + (size_t) c * W;
-		const int top = min(sr, W);
-		for(int x = sl + lane; x < top; x += 32) add[x] = (int16_t) (((int) sm.oS[x - sl] * dt.burst_win[x - sl]) >> 15);
-	}
-	__syncwarp();
-	return(out);
-}
-
-__device__ __forceinline__ SecSmem sec_smem(const htv_dparams_t &dp, unsigned char *base)
-{
-	const int W = dp.W, n = dp.burst_width + 2;
-	SecSmem sm;
-	sm.mS = reinterpret_cast<htv_c32_t *>(base);
-	sm.gS = reinterpret_cast<htv_c16_t *>(sm.mS + n);
-	sm.cbS = reinterpret_cast<short *>(sm.gS + n);
-	sm.yS = sm.cbS + ((W + 7) & ~7);
-	sm.oS = sm.yS + ((W + 2 + 7) & ~7);
-	return(sm);
-}
-
-#define SEC_RUN 4                     // lines a thread renders in sequence in the first pass ...
-#define SEC_WARM 8                    // ... after this many warm-up lines (state only, nothing written)
-#define SEC_MAXW 1536
-
-// The same line computation for ONE THREAD (one line per lane): used by pass 0, where 32 runs
-// advance in lock-step per warp. Written for instruction-level parallelism - the only serial
-// parts are the two recurrences (2 dependent fp64 ops, resp. a 64-bit multiply-add, per sample);
-// conversions, rounding, table gathers and output scaling of neighbouring samples overlap them.
-__device__ __noinline__ SecState secam_line_lane(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li,
-	const SecScratch &ss, int c, const SecState &in, bool commit, short *y)
-{
-	const int W = dp.W;
-	SecState out = in;
-	if(li.sec_clear) { out.A = 0; out.B = 0; }
-	if(!li.sec_proc) return(out);
-
-	const int A = out.A, B = out.B;
-	const int16_t *cb = ss.cb + (size_t) c * W;
-	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
-	double ix = out.ix, iy = out.iy;
-	const int Wm = (W - 8) & ~3;                                     // the last outputs need the aliased words
-	for(int x = 0; x < Wm; x += 4)
-	{
-		const short2 p0 = *reinterpret_cast<const short2 *>(cb + x), p1 = *reinterpret_cast<const short2 *>(cb + x + 2);
-		const double x0 = (double) p0.x, x1 = (double) p0.y, x2 = (double) p1.x, x3 = (double) p1.y;
-		const double t0 = __dadd_rn(__dmul_rn(x0, dp.iir_b0), __dmul_rn(ix, dp.iir_b1));
-		const double t1 = __dadd_rn(__dmul_rn(x1, dp.iir_b0), __dmul_rn(x0, dp.iir_b1));
-		const double t2 = __dadd_rn(__dmul_rn(x2, dp.iir_b0), __dmul_rn(x1, dp.iir_b1));
-		const double t3 = __dadd_rn(__dmul_rn(x3, dp.iir_b0), __dmul_rn(x2, dp.iir_b1));
-		const double y0 = __dadd_rn(t0, -__dmul_rn(iy, dp.iir_a1));
-		const double y1 = __dadd_rn(t1, -__dmul_rn(y0, dp.iir_a1));
-		const double y2 = __dadd_rn(t2, -__dmul_rn(y1, dp.iir_a1));
-		const double y3 = __dadd_rn(t3, -__dmul_rn(y2, dp.iir_a1));
-		iy = y3; ix = x3;
-		y[x + 0] = (short) round_away(fmin(fmax(y0, -32768.0), 32767.0));
-		y[x + 1] = (short) round_away(fmin(fmax(y1, -32768.0), 32767.0));
-		y[x + 2] = (short) round_away(fmin(fmax(y2, -32768.0), 32767.0));
-		y[x + 3] = (short) round_away(fmin(fmax(y3, -32768.0), 32767.0));
-	}
-	for(int x = Wm; x < W; x++)
-	{
-		int v = cb[x];
-		if(x >= W - 7)
-		{
-			int acc = tail[x - (W - 7)];
-			const int kA = W - x + 7, kB = W + 1 - x + 7;
-			if(kA <= 14) acc += A * dp.secam_lpf[kA];
-			if(kB <= 14) acc += B * dp.secam_lpf[kB];
-			v = sat16i(acc >> 15);
-		}
-		const double xin = (double) v;
-		iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
-		ix = xin;
-		y[x] = (short) round_away(fmin(fmax(iy, -32768.0), 32767.0));
-	}
-	out.ix = ix; out.iy = iy;
-	y[W] = (short) A; y[W + 1] = (short) B;
-
-	const int sl = dp.burst_left, sr = li.sec_sr;
-	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
-	int16_t *add = ss.add + (size_t) c * W;
-	const bool wr = commit && li.valid;
-	htv_c32_t m[8];
-	htv_c16_t g[8];
-	#pragma unroll
-	for(int k = 0; k < 8; k++)
-	{
-		int sv = sl + k < sr ? y[sl + k] : 0;
-		sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
-		m[k] = dt.secam_fm_lut[sv + 32768];
-		g[k] = dt.secam_bell[(unsigned short) sv];
-	}
-	for(int xb = sl; xb < sr; xb += 8)
-	{
-		htv_c32_t mn[8];
-		htv_c16_t gn[8];
-		#pragma unroll
-		for(int k = 0; k < 8; k++)                                  // gathers of the next block fly while this one is computed
-		{
-			int sv = xb + 8 + k < sr ? y[xb + 8 + k] : 0;
-			sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
-			mn[k] = dt.secam_fm_lut[sv + 32768];
-			gn[k] = dt.secam_bell[(unsigned short) sv];
-		}
-		#pragma unroll
-		for(int k = 0; k < 8; k++)
-		{
-			const int x = xb + k;
-			if(x < sr)
-			{
-				const long long ni = (long long) pi * m[k].i - (long long) pq * m[k].q;
-				const long long nq = (long long) pi * m[k].q + (long long) pq * m[k].i;
-				pi = (int) (ni >> 31); pq = (int) (nq >> 31);
-				const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g[k].i) >> 15)
-				                     - (((((pq >> 16) * dp.secam_level) >> 15) * g[k].q) >> 15));
-				if(x < W) { if(wr) add[x] = (int16_t) ((o * dt.burst_win[x - sl]) >> 15); }
-				else if(x == W) out.A = o;
-				else if(x == W + 1) out.B = o;
-			}
-		}
-		#pragma unroll
-		for(int k = 0; k < 8; k++) { m[k] = mn[k]; g[k] = gn[k]; }
-	}
-	return(out);
-}
-
-// Pass 0: each THREAD walks a run of consecutive lines (32 runs per warp in lock-step), so the
-// state handed from line to line is exact inside the run; only the run's starting state is a
-// guess, tightened by warm-up lines (the dependence on the incoming state contracts by roughly
-// 3x per line).
-__global__ void __launch_bounds__(32)
-k_secam_runs(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
-{
-	const int r = blockIdx.x * blockDim.x + threadIdx.x;
-	const int c0 = r * SEC_RUN;
-	if(c0 >= n) return;
-	short y[SEC_MAXW + 16];
-	SecState st;
-	int c = c0 - SEC_WARM;
-	if(c <= 0) { c = 0; st = *ss.carry; }
-	else { st.A = st.B = st.pad0 = st.pad1 = 0; st.ix = st.iy = 0.0; }
-	const int c1 = min(n, c0 + SEC_RUN);
-	for(; c < c1; c++)
-	{
-		const bool mine = c >= c0;
-		if(mine) ss.used[c] = st;
-		st = secam_line_lane(dp, dt, lr[c], ss, c, st, mine, y);
-		if(mine) ss.st[0][c] = st;
-	}
-}
-
-// Later passes, one warp per line: recompute a line only if the state its predecessor now
-// hands over differs from the one it was computed from - and keep walking down the following
-// lines while the outgoing state keeps changing, so a correction front is absorbed in one pass
-// instead of one line per pass. ss.claim makes sure a line has one writer per pass. dst was
-// preset to src by the host (device-to-device copy), so untouched lines keep their state.
-#define SEC_WALK 256
-__global__ void __launch_bounds__(32)
-k_secam_seq(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	int c = blockIdx.x;
-	if(c >= n) return;
-	const SecState *src = ss.st[(pass + 1) & 1];
-	SecState *dst = ss.st[pass & 1];
-	SecState in = c == 0 ? *ss.carry : src[c - 1];
-	if(sec_same(in, ss.used[c])) return;
-	const SecSmem sm = sec_smem(dp, smem_raw);
-	for(int steps = 0; steps < SEC_WALK && c < n; steps++, c++)
-	{
-		int got = 0;
-		if(threadIdx.x == 0) got = atomicMax(ss.claim + c, pass) < pass;
-		got = __shfl_sync(0xFFFFFFFFu, got, 0);
-		if(!got) break;                                             // another warp has this line in this pass
-		if(threadIdx.x == 0) { ss.used[c] = in; atomicAdd(ss.flags + 2, 1); }
-		const SecState out = secam_line_warp(dp, dt, lr[c], ss, c, in, true, sm);
-		const bool changed = !sec_same(out, src[c]);
-		if(threadIdx.x == 0) dst[c] = out;
-		if(!changed) break;
-		if(threadIdx.x == 0) atomicAdd(ss.flags, 1);                // the successor is stale unless we fix it now
-		in = out;
-	}
-}
-
-
-// ---------------------------------------------------------------------------
-// SECAM chain, line-parallel (round 2). The sample-serial parts of a line - the fp64 pre-emphasis IIR and the
-// Q31 FM recurrence (ref video.c:3068-3233, fir.c:721-735) - are run by ONE THREAD PER LINE, all lines of the
-// launch at once, from the state their predecessor produced in the previous pass (pass 0: a guess); passes repeat
-// until no line's input differs bitwise from its predecessor's output, i.e. until the sequential result is
-// reached. What makes this cheap: the IIR forgets its start within ~250 samples (a1 = -0.905), so a changed
-// predecessor state usually leaves the rounded FM input untouched, or touches only the last 7 samples (the two
-// aliased words A, B); k_sec_iir reports the first sample that changed and k_sec_fm re-runs the phasor from there -
-// from the line start, or from the checkpoint kept 8 samples before the line end.
-//   k_sec_iir  tail of the low-pass (A, B), IIR over the line -> y row, first changed sample, outgoing IIR state
-//   k_sec_fm   FM recurrence from the first changed sample -> subcarrier row, outgoing A, B
-// Rows are read and written 8 samples (16 bytes) at a time: a warp's 32 lanes walk 32 different rows.
-// ---------------------------------------------------------------------------
-
-// state handed to row c: the outgoing state of the nearest row before it that carries a subcarrier (rows without
-// one pass the state on, the two field-start lines clear A and B: ref video.c:3149-3160), or the launch's carry
-__device__ __forceinline__ SecState sec_incoming(const LineRaster *lr, const SecScratch &ss, int c, const SecState *prev_out, int &from)
-{
-	bool clr = false;
-	int p = c - 1;
-	for(; p >= 0; p--)
-	{
-		if(lr[p].sec_proc) break;
-		if(lr[p].sec_clear) clr = true;
-	}
-	from = p;
-	SecState s = p >= 0 ? prev_out[p] : *ss.carry;
-	if(clr) { s.A = 0; s.B = 0; }
-	return(s);
-}
-
-__device__ __forceinline__ double sec_iir_step(const htv_dparams_t &dp, double xin, double &ix, double &iy)
-{
-	iy = __dadd_rn(__dadd_rn(__dmul_rn(xin, dp.iir_b0), __dmul_rn(ix, dp.iir_b1)), -__dmul_rn(iy, dp.iir_a1));
-	ix = xin;
-	return(fmin(fmax(iy, -32768.0), 32767.0));
-}
-
-__global__ void __launch_bounds__(64)
-k_sec_iir(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n) return;
-	const int W = dp.W, WY = W + 8;
-	const LineRaster &li = lr[c];
-	const SecState *prev = ss.st[(pass + 1) & 1];
-	SecState *cur = ss.st[pass & 1];
-	ss.chg[c] = 0x7FFFFFFF;
-	int from;
-	SecState in;
-	if(pass == 0)
-	{
-		// guess: A = B = 0 and the IIR state the previous subcarrier line leaves when started from rest half a line
-		// before its end (its own start state has decayed by 0.905^512 there)
-		in = sec_incoming(lr, ss, c, prev, from);
-		if(from >= 0)
-		{
-			in.A = in.B = 0; in.pad0 = in.pad1 = 0;
-			double ix = 0.0, iy = 0.0;
-			const int16_t *cbp = ss.cb + (size_t) from * W;
-			for(int x = W - 512 < 0 ? 0 : W - 512; x < W; x++) sec_iir_step(dp, (double) cbp[x], ix, iy);
-			in.ix = ix; in.iy = iy;
-		}
-	}
-	else in = sec_incoming(lr, ss, c, prev, from);
-	if(li.sec_clear) { in.A = 0; in.B = 0; }
-	if(!li.sec_proc) { cur[c] = in; return; }
-	if(pass > 0 && sec_same(in, ss.used[c])) { cur[c] = prev[c]; return; }
-	ss.used[c] = in;
-	atomicAdd(ss.flags + 2, 1);
-
-	const int16_t *cb = ss.cb + (size_t) c * W;
-	const int *tail = ss.tail + (size_t) c * SEC_TAIL;
-	int16_t *y = ss.y + (size_t) c * WY;
-	double ix = in.ix, iy = in.iy;
-	int first = 0x7FFFFFFF;
-	const bool cmp = pass > 0;
-	const int Wv = (W & 7) == 0 ? W - 8 : 0;                             // vector part: whole groups of 8 before the tail
-	// the next group's loads are in flight while this group's 8 dependent steps run
-	int4 v = Wv > 0 ? *reinterpret_cast<const int4 *>(cb) : make_int4(0, 0, 0, 0);
-	int4 old = (cmp && Wv > 0) ? *reinterpret_cast<const int4 *>(y) : make_int4(0, 0, 0, 0);
-	for(int x = 0; x < Wv; x += 8)
-	{
-		const int4 vn = x + 8 < Wv ? *reinterpret_cast<const int4 *>(cb + x + 8) : make_int4(0, 0, 0, 0);
-		const int4 oldn = (cmp && x + 8 < Wv) ? *reinterpret_cast<const int4 *>(y + x + 8) : make_int4(0, 0, 0, 0);
-		const int w[4] = { v.x, v.y, v.z, v.w };
-		int o[4];
-		#pragma unroll
-		for(int k = 0; k < 4; k++)
-		{
-			const int a = round_away(sec_iir_step(dp, (double) (short) (w[k] & 0xFFFF), ix, iy));
-			const int b = round_away(sec_iir_step(dp, (double) (w[k] >> 16), ix, iy));
-			o[k] = (a & 0xFFFF) | (b << 16);
-		}
-		if(cmp && first == 0x7FFFFFFF && (old.x != o[0] || old.y != o[1] || old.z != o[2] || old.w != o[3]))
-		{
-			const int oo[4] = { old.x, old.y, old.z, old.w };
-			for(int k = 3; k >= 0; k--) if(oo[k] != o[k]) first = x + 2 * k + (((oo[k] ^ o[k]) & 0xFFFF) ? 0 : 1);
-		}
-		*reinterpret_cast<int4 *>(y + x) = make_int4(o[0], o[1], o[2], o[3]);
-		v = vn; old = oldn;
-	}
-	if(Wv > 0) { ss.chk[c].ixm = ix; ss.chk[c].iym = iy; }
-	for(int x = Wv; x < W; x++)
-	{
-		int v = cb[x];
-		if(x >= W - 7)
-		{
-			// finish the low-pass: taps reaching chrominance_buffer[W] and [W + 1]
-			int acc = tail[x - (W - 7)];
-			const int kA = W - x + 7, kB = W + 1 - x + 7;
-			if(kA <= 14) acc += in.A * dp.secam_lpf[kA];
-			if(kB <= 14) acc += in.B * dp.secam_lpf[kB];
-			v = sat16i(acc >> 15);
-		}
-		const short o = (short) round_away(sec_iir_step(dp, (double) v, ix, iy));
-		if(cmp && first == 0x7FFFFFFF && y[x] != o) first = x;
-		y[x] = o;
-	}
-	if(cmp && first == 0x7FFFFFFF && (y[W] != (short) in.A || y[W + 1] != (short) in.B)) first = W;
-	y[W] = (short) in.A; y[W + 1] = (short) in.B;
-	SecState out = in;
-	out.ix = ix; out.iy = iy;
-	// a line whose FM loop overruns the line end (sr > W) produces new A, B: those of the previous pass stand until
-	// k_sec_fm has looked at the line (it re-runs when the FM input changed); other lines pass A, B on
-	if(cmp && li.sec_sr > W) out.A = prev[c].A;
-	if(cmp && li.sec_sr > W + 1) out.B = prev[c].B;
-	cur[c] = out;
-	ss.chg[c] = cmp ? first : 0;
-}
-
-__global__ void __launch_bounds__(64)
-k_sec_fm(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n, int pass)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n) return;
-	const int W = dp.W, WY = W + 8;
-	const LineRaster &li = lr[c];
-	if(!li.sec_proc) return;
-	const int first = ss.chg[c];
-	SecState *cur = ss.st[pass & 1];
-	const SecState *prev = ss.st[(pass + 1) & 1];
-	const int sl = dp.burst_left, sr = li.sec_sr;
-	if(first >= sr)
-	{
-		// the FM input is what it was: the subcarrier stands; the IIR state (or passed-on A, B) may have moved
-		if(pass > 0 && !sec_same(cur[c], prev[c])) atomicAdd(ss.flags, 1);
-		return;
-	}
-	const int16_t *y = ss.y + (size_t) c * WY;
-	int16_t *add = ss.add + (size_t) c * W;
-	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	// restart point: the line's phasor reset, or the checkpoint before sample W - 8
-	const int ck = W - 8;
-	int x0 = sl, pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
-	const SecChk k4 = ss.chk[c];
-	if(pass > 0 && first >= ck && k4.valid && ck > sl && ck < sr) { x0 = ck; pi = k4.pi; pq = k4.pq; }
-	SecState out = cur[c];
-	const bool wr = li.valid != 0;                                      // fill lines are never emitted
-	int have_ck = 0, ckpi = 0, ckpq = 0;
-	// group of 8 samples: FM input, then its LUT entries (phasor step, bell-filter gain); the next group's are fetched
-	// while this group's 8 dependent phasor steps run
-	htv_c32_t m[8], mn[8];
-	htv_c16_t g[8], gn[8];
-	#define SEC_FETCH(XB, M, G) do { \
-		short ys_[8]; \
-		if(((W & 7) == 0) && (XB) + 8 <= WY) \
-		{ \
-			const int4 v_ = *reinterpret_cast<const int4 *>(y + (XB)); \
-			ys_[0] = (short) (v_.x & 0xFFFF); ys_[1] = (short) (v_.x >> 16); ys_[2] = (short) (v_.y & 0xFFFF); ys_[3] = (short) (v_.y >> 16); \
-			ys_[4] = (short) (v_.z & 0xFFFF); ys_[5] = (short) (v_.z >> 16); ys_[6] = (short) (v_.w & 0xFFFF); ys_[7] = (short) (v_.w >> 16); \
-		} \
-		else { _Pragma("unroll") for(int k = 0; k < 8; k++) ys_[k] = (XB) + k < WY ? y[(XB) + k] : (short) 0; } \
-		_Pragma("unroll") for(int k = 0; k < 8; k++) \
-		{ \
-			int sv_ = ys_[k]; \
-			sv_ = sv_ < dmin ? dmin : (sv_ > dmax ? dmax : sv_); \
-			M[k] = dt.secam_fm_lut[sv_ + 32768]; \
-			G[k] = dt.secam_bell[(unsigned short) sv_]; \
-		} } while(0)
-	int xb = x0 & ~7;
-	SEC_FETCH(xb, m, g);
-	for(; xb < sr; xb += 8)
-	{
-		if(xb + 8 < sr) SEC_FETCH(xb + 8, mn, gn);
-		short ov[8];
-		#pragma unroll
-		for(int k = 0; k < 8; k++)
-		{
-			const int x = xb + k;
-			ov[k] = 0;
-			if(x == ck && x >= x0) { ckpi = pi; ckpq = pq; have_ck = 1; }
-			if(x >= x0 && x < sr)
-			{
-				const long long ni = (long long) pi * m[k].i - (long long) pq * m[k].q;
-				const long long nq = (long long) pi * m[k].q + (long long) pq * m[k].i;
-				pi = (int) (ni >> 31); pq = (int) (nq >> 31);
-				const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g[k].i) >> 15)
-				                     - (((((pq >> 16) * dp.secam_level) >> 15) * g[k].q) >> 15));
-				if(x < W) ov[k] = (short) ((o * dt.burst_win[x - sl]) >> 15);
-				else if(x == W) out.A = o;
-				else if(x == W + 1) out.B = o;
-			}
-		}
-		if(wr)
-		{
-			if(((W & 7) == 0) && xb >= x0 && xb + 8 <= sr && xb + 8 <= W)
-			{
-				*reinterpret_cast<int4 *>(add + xb) = make_int4((ov[0] & 0xFFFF) | (ov[1] << 16), (ov[2] & 0xFFFF) | (ov[3] << 16),
-					(ov[4] & 0xFFFF) | (ov[5] << 16), (ov[6] & 0xFFFF) | (ov[7] << 16));
-			}
-			else
-			{
-				#pragma unroll
-				for(int k = 0; k < 8; k++) { const int x = xb + k; if(x >= x0 && x < sr && x < W) add[x] = ov[k]; }
-			}
-		}
-		#pragma unroll
-		for(int k = 0; k < 8; k++) { m[k] = mn[k]; g[k] = gn[k]; }
-	}
-	#undef SEC_FETCH
-	if(have_ck) { ss.chk[c].pi = ckpi; ss.chk[c].pq = ckpq; ss.chk[c].valid = 1; }
-	else if(x0 == sl) ss.chk[c].valid = 0;
-	cur[c] = out;
-	if(pass == 0 || !sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
-}
-
-// Predictor between pass 0 and pass 1. Pass 0 ran every line with A = B = 0; the true values ripple down the lines
-// (line L's A, B enter the last 7 low-pass outputs of line L + 1, hence its last FM inputs, hence its own A, B) and
-// the error shrinks only ~3x per line - about nine more full passes. But that coupling lives entirely in the last 8
-// samples of a line: given the checkpoints pass 0 left (IIR state and FM phasor before sample W - 8), a line's
-// outgoing state follows from the incoming A, B in 8 IIR + 10 FM steps. Every thread walks that short chain down
-// SEC_PRED lines to its own, so pass 1 starts from states that are right to 3^-SEC_PRED. It only proposes states:
-// the passes after it compute every line in full and compare bit for bit, as before.
-#define SEC_PRED 10
-__device__ __forceinline__ void sec_tail_step(const htv_dparams_t &dp, const DevTables &dt, const LineRaster &li, const SecScratch &ss,
-	int r, int &A, int &B, double &ixe, double &iye)
-{
-	const int W = dp.W;
-	const SecChk ck = ss.chk[r];
-	const int16_t *cb = ss.cb + (size_t) r * W;
-	const int *tail = ss.tail + (size_t) r * SEC_TAIL;
-	double ix = ck.ixm, iy = ck.iym;
-	short ys[10];
-	#pragma unroll
-	for(int k = 0; k < 8; k++)
-	{
-		const int x = W - 8 + k;
-		int v = cb[x];
-		if(k >= 1)
-		{
-			int acc = tail[k - 1];
-			const int kA = W - x + 7, kB = W + 1 - x + 7;
-			if(kA <= 14) acc += A * dp.secam_lpf[kA];
-			if(kB <= 14) acc += B * dp.secam_lpf[kB];
-			v = sat16i(acc >> 15);
-		}
-		ys[k] = (short) round_away(sec_iir_step(dp, (double) v, ix, iy));
-	}
-	ys[8] = (short) A; ys[9] = (short) B;
-	ixe = ix; iye = iy;
-	const int sr = li.sec_sr;
-	if(!ck.valid || sr <= W) return;                                    // the FM loop stops short of the line end: A, B pass through
-	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	int pi = ck.pi, pq = ck.pq;
-	#pragma unroll
-	for(int k = 0; k < 10; k++)
-	{
-		const int x = W - 8 + k;
-		if(x >= sr) break;
-		int sv = ys[k];
-		sv = sv < dmin ? dmin : (sv > dmax ? dmax : sv);
-		const htv_c32_t m = dt.secam_fm_lut[sv + 32768];
-		const htv_c16_t g = dt.secam_bell[(unsigned short) sv];
-		const long long ni = (long long) pi * m.i - (long long) pq * m.q;
-		const long long nq = (long long) pi * m.q + (long long) pq * m.i;
-		pi = (int) (ni >> 31); pq = (int) (nq >> 31);
-		const int o = (short) ((((((pi >> 16) * dp.secam_level) >> 15) * g.i) >> 15)
-		                     - (((((pq >> 16) * dp.secam_level) >> 15) * g.q) >> 15));
-		if(x == W) A = o;
-		else if(x == W + 1) B = o;
-	}
-}
-
-__global__ void __launch_bounds__(64)
-k_sec_predict(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int n)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n) return;
-	const SecState *src = ss.st[0];
-	SecState *dst = ss.st[1];
-	if(!lr[c].sec_proc) { dst[c] = src[c]; return; }
-	// the subcarrier rows r[0] = c, r[1], ... above it, and whether A, B are cleared on the way into each
-	int rows[SEC_PRED + 1], clr[SEC_PRED + 1], nr = 0, p = c;
-	bool cl = false;
-	while(nr <= SEC_PRED && p >= 0)
-	{
-		if(lr[p].sec_proc) { rows[nr] = p; clr[nr] = 0; if(nr > 0) clr[nr - 1] = cl; cl = false; nr++; }
-		if(lr[p].sec_clear) cl = true;                                   // a clearing row: cleared on entry, also for itself
-		p--;
-	}
-	// state entering the oldest row of the walk: pass 0's (approximate) output of the row before it, or the launch's carry
-	int A, B;
-	{
-		int q = rows[nr - 1] - 1;
-		bool c2 = lr[rows[nr - 1]].sec_clear != 0;
-		for(; q >= 0; q--) { if(lr[q].sec_proc) break; if(lr[q].sec_clear) c2 = true; }
-		const SecState s0 = q >= 0 ? src[q] : *ss.carry;
-		A = c2 ? 0 : s0.A; B = c2 ? 0 : s0.B;
-	}
-	double ixe = 0.0, iye = 0.0;
-	for(int i = nr - 1; i >= 0; i--)
-	{
-		if(i < nr - 1 && (clr[i] || lr[rows[i]].sec_clear)) { A = 0; B = 0; }
-		sec_tail_step(dp, dt, lr[rows[i]], ss, rows[i], A, B, ixe, iye);
-	}
-	SecState out = src[c];
-	out.A = A; out.B = B; out.ix = ixe; out.iy = iye;
-	dst[c] = out;
-}
-
-// carry for the next launch: the state after chain row `idx` of the final pass (rows without a subcarrier pass it on)
-__global__ void k_sec_carry(const LineRaster *lr, SecScratch ss, int idx, int pass_final)
-{
-	if(threadIdx.x == 0 && blockIdx.x == 0)
-	{
-		int from;
-		SecState s = sec_incoming(lr, ss, idx + 1, ss.st[pass_final & 1], from);
-		*ss.carry = s;
-	}
-}
+#include "htv_secam.cuh"
 
 // SECAM: the VBI stages sit behind the SECAM stage (ref video.c:4211-4357), so an overlay line is
-// folded in once the chain has produced the line's subcarrier: composite + subcarrier -> replace /
-// add -> composite, subcarrier row cleared. One CTA per row, a handful of rows per frame do work.
-__global__ void __launch_bounds__(256) k_overlay_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, int16_t *sadd)
+// folded in once k_sec_out has added the line's subcarrier to the composite row: replace / add in place. One CTA per row, a handful of rows per frame do work.
+__global__ void __launch_bounds__(256) k_overlay_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp)
 {
 	const LineRaster &li = lr[blockIdx.x];
 	if(!li.ov_any) return;
@@ -2200,20 +1596,10 @@ __global__ void __launch_bounds__(256) k_overlay_secam(const __grid_constant__ h
 	const size_t o = (size_t) blockIdx.x * W;
 	for(int x = threadIdx.x; x < W; x += blockDim.x)
 	{
-		int v = wrap16i((int) comp[o + x] + (int) sadd[o + x]);
+		int v = comp[o + x];
 		if(x >= li.ov_from && x < li.ov_to) v = li.ov_value;
 		if(li.ov_add >= 0) v += dt.ov_add[(size_t) li.ov_add * W + x];
 		comp[o + x] = (int16_t) v;
-		sadd[o + x] = 0;
-	}
-}
-
-// carry for the next launch: the state after chain line `idx` of the final pass
-__global__ void k_secam_carry(SecScratch ss, int idx, int pass_final)
-{
-	if(threadIdx.x == 0 && blockIdx.x == 0)
-	{
-		*ss.carry = ss.st[pass_final & 1][idx];
 	}
 }
 
@@ -3250,6 +2636,35 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			cudaFuncSetAttribute(k_mod_mma<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->modm_smem);
 		}
 	}
+	if(secam && !dp.have_fmv && !t->raster_only && !t->rs_taps && !(getenv("HTV_PATH") && !strcmp(getenv("HTV_PATH"), "split")))
+	{
+		// SECAM: raster and chrominance chain write the composite rows, the fused line kernel's SRC form modulates them
+		int nsm = 148;
+		cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+		if(dp.vf_type)
+		{
+			uint32_t atab[MF_ATAB_WORDS];
+			mf_build_atab(dp.vf_i, dp.vf_q, atab);
+			d->dt.mma_atab = (const uint32_t *) dev_copy(d, atab, sizeof(atab));
+		}
+		if(!dp.vf_type || d->dt.mma_atab)
+		{
+			const int T = mf_tiles(W);
+			d->kl_threads = 32 * T;
+			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : (d->kl_threads <= 320 ? 3 : 2));
+			const size_t rowb = (size_t) mf_row_bytes(W) + 16, uvb = (size_t) MF_TILE * T + 32;
+			d->kl_smem = 2 * sizeof(LineA2) + 2 * sizeof(LineR2) + (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
+				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
+			d->sec_line = 1;
+			#define KL_ATTR2(VF, HQ, FU) do { \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 320, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 384, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+			KL_ATTR2(false, false, true); KL_ATTR2(false, false, false); KL_ATTR2(true, false, true); KL_ATTR2(true, false, false);
+			KL_ATTR2(true, true, true); KL_ATTR2(true, true, false);
+			#undef KL_ATTR2
+		}
+	}
 	{
 		// The fused line kernel (htv_line.cuh) is the default wherever it applies: PAL / NTSC / mono rasters, AM or
 		// VSB modulation (or baseband), a chroma low-pass the tensor-core form holds (11 .. 17 taps), no resampler
@@ -3296,22 +2711,23 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	if(secam)
 	{
 		const size_t rows = (size_t) d->sub_lines + 3;
-		d->sec.cb = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W);
+		const size_t groups = (size_t) (W + 2 + 7) / 8 + 1;
+		d->sec.rows = (int) rows;
+		d->sec.cbT = (int16_t *) dev_zero(d, sizeof(int16_t) * groups * rows * 8);
 		d->sec.tail = (int *) dev_zero(d, sizeof(int) * rows * SEC_TAIL);
-		d->sec.add = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * W + 256);
 		d->sec.st[0] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
 		d->sec.st[1] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
 		d->sec.used = (SecState *) dev_zero(d, sizeof(SecState) * rows);
+		d->sec.outc = (SecState *) dev_zero(d, sizeof(SecState) * rows);
 		d->sec.carry = (SecState *) dev_zero(d, sizeof(SecState));
 		d->sec.flags = (int *) dev_zero(d, sizeof(int) * 4);
-		d->sec.claim = (int *) dev_zero(d, sizeof(int) * rows);
-		d->sec.y = (int16_t *) dev_zero(d, sizeof(int16_t) * rows * (W + 8) + 256);
-		d->sec.chg = (int *) dev_zero(d, sizeof(int) * rows);
+		d->sec.yT = (int16_t *) dev_zero(d, sizeof(int16_t) * groups * rows * 8);
+		d->sec.phT = (int *) dev_zero(d, sizeof(int) * groups * rows * 8);
+		d->sec.iyc = (double *) dev_zero(d, sizeof(double) * ((size_t) W / SEC_IYC + 2) * rows);
 		d->sec.chk = (SecChk *) dev_zero(d, sizeof(SecChk) * rows);
+		d->sec.list = (int *) dev_zero(d, sizeof(int) * rows);
 		d->sec_passes = 64;
-		d->sec_smem = (size_t) (dp.burst_width + 2) * 12 + 2 * (((W + 7) & ~7) + ((W + 2 + 7) & ~7) + ((dp.burst_width + 2 + 7) & ~7)) + 64;
-		cudaFuncSetAttribute(k_secam_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->sec_smem);
-		if(!d->sec.cb || !d->sec.add || !d->sec.flags || !d->sec.y || !d->sec.chg || !d->sec.chk)
+		if(!d->sec.cbT || !d->sec.flags || !d->sec.yT || !d->sec.phT || !d->sec.iyc || !d->sec.chk || !d->sec.list || !d->sec.outc)
 		{
 			snprintf(err, errlen, "device allocation failed");
 			htv_dev_destroy(d);
@@ -3524,7 +2940,7 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 		k_nicam_scan<<<1, 1024, 0, st>>>(d->dt, k_lo, k_hi);
 		d->launches += 2;
 		d->nic_kc = k_hi;                                          // fstart[k_hi] is valid; recompute from there next time
-		if(!d->use_line)
+		if(!d->use_line && !d->sec_line)
 		{
 			// the split kernels' descriptor kernel (on `side`) reads both chains
 			CK(cudaEventRecord(d->ev_nic, d->side2));
@@ -3550,16 +2966,10 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2);
 		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = NULL;
 		d->desc_cap = 0;
-		if(d->use_line)
-		{
-			CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
-			CK(cudaMalloc(&d->d_desc_a2, sizeof(LineA2) * ((size_t) nlines + 1)));
-		}
-		else
-		{
-			CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
-			CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
-		}
+		if(d->use_line) CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
+		else CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
+		if(d->use_line || d->sec_line) CK(cudaMalloc(&d->d_desc_a2, sizeof(LineA2) * ((size_t) nlines + 1)));
+		else CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
 		d->desc_cap = nlines;
 	}
 	LineDescs ld = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
@@ -3616,7 +3026,18 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		CK(cudaEventRecord(d->ev_in, st));
 		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 	}
-	k_line_desc_a<<<(nlines + fm_skip + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0 - fm_skip, nlines + fm_skip);
+	LineA2 *la2 = (LineA2 *) d->d_desc_a2;
+	if(d->sec_line)
+	{
+		// the sound descriptors of the fused line kernel, each half on the side stream of the pre-pass chain it depends on
+		const int dgrid = (nlines + KD_LINES * KD_WARPS - 1) / (KD_LINES * KD_WARPS);
+		CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));
+		k_line_desc_a2<1><<<dgrid, 32 * KD_WARPS, 0, d->side>>>(d->dp, d->dt, la2, line0, nlines);
+		k_line_desc_a2<2><<<dgrid, 32 * KD_WARPS, 0, d->side2>>>(d->dp, d->dt, la2, line0, nlines);
+		CK(cudaEventRecord(d->ev_nic, d->side2));
+		d->launches++;
+	}
+	else k_line_desc_a<<<(nlines + fm_skip + 63) / 64, 64, 0, d->side>>>(d->dp, d->dt, ld, line0 - fm_skip, nlines + fm_skip);
 	CK(cudaEventRecord(d->ev_audio, d->side));
 	d->launches += 2;
 	d->side_armed = 0;
@@ -3636,46 +3057,30 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			// rows 0 .. n+2 <-> lines first-2 .. first+n; the chain covers rows 0 .. n+1
 			const LineRaster *lr = ld.r + done - 1;
 			k_raster_secam<<<n + 3, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec);
-			// pass 0 in runs, then per-line passes until no line's outgoing state changes: at that
-			// fixed point every line was computed from its true predecessor state = the sequential
-			// result. The loop needs the change count on the host, so SECAM launches synchronise.
-			const int nch = n + 2;
+			// the chain (htv_secam.cuh): pass 0 over every line, the predictor, then refinement passes until no line's
+			// outgoing state changes - at that fixed point every line was computed from its true predecessor state =
+			// the sequential result. The loop needs the change count on the host, so SECAM launches synchronise.
+			const int nch = n + 2, nb = (nch + 31) / 32;
 			cudaEvent_t dbg0 = NULL, dbg1 = NULL;
 			const bool dbg = getenv("HTV_DEBUG") != NULL;
 			if(dbg) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, st); }
-			const bool old_chain = getenv("HTV_SECAM") && !strcmp(getenv("HTV_SECAM"), "runs");   // round 1's warp-per-line chain (A/B)
 			int pass = 0, changed = 1;
-			if(old_chain)
-			{
-				cudaMemsetAsync(d->sec.claim, 0, sizeof(int) * nch, st);
-				k_secam_runs<<<((nch + SEC_RUN - 1) / SEC_RUN + 31) / 32, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
-				d->launches += 2;
-				pass = 1;
-			}
 			for(; pass <= d->sec_passes && changed; pass++)
 			{
 				int fl[4];
 				cudaMemsetAsync(d->sec.flags, 0, sizeof(int) * 4, st);
-				if(old_chain)
+				if(pass == 0)
 				{
-					cudaMemcpyAsync(d->sec.st[pass & 1], d->sec.st[(pass + 1) & 1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
-					k_secam_seq<<<nch, 32, d->sec_smem, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
-					d->launches++;
-				}
-				else
-				{
-					// one thread per line: IIR (reports the first FM input sample that changed), then the FM recurrence from there
-					k_sec_iir<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
-					k_sec_fm<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
-					d->launches += 2;
-				}
-				if(!old_chain && pass == 0 && (d->dp.W & 7) == 0 && !getenv("HTV_SECAM_NOPRED"))
-				{
+					k_sec_pass0<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
 					// propose the states pass 1 starts from (see k_sec_predict); st[0] takes them over
-					k_sec_predict<<<(nch + 63) / 64, 64, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+					k_sec_predict<<<(nch + SEC_PRED_T - SEC_PRED_HALO - 1) / (SEC_PRED_T - SEC_PRED_HALO), SEC_PRED_T, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
 					cudaMemcpyAsync(d->sec.st[0], d->sec.st[1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
-					d->launches++;
+					d->launches += 2;
+					continue;
 				}
+				k_sec_refine<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
+				k_sec_fm_list<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, pass);
+				d->launches += 2;
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
 				changed = fl[0];
@@ -3683,7 +3088,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				{
 					float ms = 0;
 					cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1); cudaEventElapsedTime(&ms, dbg0, dbg1);
-					fprintf(stderr, "secam pass %d: recomputed %d, output changed %d, cumulative %.3f ms\n", pass, fl[2], fl[0], ms);
+					fprintf(stderr, "secam pass %d: recomputed %d (FM in full: %d), output changed %d, cumulative %.3f ms\n", pass, fl[2], fl[3], fl[0], ms);
 				}
 			}
 			if(changed)
@@ -3691,15 +3096,15 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				fprintf(stderr, "hacktv_b200: SECAM cross-line state did not converge in %d passes\n", d->sec_passes);
 				return(HTV_ERROR);
 			}
-			if(old_chain) k_secam_carry<<<1, 32, 0, st>>>(d->sec, n - 1, pass - 1);
-			else k_sec_carry<<<1, 32, 0, st>>>(lr, d->sec, n - 1, pass - 1);
+			k_sec_carry<<<1, 32, 0, st>>>(lr, d->sec, n - 1, pass - 1);
+			k_sec_out<<<dim3((d->dp.W + 63) / 64, (nch + 31) / 32), 256, 0, st>>>(d->dp, d->dt, lr, d->sec, d->d_comp, nch);
+			d->launches += 2;
 			if(d->dt.ov_n > 0)
 			{
-				k_overlay_secam<<<n + 3, 256, 0, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec.add);
+				k_overlay_secam<<<n + 3, 256, 0, st>>>(d->dp, d->dt, lr, d->d_comp);
 				d->launches++;
 			}
 			cstream = d->d_comp + d->dp.W;          // k_mod's line b sits at row b + 2
-			sadd = d->sec.add + d->dp.W;
 		}
 		else
 		{
@@ -3707,7 +3112,12 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_raster<<<n + 2, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, ld.r + done, d->d_comp, d->d_comp32, d->d_planes, d->plane_stride, d->plane_pitch);
 			d->launches++;
 		}
-		if(!joined) { CK(cudaStreamWaitEvent(st, d->ev_audio, 0)); joined = true; }
+		if(!joined)
+		{
+			CK(cudaStreamWaitEvent(st, d->ev_audio, 0));
+			if(d->sec_line) CK(cudaStreamWaitEvent(st, d->ev_nic, 0));
+			joined = true;
+		}
 		if(d->timing && last) cudaEventRecord(d->ev0, st);
 		if(d->dp.have_fmv)
 		{
@@ -3721,6 +3131,24 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			k_fmv_scan<<<1, 1024, 0, st>>>(d->dt, rows);
 			k_fmv_mod<<<rows, d->line_threads, 0, st>>>(dp, d->dt, lap, o, acc, acc_rows, -pre);
 			d->launches += 2;
+		}
+		else if(d->sec_line)
+		{
+			// runs of at least 4 lines (every run stages two lines more than it emits)
+			const htv_dparams_t &dp = d->dp;
+			int run = (n + d->kl_ctas - 1) / d->kl_ctas;
+			if(run < 4) run = 4;
+			const int grid = (n + run - 1) / run;
+			#define KL_GO2(VF, HQ, FU) do { \
+				if(d->kl_threads <= 256) k_line<VF, HQ, FU, false, 256, 4, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
+				else if(d->kl_threads <= 320) k_line<VF, HQ, FU, false, 320, 3, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
+				else k_line<VF, HQ, FU, false, 384, 2, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); } while(0)
+			#define KL_GO(VF, HQ) do { if(dp.W % MF_TILE == 0) KL_GO2(VF, HQ, true); else KL_GO2(VF, HQ, false); } while(0)
+			if(!dp.vf_type) KL_GO(false, false);
+			else if(dp.vf_type == 3) KL_GO(true, true);
+			else KL_GO(true, false);
+			#undef KL_GO
+			#undef KL_GO2
 		}
 		else if(d->d_planes)
 		{

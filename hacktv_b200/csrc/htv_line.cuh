@@ -278,10 +278,13 @@ __device__ __forceinline__ void kl_cp_wait() { asm volatile("cp.async.wait_all;"
 //   M(q-1)  ... and arrive while line q - 1 (whose right-hand halo R2(q) has just written) is filtered (mma),
 //           gets its sound carriers and is stored.
 // The line descriptors (LineR2 of q + 1, LineA2 of q - 1) come in by cp.async at the top of the iteration.
-template<bool VF, bool HASQ, bool FULL, bool CSAT, int MAXT, int MINB>
+//
+// SRC: the composite lines are not rastered here but read from `src` (row q + 2 = relative line q, int16): SECAM, whose
+// chrominance chain (htv_secam.cuh) runs between the raster and the modulator. R1b / R2 fold away, the rest is the same.
+template<bool VF, bool HASQ, bool FULL, bool CSAT, int MAXT, int MINB, bool SRC = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR2 *lrp, const LineA2 *lap,
-	int nlines, int run, int16_t *out, const int16_t *acc, int acc_rows)
+	int nlines, int run, int16_t *out, const int16_t *acc, int acc_rows, const int16_t *src = nullptr)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int W = dp.W;
@@ -313,7 +316,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 		int4 *dst = reinterpret_cast<int4 *>(ntp);
 		for(int i = tid; i < (dp.nicam_tpad_len + 7) / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
-	if(tid < 4) reinterpret_cast<int4 *>(slr + (q0 & 1))[tid] = __ldg(reinterpret_cast<const int4 *>(lrp + q0 + 1) + tid);
+	if(!SRC && tid < 4) reinterpret_cast<int4 *>(slr + (q0 & 1))[tid] = __ldg(reinterpret_cast<const int4 *>(lrp + q0 + 1) + tid);
 	__syncthreads();
 
 	const int full_l = dp.active_left, full_r = dp.active_left + dp.active_width;
@@ -329,6 +332,13 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	int tm[4];
 	unsigned px[4];
 	#define KL_R1A(QQ) do { \
+		if(SRC) \
+		{ \
+			const int16_t *sp_ = src + (size_t) ((QQ) + 2) * W + xb; \
+			_Pragma("unroll") for(int j = 0; j < 4; j++) tm[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(sp_ + 8 * j) : 0; \
+			px[0] = px[1] = px[2] = px[3] = 0u; \
+			break; \
+		} \
 		const LineR2 &ln = slr[(QQ) & 1]; \
 		const int16_t *tp_ = dt.tmpl_out + (size_t) ln.tmpl * W + xb; \
 		_Pragma("unroll") for(int j = 0; j < 4; j++) tm[j] = (FULL || xb + 8 * j < W) ? (int) __ldg(tp_ + 8 * j) : 0; \
@@ -350,12 +360,12 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	{
 		const int mrow = VF ? q - 1 : q;                                    // the line modulated in this iteration
 		// ---- descriptors of the next raster line and of the line modulated below -> shared memory -----
-		if(tid < 4) { if(q + 1 <= q1) kl_cp16(reinterpret_cast<int4 *>(slr + ((q + 1) & 1)) + tid, reinterpret_cast<const int4 *>(lrp + q + 2) + tid); }
+		if(tid < 4) { if(!SRC && q + 1 <= q1) kl_cp16(reinterpret_cast<int4 *>(slr + ((q + 1) & 1)) + tid, reinterpret_cast<const int4 *>(lrp + q + 2) + tid); }
 		else if(tid < 4 + NA16) { if(mrow >= a) kl_cp16(reinterpret_cast<int4 *>(sla + (mrow & 1)) + (tid - 4), reinterpret_cast<const int4 *>(lap + mrow) + (tid - 4)); }
 
 		// ---- R1b: picture values of line q ---------------------------------------
 		const LineR2 &li = slr[q & 1];
-		const int li_al = li.al, li_ar = li.ar, li_pal = li.pal;
+		const int li_al = SRC ? 0 : li.al, li_ar = SRC ? 0 : li.ar, li_pal = SRC ? 0 : li.pal;
 		int val[4] = { tm[0], tm[1], tm[2], tm[3] };
 		int uu[4] = { 0, 0, 0, 0 }, vv[4] = { 0, 0, 0, 0 };
 		if(in_full && li_al < li_ar)
@@ -457,7 +467,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			#pragma unroll
 			for(int j = 0; j < 4; j++) val[j] += ((int) cl[j].x * cv[j] * li_pal + (int) cl[j].y * cu[j]) >> 15;
 		}
-		if(li.ov_any)
+		if(!SRC && li.ov_any)
 		{
 			// VBI stages run on the finished line (ref video.c:4213-4357 register them behind the raster)
 			#pragma unroll
