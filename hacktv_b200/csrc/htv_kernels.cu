@@ -66,6 +66,7 @@ struct DevTables {
 	const int16_t *burst_win;
 	const uint64_t *fm_ang;
 	const float2 *fm_rot8;            // (cos, sin) of 8 steps of fm_ang (fused line kernel)
+	const uint32_t *notch_atab;       // SECAM luma notch as a tensor-core tap operand: [k-step][hi, lo][lane] x 4 registers
 	const int32_t *afir_v, *afir_f;
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
@@ -174,6 +175,8 @@ struct htv_dev_t {
 	cudaEvent_t ev_up, ev_chunk[2];
 	unsigned chunk_i;
 	cudaEvent_t ev_in, ev_audio;
+	cudaEvent_t ev_kl[2];             // the fused line kernel has read descriptor buffer 0 / 1
+	int kl_buf, ahead;                // descriptor buffer of the next call; the sound pre-pass may run ahead of the caller's stream
 	int side_armed;
 	int ev_pending;
 	int line_threads;
@@ -1428,6 +1431,19 @@ k_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Lin
 //                   which is the sequential result bit for bit.
 // ---------------------------------------------------------------------------
 
+// mma.sync.m16n8k32 in its four signedness mixes (htv_mma_fir.h: the byte-split int16 FIR)
+#define MMA_I8(NAME, AT, BT) \
+__device__ __forceinline__ void NAME(int (&d)[4], const uint4 &a, const uint2 &b) \
+{ \
+	asm("mma.sync.aligned.m16n8k32.row.col.s32." AT "." BT ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+		: "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) \
+		: "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y)); \
+}
+MMA_I8(mma_ss, "s8", "s8")
+MMA_I8(mma_su, "s8", "u8")
+MMA_I8(mma_us, "u8", "s8")
+MMA_I8(mma_uu, "u8", "u8")
+
 __global__ void __launch_bounds__(384, 3)
 k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, int16_t *comp, SecScratch ss)
 {
@@ -1437,6 +1453,9 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 	const int LW = W4 + 2 * LOFF + 14;
 	int *line = reinterpret_cast<int *>(smem_raw);                  // index = x + LOFF
 	int *cbin = line + ((LW + 3) & ~3);                             // index = x + 8
+	// luma as high / low byte planes for the notch on the tensor cores: byte i = sample i - MF_LEAD, zero outside 0 .. W-1
+	const int RBn = mf_row_bytes(W);
+	unsigned char *pl = reinterpret_cast<unsigned char *>(cbin + W4 + 32);
 	__shared__ LineRaster li;
 	const int tid = threadIdx.x;
 
@@ -1447,6 +1466,11 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 	}
 	for(int i = tid; i < LOFF; i += blockDim.x) { line[i] = 0; line[W4 + LOFF + i] = 0; }
 	if(tid < 16) { cbin[tid < 8 ? tid : W4 + tid] = 0; }
+	if(dt.notch_atab)
+	{
+		for(int i = tid; i < MF_LEAD / 4; i += blockDim.x) { reinterpret_cast<unsigned *>(pl)[i] = 0; reinterpret_cast<unsigned *>(pl + RBn)[i] = 0; }
+		for(int i = (MF_LEAD + W4) / 4 + tid; i < RBn / 4; i += blockDim.x) { reinterpret_cast<unsigned *>(pl)[i] = 0; reinterpret_cast<unsigned *>(pl + RBn)[i] = 0; }
+	}
 	__syncthreads();
 
 	const int x0 = tid * SPT;
@@ -1496,15 +1520,55 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 				val[k] += __ldg(dt.pulse_values + li.ent_pos[e] + d);
 			}
 		}
+		unsigned ph4 = 0, pl4 = 0;
 		#pragma unroll
 		for(int k = 0; k < SPT; k++)
 		{
 			const int x = x0 + k;
-			line[x + LOFF] = x < W ? wrap16i(val[k]) : 0;
+			const int lv = x < W ? wrap16i(val[k]) : 0;
+			line[x + LOFF] = lv;
 			cbin[x + 8] = x < W ? cbv[k] : 0;
+			// the notch reads samples left of the picture as zero (ref fir.c:357-375)
+			const int nv = x >= dp.active_left ? lv : 0;
+			ph4 |= ((unsigned) (nv >> 8) & 0xFFu) << (8 * k);
+			pl4 |= ((unsigned) nv & 0xFFu) << (8 * k);
+		}
+		if(dt.notch_atab && li.sec_proc)
+		{
+			*reinterpret_cast<unsigned *>(pl + MF_LEAD + x0) = ph4;
+			*reinterpret_cast<unsigned *>(pl + RBn + MF_LEAD + x0) = pl4;
 		}
 	}
 	__syncthreads();
+	if(dt.notch_atab && li.sec_proc)
+	{
+		// luma notch over the picture region (ref video.c:3082-3090, fir.c:304-355): the 51-tap FIR as the byte-split
+		// int8 contraction of htv_mma_fir.h, one tile of 128 samples per warp; results replace the line's samples
+		const int a0 = dp.active_left, a1 = dp.active_left + dp.active_width;
+		const int lane = tid & 31;
+		const uint4 *at = reinterpret_cast<const uint4 *>(dt.notch_atab);
+		for(int w = tid >> 5; w < mf_tiles(W); w += blockDim.x >> 5)
+		{
+			if(MF_TILE * w >= a1 || MF_TILE * (w + 1) <= a0) continue;
+			const unsigned char *ph = pl + mf_b_offset(w, 0, lane), *plo = ph + RBn;
+			int hh[4] = { 0, 0, 0, 0 }, mid[4] = { 0, 0, 0, 0 }, ll[4] = { 0, 0, 0, 0 };
+			#pragma unroll
+			for(int s = 0; s < MF_KSTEPS; s++)
+			{
+				const uint2 xh = *reinterpret_cast<const uint2 *>(ph + 32 * s);
+				const uint2 xl = *reinterpret_cast<const uint2 *>(plo + 32 * s);
+				const uint4 ah = __ldg(at + (s * 2 + 0) * 32 + lane), al = __ldg(at + (s * 2 + 1) * 32 + lane);
+				mma_ss(hh, ah, xh); mma_su(mid, ah, xl); mma_us(mid, al, xh); mma_uu(ll, al, xl);
+			}
+			#pragma unroll
+			for(int ci = 0; ci < 4; ci++)
+			{
+				const int x = mf_out_x(w, lane, ci);
+				if(x >= a0 && x < a1) line[x + LOFF] = sat16i(mf_combine(hh[ci], mid[ci], ll[ci]) >> 15);
+			}
+		}
+		__syncthreads();
+	}
 	if(x0 >= W) return;
 
 	int outv[SPT];
@@ -1512,9 +1576,9 @@ k_raster_secam(const __grid_constant__ htv_dparams_t dp, const DevTables dt, con
 	for(int k = 0; k < SPT; k++) outv[k] = line[x0 + k + LOFF];
 	if(li.sec_proc)
 	{
-		// luma notch over the picture region; samples left of it read as zero (ref fir.c:357-375)
+		// without the tensor-core operand (never on the shipped path): the scalar notch
 		const int a0 = dp.active_left, a1 = dp.active_left + dp.active_width;
-		if(x0 + SPT - 1 >= a0 && x0 < a1)
+		if(!dt.notch_atab && x0 + SPT - 1 >= a0 && x0 < a1)
 		{
 			if(dp.secam_pad)
 			{
@@ -2263,18 +2327,6 @@ k_mod_tma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 // Used whenever 128 | W, a video filter is on, and the mode is not SECAM / FM video.
 // ---------------------------------------------------------------------------
 
-#define MMA_I8(NAME, AT, BT) \
-__device__ __forceinline__ void NAME(int (&d)[4], const uint4 &a, const uint2 &b) \
-{ \
-	asm("mma.sync.aligned.m16n8k32.row.col.s32." AT "." BT ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
-		: "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) \
-		: "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y)); \
-}
-MMA_I8(mma_ss, "s8", "s8")
-MMA_I8(mma_su, "s8", "u8")
-MMA_I8(mma_us, "u8", "s8")
-MMA_I8(mma_uu, "u8", "u8")
-
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineAudio *lap, const uint8_t *planes, size_t plane_stride,
@@ -2733,8 +2785,15 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			htv_dev_destroy(d);
 			return(NULL);
 		}
+		if(!(getenv("HTV_FIR") && !strcmp(getenv("HTV_FIR"), "scalar")))
+		{
+			uint32_t nt[MF_KSTEPS * 2 * 32 * 4];
+			for(int s3 = 0; s3 < MF_KSTEPS; s3++) for(int lo = 0; lo < 2; lo++) for(int lane = 0; lane < 32; lane++) for(int reg = 0; reg < 4; reg++)
+				nt[((s3 * 2 + lo) * 32 + lane) * 4 + reg] = mf_a_word(dp.secam_notch, s3, lane, reg, lo);
+			d->dt.notch_atab = (const uint32_t *) dev_copy(d, nt, sizeof(nt));
+		}
 		const int W4s = (W + 3) & ~3;
-		const size_t sm = sizeof(int) * ((((W4s + 2 * LOFF + 14) + 3) & ~3) + W4s + 32);
+		const size_t sm = sizeof(int) * ((((W4s + 2 * LOFF + 14) + 3) & ~3) + W4s + 32) + 2 * (size_t) mf_row_bytes(W) + 32;
 		d->raster_smem = sm > d->raster_smem ? sm : d->raster_smem;
 		cudaFuncSetAttribute(k_raster_secam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->raster_smem);
 	}
@@ -2748,6 +2807,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreateWithFlags(&d->ev_chunk[0], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_kl[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_kl[1], cudaEventDisableTiming);
+	d->ahead = d->use_line && !(getenv("HTV_AHEAD") && !strcmp(getenv("HTV_AHEAD"), "0"));
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
 	// the table build and the memsets above ran on the default stream, which the (non-blocking)
 	// streams the encoder works on do not wait for
@@ -2774,6 +2836,8 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
+	if(d->ev_kl[0]) cudaEventDestroy(d->ev_kl[0]);
+	if(d->ev_kl[1]) cudaEventDestroy(d->ev_kl[1]);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
 	if(d->side2) cudaStreamDestroy(d->side2);
@@ -2900,8 +2964,15 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	if(m1 <= m0) return(HTV_OK);
 	// everything the caller queued so far (PCM uploads) precedes the pre-pass, which runs on the
 	// side stream so that it overlaps the raster kernels of the same call
-	CK(cudaEventRecord(d->ev_in, (cudaStream_t) stream));
-	CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+	// Fused line kernel: the pre-pass chain and the sound descriptors touch nothing the caller's stream produces - the
+	// PCM comes up on the upload stream (ev_up), the descriptors are double-buffered - so they do not wait for the
+	// previous call's line kernel but run beside its tail (HTV_AHEAD=0: in the caller's stream order, for A/B)
+	if(d->ahead) CK(cudaStreamWaitEvent(d->side, d->ev_up, 0));
+	else
+	{
+		CK(cudaEventRecord(d->ev_in, (cudaStream_t) stream));
+		CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
+	}
 	d->side_armed = 1;
 	cudaStream_t st = d->side;
 	if(dp.have_fm)
@@ -2929,7 +3000,7 @@ extern "C" int htv_dev_audio_prepass(htv_dev_t *d, int64_t m0, int64_t m1, void 
 	if(dp.have_nicam)
 	{
 		// its own stream beside the FM chain; `side` (where the descriptors follow) joins below
-		CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));
+		CK(cudaStreamWaitEvent(d->side2, d->ahead ? d->ev_up : d->ev_in, 0));
 		st = d->side2;
 		const int64_t s_lo = (int64_t) (((unsigned long long) (m0 > dp.nicam_ntaps ? m0 - dp.nicam_ntaps : 0) * dp.nicam_D) / dp.nicam_F);
 		const int64_t s_hi = (int64_t) (((unsigned long long) (m1 - 1) * dp.nicam_D) / dp.nicam_F);
@@ -2963,12 +3034,13 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	{
 		cudaStreamSynchronize(st);
 		cudaStreamSynchronize(d->side);
+		cudaStreamSynchronize(d->side2);
 		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2);
 		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = NULL;
 		d->desc_cap = 0;
 		if(d->use_line) CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
 		else CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
-		if(d->use_line || d->sec_line) CK(cudaMalloc(&d->d_desc_a2, sizeof(LineA2) * ((size_t) nlines + 1)));
+		if(d->use_line || d->sec_line) CK(cudaMalloc(&d->d_desc_a2, 2 * sizeof(LineA2) * ((size_t) nlines + 1)));
 		else CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
 		d->desc_cap = nlines;
 	}
@@ -2984,10 +3056,18 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			CK(cudaEventRecord(d->ev_in, st));
 			CK(cudaStreamWaitEvent(d->side, d->ev_in, 0));
 		}
-		LineA2 *la2 = (LineA2 *) d->d_desc_a2;
+		// sound descriptors: two buffers, so that the next call's may be written while this call's line kernel runs
+		const int buf = d->kl_buf;
+		d->kl_buf ^= 1;
+		LineA2 *la2 = (LineA2 *) d->d_desc_a2 + (size_t) buf * ((size_t) d->desc_cap + 1);
 		// the two halves of the sound descriptors, each on the side stream of the pre-pass chain it depends on
 		const int dgrid = (nlines + KD_LINES * KD_WARPS - 1) / (KD_LINES * KD_WARPS);
-		CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));                  // ev_in: this call's place in the caller's stream (pre-pass or above)
+		if(d->ahead && d->side_armed)
+		{
+			CK(cudaStreamWaitEvent(d->side, d->ev_kl[buf], 0));
+			CK(cudaStreamWaitEvent(d->side2, d->ev_kl[buf], 0));
+		}
+		else CK(cudaStreamWaitEvent(d->side2, d->ev_in, 0));             // ev_in: this call's place in the caller's stream (pre-pass or above)
 		k_line_desc_a2<1><<<dgrid, 32 * KD_WARPS, 0, d->side>>>(dp, d->dt, la2, line0, nlines);
 		k_line_desc_a2<2><<<dgrid, 32 * KD_WARPS, 0, d->side2>>>(dp, d->dt, la2, line0, nlines);
 		CK(cudaEventRecord(d->ev_audio, d->side));
@@ -3012,6 +3092,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		else KL_GO(true, false);
 		#undef KL_GO
 		#undef KL_GO2
+		CK(cudaEventRecord(d->ev_kl[buf], st));
 		d->launches += 4;
 		d->last_mod_lines = nlines;
 		if(d->timing) { cudaEventRecord(d->ev1, st); d->ev_pending = 1; }
@@ -3079,7 +3160,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 					continue;
 				}
 				k_sec_refine<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
-				k_sec_fm_list<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, pass);
+				k_sec_fm_list<<<512, 32 * SEC_LIST_WARPS, 0, st>>>(d->dp, d->dt, lr, d->sec, pass);
 				d->launches += 2;
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));

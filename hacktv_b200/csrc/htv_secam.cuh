@@ -432,44 +432,75 @@ k_sec_refine(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 	if(!sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
 }
 
-// lines of the work list: the FM recurrence in full from the stored FM input, then the tail
-__global__ void __launch_bounds__(32)
+// Lines of the work list: the FM recurrence in full from the stored FM input, then the tail. The list is short (a
+// fraction of a percent of the lines), so a thread per line would leave the run time at one line's worth of exposed
+// look-up latency per group. One WARP per line instead: lane l fetches FM input and look-up of sample base + l for the
+// next 32 samples while all lanes step through the current 32 (the entries arrive by shuffle), so a step costs the
+// recurrence's own latency and nothing else.
+#define SEC_LIST_WARPS 4
+__global__ void __launch_bounds__(32 * SEC_LIST_WARPS)
 k_sec_fm_list(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int pass)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= ss.flags[3]) return;
-	const int c = ss.list[i];
-	const int W = dp.W, ck = sec_ck(W), G0 = ck >> 3;
-	const LineRaster &li = lr[c];
+	const int lane = threadIdx.x & 31;
+	const int nw = gridDim.x * SEC_LIST_WARPS, count = ss.flags[3];
+	const int W = dp.W, ck = sec_ck(W), sl = dp.burst_left;
 	const SecState *prev = ss.st[(pass + 1) & 1];
 	SecState *cur = ss.st[pass & 1];
-	const int sl = dp.burst_left, sr = li.sec_sr, lim = min(sr, ck);
-	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
-	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
-	const int4 *yp = reinterpret_cast<const int4 *>(ss.yT) + c;
-	const int g0 = sl >> 3, g1 = (lim + 7) >> 3;
-	// FM inputs are loaded two groups ahead, their look-ups issued one group ahead of the recurrence
-	const int ge = min(g1, G0);
-	htv_c32_t m[8];
-	int4 yn = make_int4(0, 0, 0, 0);
-	if(g0 < ge) sec_gather8(dt, yp[(size_t) g0 * ss.rows], dmin, dmax, m);
-	if(g0 + 1 < ge) yn = yp[(size_t) (g0 + 1) * ss.rows];
-	for(int g = g0; g < ge; g++)
+	for(int i = blockIdx.x * SEC_LIST_WARPS + (threadIdx.x >> 5); i < count; i += nw)
 	{
-		const int4 ynn = g + 2 < ge ? yp[(size_t) (g + 2) * ss.rows] : make_int4(0, 0, 0, 0);
-		htv_c32_t mn[8];
-		if(g + 1 < ge) sec_gather8(dt, yn, dmin, dmax, mn);
-		sec_fm8(ss, c, g << 3, sl, lim, m, pi, pq);
-		#pragma unroll
-		for(int k = 0; k < 8; k++) m[k] = mn[k];
-		yn = ynn;
+		const int c = ss.list[i];
+		const LineRaster &li = lr[c];
+		const int sr = li.sec_sr, lim = min(sr, ck);
+		const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+		int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+		const int xs = sl & ~31;
+		htv_c32_t m, mn;
+		m.i = m.q = mn.i = mn.q = 0;
+		if(xs + lane >= sl && xs + lane < lim) m = dt.secam_fm_lut[max(dmin, min(dmax, (int) ss.yT[sec_t(ss, c, xs + lane)])) + 32768];
+		for(int xb = xs; xb < lim; xb += 32)
+		{
+			const int xn = xb + 32 + lane;
+			if(xn < lim) mn = dt.secam_fm_lut[max(dmin, min(dmax, (int) ss.yT[sec_t(ss, c, xn)])) + 32768];
+			int ph = 0;
+			if(xb >= sl && xb + 32 <= lim)
+			{
+				#pragma unroll
+				for(int k = 0; k < 32; k++)
+				{
+					htv_c32_t mk;
+					mk.i = __shfl_sync(0xFFFFFFFFu, m.i, k); mk.q = __shfl_sync(0xFFFFFFFFu, m.q, k);
+					sec_fm_step(pi, pq, mk);
+					ph = lane == k ? sec_ph(pi, pq) : ph;
+				}
+			}
+			else
+			{
+				#pragma unroll 4
+				for(int k = 0; k < 32; k++)
+				{
+					htv_c32_t mk;
+					mk.i = __shfl_sync(0xFFFFFFFFu, m.i, k); mk.q = __shfl_sync(0xFFFFFFFFu, m.q, k);
+					if(xb + k >= sl && xb + k < lim)
+					{
+						sec_fm_step(pi, pq, mk);
+						if(lane == k) ph = sec_ph(pi, pq);
+					}
+				}
+			}
+			if(xb + lane < ck) ss.phT[sec_t(ss, c, xb + lane)] = ph;
+			m = mn;
+		}
+		if(lane == 0)
+		{
+			SecChk k4 = ss.chk[c];
+			k4.pi = pi; k4.pq = pq; k4.valid = ck < sr;
+			ss.chk[c] = k4;
+			const SecState out = sec_tail(dp, dt, li, ss, c, ss.used[c], k4, true);
+			cur[c] = ss.outc[c] = out;
+			if(!sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
+		}
+		__syncwarp();
 	}
-	SecChk k4 = ss.chk[c];
-	k4.pi = pi; k4.pq = pq; k4.valid = ck < sr;
-	ss.chk[c] = k4;
-	const SecState out = sec_tail(dp, dt, li, ss, c, ss.used[c], k4, true);
-	cur[c] = ss.outc[c] = out;
-	if(!sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
 }
 
 // carry for the next launch: the state after chain row `idx` of the final pass (rows without a subcarrier pass it on)
