@@ -177,6 +177,9 @@ struct htv_dev_t {
 	cudaEvent_t ev_in, ev_audio;
 	cudaEvent_t ev_kl[2];             // the fused line kernel has read descriptor buffer 0 / 1
 	int kl_buf, ahead;                // descriptor buffer of the next call; the sound pre-pass may run ahead of the caller's stream
+	cudaStream_t side3;               // ... and so may the frame map and the raster descriptors, on a stream of their own
+	cudaEvent_t ev_r2;
+	int r2_armed;
 	int side_armed;
 	int ev_pending;
 	int line_threads;
@@ -2554,7 +2557,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	d->max_slots = max_frame_slots < 1 ? 1 : max_frame_slots;
 	d->d_frames = (uint32_t *) dev_zero(d, d->frame_pixels * 4 * d->max_slots);
 	d->frame_map_cap = 4096;
-	d->d_frame_map = (int32_t *) dev_zero(d, sizeof(int32_t) * d->frame_map_cap);
+	d->d_frame_map = (int32_t *) dev_zero(d, sizeof(int32_t) * d->frame_map_cap * 2);      // two halves: see htv_dev_set_frame_map
 	if(cudaMallocHost((void **) &d->h_map, sizeof(int32_t) * d->frame_map_cap * MAPBUFS) != cudaSuccess) d->h_map = NULL;
 	for(int i = 0; i < MAPBUFS; i++) cudaEventCreateWithFlags(&d->ev_map[i], cudaEventDisableTiming);
 	d->d_pcm = (int16_t *) dev_zero(d, sizeof(int16_t) * 2 * RA);
@@ -2808,6 +2811,8 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 	cudaEventCreateWithFlags(&d->ev_chunk[1], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&d->ev_kl[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&d->ev_r2, cudaEventDisableTiming);
+	cudaStreamCreateWithFlags(&d->side3, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags(&d->ev_kl[1], cudaEventDisableTiming);
 	d->ahead = d->use_line && !(getenv("HTV_AHEAD") && !strcmp(getenv("HTV_AHEAD"), "0"));
 	cudaEventCreateWithFlags(&d->ev_audio, cudaEventDisableTiming);
@@ -2837,6 +2842,8 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	if(d->ev_in) cudaEventDestroy(d->ev_in);
 	if(d->ev_kl[0]) cudaEventDestroy(d->ev_kl[0]);
+	if(d->ev_r2) cudaEventDestroy(d->ev_r2);
+	if(d->side3) cudaStreamDestroy(d->side3);
 	if(d->ev_kl[1]) cudaEventDestroy(d->ev_kl[1]);
 	if(d->ev_audio) cudaEventDestroy(d->ev_audio);
 	if(d->side) cudaStreamDestroy(d->side);
@@ -2937,8 +2944,23 @@ extern "C" int htv_dev_set_frame_map(htv_dev_t *d, const int32_t *slot_of_frame,
 	int32_t *hm = d->h_map + (size_t) b * d->frame_map_cap;
 	CK(cudaEventSynchronize(d->ev_map[b]));                        // its previous use (MAPBUFS calls ago) has been consumed
 	memcpy(hm, slot_of_frame, sizeof(int32_t) * n);
-	CK(cudaMemcpyAsync(d->d_frame_map, hm, sizeof(int32_t) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
-	CK(cudaEventRecord(d->ev_map[b], (cudaStream_t) stream));
+	if(d->ahead)
+	{
+		// fused line kernel: the map of the coming call goes into the half its raster descriptors will read, on the
+		// stream they run on - beside the previous call's line kernel, once the call before that has let go of the half
+		int32_t *dm = d->d_frame_map + (size_t) d->kl_buf * d->frame_map_cap;
+		CK(cudaStreamWaitEvent(d->side3, d->ev_kl[d->kl_buf], 0));
+		CK(cudaStreamWaitEvent(d->side3, d->ev_up, 0));               // the overlay table, which the raster descriptors read, came up on the upload stream
+		CK(cudaMemcpyAsync(dm, hm, sizeof(int32_t) * n, cudaMemcpyHostToDevice, d->side3));
+		CK(cudaEventRecord(d->ev_map[b], d->side3));
+		d->dt.frame_map = dm;
+		d->r2_armed = 1;
+	}
+	else
+	{
+		CK(cudaMemcpyAsync(d->d_frame_map, hm, sizeof(int32_t) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+		CK(cudaEventRecord(d->ev_map[b], (cudaStream_t) stream));
+	}
 	d->dt.frame_map_first = first_frame;
 	d->dt.frame_map_len = n;
 	return(HTV_OK);
@@ -3035,10 +3057,11 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		cudaStreamSynchronize(st);
 		cudaStreamSynchronize(d->side);
 		cudaStreamSynchronize(d->side2);
+		cudaStreamSynchronize(d->side3);
 		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2);
 		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = NULL;
 		d->desc_cap = 0;
-		if(d->use_line) CK(cudaMalloc(&d->d_desc_r2, sizeof(LineR2) * ((size_t) nlines + 2)));
+		if(d->use_line) CK(cudaMalloc(&d->d_desc_r2, 2 * sizeof(LineR2) * ((size_t) nlines + 2)));
 		else CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
 		if(d->use_line || d->sec_line) CK(cudaMalloc(&d->d_desc_a2, 2 * sizeof(LineA2) * ((size_t) nlines + 1)));
 		else CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
@@ -3049,8 +3072,16 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 	{
 		// one persistent launch for the whole call: every CTA walks its own run of consecutive lines
 		const htv_dparams_t &dp = d->dp;
-		LineR2 *lr2 = (LineR2 *) d->d_desc_r2;
-		k_line_desc_r2<<<(nlines + 2 + 63) / 64, 64, 0, st>>>(dp, d->dt, lr2, line0, nlines);
+		LineR2 *lr2 = (LineR2 *) d->d_desc_r2 + (size_t) d->kl_buf * ((size_t) d->desc_cap + 2);
+		if(d->ahead && d->r2_armed)
+		{
+			// behind the frame map on side3 (htv_dev_set_frame_map); overlays were staged by the host before this call
+			k_line_desc_r2<<<(nlines + 2 + 63) / 64, 64, 0, d->side3>>>(dp, d->dt, lr2, line0, nlines);
+			CK(cudaEventRecord(d->ev_r2, d->side3));
+			CK(cudaStreamWaitEvent(st, d->ev_r2, 0));
+			d->r2_armed = 0;
+		}
+		else k_line_desc_r2<<<(nlines + 2 + 63) / 64, 64, 0, st>>>(dp, d->dt, lr2, line0, nlines);
 		if(!d->side_armed)
 		{
 			CK(cudaEventRecord(d->ev_in, st));
