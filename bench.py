@@ -244,6 +244,35 @@ def bind_to_gpu_numa(local):
     return None
 
 
+def prefer_gpu_memory_node(local):
+    """Pinned staging buffers on the NUMA node the GPU hangs off (sysfs numa_node of its PCI function), by a
+    MPOL_PREFERRED memory policy set before anything is allocated: DMA that crosses the socket link costs duplex
+    bandwidth. Returns what was found and done, for the e2e record; never raises."""
+    info = {}
+    try:
+        import ctypes
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        try:
+            with open("/sys/devices/system/node/online") as f:
+                info["nodes_online"] = f.read().strip()
+        except OSError:
+            pass
+        if node >= 0:
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            libc = ctypes.CDLL(None, use_errno=True)
+            r = libc.syscall(238, 1, ctypes.byref(mask), 1024)          # set_mempolicy(MPOL_PREFERRED, mask, maxnode)
+            info["mempolicy"] = "preferred node %d" % node if r == 0 else "set_mempolicy errno %d" % ctypes.get_errno()
+    except Exception as e:                                                # sysfs not there, not x86-64, ...
+        info["note"] = type(e).__name__
+    return info
+
+
 def device_resident(H, torch, mode, rate, filt, frames, steps, warmup, stream, clock_index=None, **kw):
     """K steps of `frames` frames each, rendered in calls of CHUNK_FRAMES into one device buffer; CUDA events."""
     enc = H.Encoder(H.mode_config(mode, vfilter=filt, **kw), rate)
@@ -354,7 +383,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
-    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
+    numa_cpus = bind_to_gpu_numa(local)
+    numa_mem = prefer_gpu_memory_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -427,7 +457,7 @@ def main():
                "frames_per_step": e2e_frames, "ms_per_step": round(1000 * e2e_s / args.steps, 3),
                "checksum": int(host[:4096].to(torch.int32).sum().item()),
                "api": "htv_av_memory_open (ring of 8 pinned pictures, every frame uploaded) + htv_render_host (C-ABI), pinned host buffers",
-               "numa_bound_cpus": numa_cpus}
+               "numa_bound_cpus": numa_cpus, "numa_memory": numa_mem}
         enc2.close()
 
     step_samples = nlines * width
@@ -452,7 +482,7 @@ def main():
             extra = {"configs": [
                 quick_config(H, torch, stream, "cfg1: -m pal -s 16000000 (baseband, real int16)", "pal", 16_000_000, False),
                 quick_config(H, torch, stream, "cfg3: -m m -s 13500000 --filter", "m", 13_500_000, True),
-                quick_config(H, torch, stream, "cfg4: -m l -s 16000000 --filter (SECAM)", "l", 16_000_000, True, frames=26, iters=5),
+                quick_config(H, torch, stream, "cfg4: -m l -s 16000000 --filter (SECAM)", "l", 16_000_000, True),
                 quick_config(H, torch, stream, "cfg5 (one channel): -m i -s 20000000 --filter", "i", 20_000_000, True)],
                 "dropin_cli": dropin_throughput()}
         per_line = 1.0 / NCU["lines"]

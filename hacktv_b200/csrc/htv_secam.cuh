@@ -454,13 +454,16 @@ k_sec_fm_list(const __grid_constant__ htv_dparams_t dp, const DevTables dt, cons
 		const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
 		int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
 		const int xs = sl & ~31;
+		// FM inputs are fetched two chunks ahead, their look-ups one chunk ahead of the recurrence
 		htv_c32_t m, mn;
 		m.i = m.q = mn.i = mn.q = 0;
+		int yn = 0, ynn = 0;
 		if(xs + lane >= sl && xs + lane < lim) m = dt.secam_fm_lut[max(dmin, min(dmax, (int) ss.yT[sec_t(ss, c, xs + lane)])) + 32768];
+		if(xs + 32 + lane < lim) yn = ss.yT[sec_t(ss, c, xs + 32 + lane)];
 		for(int xb = xs; xb < lim; xb += 32)
 		{
-			const int xn = xb + 32 + lane;
-			if(xn < lim) mn = dt.secam_fm_lut[max(dmin, min(dmax, (int) ss.yT[sec_t(ss, c, xn)])) + 32768];
+			if(xb + 64 + lane < lim) ynn = ss.yT[sec_t(ss, c, xb + 64 + lane)];
+			if(xb + 32 + lane < lim) mn = dt.secam_fm_lut[max(dmin, min(dmax, yn)) + 32768];
 			int ph = 0;
 			if(xb >= sl && xb + 32 <= lim)
 			{
@@ -488,7 +491,7 @@ k_sec_fm_list(const __grid_constant__ htv_dparams_t dp, const DevTables dt, cons
 				}
 			}
 			if(xb + lane < ck) ss.phT[sec_t(ss, c, xb + lane)] = ph;
-			m = mn;
+			m = mn; yn = ynn;
 		}
 		if(lane == 0)
 		{

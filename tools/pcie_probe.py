@@ -1,7 +1,12 @@
 """Host<->device copy bandwidth of this box (pinned memory), alone and in both directions at
 once: the ceiling for bench.py's e2e figure (164 MB D2H + 123 MB H2D per 64-frame step)."""
-import json
+import json, os, sys
 import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if "--numa" in sys.argv:
+    # as bench.py does before it allocates anything: cores and pinned pages next to the GPU
+    import bench
+    print(json.dumps({"numa_bound_cpus": bench.bind_to_gpu_numa(0), "numa_memory": bench.prefer_gpu_memory_node(0)}))
 
 n = 256 << 20
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -67,3 +72,20 @@ def both_small():
 t_h, t_d, t_b = wall(h2d_small), wall(d2h_pieces), wall(both_small)
 print(json.dumps({"h2d_64x1.9MB_ms": t_h * 1e3, "h2d_gbs": 64 * fb / t_h / 1e9, "d2h_7x24MB_ms": t_d * 1e3,
                   "d2h_gbs": 7 * (24 << 20) / t_d / 1e9, "both_ms": t_b * 1e3}))
+
+# round 2's pattern: the step's pictures in 8 contiguous uploads (15.4 MB each) beside the IQ in 8 MB pieces
+def h2d_runs():
+    with torch.cuda.stream(s1):
+        rb = 8 * fb
+        for i in range(8):
+            d_a[i * rb:(i + 1) * rb].copy_(h_in[i * rb:(i + 1) * rb], non_blocking=True)
+def d2h_8mb():
+    with torch.cuda.stream(s2):
+        pb = 8 << 20
+        for i in range(20):
+            h_out[i * pb:(i + 1) * pb].copy_(d_b[i * pb:(i + 1) * pb], non_blocking=True)
+def both_r2():
+    h2d_runs(); d2h_8mb()
+t_h, t_d, t_b = wall(h2d_runs), wall(d2h_8mb), wall(both_r2)
+print(json.dumps({"h2d_8x15.3MB_ms": t_h * 1e3, "d2h_20x8MB_ms": t_d * 1e3, "both_ms": t_b * 1e3,
+                  "floor_for_123MB_up_164MB_down_ms": 1e3 * max(t_h, t_d * 163.84 / 167.77, t_b * 163.84 / 167.77)}))
