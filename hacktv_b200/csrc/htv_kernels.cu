@@ -67,6 +67,7 @@ struct DevTables {
 	const uint64_t *fm_ang;
 	const float2 *fm_rot8;            // (cos, sin) of 8 steps of fm_ang (fused line kernel)
 	const uint32_t *notch_atab;       // SECAM luma notch as a tensor-core tap operand: [k-step][hi, lo][lane] x 4 registers
+	const uint32_t *sec_lpf_atab;     // SECAM baseband low-pass, one k-step: [hi, lo][lane] x 4 registers
 	const int32_t *afir_v, *afir_f;
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
@@ -185,10 +186,12 @@ struct htv_dev_t {
 	int line_threads;
 	void *d_desc_r, *d_desc_a;        // LineRaster[cap + 2], LineAudio[cap]
 	void *d_desc_r2, *d_desc_a2;      // LineR2[cap + 2], LineA2[cap] (fused line kernel)
+	void *d_desc_s2;                  // LineS2[cap + 3] (SECAM raster in the fused kernel's form)
 	int desc_cap;
 	// the fused line kernel (htv_line.cuh): PAL / NTSC / mono, AM or VSB, no resampler
 	int use_line, kl_threads, kl_ctas, kl_csat;
 	int sec_line;                     // SECAM: the modulator is the fused line kernel in its SRC form (composite rows from d_comp)
+	size_t ks_smem;                   // ... and the raster is k_sec_raster (0: k_raster_secam)
 	size_t kl_smem;
 	SecScratch sec;                   // SECAM scratch (same sub-batch rows as d_comp)
 	int sec_passes;
@@ -2460,6 +2463,7 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 }
 
 #include "htv_line.cuh"
+#include "htv_secam_raster.cuh"
 
 // ---------------------------------------------------------------------------
 // Device layer (C linkage)
@@ -2711,6 +2715,27 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			d->kl_smem = 2 * sizeof(LineA2) + 2 * sizeof(LineR2) + (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
 			d->sec_line = 1;
+			if(!(getenv("HTV_FIR") && !strcmp(getenv("HTV_FIR"), "scalar")))
+			{
+				uint32_t nt[MF_KSTEPS * 2 * 32 * 4];
+				for(int s3 = 0; s3 < MF_KSTEPS; s3++) for(int lo = 0; lo < 2; lo++) for(int lane = 0; lane < 32; lane++) for(int reg = 0; reg < 4; reg++)
+					nt[((s3 * 2 + lo) * 32 + lane) * 4 + reg] = mf_a_word(dp.secam_notch, s3, lane, reg, lo);
+				d->dt.notch_atab = (const uint32_t *) dev_copy(d, nt, sizeof(nt));
+			}
+			if(d->dt.notch_atab && dt.tmpl_out)
+			{
+				uint32_t ctab[256];
+				for(int lo = 0; lo < 2; lo++) for(int lane = 0; lane < 32; lane++) for(int reg = 0; reg < 4; reg++)
+					ctab[(lo * 32 + lane) * 4 + reg] = kl_chroma_a_word(dp.secam_lpf, 15, lane, reg, lo);
+				d->dt.sec_lpf_atab = (const uint32_t *) dev_copy(d, ctab, sizeof(ctab));
+				d->ks_smem = 2 * sizeof(LineS2) + 4 * rowb + 4 * uvb + sizeof(uint4) * (MF_KSTEPS * 2 * 32 + 64) + 64;
+				cudaFuncSetAttribute(k_sec_raster<true, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<true, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<true, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+			}
 			#define KL_ATTR2(VF, HQ, FU) do { \
 				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
 				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 320, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
@@ -2788,7 +2813,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			htv_dev_destroy(d);
 			return(NULL);
 		}
-		if(!(getenv("HTV_FIR") && !strcmp(getenv("HTV_FIR"), "scalar")))
+		if(!d->dt.notch_atab && !(getenv("HTV_FIR") && !strcmp(getenv("HTV_FIR"), "scalar")))
 		{
 			uint32_t nt[MF_KSTEPS * 2 * 32 * 4];
 			for(int s3 = 0; s3 < MF_KSTEPS; s3++) for(int lo = 0; lo < 2; lo++) for(int lane = 0; lane < 32; lane++) for(int reg = 0; reg < 4; reg++)
@@ -2832,7 +2857,7 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 	if(!d) return;
 	DevGuard guard(d->device);
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
-	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
+	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2); cudaFree(d->d_desc_s2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
 	if(d->h_ov_line) { cudaFreeHost(d->h_ov_line); cudaFreeHost(d->h_ov_meta); cudaFreeHost(d->h_ov_add); }
 	cudaFree(d->d_ov_line); cudaFree(d->d_ov_meta); cudaFree(d->d_ov_add);
@@ -3058,12 +3083,13 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		cudaStreamSynchronize(d->side);
 		cudaStreamSynchronize(d->side2);
 		cudaStreamSynchronize(d->side3);
-		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2);
-		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = NULL;
+		cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2); cudaFree(d->d_desc_s2);
+		d->d_desc_r = d->d_desc_a = d->d_desc_r2 = d->d_desc_a2 = d->d_desc_s2 = NULL;
 		d->desc_cap = 0;
 		if(d->use_line) CK(cudaMalloc(&d->d_desc_r2, 2 * sizeof(LineR2) * ((size_t) nlines + 2)));
 		else CK(cudaMalloc(&d->d_desc_r, sizeof(LineRaster) * ((size_t) nlines + 3)));
 		if(d->use_line || d->sec_line) CK(cudaMalloc(&d->d_desc_a2, 2 * sizeof(LineA2) * ((size_t) nlines + 1)));
+		if(d->ks_smem) CK(cudaMalloc(&d->d_desc_s2, sizeof(LineS2) * ((size_t) nlines + 3)));
 		else CK(cudaMalloc(&d->d_desc_a, sizeof(LineAudio) * ((size_t) nlines + 1)));
 		d->desc_cap = nlines;
 	}
@@ -3168,7 +3194,25 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		{
 			// rows 0 .. n+2 <-> lines first-2 .. first+n; the chain covers rows 0 .. n+1
 			const LineRaster *lr = ld.r + done - 1;
-			k_raster_secam<<<n + 3, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec);
+			if(d->ks_smem)
+			{
+				// rows 0 .. n+2: their own compact descriptors, then runs of rows per persistent CTA
+				LineS2 *ls = (LineS2 *) d->d_desc_s2;
+				const int nr = n + 3;
+				k_line_desc_s2<<<(nr + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ls, line0 + done - 2, nr);
+				int run = (nr + d->kl_ctas - 1) / d->kl_ctas;
+				if(run < 4) run = 4;
+				const int grid = (nr + run - 1) / run;
+				const bool full = d->dp.W % MF_TILE == 0;
+				#define KS_GO(FU) do { \
+					if(d->kl_threads <= 256) k_sec_raster<FU, 256, 4><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
+					else if(d->kl_threads <= 320) k_sec_raster<FU, 320, 3><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
+					else k_sec_raster<FU, 384, 2><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); } while(0)
+				if(full) KS_GO(true); else KS_GO(false);
+				#undef KS_GO
+				d->launches++;
+			}
+			else k_raster_secam<<<n + 3, d->line_threads, d->raster_smem, st>>>(d->dp, d->dt, lr, d->d_comp, d->sec);
 			// the chain (htv_secam.cuh): pass 0 over every line, the predictor, then refinement passes until no line's
 			// outgoing state changes - at that fixed point every line was computed from its true predecessor state =
 			// the sequential result. The loop needs the change count on the host, so SECAM launches synchronise.
