@@ -68,6 +68,7 @@ struct DevTables {
 	const float2 *fm_rot8;            // (cos, sin) of 8 steps of fm_ang (fused line kernel)
 	const uint32_t *notch_atab;       // SECAM luma notch as a tensor-core tap operand: [k-step][hi, lo][lane] x 4 registers
 	const uint32_t *sec_lpf_atab;     // SECAM baseband low-pass, one k-step: [hi, lo][lane] x 4 registers
+	const int16_t *sec_win;           // burst window by sample of the line (0 outside the subcarrier range), W rounded up to 8
 	const int32_t *afir_v, *afir_f;
 	const int16_t *lim_shape;
 	const int16_t *nicam_taps;
@@ -2793,6 +2794,17 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		const size_t rows = (size_t) d->sub_lines + 3;
 		const size_t groups = (size_t) (W + 2 + 7) / 8 + 1;
 		d->sec.rows = (int) rows;
+		{
+			// the subcarrier's window indexed by line sample, so that k_sec_out loads 8 entries at a time
+			const int W8 = (W + 7) & ~7;
+			int16_t *w = (int16_t *) calloc((size_t) W8, sizeof(int16_t));
+			if(w && t->burst_win)
+			{
+				for(int x = dp.burst_left; x < W && x - dp.burst_left < t->burst_width; x++) w[x] = t->burst_win[x - dp.burst_left];
+				d->dt.sec_win = (const int16_t *) dev_copy(d, w, sizeof(int16_t) * W8);
+			}
+			free(w);
+		}
 		d->sec.cbT = (int16_t *) dev_zero(d, sizeof(int16_t) * groups * rows * 8);
 		d->sec.tail = (int *) dev_zero(d, sizeof(int) * rows * SEC_TAIL);
 		d->sec.st[0] = (SecState *) dev_zero(d, sizeof(SecState) * rows);
@@ -3220,7 +3232,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			cudaEvent_t dbg0 = NULL, dbg1 = NULL;
 			const bool dbg = getenv("HTV_DEBUG") != NULL;
 			if(dbg) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, st); }
-			int pass = 0, changed = 1;
+			int pass = 0, changed = 1, repredict = 2;
 			for(; pass <= d->sec_passes && changed; pass++)
 			{
 				int fl[4];
@@ -3236,7 +3248,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				}
 				k_sec_refine<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, nch, pass);
 				k_sec_fm_list<<<512, 32 * SEC_LIST_WARPS, 0, st>>>(d->dp, d->dt, lr, d->sec, pass);
-				d->launches += 2;
+				k_sec_fm_list_t<<<nb, 32, 0, st>>>(d->dp, d->dt, lr, d->sec, pass);
+				d->launches += 3;
 				CK(cudaMemcpyAsync(fl, d->sec.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
 				changed = fl[0];
@@ -3245,6 +3258,16 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 					float ms = 0;
 					cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1); cudaEventElapsedTime(&ms, dbg0, dbg1);
 					fprintf(stderr, "secam pass %d: recomputed %d (FM in full: %d), output changed %d, cumulative %.3f ms\n", pass, fl[2], fl[3], fl[0], ms);
+				}
+				if(changed && fl[3] > 64 && repredict > 0)
+				{
+					// many lines had their FM recurrence re-run: their A, B moved, and plain iteration would carry that down
+					// the lines at 3x per pass - propose again from the new checkpoints (the pass's outputs go to st[0] first)
+					repredict--;
+					if(pass & 1) cudaMemcpyAsync(d->sec.st[0], d->sec.st[1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
+					k_sec_predict<<<(nch + SEC_PRED_T - SEC_PRED_HALO - 1) / (SEC_PRED_T - SEC_PRED_HALO), SEC_PRED_T, 0, st>>>(d->dp, d->dt, lr, d->sec, nch);
+					if(!(pass & 1)) cudaMemcpyAsync(d->sec.st[0], d->sec.st[1], sizeof(SecState) * nch, cudaMemcpyDeviceToDevice, st);
+					d->launches++;
 				}
 			}
 			if(changed)

@@ -438,11 +438,13 @@ k_sec_refine(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 // next 32 samples while all lanes step through the current 32 (the entries arrive by shuffle), so a step costs the
 // recurrence's own latency and nothing else.
 #define SEC_LIST_WARPS 4
+#define SEC_LIST_MANY 2048             // above this many lines a thread per line has the better throughput (k_sec_fm_list_t)
 __global__ void __launch_bounds__(32 * SEC_LIST_WARPS)
 k_sec_fm_list(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int pass)
 {
 	const int lane = threadIdx.x & 31;
 	const int nw = gridDim.x * SEC_LIST_WARPS, count = ss.flags[3];
+	if(count > SEC_LIST_MANY) return;                                       // a long list: k_sec_fm_list_t
 	const int W = dp.W, ck = sec_ck(W), sl = dp.burst_left;
 	const SecState *prev = ss.st[(pass + 1) & 1];
 	SecState *cur = ss.st[pass & 1];
@@ -506,6 +508,47 @@ k_sec_fm_list(const __grid_constant__ htv_dparams_t dp, const DevTables dt, cons
 	}
 }
 
+// A long work list (low sample rates put more FM inputs within reach of the corrected IIR state; noise pictures too):
+// one THREAD per listed line, 32 listed lines per warp - pass 0's arrangement, on the compacted list. FM inputs are
+// loaded two groups ahead, their look-ups issued one group ahead of the recurrence.
+__global__ void __launch_bounds__(32)
+k_sec_fm_list_t(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineRaster *lr, SecScratch ss, int pass)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int count = ss.flags[3];
+	if(count <= SEC_LIST_MANY || i >= count) return;
+	const int c = ss.list[i];
+	const int W = dp.W, ck = sec_ck(W), G0 = ck >> 3;
+	const LineRaster &li = lr[c];
+	const SecState *prev = ss.st[(pass + 1) & 1];
+	SecState *cur = ss.st[pass & 1];
+	const int sl = dp.burst_left, sr = li.sec_sr, lim = min(sr, ck);
+	const int dmin = dp.secam_dmin[li.sec_dr], dmax = dp.secam_dmax[li.sec_dr];
+	int pi = li.sec_sign > 0 ? 2147483647 : -2147483647, pq = 0;
+	const int4 *yp = reinterpret_cast<const int4 *>(ss.yT) + c;
+	const int g0 = sl >> 3, ge = min((lim + 7) >> 3, G0);
+	htv_c32_t m[8];
+	int4 yn = make_int4(0, 0, 0, 0);
+	if(g0 < ge) sec_gather8(dt, yp[(size_t) g0 * ss.rows], dmin, dmax, m);
+	if(g0 + 1 < ge) yn = yp[(size_t) (g0 + 1) * ss.rows];
+	for(int g = g0; g < ge; g++)
+	{
+		const int4 ynn = g + 2 < ge ? yp[(size_t) (g + 2) * ss.rows] : make_int4(0, 0, 0, 0);
+		htv_c32_t mn[8];
+		if(g + 1 < ge) sec_gather8(dt, yn, dmin, dmax, mn);
+		sec_fm8(ss, c, g << 3, sl, lim, m, pi, pq);
+		#pragma unroll
+		for(int k = 0; k < 8; k++) m[k] = mn[k];
+		yn = ynn;
+	}
+	SecChk k4 = ss.chk[c];
+	k4.pi = pi; k4.pq = pq; k4.valid = ck < sr;
+	ss.chk[c] = k4;
+	const SecState out = sec_tail(dp, dt, li, ss, c, ss.used[c], k4, true);
+	cur[c] = ss.outc[c] = out;
+	if(!sec_same(out, prev[c])) atomicAdd(ss.flags, 1);
+}
+
 // carry for the next launch: the state after chain row `idx` of the final pass (rows without a subcarrier pass it on)
 __global__ void k_sec_carry(const LineRaster *lr, SecScratch ss, int idx, int pass_final)
 {
@@ -546,11 +589,21 @@ k_sec_out(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 				const int4 *pp = reinterpret_cast<const int4 *>(ss.phT + sec_t(ss, c, xb));
 				const int4 p0 = pp[0], p1 = pp[1];
 				const int ph[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
-				#pragma unroll
-				for(int k = 0; k < 8; k++)
+				int w[8];
+				sec_unpack8(*reinterpret_cast<const int4 *>(dt.sec_win + xb), w);
+				if(xb >= sl && xb + 8 <= top)
 				{
-					const int x = xb + k;
-					if(x >= sl && x < top) o[k] = (short) ((sec_out(dp, dt, ph[k], max(dmin, min(dmax, s[k]))) * dt.burst_win[x - sl]) >> 15);
+					#pragma unroll
+					for(int k = 0; k < 8; k++) o[k] = (short) ((sec_out(dp, dt, ph[k], max(dmin, min(dmax, s[k]))) * w[k]) >> 15);
+				}
+				else
+				{
+					#pragma unroll
+					for(int k = 0; k < 8; k++)
+					{
+						const int x = xb + k;
+						if(x >= sl && x < top) o[k] = (short) ((sec_out(dp, dt, ph[k], max(dmin, min(dmax, s[k]))) * w[k]) >> 15);
+					}
 				}
 				any[l] = 1;
 			}
