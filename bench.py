@@ -170,7 +170,7 @@ def bench_reference(args, rank, world):
     mode, rate, filt, workload = WORKLOADS[args.workload]
     cores = cpu_budget()
     if not os.path.exists(REF_HARNESS):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness was not built (no reference tree at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_harness was not built (no reference tree at build time)"})
         return
     # one reference encoder = main + video-filter + audio thread and cannot use more: as many encoders as fit the
     # threads this process may use (affinity mask and cgroup quota, not the machine's core count)
@@ -188,7 +188,7 @@ def bench_reference(args, rank, world):
     v = sum(vals) / len(vals)
     pers.sort()
     sample = f"{ninst} concurrent reference encoders x {frames} frames ({frames * 625 * (rate // 15625) / 1e6:.1f} Msamples each) per step, vid_next_line loop, no sink I/O"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "IQ Msamples/s", "value": round(v, 3), "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1000 * t / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -199,7 +199,7 @@ def bench_reference(args, rank, world):
                          "single_encoder_alone_msamples_per_s": round(single, 2)},
         "e2e": {"value": round(v, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def channel_of_rank(rank, world, nchannels):
@@ -352,7 +352,27 @@ def dropin_throughput(seconds=4.0):
     return out
 
 
+_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version line at the first
+    collective when NCCL_DEBUG=VERSION): everything but the result goes to stderr."""
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _STDOUT is not None:
+        os.dup2(_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -486,7 +506,7 @@ def main():
                 quick_config(H, torch, stream, "cfg5 (one channel): -m i -s 20000000 --filter", "i", 20_000_000, True)],
                 "dropin_cli": dropin_throughput()}
         per_line = 1.0 / NCU["lines"]
-        print(json.dumps({
+        emit({
             "metric": "IQ Msamples/s", "value": round(value, 2), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
@@ -513,7 +533,7 @@ def main():
             "clocks": clocks,
             "checksum": checksum,
             "extra": extra,
-        }))
+        })
 
     if world > 1:
         dist.destroy_process_group()
