@@ -45,6 +45,11 @@ CASES = [
     ("i", 16000000, 700, dict(vfilter=True, swap_iq=True, offset=1500000), 2),
     ("l", 16000000, 700, dict(vfilter=True, nocolour=True), 1),      # AM sound + NICAM through the fused kernel
     ("i", 14000000, 700, dict(vfilter=True), 1),                     # W = 896
+    # SECAM: k_sec_raster + chain + k_line<SRC> against round 1's raster (k_raster_secam) + scalar modulator (k_mod)
+    ("l", 16000000, 1300, dict(vfilter=True), 1),                    # BASELINE config 4
+    ("l", 13500000, 900, dict(vfilter=True), 1),                     # W = 864: partial last tile, long FM work list
+    ("secam", 16000000, 900, dict(), 0),                             # baseband: chroma chain only, bit-exact
+    ("d", 20000000, 700, dict(vfilter=True), 1),                     # W = 1280, FM sound
 ]
 
 
@@ -61,6 +66,38 @@ def test_fused_equals_split_and_oracle(built, mode, rate, nlines, kw, tol):
     o = orc.Oracle(H.mode_config(mode, **kw), rate); o.open_test_source()
     want = o.render(nlines); o.close()
     assert np.abs(fused.astype(np.int32) - want.astype(np.int32)).max() <= tol
+
+
+def test_secam_scalar_notch_equals_tensor_core_notch(built):
+    """HTV_FIR=scalar keeps round 1's raster with the scalar luma notch; the default rasters with k_sec_raster (notch and
+    baseband low-pass as int8 contractions). Bit-identical on the baseband mode, where no NCO contributes."""
+    H = built
+    a = _render(H, None, "secam", 16000000, [1000])
+    old = os.environ.get("HTV_FIR")
+    os.environ["HTV_FIR"] = "scalar"
+    try:
+        b = _render(H, "split", "secam", 16000000, [1000])
+    finally:
+        if old is None:
+            os.environ.pop("HTV_FIR", None)
+        else:
+            os.environ["HTV_FIR"] = old
+    assert np.array_equal(a, b)
+
+
+def test_secam_runs_and_calls_are_invisible(built):
+    """SECAM: the chain's state (IIR, aliased words) is carried across calls of any size; a persistent raster CTA walks
+    a run of rows. Random pictures put many lines on the FM work list."""
+    H = built
+    rng = np.random.default_rng(5)
+    e = H.Encoder(H.mode_config("l", vfilter=True), 16000000); al, aw = e.active_lines, e.active_width; e.close()
+    frames = rng.integers(0, 1 << 24, size=(4, al, aw), dtype=np.uint32)
+    whole = _render(H, None, "l", 16000000, [2600], frames=frames, vfilter=True)
+    parts = _render(H, None, "l", 16000000, [1, 2, 311, 1000, 625, 661], frames=frames, vfilter=True)
+    assert np.array_equal(whole, parts)
+    split = _render(H, "split", "l", 16000000, [2600], frames=frames, vfilter=True)
+    d = np.abs(whole.astype(np.int32) - split.astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 0.01, (d.max(), (d != 0).mean())
 
 
 def test_runs_and_calls_are_invisible(built):
