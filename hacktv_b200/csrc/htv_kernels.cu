@@ -2868,6 +2868,8 @@ extern "C" void htv_dev_destroy(htv_dev_t *d)
 {
 	if(!d) return;
 	DevGuard guard(d->device);
+	// the side streams may still be ahead of the caller's; nothing of this encoder is freed under running work
+	cudaDeviceSynchronize();
 	for(int i = 0; i < d->nalloc; i++) cudaFree(d->alloc[i]);
 	cudaFree(d->d_desc_r); cudaFree(d->d_desc_a); cudaFree(d->d_desc_r2); cudaFree(d->d_desc_a2); cudaFree(d->d_desc_s2); cudaFree(d->d_comp); cudaFree(d->d_comp32); cudaFree(d->d_planes);
 	if(d->h_map) cudaFreeHost(d->h_map);
