@@ -1114,11 +1114,43 @@ k_line_desc_a2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, Lin
 }
 
 // raster descriptors: index -1 .. nlines+1 <-> line line0-2 .. line0+nlines
-__global__ void k_line_desc_r(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines)
+// SECAM raster in the fused kernel's form (k_sec_raster, htv_secam_raster.cuh): what it needs to know about a line
+struct __align__(16) LineS2 {
+	int valid;                        // 0: before the stream
+	int tmpl;                         // row of the line templates
+	int al, ar;                       // active sample range [al, ar), -1 if none
+	int keep;                         // the template's keep part is non-zero somewhere
+	int sec_proc, sec_dr;             // the line carries a subcarrier; 1: D'r line (uses v), 0: D'b (uses u)
+	int sec_prev_kind;                // what the line-average store holds: 0 zeros, 1 black, 2 a picture row
+	int sec_prev_comp;                // ... and which component of it: 1 u, 2 v
+	int pad0, pad1, pad2;
+	long long row_off;                // pixel offset of the source row in the frame store, -1 = black
+	long long sec_prev_row;           // pixel offset of the stored row
+};
+static_assert(sizeof(LineS2) == 64, "LineS2 is read as four int4");
+
+// the compact descriptor of line L from its full one (written by k_line_desc_r, which describes the same lines for the chain)
+__device__ __forceinline__ void line_s2(const htv_dparams_t &dp, const DevTables &dt, int64_t L, const LineRaster &li, LineS2 &out)
+{
+	LineS2 o;
+	o.valid = li.valid;
+	o.tmpl = L < 0 ? dp.lines + 1 : (L == 0 ? dp.lines : li.line - 1);
+	o.al = li.al; o.ar = li.ar;
+	o.keep = dt.tmpl_keep_any[o.tmpl];
+	o.sec_proc = li.sec_proc; o.sec_dr = li.sec_dr;
+	o.sec_prev_kind = li.sec_prev_kind; o.sec_prev_comp = li.sec_prev_comp;
+	o.pad0 = o.pad1 = o.pad2 = 0;
+	o.row_off = li.row_off; o.sec_prev_row = li.sec_prev_row;
+	out = o;
+}
+
+// s2 (SECAM with k_sec_raster): the same lines once more in that kernel's compact form, s2[i] <-> line line0 - 2 + i
+__global__ void k_line_desc_r(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineDescs ld, int64_t line0, int nlines, LineS2 *s2)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= nlines + 3) return;
 	line_raster(dp, dt, line0 - 2 + i, ld.r[i - 1]);
+	if(s2) line_s2(dp, dt, line0 - 2 + i, ld.r[i - 1], s2[i]);
 }
 
 // the same for the fused line kernel (htv_line.cuh): compact descriptors, index 0 .. nlines+1 <-> line line0-1 .. line0+nlines
@@ -3172,7 +3204,7 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		CK(cudaGetLastError());
 		return(HTV_OK);
 	}
-	k_line_desc_r<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines);
+	k_line_desc_r<<<(nlines + 3 + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ld, line0, nlines, d->ks_smem ? (LineS2 *) d->d_desc_s2 : NULL);
 	if(!d->side_armed)
 	{
 		CK(cudaEventRecord(d->ev_in, st));
@@ -3211,9 +3243,8 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			if(d->ks_smem)
 			{
 				// rows 0 .. n+2: their own compact descriptors, then runs of rows per persistent CTA
-				LineS2 *ls = (LineS2 *) d->d_desc_s2;
+				const LineS2 *ls = (const LineS2 *) d->d_desc_s2 + done;
 				const int nr = n + 3;
-				k_line_desc_s2<<<(nr + 63) / 64, 64, 0, st>>>(d->dp, d->dt, ls, line0 + done - 2, nr);
 				int run = (nr + d->kl_ctas - 1) / d->kl_ctas;
 				if(run < 4) run = 4;
 				const int grid = (nr + run - 1) / run;
@@ -3428,7 +3459,7 @@ extern "C" int htv_dev_render_lines_rs(htv_dev_t *d, htv_dev_t *r, int64_t line0
 	// the emitted line t is resampled line t + 1 and the video filter looks into t + 2)
 	LineDescs ldr = { (LineRaster *) r->d_desc_r + 1, (LineAudio *) r->d_desc_a };
 	LineDescs lda = { (LineRaster *) d->d_desc_r + 1, (LineAudio *) d->d_desc_a };
-	k_line_desc_r<<<(nlines + 4 + 63) / 64, 64, 0, st>>>(r->dp, r->dt, ldr, line0, nlines + 1);
+	k_line_desc_r<<<(nlines + 4 + 63) / 64, 64, 0, st>>>(r->dp, r->dt, ldr, line0, nlines + 1, NULL);
 	if(!d->side_armed)
 	{
 		CK(cudaEventRecord(d->ev_in, st));

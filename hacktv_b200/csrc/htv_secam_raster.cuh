@@ -10,40 +10,6 @@
 // Outputs as before: composite rows (int16, luma only - k_sec_out adds the subcarrier), the baseband in the chain's
 // transposed layout, the raw sums of the last 7 low-pass outputs.
 
-struct __align__(16) LineS2 {
-	int valid;                        // 0: before the stream
-	int tmpl;                         // row of the line templates
-	int al, ar;                       // active sample range [al, ar), -1 if none
-	int keep;                         // the template's keep part is non-zero somewhere
-	int sec_proc, sec_dr;             // the line carries a subcarrier; 1: D'r line (uses v), 0: D'b (uses u)
-	int sec_prev_kind;                // what the line-average store holds: 0 zeros, 1 black, 2 a picture row
-	int sec_prev_comp;                // ... and which component of it: 1 u, 2 v
-	int pad0, pad1, pad2;
-	long long row_off;                // pixel offset of the source row in the frame store, -1 = black
-	long long sec_prev_row;           // pixel offset of the stored row
-};
-static_assert(sizeof(LineS2) == 64, "LineS2 is read as four int4");
-
-// descriptors for rows 0 .. n-1 <-> lines first .. first+n-1 (the same lines k_line_desc_r describes for the chain)
-__global__ void k_line_desc_s2(const __grid_constant__ htv_dparams_t dp, const DevTables dt, LineS2 *out, int64_t first, int n)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= n) return;
-	const int64_t L = first + i;
-	LineRaster li;
-	line_raster(dp, dt, L, li);
-	LineS2 o;
-	o.valid = li.valid;
-	o.tmpl = L < 0 ? dp.lines + 1 : (L == 0 ? dp.lines : li.line - 1);
-	o.al = li.al; o.ar = li.ar;
-	o.keep = dt.tmpl_keep_any[o.tmpl];
-	o.sec_proc = li.sec_proc; o.sec_dr = li.sec_dr;
-	o.sec_prev_kind = li.sec_prev_kind; o.sec_prev_comp = li.sec_prev_comp;
-	o.pad0 = o.pad1 = o.pad2 = 0;
-	o.row_off = li.row_off; o.sec_prev_row = li.sec_prev_row;
-	out[i] = o;
-}
-
 template<bool FULL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_sec_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineS2 *ls, int nrows, int run, int16_t *comp, SecScratch ss)
