@@ -50,6 +50,9 @@ CASES = [
     ("l", 13500000, 900, dict(vfilter=True), 1),                     # W = 864: partial last tile, long FM work list
     ("secam", 16000000, 900, dict(), 0),                             # baseband: chroma chain only, bit-exact
     ("d", 20000000, 700, dict(vfilter=True), 1),                     # W = 1280, FM sound
+    ("secam", 15109375, 700, dict(), 0),                             # W = 967: 8 does not divide W (chain tail of 7, scalar row ends)
+    ("secam", 15218750, 700, dict(), 0),                             # W = 974: chain tail of 14 samples over two groups
+    ("l", 14062500, 700, dict(vfilter=True), 1),                     # W = 900: 4 | W only
 ]
 
 
