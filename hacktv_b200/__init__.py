@@ -21,7 +21,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhacktv_b200.so")
+# HTV_LIB: another build of the same library (A/B runs of compile-time variants, tools/occ_ab.sh)
+LIB_PATH = os.environ.get("HTV_LIB") or os.path.join(_HERE, "libhacktv_b200.so")
 
 HTV_OK, HTV_ERROR, HTV_OUT_OF_MEMORY = 0, -1, -2
 

@@ -2495,6 +2495,18 @@ k_mod_mma(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const Li
 	}
 }
 
+// resident CTAs per SM of the persistent line kernels, by CTA size (256 / 320 / 384 threads <-> W <= 1024 / 1280 / 1536).
+// tools/occ_ab.sh builds and times the alternatives: 5 or 6 CTAs of 256 threads (48 / 40 registers) are 3 % / 10 % slower
+// than 4 (62 registers) - the compiler pays for the registers with instructions - while 4 CTAs of 320 threads beat 3.
+#ifndef KL_B256
+#define KL_B256 4
+#endif
+#ifndef KL_B320
+#define KL_B320 4                     // 48 registers, no spills; measured against 3 (64 registers): 0.504 -> 0.481 ms per 64 frames at W = 1280
+#endif
+#ifndef KL_B384
+#define KL_B384 2
+#endif
 #include "htv_line.cuh"
 #include "htv_secam_raster.cuh"
 
@@ -2743,7 +2755,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 		{
 			const int T = mf_tiles(W);
 			d->kl_threads = 32 * T;
-			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : (d->kl_threads <= 320 ? 3 : 2));
+			d->kl_ctas = nsm * (d->kl_threads <= 256 ? KL_B256 : (d->kl_threads <= 320 ? KL_B320 : KL_B384));
 			const size_t rowb = (size_t) mf_row_bytes(W) + 16, uvb = (size_t) MF_TILE * T + 32;
 			d->kl_smem = 2 * sizeof(LineA2) + 2 * sizeof(LineR2) + (dp.vf_type ? 6 * rowb + sizeof(uint32_t) * MF_ATAB_WORDS : 0) + 4 * uvb + 1024 +
 				sizeof(short) * ((dp.nicam_tpad_len + 7) & ~7) + 128;
@@ -2762,17 +2774,17 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 					ctab[(lo * 32 + lane) * 4 + reg] = kl_chroma_a_word(dp.secam_lpf, 15, lane, reg, lo);
 				d->dt.sec_lpf_atab = (const uint32_t *) dev_copy(d, ctab, sizeof(ctab));
 				d->ks_smem = 2 * sizeof(LineS2) + 4 * rowb + 4 * uvb + sizeof(uint4) * (MF_KSTEPS * 2 * 32 + 64) + 64;
-				cudaFuncSetAttribute(k_sec_raster<true, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
-				cudaFuncSetAttribute(k_sec_raster<false, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
-				cudaFuncSetAttribute(k_sec_raster<true, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
-				cudaFuncSetAttribute(k_sec_raster<false, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
-				cudaFuncSetAttribute(k_sec_raster<true, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
-				cudaFuncSetAttribute(k_sec_raster<false, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<true, 256, KL_B256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 256, KL_B256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<true, 320, KL_B320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 320, KL_B320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<true, 384, KL_B384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
+				cudaFuncSetAttribute(k_sec_raster<false, 384, KL_B384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->ks_smem);
 			}
 			#define KL_ATTR2(VF, HQ, FU) do { \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 320, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 384, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 256, KL_B256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 320, KL_B320, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, false, 384, KL_B384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
 			KL_ATTR2(false, false, true); KL_ATTR2(false, false, false); KL_ATTR2(true, false, true); KL_ATTR2(true, false, false);
 			KL_ATTR2(true, true, true); KL_ATTR2(true, true, false);
 			#undef KL_ATTR2
@@ -2793,7 +2805,7 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
 			const int T = mf_tiles(W);
 			d->kl_threads = 32 * T;
-			d->kl_ctas = nsm * (d->kl_threads <= 256 ? 4 : (d->kl_threads <= 320 ? 3 : 2));
+			d->kl_ctas = nsm * (d->kl_threads <= 256 ? KL_B256 : (d->kl_threads <= 320 ? KL_B320 : KL_B384));
 			if(dp.colour_mode != HTV_MONOCHROME)
 			{
 				uint32_t ctab[256];
@@ -2812,9 +2824,9 @@ extern "C" htv_dev_t *htv_dev_create(const struct htv_tables_t *t, int max_frame
 				d->kl_csat = sum > 32768;
 			}
 			#define KL_ATTR2(VF, HQ, FU, CS) do { \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
-				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 256, KL_B256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 320, KL_B320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); \
+				cudaFuncSetAttribute(k_line<VF, HQ, FU, CS, 384, KL_B384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) d->kl_smem); } while(0)
 			#define KL_ATTR(VF, HQ) do { KL_ATTR2(VF, HQ, true, false); KL_ATTR2(VF, HQ, false, false); KL_ATTR2(VF, HQ, false, true); } while(0)
 			KL_ATTR(false, false); KL_ATTR(true, false); KL_ATTR(true, true);
 			#undef KL_ATTR
@@ -3184,9 +3196,9 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 		const int grid = (nlines + run - 1) / run;
 		if(d->timing) cudaEventRecord(d->ev0, st);
 		#define KL_GO2(VF, HQ, FU, CS) do { \
-			if(d->kl_threads <= 256) k_line<VF, HQ, FU, CS, 256, 4><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
-			else if(d->kl_threads <= 320) k_line<VF, HQ, FU, CS, 320, 3><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
-			else k_line<VF, HQ, FU, CS, 384, 2><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
+			if(d->kl_threads <= 256) k_line<VF, HQ, FU, CS, 256, KL_B256><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
+			else if(d->kl_threads <= 320) k_line<VF, HQ, FU, CS, 320, KL_B320><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); \
+			else k_line<VF, HQ, FU, CS, 384, KL_B384><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, lr2, la2, nlines, run, d_out, d_acc, d_acc ? acc_lines : 0); } while(0)
 		// the common case (128 | W, a chroma filter that cannot overflow) gets its own instantiation; everything else the general one
 		#define KL_GO(VF, HQ) do { if(dp.W % MF_TILE == 0 && !d->kl_csat) KL_GO2(VF, HQ, true, false); \
 			else if(!d->kl_csat) KL_GO2(VF, HQ, false, false); else KL_GO2(VF, HQ, false, true); } while(0)
@@ -3250,9 +3262,9 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 				const int grid = (nr + run - 1) / run;
 				const bool full = d->dp.W % MF_TILE == 0;
 				#define KS_GO(FU) do { \
-					if(d->kl_threads <= 256) k_sec_raster<FU, 256, 4><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
-					else if(d->kl_threads <= 320) k_sec_raster<FU, 320, 3><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
-					else k_sec_raster<FU, 384, 2><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); } while(0)
+					if(d->kl_threads <= 256) k_sec_raster<FU, 256, KL_B256><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
+					else if(d->kl_threads <= 320) k_sec_raster<FU, 320, KL_B320><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); \
+					else k_sec_raster<FU, 384, KL_B384><<<grid, d->kl_threads, d->ks_smem, st>>>(d->dp, d->dt, ls, nr, run, d->d_comp, d->sec); } while(0)
 				if(full) KS_GO(true); else KS_GO(false);
 				#undef KS_GO
 				d->launches++;
@@ -3352,9 +3364,9 @@ extern "C" int htv_dev_render_lines(htv_dev_t *d, int64_t line0, int nlines, int
 			if(run < 4) run = 4;
 			const int grid = (n + run - 1) / run;
 			#define KL_GO2(VF, HQ, FU) do { \
-				if(d->kl_threads <= 256) k_line<VF, HQ, FU, false, 256, 4, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
-				else if(d->kl_threads <= 320) k_line<VF, HQ, FU, false, 320, 3, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
-				else k_line<VF, HQ, FU, false, 384, 2, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); } while(0)
+				if(d->kl_threads <= 256) k_line<VF, HQ, FU, false, 256, KL_B256, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
+				else if(d->kl_threads <= 320) k_line<VF, HQ, FU, false, 320, KL_B320, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); \
+				else k_line<VF, HQ, FU, false, 384, KL_B384, true><<<grid, d->kl_threads, d->kl_smem, st>>>(dp, d->dt, NULL, la2 + done, n, run, o, acc, acc_rows, d->d_comp); } while(0)
 			#define KL_GO(VF, HQ) do { if(dp.W % MF_TILE == 0) KL_GO2(VF, HQ, true); else KL_GO2(VF, HQ, false); } while(0)
 			if(!dp.vf_type) KL_GO(false, false);
 			else if(dp.vf_type == 3) KL_GO(true, true);
