@@ -262,7 +262,8 @@ def prefer_gpu_memory_node(local):
                 info["nodes_online"] = f.read().strip()
         except OSError:
             pass
-        if node >= 0:
+        import platform
+        if node >= 0 and platform.machine() == "x86_64":              # the syscall number below is x86-64's
             mask = (ctypes.c_ulong * 16)()
             mask[node // 64] = 1 << (node % 64)
             libc = ctypes.CDLL(None, use_errno=True)
