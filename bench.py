@@ -50,7 +50,7 @@ REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 REF_THREADS = 3          # main/raster + vfilter + audio (reference video.c:4692: 1 + nthreads)
 # From the ncu --set full capture of the shipped k_line (profiles/r02_summary.md), per scan line of 1024 samples:
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 40 000 lines, and the issue-slot figures.
-NCU = {"file": "profiles/r02_ncu_k_line_raw.txt", "lines": 40000, "dram_read": 47_766_784, "dram_write": 110_873_600,
+NCU = {"file": "profiles/r02_ncu_k_line_raw.txt", "lines": 40000, "dram_read": 47_632_128, "dram_write": 113_646_080,
        "warp_instructions": 238_153_871, "issue_active_pct": 61.8}
 KERNEL = "k_line (fused line kernel: raster + chroma and video filters on the tensor cores + sound carriers + IQ store)"
 
