@@ -19,29 +19,14 @@
 // samples between a lane's values are still sector-exact (8 lanes x 4 bytes = one 32-byte sector).
 
 #define KL_LEAD   MF_LEAD   // composite row: byte i = sample i - 32 of the line (htv_mma_fir.h pitched row)
-#define KL_UVLEAD 8         // chroma planes: byte i = sample i - 8
+#define KL_UVLEAD MF_LP_LEAD // chroma planes: byte i = sample i - 8
 #define KL_BIAS   2048      // NICAM pulse-table index bias (LineAudio.symb)
 
 __device__ __forceinline__ int kl_row_bytes(int W) { return(mf_row_bytes(W) + 16); }
 __device__ __forceinline__ int kl_uv_bytes(int W) { return(MF_TILE * mf_tiles(W) + 32); }
 
-// tap operand of the chroma low-pass (one k-step of 32): out[x] = sum_y u[x - h + y] tap[y], stream window byte 0 =
-// sample -8: A[m][k'] = tap[k' - m - (8 - h)]. Same fragment convention as mf_a_word (htv_mma_fir.h).
-__host__ __device__ inline uint32_t kl_chroma_a_word(const int32_t *taps, int ntaps, int lane, int reg, int lo)
-{
-	const int g = lane >> 2, t = lane & 3, h = ntaps / 2;
-	const int m = g + ((reg & 1) ? 8 : 0);
-	const int kp0 = 8 * t + ((reg & 2) ? 4 : 0);
-	uint32_t r = 0;
-	for(int e = 0; e < 4; e++)
-	{
-		const int y = kp0 + e - (KL_UVLEAD - h) - m;
-		const int v = (y >= 0 && y < ntaps) ? taps[y] : 0;
-		const uint32_t b = lo ? ((uint32_t) v & 0xFFu) : (((uint32_t) v >> 8) & 0xFFu);
-		r |= b << (8 * e);
-	}
-	return(r);
-}
+// tap operand of the chroma low-pass (one k-step of 32): mf_lp_a_word (htv_mma_fir.h, shared with the host-side emulation)
+#define kl_chroma_a_word mf_lp_a_word
 
 // one complex int16 table entry through the read-only path: x = i, y = q
 __device__ __forceinline__ short2 kl_ldc16(const htv_c16_t *p) { return(__ldg(reinterpret_cast<const short2 *>(p))); }
@@ -299,7 +284,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	short *ntp = reinterpret_cast<short *>(ctab + 64);
 	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
-	const int xb = MF_TILE * nt + 32 * t + g;                               // the lane's samples: xb + 8 j
+	const int xb = mf_lane_x(nt, lane, 0);                                  // the lane's samples: xb + 8 j
 
 	const int a = blockIdx.x * run, bnd = min(a + run, nlines);
 	if(a >= nlines) return;
@@ -324,7 +309,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 	const bool all_full = xb >= full_l && xb + 24 < full_r;                 // ... with all four samples
 	const bool in_burst = xb + 24 >= dp.burst_left && xb < dp.burst_left + dp.burst_width;
 	unsigned char *const uv0 = uvp + KL_UVLEAD + xb;                        // the lane's bytes in the four chroma planes
-	const unsigned char *const uvb = uvp + MF_M * (8 * nt + g) + 8 * t;     // ... and its chroma B fragment
+	const unsigned char *const uvb = uvp + mf_lp_b_offset(nt, lane);        // ... and its chroma B fragment
 	const int fo0 = mf_b_offset(nt, 0, lane);
 	constexpr int NA16 = (int) (sizeof(LineA2) / 16);
 
@@ -444,7 +429,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					const int ci = ((j & 1) << 1) | (j >> 1);
+					const int ci = mf_lane_ci(j);
 					cu[j] = kl_acc15(uhh[ci], umid[ci], ull[ci]);
 					cv[j] = kl_acc15(vhh[ci], vmid[ci], vll[ci]);
 					if(CSAT) { cu[j] = sat16i(cu[j]); cv[j] = sat16i(cv[j]); }
@@ -541,7 +526,7 @@ k_line(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const LineR
 			#pragma unroll
 			for(int j = 0; j < 4; j++)
 			{
-				const int ci = ((j & 1) << 1) | (j >> 1);
+				const int ci = mf_lane_ci(j);
 				oi[j] = kl_fir_out(ihh[ci], imid[ci], ill[ci]);
 				oq[j] = HASQ ? kl_fir_out(qhh[ci], qmid[ci], qll[ci]) : 0;
 			}

@@ -105,4 +105,35 @@ MF_HD int32_t mf_combine(int32_t hh, int32_t mid, int32_t ll)
 	return((int32_t) (((uint32_t) hh << 16) + ((uint32_t) mid << 8) + (uint32_t) ll));
 }
 
+/* ---- the fused line kernels' lane layout and their short low-pass (k_line's chroma low-pass, k_sec_raster's baseband
+ * low-pass: up to 17 taps, one k-step of 32) ------------------------------------------------------------------------
+ * A lane keeps four samples of its warp's tile in the order the accumulators of an m16n8k32 contraction arrive:
+ * sample j of lane (g, t) is x = 128 nt + 32 t + g + 8 j, held by accumulator register ci = ((j & 1) << 1) | (j >> 1).
+ * The low-pass reads byte planes whose byte 0 is sample -MF_LP_LEAD of the line:
+ *   out[x] = sum_y u[x - h + y] tap[y], h = ntaps / 2;   A[m][k'] = tap[k' - m - (MF_LP_LEAD - h)]. */
+#define MF_LP_LEAD 8
+
+MF_HD int mf_lane_x(int nt, int lane, int j) { return(MF_TILE * nt + 32 * (lane & 3) + (lane >> 2) + 8 * j); }
+MF_HD int mf_lane_ci(int j) { return(((j & 1) << 1) | (j >> 1)); }
+
+/* byte offset, inside a low-pass plane, of the 8 stream bytes lane (g, t) loads for tile nt */
+MF_HD int mf_lp_b_offset(int nt, int lane) { return(MF_M * (8 * nt + (lane >> 2)) + 8 * (lane & 3)); }
+
+/* one 32-bit register of the low-pass tap operand (same fragment convention as mf_a_word) */
+MF_HD uint32_t mf_lp_a_word(const int32_t *taps, int ntaps, int lane, int reg, int lo)
+{
+	const int g = lane >> 2, t = lane & 3, h = ntaps / 2;
+	const int m = g + ((reg & 1) ? 8 : 0);
+	const int kp0 = 8 * t + ((reg & 2) ? 4 : 0);
+	uint32_t r = 0;
+	for(int e = 0; e < 4; e++)
+	{
+		const int y = kp0 + e - (MF_LP_LEAD - h) - m;
+		const int v = (y >= 0 && y < ntaps) ? taps[y] : 0;
+		const uint32_t b = lo ? ((uint32_t) v & 0xFFu) : (((uint32_t) v >> 8) & 0xFFu);
+		r |= b << (8 * e);
+	}
+	return(r);
+}
+
 #endif

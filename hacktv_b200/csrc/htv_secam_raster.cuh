@@ -25,7 +25,7 @@ k_sec_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 	uint4 *ctab = ntab + MF_KSTEPS * 2 * 32;                                // [hi, lo][lane]
 	const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
-	const int xb = MF_TILE * nt + 32 * t + g;                               // the lane's samples: xb + 8 j
+	const int xb = mf_lane_x(nt, lane, 0);                                  // the lane's samples: xb + 8 j
 
 	const int a = blockIdx.x * run, bnd = min(a + run, nrows);
 	if(a >= nrows) return;
@@ -39,7 +39,7 @@ k_sec_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 	const int a0 = dp.active_left, a1 = dp.active_left + dp.active_width;
 	const bool in_pic = xb + 24 >= a0 && xb < a1;                           // the lane touches the picture area at all
 	const int fo0 = mf_b_offset(nt, 0, lane);
-	const int uo0 = MF_M * (8 * nt + g) + 8 * t;
+	const int uo0 = mf_lp_b_offset(nt, lane);
 	const bool notch_tile = MF_TILE * nt < a1 && MF_TILE * (nt + 1) > a0;
 
 	// loads of a row issued one phase early: template (int16 x 4), this line's pixels and the stored line's (RGBx x 4)
@@ -155,7 +155,7 @@ k_sec_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					const int ci = ((j & 1) << 1) | (j >> 1), x = xb + 8 * j;
+					const int ci = mf_lane_ci(j), x = xb + 8 * j;
 					if(x >= a0 && x < a1) lv[j] = kl_fir_out(hh[ci], mid[ci], ll[ci]);
 				}
 			}
@@ -170,7 +170,7 @@ k_sec_raster(const __grid_constant__ htv_dparams_t dp, const DevTables dt, const
 				#pragma unroll
 				for(int j = 0; j < 4; j++)
 				{
-					const int ci = ((j & 1) << 1) | (j >> 1), x = xb + 8 * j;
+					const int ci = mf_lane_ci(j), x = xb + 8 * j;
 					if(!FULL && x >= W) continue;
 					const int raw = mf_combine(hh[ci], mid[ci], ll[ci]);
 					ss.cbT[(((size_t) (x >> 3) * ss.rows + r) << 3) + (x & 7)] = (int16_t) sat16i(raw >> 15);

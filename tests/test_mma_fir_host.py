@@ -34,3 +34,23 @@ def test_pitched_plane_layout_for_any_width(emu, W):
         for extreme in (0, 1):
             out = subprocess.run([emu, str(W), str(seed), str(extreme), "1"], capture_output=True, text=True)
             assert out.returncode == 0 and out.stdout.startswith("OK %d" % W), out.stdout
+
+
+@pytest.fixture(scope="module")
+def lp_emu(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("lp") / "lp_mma_emu")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-I", os.path.join(ROOT, "hacktv_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "lp_mma_emu.c")])
+    return exe
+
+
+@pytest.mark.parametrize("W", [1024, 1280, 858, 864, 967, 128])
+@pytest.mark.parametrize("ntaps", [11, 13, 15, 17])
+def test_short_low_pass_and_lane_layout(lp_emu, W, ntaps):
+    """k_line's chroma low-pass (11 .. 17 taps by sample rate) and k_sec_raster's 15-tap baseband low-pass: one k-step of
+    32, the lane's four samples x = 128 nt + 32 t + g + 8 j in accumulator order - every sample owned once, the sums equal
+    the zero-padded direct form including int32 wrap-around."""
+    for seed in (1, 2):
+        for extreme in (0, 1):
+            out = subprocess.run([lp_emu, str(W), str(ntaps), str(seed), str(extreme)], capture_output=True, text=True)
+            assert out.returncode == 0 and out.stdout.startswith("OK %d" % W), out.stdout
